@@ -1,0 +1,269 @@
+// almops.cu -- K6: the alm helpers of pixell.cmisc (reference cython/cmisc_core.c:16-304,
+// cython/cmisc.pyx:8-191) as HBM-bound kernels.  All kernels walk the alm m-row by m-row with l as
+// the fast (coalesced) index; reductions are done in a fixed order (bit-reproducible).
+#include "common.cuh"
+#include <algorithm>
+
+#define B2_F64 0
+#define B2_F32 1
+#define MB 32        // m values per CTA in alm2cl
+
+template<typename T> struct cplx_of;
+template<> struct cplx_of<double> { typedef double2 type; };
+template<> struct cplx_of<float>  { typedef float2 type; };
+
+// ---- alm2cl: cmisc_core.c:16-110.  partial[mb][l] = sum over the m block, then a fixed-order sum.
+template<typename T> __global__ void k_alm2cl_partial(int lmax, int mmax, const int64_t *mstart,
+	const typename cplx_of<T>::type *a1, const typename cplx_of<T>::type *a2, double *partial)
+{
+	int l = blockIdx.x*blockDim.x + threadIdx.x;
+	int mb = blockIdx.y;
+	if (l > lmax) return;
+	double acc = 0;
+	int m0 = mb*MB, m1 = min(min(m0 + MB - 1, mmax), l);
+	for (int m = m0; m <= m1; m++) {
+		int64_t i = mstart[m] + l;
+		typename cplx_of<T>::type u = a1[i], v = a2[i];
+		// m = 0 uses the real parts only (cmisc_core.c:26, :58, :90)
+		if (m == 0) acc += (double)u.x*(double)v.x*0.5;
+		else acc += (double)u.x*(double)v.x + (double)u.y*(double)v.y;
+	}
+	partial[(int64_t)mb*(lmax + 1) + l] = acc;
+}
+
+template<typename CT> __global__ void k_alm2cl_final(int lmax, int nmb, const double *partial, CT *cl)
+{
+	int l = blockIdx.x*blockDim.x + threadIdx.x;
+	if (l > lmax) return;
+	double s = 0;
+	for (int b = 0; b < nmb; b++) s += partial[(int64_t)b*(lmax + 1) + l];
+	cl[l] = (CT)(s*(2.0/(2*l + 1)));
+}
+
+// ---- lmul: cmisc_core.c:159-182
+template<typename T> __global__ void k_lmul(int lmax, int mmax, const int64_t *mstart,
+	typename cplx_of<T>::type *alm, int lfmax, const T *lfun)
+{
+	int m = blockIdx.y;
+	int l = m + blockIdx.x*blockDim.x + threadIdx.x;
+	if (l > lmax) return;
+	int64_t i = mstart[m] + l;
+	T v = l <= lfmax ? lfun[l] : (T)0;
+	typename cplx_of<T>::type a = alm[i];
+	a.x *= v; a.y *= v;
+	alm[i] = a;
+}
+
+// ---- lmatmul: cmisc_core.c:185-274.  In-place safe: a thread reads all M inputs before it writes.
+#define LMAT_MAX 8
+template<typename T> __global__ void k_lmatmul(int N, int M, int lmax, int mmax, const int64_t *mstart,
+	const typename cplx_of<T>::type *alm, int64_t acs, int lfmax, const T *lmat,
+	typename cplx_of<T>::type *oalm, int64_t ocs)
+{
+	int m = blockIdx.y;
+	int l = m + blockIdx.x*blockDim.x + threadIdx.x;
+	if (l > lmax) return;
+	int64_t i = mstart[m] + l;
+	typename cplx_of<T>::type in[LMAT_MAX];
+	for (int c = 0; c < M; c++) in[c] = alm[c*acs + i];
+	for (int r = 0; r < N; r++) {
+		T vr = 0, vi = 0;
+		if (l <= lfmax) for (int c = 0; c < M; c++) {
+			T f = lmat[((int64_t)r*M + c)*(lfmax + 1) + l];
+			vr += f*in[c].x; vi += f*in[c].y;
+		}
+		typename cplx_of<T>::type o; o.x = vr; o.y = vi;
+		oalm[r*ocs + i] = o;
+	}
+}
+
+// ---- transpose_alm: cmisc_core.c:116-156.  The k-th element in m-major address order holds the
+// k-th (l,m) pair of the l-major enumeration and moves to that pair's address.
+template<typename C> __global__ void k_transpose_alm(int lmax, int mmax, const int64_t *mstart, const C *ialm, C *oalm)
+{
+	int m = blockIdx.y;
+	int l = m + blockIdx.x*blockDim.x + threadIdx.x;
+	if (l > lmax) return;
+	// rank of (m,l) in m-major order
+	int64_t k = (int64_t)m*(lmax + 1) - (int64_t)m*(m - 1)/2 + (l - m);
+	// k-th pair of the l-major enumeration: rows l' <= mmax hold l'+1 entries, later rows mmax+1
+	int64_t ntri = (int64_t)(mmax + 1)*(mmax + 2)/2;
+	int64_t lp, mp;
+	if (k < ntri) {
+		lp = (int64_t)((sqrt(8.0*(double)k + 1.0) - 1.0)*0.5);
+		while (lp*(lp + 1)/2 > k) lp--;
+		while ((lp + 1)*(lp + 2)/2 <= k) lp++;
+		mp = k - lp*(lp + 1)/2;
+	} else {
+		int64_t r = k - ntri;
+		lp = mmax + 1 + r/(mmax + 1);
+		mp = r % (mmax + 1);
+	}
+	oalm[mstart[mp] + lp] = ialm[mstart[m] + l];
+}
+
+// ---- transfer_alm: cmisc.pyx:131-150
+template<typename C> __global__ void k_transfer_alm(int lmax, int mmax, const int64_t *ms1, int64_t ls1, const C *a1,
+	const int64_t *ms2, int64_t ls2, C *a2)
+{
+	int m = blockIdx.y;
+	int l = m + blockIdx.x*blockDim.x + threadIdx.x;
+	if (l > lmax) return;
+	a2[ms2[m] + l*ls2] = a1[ms1[m] + l*ls1];
+}
+
+// ------------------------------------------------------------------------------------ host side
+
+struct Staged {       // host <-> device staging of one buffer
+	void *dev = nullptr; void *host = nullptr; size_t bytes = 0; bool owned = false, out = false;
+	int in(const void *p, size_t nbytes, int mem, bool copy_in, bool copy_out, cudaStream_t st) {
+		bytes = nbytes; out = copy_out;
+		if (mem == 1 || p == nullptr) { dev = (void*)p; return 0; }
+		host = (void*)p; owned = true;
+		B2_CHECK(cudaMalloc(&dev, std::max<size_t>(nbytes, 16)));
+		if (copy_in) B2_CHECK(cudaMemcpyAsync(dev, p, nbytes, cudaMemcpyHostToDevice, st));
+		return 0;
+	}
+	int finish(cudaStream_t st) {
+		if (owned && out) B2_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st));
+		return 0;
+	}
+	~Staged() { if (owned && dev) cudaFree(dev); }
+};
+
+static int64_t span_of(int lmax, int mmax, const int64_t *mstart, int64_t lstride)
+{
+	int64_t hi = 0;
+	for (int m = 0; m <= mmax; m++) hi = std::max(hi, mstart[m] + (int64_t)lmax*lstride + 1);
+	return hi;
+}
+
+static int check_mstart(int lmax, int mmax, const int64_t *mstart)
+{
+	B2_REQUIRE(lmax >= 0 && mmax >= 0 && mmax <= lmax && mstart, "bad alm layout (lmax=%d mmax=%d)", lmax, mmax);
+	for (int m = 0; m <= mmax; m++) B2_REQUIRE(mstart[m] + m >= 0, "negative alm index for m=%d", m);
+	return 0;
+}
+
+extern "C" int b2_alm2cl(int lmax, int mmax, const int64_t *mstart, int dtype, const void *alm1, const void *alm2,
+	int cl_dtype, void *cl, int mem, void *stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (check_mstart(lmax, mmax, mstart)) return 1;
+	B2_REQUIRE(alm1 && cl, "alm2cl: null buffer");
+	if (!alm2) alm2 = alm1;
+	size_t esz = dtype == B2_F64 ? 16 : 8, csz = cl_dtype == B2_F64 ? 8 : 4;
+	int64_t span = span_of(lmax, mmax, mstart, 1);
+	DevBuf<int64_t> ms; if (ms.upload(std::vector<int64_t>(mstart, mstart + mmax + 1))) return 1;
+	Staged a, b, c;
+	if (a.in(alm1, span*esz, mem, true, false, st)) return 1;
+	if (alm2 == alm1) b.dev = a.dev; else if (b.in(alm2, span*esz, mem, true, false, st)) return 1;
+	if (c.in(cl, (lmax + 1)*csz, mem, false, true, st)) return 1;
+	int nmb = mmax/MB + 1;
+	DevBuf<double> partial; if (partial.alloc((size_t)nmb*(lmax + 1))) return 1;
+	dim3 grid((lmax + 256)/256, nmb);
+	if (dtype == B2_F64) k_alm2cl_partial<double><<<grid, 256, 0, st>>>(lmax, mmax, ms.p, (const double2*)a.dev, (const double2*)b.dev, partial.p);
+	else                 k_alm2cl_partial<float><<<grid, 256, 0, st>>>(lmax, mmax, ms.p, (const float2*)a.dev, (const float2*)b.dev, partial.p);
+	B2_LAUNCH_CHECK();
+	if (cl_dtype == B2_F64) k_alm2cl_final<double><<<(lmax + 256)/256, 256, 0, st>>>(lmax, nmb, partial.p, (double*)c.dev);
+	else                    k_alm2cl_final<float><<<(lmax + 256)/256, 256, 0, st>>>(lmax, nmb, partial.p, (float*)c.dev);
+	B2_LAUNCH_CHECK();
+	if (c.finish(st)) return 1;
+	B2_CHECK(cudaStreamSynchronize(st));      // temporaries die here
+	return 0;
+}
+
+extern "C" int b2_lmul(int lmax, int mmax, const int64_t *mstart, int dtype, void *alm, int lfmax, const void *lfun,
+	int mem, void *stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (check_mstart(lmax, mmax, mstart)) return 1;
+	B2_REQUIRE(alm && lfun && lfmax >= 0, "lmul: bad arguments");
+	size_t esz = dtype == B2_F64 ? 16 : 8;
+	int64_t span = span_of(lmax, mmax, mstart, 1);
+	DevBuf<int64_t> ms; if (ms.upload(std::vector<int64_t>(mstart, mstart + mmax + 1))) return 1;
+	Staged a, f;
+	if (a.in(alm, span*esz, mem, true, true, st)) return 1;
+	if (f.in(lfun, (size_t)(lfmax + 1)*esz/2, mem, true, false, st)) return 1;
+	dim3 grid((lmax + 256)/256, mmax + 1);
+	if (dtype == B2_F64) k_lmul<double><<<grid, 256, 0, st>>>(lmax, mmax, ms.p, (double2*)a.dev, lfmax, (const double*)f.dev);
+	else                 k_lmul<float><<<grid, 256, 0, st>>>(lmax, mmax, ms.p, (float2*)a.dev, lfmax, (const float*)f.dev);
+	B2_LAUNCH_CHECK();
+	if (a.finish(st)) return 1;
+	B2_CHECK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+extern "C" int b2_lmatmul(int N, int M, int lmax, int mmax, const int64_t *mstart, int dtype,
+	const void *alm, int64_t acs, int lfmax, const void *lmat, void *oalm, int64_t ocs, int mem, void *stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (check_mstart(lmax, mmax, mstart)) return 1;
+	B2_REQUIRE(alm && lmat && oalm && lfmax >= 0, "lmatmul: bad arguments");
+	B2_REQUIRE(N >= 1 && M >= 1 && M <= LMAT_MAX && N <= LMAT_MAX, "lmatmul supports up to %d components", LMAT_MAX);
+	size_t esz = dtype == B2_F64 ? 16 : 8;
+	int64_t span = span_of(lmax, mmax, mstart, 1);
+	DevBuf<int64_t> ms; if (ms.upload(std::vector<int64_t>(mstart, mstart + mmax + 1))) return 1;
+	Staged a, o, f;
+	bool inplace = (alm == oalm);
+	if (mem == 0) {
+		B2_REQUIRE(acs >= span && ocs >= span, "lmatmul: component stride smaller than the alm span");
+		if (a.in(alm, ((M - 1)*acs + span)*esz, mem, true, false, st)) return 1;
+		if (inplace) { o.dev = a.dev; }
+		else if (o.in(oalm, ((N - 1)*ocs + span)*esz, mem, true, true, st)) return 1;
+	} else { a.dev = (void*)alm; o.dev = oalm; }
+	if (f.in(lmat, (size_t)N*M*(lfmax + 1)*esz/2, mem, true, false, st)) return 1;
+	dim3 grid((lmax + 256)/256, mmax + 1);
+	if (dtype == B2_F64) k_lmatmul<double><<<grid, 256, 0, st>>>(N, M, lmax, mmax, ms.p, (const double2*)a.dev, acs, lfmax, (const double*)f.dev, (double2*)o.dev, ocs);
+	else                 k_lmatmul<float><<<grid, 256, 0, st>>>(N, M, lmax, mmax, ms.p, (const float2*)a.dev, acs, lfmax, (const float*)f.dev, (float2*)o.dev, ocs);
+	B2_LAUNCH_CHECK();
+	if (mem == 0) {
+		if (inplace) B2_CHECK(cudaMemcpyAsync(oalm, a.dev, ((N - 1)*ocs + span)*esz, cudaMemcpyDeviceToHost, st));
+		else if (o.finish(st)) return 1;
+	}
+	B2_CHECK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+extern "C" int b2_transpose_alm(int lmax, int mmax, const int64_t *mstart, int dtype, const void *ialm, void *oalm,
+	int mem, void *stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (check_mstart(lmax, mmax, mstart)) return 1;
+	B2_REQUIRE(ialm && oalm && ialm != oalm, "transpose_alm: needs distinct input and output");
+	size_t esz = dtype == B2_F64 ? 16 : 8;
+	int64_t span = span_of(lmax, mmax, mstart, 1);
+	DevBuf<int64_t> ms; if (ms.upload(std::vector<int64_t>(mstart, mstart + mmax + 1))) return 1;
+	Staged a, o;
+	if (a.in(ialm, span*esz, mem, true, false, st)) return 1;
+	if (o.in(oalm, span*esz, mem, true, true, st)) return 1;
+	dim3 grid((lmax + 256)/256, mmax + 1);
+	if (dtype == B2_F64) k_transpose_alm<double2><<<grid, 256, 0, st>>>(lmax, mmax, ms.p, (const double2*)a.dev, (double2*)o.dev);
+	else                 k_transpose_alm<float2><<<grid, 256, 0, st>>>(lmax, mmax, ms.p, (const float2*)a.dev, (float2*)o.dev);
+	B2_LAUNCH_CHECK();
+	if (o.finish(st)) return 1;
+	B2_CHECK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+extern "C" int b2_transfer_alm(int lmax1, int mmax1, const int64_t *mstart1, int64_t ls1, const void *alm1,
+	int lmax2, int mmax2, const int64_t *mstart2, int64_t ls2, void *alm2, int dtype, int mem, void *stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (check_mstart(lmax1, mmax1, mstart1) || check_mstart(lmax2, mmax2, mstart2)) return 1;
+	B2_REQUIRE(alm1 && alm2 && ls1 >= 1 && ls2 >= 1, "transfer_alm: bad arguments");
+	size_t esz = dtype == B2_F64 ? 16 : 8;
+	int lmax = std::min(lmax1, lmax2), mmax = std::min(mmax1, mmax2);
+	DevBuf<int64_t> m1, m2;
+	if (m1.upload(std::vector<int64_t>(mstart1, mstart1 + mmax1 + 1)) || m2.upload(std::vector<int64_t>(mstart2, mstart2 + mmax2 + 1))) return 1;
+	Staged a, o;
+	if (a.in(alm1, span_of(lmax1, mmax1, mstart1, ls1)*esz, mem, true, false, st)) return 1;
+	if (o.in(alm2, span_of(lmax2, mmax2, mstart2, ls2)*esz, mem, true, true, st)) return 1;
+	dim3 grid((lmax + 256)/256, mmax + 1);
+	if (dtype == B2_F64) k_transfer_alm<double2><<<grid, 256, 0, st>>>(lmax, mmax, m1.p, ls1, (const double2*)a.dev, m2.p, ls2, (double2*)o.dev);
+	else                 k_transfer_alm<float2><<<grid, 256, 0, st>>>(lmax, mmax, m1.p, ls1, (const float2*)a.dev, m2.p, ls2, (float2*)o.dev);
+	B2_LAUNCH_CHECK();
+	if (o.finish(st)) return 1;
+	B2_CHECK(cudaStreamSynchronize(st));
+	return 0;
+}

@@ -1,0 +1,432 @@
+// api.cu -- the C ABI of libb200sht.so (include/b200sht.h): plans, transforms, grid weights.
+#include "../../include/b200sht.h"
+#include "plan.cuh"
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+
+// ------------------------------------------------------------------------------------ errors
+
+static thread_local char g_err[1024] = "";
+void b2_set_error(const char *fmt, ...)
+{
+	va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+extern "C" const char *b2_last_error(void) { return g_err; }
+extern "C" int b2_version(void) { return 100; }
+
+extern "C" int b2_init(int device)
+{
+	int n = 0;
+	B2_CHECK(cudaGetDeviceCount(&n));
+	B2_REQUIRE(device >= 0 && device < n, "device %d out of range (%d visible)", device, n);
+	B2_CHECK(cudaSetDevice(device));
+	B2_CHECK(cudaFree(0));
+	return 0;
+}
+extern "C" int b2_device_synchronize(void) { B2_CHECK(cudaDeviceSynchronize()); return 0; }
+extern "C" int b2_dfma_peak_gflops(double *out) { return dfma_peak_gflops(out); }
+
+// ------------------------------------------------------------------------------------ grids
+
+int grid_theta_host(const char *g, int n, std::vector<double> &theta)
+{
+	std::string s(g);
+	theta.resize(n);
+	for (int k = 0; k < n; k++) {
+		// ring colatitudes of the named equiangular grids (pole offsets: pixell/curvedsky.py:1334-1342)
+		if      (s == "CC")     theta[k] = n > 1 ? k*M_PI/(n - 1) : 0.0;
+		else if (s == "F1")     theta[k] = (k + 0.5)*M_PI/n;
+		else if (s == "MW")     theta[k] = (2*k + 1)*M_PI/(2*n - 1);
+		else if (s == "MWflip") theta[k] = 2*k*M_PI/(2*n - 1);
+		else if (s == "DH")     theta[k] = k*M_PI/n;
+		else if (s == "F2")     theta[k] = (k + 1)*M_PI/(n + 1);
+		else { b2_set_error("unknown geometry '%s'", g); return 1; }
+	}
+	return 0;
+}
+
+// interpolatory ring weights (sum = 4 pi).  kind 0: Fourier-series rule on a circle of N points with
+// node offset o2/2 (CC, F1, MW, MWflip); kind 1: Fejer-2 nodes (k+1) pi/(nn+1), shifted by `shift` rings (DH)
+__global__ void k_gridweights(double *w, int n, int kind, int N, int o2, int K, int cc, int nn, int shift)
+{
+	int k = blockIdx.x*blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	if (kind == 0) {
+		long long t = 2LL*k + o2;                      // theta_k = t pi / N
+		double sum = 0;
+		for (int j = K/2; j >= 1; j--) {
+			double c = (cc && 2*j == n - 1) ? 1.0 : 2.0;
+			long long r = (2LL*j*t) % (2LL*N);
+			sum += c*cospi((double)r/(double)N)/(4.0*j*j - 1.0);
+		}
+		bool single = (t % N) == 0;                    // pole ring: appears once on the circle
+		w[k] = 4.0*M_PI/N*(single ? 1.0 : 2.0)*(1.0 - sum);
+	} else {
+		int kk = k - shift;
+		if (kk < 0) { w[k] = 0; return; }
+		long long t = kk + 1;                          // theta = t pi/(nn+1)
+		double sum = 0;
+		for (int j = (nn + 1)/2; j >= 1; j--) {
+			long long r = ((2LL*j - 1)*t) % (2LL*(nn + 1));
+			sum += sinpi((double)r/(double)(nn + 1))/(2.0*j - 1.0);
+		}
+		w[k] = 2.0*M_PI*(4.0/(nn + 1))*sinpi((double)t/(double)(nn + 1))*sum;
+	}
+}
+
+int gridweights_device(const char *g, int n, double *out_host, double *out_dev)
+{
+	std::string s(g);
+	B2_REQUIRE(n >= 1, "get_gridweights: ntheta must be positive");
+	DevBuf<double> tmp;
+	double *d = out_dev;
+	if (!d) { if (tmp.alloc(n)) return 1; d = tmp.p; }
+	int kind = 0, N = 0, o2 = 0, cc = 0, nn = 0, shift = 0;
+	if      (s == "CC")     { N = 2*(n - 1); o2 = 0; cc = 1; }
+	else if (s == "F1")     { N = 2*n;       o2 = 1; }
+	else if (s == "MW")     { N = 2*n - 1;   o2 = 1; }
+	else if (s == "MWflip") { N = 2*n - 1;   o2 = 0; }
+	else if (s == "F2")     { kind = 1; nn = n; shift = 0; }
+	else if (s == "DH")     { kind = 1; nn = n - 1; shift = 1; }
+	else { b2_set_error("unknown geometry '%s'", g); return 1; }
+	if (kind == 0 && N == 0) {        // CC with a single ring
+		double v = 4.0*M_PI;
+		B2_CHECK(cudaMemcpy(d, &v, sizeof(double), cudaMemcpyHostToDevice));
+	} else {
+		k_gridweights<<<(n + 127)/128, 128>>>(d, n, kind, N, o2, n - 1, cc, nn, shift);
+		B2_LAUNCH_CHECK();
+	}
+	if (out_host) B2_CHECK(cudaMemcpy(out_host, d, n*sizeof(double), cudaMemcpyDeviceToHost));
+	else B2_CHECK(cudaDeviceSynchronize());
+	return 0;
+}
+
+extern "C" int b2_gridweights(const char *geometry, int ntheta, double *out)
+{
+	B2_REQUIRE(geometry && out, "get_gridweights: null argument");
+	return gridweights_device(geometry, ntheta, out, nullptr);
+}
+
+// ------------------------------------------------------------------------------------ plans
+
+b2_sht_plan::~b2_sht_plan() { for (auto &e : ev) if (e) cudaEventDestroy(e); }
+
+size_t b2_sht_plan::bytes() const
+{
+	size_t b = mstart.bytes() + geom.bytes() + fft.bytes() + leg.bytes() + w2d.bytes() + stage_alm.bytes() + stage_map.bytes();
+	for (auto &t : tables) b += t.second->bytes();
+	if (resamp) b += resamp->bytes();
+	return b;
+}
+
+LegTables *b2_sht_plan::get_tables(int spin)
+{
+	auto it = tables.find(spin);
+	if (it != tables.end()) return it->second.get();
+	std::unique_ptr<LegTables> t(new LegTables());
+	if (t->build(lmax, mmax, spin)) return nullptr;
+	LegTables *p = t.get();
+	tables[spin] = std::move(t);
+	return p;
+}
+
+static int plan_common(b2_sht_plan *p, int nring, const double *theta, int64_t nphi, double phi0, int xdir,
+	int64_t npix, const int64_t *ringstart, const double *weight, int lmax, int mmax, const int64_t *mstart, int64_t lstride)
+{
+	B2_REQUIRE(nring >= 1 && theta && ringstart, "plan: need at least one ring");
+	B2_REQUIRE(lmax >= 0 && mmax >= 0 && mmax <= lmax, "plan: need 0 <= mmax <= lmax (got lmax=%d mmax=%d)", lmax, mmax);
+	B2_REQUIRE(mstart && lstride >= 1, "plan: bad alm layout");
+	for (int r = 0; r < nring; r++) {
+		B2_REQUIRE(theta[r] >= 0 && theta[r] <= M_PI, "plan: theta[%d]=%g outside [0,pi]", r, theta[r]);
+		B2_REQUIRE(ringstart[r] >= 0, "plan: negative ringstart");
+	}
+	p->lmax = lmax; p->mmax = mmax; p->lstride = lstride;
+	p->mstart_h.assign(mstart, mstart + mmax + 1);
+	p->alm_span = 0;
+	for (int m = 0; m <= mmax; m++) {
+		B2_REQUIRE(mstart[m] + (int64_t)m*lstride >= 0, "plan: negative alm index for m=%d", m);
+		p->alm_span = std::max(p->alm_span, mstart[m] + (int64_t)lmax*lstride + 1);
+	}
+	if (p->mstart.upload(p->mstart_h)) return 1;
+	p->nring = nring; p->nphi = nphi; p->npix = npix;
+	p->ringstart_h.assign(ringstart, ringstart + nring);
+	p->map_lo = *std::min_element(ringstart, ringstart + nring);
+	p->map_hi = *std::max_element(ringstart, ringstart + nring) + npix;
+	p->row_pitch = 0;
+	if (nring > 1) {
+		int64_t d = ringstart[1] - ringstart[0];
+		bool ok = d != 0;
+		for (int r = 1; r < nring && ok; r++) ok = (ringstart[r] - ringstart[r - 1] == d);
+		if (ok) p->row_pitch = d;
+	} else p->row_pitch = npix;
+	if (p->geom.build(nring, theta)) return 1;
+	if (p->fft.build(nphi, phi0, xdir, npix, nring, ringstart, weight, mmax)) return 1;
+	if (p->leg.alloc((size_t)2*(mmax + 1)*p->geom.nring_pad)) return 1;
+	B2_CHECK(cudaMemset(p->leg.p, 0, p->leg.bytes()));
+	for (auto &e : p->ev) B2_CHECK(cudaEventCreate(&e));
+	return 0;
+}
+
+extern "C" int b2_sht_plan_rings(b2_sht_plan **out, int nring, const double *theta, int64_t nphi, double phi0,
+	int xdir, int64_t npix_ring, const int64_t *ringstart, const double *weight,
+	int lmax, int mmax, const int64_t *mstart, int64_t lstride)
+{
+	B2_REQUIRE(out, "plan: null output pointer");
+	std::unique_ptr<b2_sht_plan> p(new b2_sht_plan());
+	if (plan_common(p.get(), nring, theta, nphi, phi0, xdir, npix_ring, ringstart, weight, lmax, mmax, mstart, lstride)) return 1;
+	*out = p.release();
+	return 0;
+}
+
+static int maxlmax_2d(const std::string &g, int ny)
+{
+	// pixell/curvedsky.py:1349-1353
+	if (g == "CC") return ny - 2;
+	if (g == "DH") return (ny - 2)/2;
+	if (g == "F2") return (ny - 1)/2;
+	return ny - 1;
+}
+
+extern "C" int b2_sht_plan_2d(b2_sht_plan **out, const char *geometry, int ntheta, int64_t nphi, double phi0,
+	int flip_y, int flip_x, int lmax, int mmax, const int64_t *mstart, int64_t lstride)
+{
+	B2_REQUIRE(out && geometry, "plan: null argument");
+	std::unique_ptr<b2_sht_plan> p(new b2_sht_plan());
+	std::vector<double> theta;
+	if (grid_theta_host(geometry, ntheta, theta)) return 1;
+	std::vector<int64_t> rs(ntheta);
+	for (int k = 0; k < ntheta; k++) rs[k] = (int64_t)(flip_y ? ntheta - 1 - k : k)*nphi;
+	if (plan_common(p.get(), ntheta, theta.data(), nphi, phi0, flip_x ? -1 : 1, nphi, rs.data(), nullptr, lmax, mmax, mstart, lstride)) return 1;
+	p->is2d = true; p->geometry = geometry; p->ntheta = ntheta;
+	// exact analysis: either direct quadrature weights or the folded theta weighting (K5)
+	if (lmax <= maxlmax_2d(p->geometry, ntheta)) {
+		if (ThetaResampler::needed(p->geometry, ntheta, lmax)) {
+			p->resamp.reset(new ThetaResampler());
+			if (p->resamp->build(p->geometry, ntheta, nphi, lmax, mmax, p->geom.nring_pad)) return 1;
+		} else {
+			std::vector<double> w(ntheta);
+			if (gridweights_device(geometry, ntheta, w.data(), nullptr)) return 1;
+			for (auto &v : w) v /= (double)nphi;
+			if (p->w2d.upload(w)) return 1;
+		}
+	}
+	*out = p.release();
+	return 0;
+}
+
+extern "C" void b2_sht_plan_destroy(b2_sht_plan *plan) { delete plan; }
+extern "C" int64_t b2_sht_plan_bytes(const b2_sht_plan *plan) { return plan ? (int64_t)plan->bytes() : 0; }
+
+// ------------------------------------------------------------------------------------ conversions
+
+__global__ void k_c64_to_c128(const float2 *in, double2 *out, int64_t n)
+{
+	int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x;
+	if (i < n) { float2 v = in[i]; out[i] = make_double2(v.x, v.y); }
+}
+__global__ void k_c128_to_c64(const double2 *in, float2 *out, int64_t n)
+{
+	int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x;
+	if (i < n) { double2 v = in[i]; out[i] = make_float2((float)v.x, (float)v.y); }
+}
+__global__ void k_scale_rows(double2 *leg, const double *w, int nring, int64_t nring_pad, int64_t nrow)
+{
+	int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x;
+	if (i >= nrow*nring_pad) return;
+	int r = (int)(i % nring_pad);
+	if (r < nring) { double2 v = leg[i]; double s = w[r]; leg[i] = make_double2(v.x*s, v.y*s); }
+}
+
+// ------------------------------------------------------------------------------------ execution
+
+enum { OP_SYNTH, OP_ADJ_SYNTH, OP_ANALYSIS, OP_ADJ_ANALYSIS };
+
+struct Exec {
+	b2_sht_plan *p; int op, spin, mode, dtype, mem; cudaStream_t st;
+	int nca, ncm;              // alm / map components
+	size_t asz, msz;           // bytes per complex alm element / real map element
+};
+
+static int copy_map(Exec &E, void *host, void *dev, bool to_dev)
+{
+	b2_sht_plan *p = E.p;
+	// host component pointer `host` addresses element 0; the rings occupy [map_lo, map_hi)
+	char *h = (char*)host + p->map_lo*E.msz; char *d = (char*)dev;
+	cudaMemcpyKind kind = to_dev ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+	if (p->row_pitch == p->npix || p->row_pitch == -p->npix || p->nring == 1) {
+		if (to_dev) B2_CHECK(cudaMemcpyAsync(d, h, (p->map_hi - p->map_lo)*E.msz, kind, E.st));
+		else        B2_CHECK(cudaMemcpyAsync(h, d, (p->map_hi - p->map_lo)*E.msz, kind, E.st));
+	} else {
+		// only the ring pixels move (rows with gaps between them)
+		for (int r = 0; r < p->nring; r++) {
+			size_t off = (p->ringstart_h[r] - p->map_lo)*E.msz;
+			if (to_dev) B2_CHECK(cudaMemcpyAsync(d + off, h + off, p->npix*E.msz, kind, E.st));
+			else        B2_CHECK(cudaMemcpyAsync(h + off, d + off, p->npix*E.msz, kind, E.st));
+		}
+	}
+	return 0;
+}
+
+static int run_one(Exec &E, void *alm, int64_t alm_cstride, void *map, int64_t map_cstride)
+{
+	b2_sht_plan *p = E.p;
+	const bool to_map = (E.op == OP_SYNTH || E.op == OP_ADJ_ANALYSIS);
+	LegTables *T = p->get_tables(E.spin);
+	if (!T) return 1;
+	AlmLayout L; L.lmax = p->lmax; L.mmax = p->mmax; L.mstart_d = p->mstart.p; L.lstride = p->lstride;
+	const int deriv1 = E.mode == B2_MODE_DERIV1;
+	B2_CHECK(cudaEventRecord(p->ev[0], E.st));
+
+	// ---- stage alm on the device as complex128
+	double2 *dalm = nullptr; int64_t dalm_cs = alm_cstride;
+	const bool alm_direct = (E.mem == B2_MEM_DEVICE && E.dtype == B2_F64);
+	if (alm_direct) dalm = (double2*)alm;
+	else {
+		size_t need = (size_t)E.nca*p->alm_span*16 + (E.dtype == B2_F32 ? (size_t)E.nca*p->alm_span*8 : 0);
+		if (p->stage_alm.n < need && p->stage_alm.alloc(need)) return 1;
+		dalm = (double2*)p->stage_alm.p; dalm_cs = p->alm_span;
+		float2 *tmp32 = (float2*)(p->stage_alm.p + (size_t)E.nca*p->alm_span*16);
+		// the input direction needs the values; the output direction needs them too so that entries the
+		// transform does not own survive the round trip
+		for (int c = 0; c < E.nca; c++) {
+			char *src = (char*)alm + (size_t)c*alm_cstride*E.asz;
+			if (E.dtype == B2_F64) B2_CHECK(cudaMemcpyAsync(dalm + c*dalm_cs, src, p->alm_span*16, cudaMemcpyDefault, E.st));
+			else {
+				const float2 *s32 = (const float2*)src;
+				if (E.mem == B2_MEM_HOST) { B2_CHECK(cudaMemcpyAsync(tmp32 + c*p->alm_span, src, p->alm_span*8, cudaMemcpyHostToDevice, E.st)); s32 = tmp32 + c*p->alm_span; }
+				k_c64_to_c128<<<(unsigned)((p->alm_span + 255)/256), 256, 0, E.st>>>(s32, dalm + c*dalm_cs, p->alm_span);
+				B2_LAUNCH_CHECK();
+			}
+		}
+	}
+	// ---- stage the map
+	void *dmap = map; int64_t dmap_cs = map_cstride;
+	if (E.mem == B2_MEM_HOST) {
+		size_t span = (size_t)(p->map_hi - p->map_lo);
+		size_t need = (size_t)E.ncm*span*E.msz;
+		if (p->stage_map.n < need && p->stage_map.alloc(need)) return 1;
+		dmap_cs = (int64_t)span;
+		dmap = p->stage_map.p - p->map_lo*E.msz;      // so that element offsets keep their meaning
+		if (!to_map) for (int c = 0; c < E.ncm; c++)
+			if (copy_map(E, (char*)map + (size_t)c*map_cstride*E.msz, p->stage_map.p + (size_t)c*span*E.msz, true)) return 1;
+	}
+	B2_CHECK(cudaEventRecord(p->ev[1], E.st));
+
+	if (to_map) {
+		if (leg_alm2leg(*T, p->geom, L, deriv1, dalm, dalm_cs, p->leg.p, E.st)) return 1;
+		B2_CHECK(cudaEventRecord(p->ev[2], E.st));
+		if (E.op == OP_ADJ_ANALYSIS) { b2_set_error("adjoint_analysis_2d is not implemented yet"); return 1; }
+		B2_CHECK(cudaEventRecord(p->ev[3], E.st));
+		if (ring_leg2map(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, dmap, dmap_cs, E.dtype, E.st)) return 1;
+		B2_CHECK(cudaEventRecord(p->ev[4], E.st));
+	} else {
+		if (ring_map2leg(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, dmap, dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, E.st)) return 1;
+		B2_CHECK(cudaEventRecord(p->ev[2], E.st));
+		if (E.op == OP_ANALYSIS) {
+			if (p->resamp) { if (p->resamp->apply(p->leg.p, E.ncm, E.spin, E.st)) return 1; }
+			else {
+				int64_t nrow = (int64_t)E.ncm*(p->mmax + 1);
+				k_scale_rows<<<(unsigned)((nrow*p->geom.nring_pad + 255)/256), 256, 0, E.st>>>(p->leg.p, p->w2d.p, p->nring, p->geom.nring_pad, nrow);
+				B2_LAUNCH_CHECK();
+			}
+		}
+		B2_CHECK(cudaEventRecord(p->ev[3], E.st));
+		if (leg_leg2alm(*T, p->geom, L, deriv1, dalm, dalm_cs, p->leg.p, E.st)) return 1;
+		B2_CHECK(cudaEventRecord(p->ev[4], E.st));
+	}
+
+	// ---- results back
+	if (to_map) {
+		if (E.mem == B2_MEM_HOST) {
+			size_t span = (size_t)(p->map_hi - p->map_lo);
+			for (int c = 0; c < E.ncm; c++)
+				if (copy_map(E, (char*)map + (size_t)c*map_cstride*E.msz, p->stage_map.p + (size_t)c*span*E.msz, false)) return 1;
+		}
+	} else if (!alm_direct) {
+		float2 *tmp32 = (float2*)(p->stage_alm.p + (size_t)E.nca*p->alm_span*16);
+		for (int c = 0; c < E.nca; c++) {
+			char *dst = (char*)alm + (size_t)c*alm_cstride*E.asz;
+			if (E.dtype == B2_F64) B2_CHECK(cudaMemcpyAsync(dst, dalm + c*dalm_cs, p->alm_span*16, cudaMemcpyDefault, E.st));
+			else {
+				float2 *d32 = E.mem == B2_MEM_HOST ? tmp32 + c*p->alm_span : (float2*)dst;
+				k_c128_to_c64<<<(unsigned)((p->alm_span + 255)/256), 256, 0, E.st>>>(dalm + c*dalm_cs, d32, p->alm_span);
+				B2_LAUNCH_CHECK();
+				if (E.mem == B2_MEM_HOST) B2_CHECK(cudaMemcpyAsync(dst, d32, p->alm_span*8, cudaMemcpyDeviceToHost, E.st));
+			}
+		}
+	}
+	p->timing[0] = to_map ? 1 : -1;
+	return 0;
+}
+
+static int execute(b2_sht_plan *plan, int op, int spin, int mode, int dtype, int nbatch,
+	void *alm, int64_t alm_cstride, int64_t alm_bstride, void *map, int64_t map_cstride, int64_t map_bstride,
+	int mem, void *stream)
+{
+	B2_REQUIRE(plan && alm && map, "transform: null argument");
+	B2_REQUIRE(spin >= 0 && spin <= 32, "transform: spin %d out of range", spin);
+	B2_REQUIRE(dtype == B2_F64 || dtype == B2_F32, "transform: bad dtype");
+	B2_REQUIRE(mem == B2_MEM_HOST || mem == B2_MEM_DEVICE, "transform: bad memory kind");
+	B2_REQUIRE(mode == B2_MODE_STANDARD || (mode == B2_MODE_DERIV1 && spin == 1), "transform: DERIV1 needs spin=1");
+	B2_REQUIRE(nbatch >= 1, "transform: nbatch must be >= 1");
+	if (op == OP_ANALYSIS || op == OP_ADJ_ANALYSIS) {
+		B2_REQUIRE(plan->is2d, "analysis_2d needs a plan made by b2_sht_plan_2d");
+		B2_REQUIRE(plan->resamp || plan->w2d.n, "lmax=%d too large for geometry %s with %d rings", plan->lmax, plan->geometry.c_str(), plan->ntheta);
+	}
+	Exec E; E.p = plan; E.op = op; E.spin = spin; E.mode = mode; E.dtype = dtype; E.mem = mem; E.st = (cudaStream_t)stream;
+	E.ncm = spin == 0 ? 1 : 2;
+	E.nca = (spin == 0 || mode == B2_MODE_DERIV1) ? 1 : 2;
+	E.asz = dtype == B2_F64 ? 16 : 8; E.msz = dtype == B2_F64 ? 8 : 4;
+	for (int b = 0; b < nbatch; b++) {
+		if (run_one(E, (char*)alm + (size_t)b*alm_bstride*E.asz, alm_cstride, (char*)map + (size_t)b*map_bstride*E.msz, map_cstride)) return 1;
+	}
+	if (mem == B2_MEM_HOST) B2_CHECK(cudaStreamSynchronize(E.st));
+	return 0;
+}
+
+extern "C" int b2_synthesis(b2_sht_plan *plan, int spin, int mode, int dtype, int nbatch,
+	const void *alm, int64_t acs, int64_t abs_, void *map, int64_t mcs, int64_t mbs, int mem, void *stream)
+{ return execute(plan, OP_SYNTH, spin, mode, dtype, nbatch, (void*)alm, acs, abs_, map, mcs, mbs, mem, stream); }
+
+extern "C" int b2_adjoint_synthesis(b2_sht_plan *plan, int spin, int mode, int dtype, int nbatch,
+	void *alm, int64_t acs, int64_t abs_, const void *map, int64_t mcs, int64_t mbs, int mem, void *stream)
+{ return execute(plan, OP_ADJ_SYNTH, spin, mode, dtype, nbatch, alm, acs, abs_, (void*)map, mcs, mbs, mem, stream); }
+
+extern "C" int b2_analysis_2d(b2_sht_plan *plan, int spin, int dtype, int nbatch,
+	void *alm, int64_t acs, int64_t abs_, const void *map, int64_t mcs, int64_t mbs, int mem, void *stream)
+{ return execute(plan, OP_ANALYSIS, spin, B2_MODE_STANDARD, dtype, nbatch, alm, acs, abs_, (void*)map, mcs, mbs, mem, stream); }
+
+extern "C" int b2_adjoint_analysis_2d(b2_sht_plan *plan, int spin, int dtype, int nbatch,
+	const void *alm, int64_t acs, int64_t abs_, void *map, int64_t mcs, int64_t mbs, int mem, void *stream)
+{ return execute(plan, OP_ADJ_ANALYSIS, spin, B2_MODE_STANDARD, dtype, nbatch, (void*)alm, acs, abs_, map, mcs, mbs, mem, stream); }
+
+extern "C" int b2_sht_last_timing(b2_sht_plan *p, double out[4])
+{
+	B2_REQUIRE(p && out, "timing: null argument");
+	B2_CHECK(cudaEventSynchronize(p->ev[4]));
+	float t01, t12, t23, t34;
+	B2_CHECK(cudaEventElapsedTime(&t01, p->ev[0], p->ev[1]));
+	B2_CHECK(cudaEventElapsedTime(&t12, p->ev[1], p->ev[2]));
+	B2_CHECK(cudaEventElapsedTime(&t23, p->ev[2], p->ev[3]));
+	B2_CHECK(cudaEventElapsedTime(&t34, p->ev[3], p->ev[4]));
+	// ev1..ev2 and ev3..ev4 are (Legendre, ring FFT) for alm->map and (ring FFT, Legendre) for map->alm
+	out[0] = p->timing[0] < 0 ? t34 : t12; out[1] = p->timing[0] < 0 ? t12 : t34; out[2] = t23; out[3] = t01;
+	return 0;
+}
+
+extern "C" int b2_alm2leg(b2_sht_plan *p, int spin, int mode, const void *alm_dev, int64_t acs, void *leg_dev, void *stream)
+{
+	B2_REQUIRE(p && alm_dev && leg_dev, "alm2leg: null argument");
+	LegTables *T = p->get_tables(spin); if (!T) return 1;
+	AlmLayout L; L.lmax = p->lmax; L.mmax = p->mmax; L.mstart_d = p->mstart.p; L.lstride = p->lstride;
+	return leg_alm2leg(*T, p->geom, L, mode == B2_MODE_DERIV1, (const double2*)alm_dev, acs, (double2*)leg_dev, (cudaStream_t)stream);
+}
+
+extern "C" int b2_leg2alm(b2_sht_plan *p, int spin, int mode, void *alm_dev, int64_t acs, const void *leg_dev, void *stream)
+{
+	B2_REQUIRE(p && alm_dev && leg_dev, "leg2alm: null argument");
+	LegTables *T = p->get_tables(spin); if (!T) return 1;
+	AlmLayout L; L.lmax = p->lmax; L.mmax = p->mmax; L.mstart_d = p->mstart.p; L.lstride = p->lstride;
+	return leg_leg2alm(*T, p->geom, L, mode == B2_MODE_DERIV1, (double2*)alm_dev, acs, (const double2*)leg_dev, (cudaStream_t)stream);
+}

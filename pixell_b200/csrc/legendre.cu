@@ -1,0 +1,773 @@
+// legendre.cu -- K1 (alm -> leg) and K2 (leg -> alm): the FP64-FMA-bound Legendre stage.
+//
+// Replaces the theta-dependent half of ducc0.sht.experimental.synthesis / adjoint_synthesis that
+// pixell calls at pixell/curvedsky.py:907-924, 936-960, 1068-1084.  Not a port: the formulation is
+// built for the B200 FP64 pipe (one DFMA per 2 clk per SM sub-partition, 64/clk/SM):
+//   * one CTA per m; lanes = ring pairs (theta, pi-theta), R pairs per lane, so every recurrence
+//     coefficient and alm value is a warp-uniform shared-memory broadcast that feeds 12R (spin>0)
+//     or 4R (spin 0) DFMAs;
+//   * alpha-normalised three-term recurrence in l for the Wigner functions n_l d^l_{m,-+s}
+//     (2 DFMA per step and sequence), accumulation in the +- basis with north/south parity split;
+//   * start values in extended-exponent form (binary powering), a rescaling pre-phase (window
+//     variants A/B) and a check-free main phase (variant C); rings beyond the evanescent tail are
+//     skipped (Airy-tail bound, see ring_dead());
+//   * K2 reduces over rings with a halving warp-shuffle butterfly (about one 64-bit exchange per
+//     output value and l), then across warps through shared memory, and accumulates into alm in
+//     a fixed order: results are bit-reproducible run to run.
+#include "legendre.cuh"
+#include <algorithm>
+#include <cmath>
+
+#define TL 32                 // l values per shared-memory tile
+#define BIGV   0x1p256
+#define SMALLV 0x1p-512
+
+// ------------------------------------------------------------------------------------ tables
+
+__global__ void k_build_tables(int lmax, int mmax, int s, const int64_t *toff, double *ta, double *tb, double *talpha)
+{
+	int m = blockIdx.x*blockDim.x + threadIdx.x;
+	if (m > mmax) return;
+	int l0 = m > s ? m : s;
+	if (l0 > lmax) return;
+	int n = lmax - l0 + 1;
+	double *a = ta + toff[m], *b = tb ? tb + toff[m] : nullptr, *al = talpha + toff[m];
+	double al_prev = 1.0, al_cur = 1.0;
+	for (int i = 0; i < n; i++) {
+		int l = l0 + i;
+		double l1 = l + 1.0;
+		double den = sqrt((l1 - m)*(l1 + m)*(l1 - s)*(l1 + s));
+		double c0 = sqrt((2*l + 3.0)/(2*l + 1.0))*(2*l + 1.0)*l1/den;
+		double c1 = (l == 0) ? 0.0 : c0*((double)m*s)/((double)l*l1);
+		double c2 = (i == 0 || l == 0) ? 0.0 :
+			sqrt((2*l + 3.0)/(2*l - 1.0))*l1*sqrt(((double)l - m)*((double)l + m)*((double)l - s)*((double)l + s))/(l*den);
+		double al_next = (i == 0) ? 1.0 : c2*al_prev;
+		al[i] = al_cur;
+		a[i] = c0*al_cur/al_next;
+		if (b) b[i] = c1*al_cur/al_next;
+		al_prev = al_cur; al_cur = al_next;
+	}
+}
+
+int LegTables::build(int lmax_, int mmax_, int spin_)
+{
+	lmax = lmax_; mmax = mmax_; spin = spin_;
+	std::vector<int64_t> off(mmax + 2);
+	int64_t tot = 0;
+	for (int m = 0; m <= mmax; m++) { off[m] = tot; int l0 = std::max(m, spin); if (l0 <= lmax) tot += lmax - l0 + 1; }
+	off[mmax + 1] = tot;
+	// keep every row 16-byte friendly is not needed (rows are read element-wise)
+	if (toff.upload(off)) return 1;
+	if (a.alloc(tot) || alpha.alloc(tot)) return 1;
+	if (spin > 0 && b.alloc(tot)) return 1;
+	// start-value prefactors (host, long double): see legendre.cu header / DESIGN.md
+	std::vector<double> pr(mmax + 1, 0.0);
+	const long double pi = 3.141592653589793238462643383279502884L;
+	{
+		long double p2 = (2*spin + 1)/(4*pi);
+		for (int m = spin; m <= mmax; m++) {
+			pr[m] = (double)sqrtl(p2);
+			p2 *= ((long double)(2*m + 3)*(2*m + 2))/(4.0L*(m + 1 + spin)*(m + 1 - spin));
+		}
+		for (int m = 0; m < spin && m <= mmax; m++) {
+			long double f = (2*spin + 1)/(4*pi);     // n_s^2 (2s)!/((s+m)!(s-m)!)
+			for (int k = 1; k <= 2*spin; k++) f *= k;
+			for (int k = 1; k <= spin + m; k++) f /= k;
+			for (int k = 1; k <= spin - m; k++) f /= k;
+			pr[m] = (double)sqrtl(f);
+		}
+	}
+	if (pref.upload(pr)) return 1;
+	int nt = 128;
+	k_build_tables<<<(mmax + nt)/nt, nt>>>(lmax, mmax, spin, toff.p, a.p, spin > 0 ? b.p : nullptr, alpha.p);
+	B2_LAUNCH_CHECK();
+	B2_CHECK(cudaDeviceSynchronize());
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------ ring pairs
+
+int LegGeom::build(int nring_, const double *theta)
+{
+	nring = nring_;
+	nring_pad = b2_round_up(nring, 32);
+	std::vector<int> order(nring);
+	for (int i = 0; i < nring; i++) order[i] = i;
+	std::sort(order.begin(), order.end(), [&](int a, int b) { return theta[a] < theta[b]; });
+	std::vector<char> used(nring, 0);
+	std::vector<PairInfo> pr;
+	int lo = 0, hi = nring - 1;
+	const double tol = 1e-14*M_PI;
+	// two-pointer match of theta_lo + theta_hi == pi on the sorted list
+	while (lo <= hi) {
+		int i = order[lo], j = order[hi];
+		double s = theta[i] + theta[j] - M_PI;
+		PairInfo p;
+		if (lo < hi && fabs(s) < tol) { p.rn = i; p.rs = j; lo++; hi--; }
+		else if (lo == hi || s < 0) { p.rn = i; p.rs = -1; lo++; }
+		else { p.rn = j; p.rs = -1; hi--; }
+		double t = theta[p.rn];
+		p.x = cos(t);
+		// half-angle functions accurate near both poles
+		if (t <= M_PI_2) { p.sh = sin(0.5*t); p.ch = cos(0.5*t); }
+		else { double u = M_PI - t; p.sh = cos(0.5*u); p.ch = sin(0.5*u); }
+		pr.push_back(p);
+	}
+	// pole -> equator: chunks of neighbouring pairs become live at similar l
+	std::stable_sort(pr.begin(), pr.end(), [](const PairInfo &a, const PairInfo &b) { return a.sh*a.ch < b.sh*b.ch; });
+	npair = (int)pr.size();
+	npair_pad = (int)b2_round_up(npair, 128);
+	PairInfo dead; dead.x = 0; dead.sh = 0; dead.ch = 1; dead.rn = -1; dead.rs = -1;
+	pr.resize(npair_pad, dead);
+	return pairs.upload(pr);
+}
+
+// ------------------------------------------------------------------------------------ device helpers
+
+struct LegArgs {
+	int lmax, mmax, spin, deriv1;
+	const int64_t *toff; const double *ta, *tb, *talpha, *pref;
+	const PairInfo *pairs; int npair_pad;
+	const int64_t *mstart; int64_t lstride;
+	double2 *alm0, *alm1;
+	double2 *leg0, *leg1;
+	int64_t leg_mstride;
+};
+
+// base^n = mant*2^ex with mant in [0.5,1) (or mant = 1, ex = 0 for n = 0; mant = 0 for base = 0)
+__device__ __forceinline__ void scaled_pow(double base, int n, double &mant, int &ex)
+{
+	if (n == 0) { mant = 1.0; ex = 0; return; }
+	if (base == 0.0) { mant = 0.0; ex = 0; return; }
+	int be; double b = frexp(base, &be);
+	double r = 1.0; int re = 0;
+	while (true) {
+		if (n & 1) { r *= b; re += be; int t; r = frexp(r, &t); re += t; }
+		n >>= 1;
+		if (!n) break;
+		b *= b; be *= 2; { int t; b = frexp(b, &t); be += t; }
+	}
+	mant = r; ex = re;
+}
+
+__device__ __forceinline__ double ipow(double b, int n) { double r = 1.0; for (int i = 0; i < n; i++) r *= b; return r; }
+
+// true value t*2^ex -> (v, sc) with value = v * 2^(512 sc), sc <= 0; sc == 0 ("live") iff |value| >= 2^-257
+__device__ __forceinline__ void init_scaled(double t, int ex, double &v, int &sc)
+{
+	if (t == 0.0) { v = 0.0; sc = 0; return; }
+	int te; frexp(t, &te);
+	int E = ex + te;
+	if (E >= -256) { v = ldexp(t, ex); sc = 0; }
+	else { int k = (-256 - E + 511)/512; v = ldexp(t, ex + 512*k); sc = -k; }
+}
+
+__device__ __forceinline__ void rescale(double &v, double &vp, int &sc)
+{
+	if (sc < 0 && fabs(v) >= BIGV) { v *= SMALLV; vp *= SMALLV; sc++; }
+}
+
+// A ring contributes nothing for this m when m lies beyond the evanescent tail of the turning point
+// m_t = (lmax+1/2) sin(theta): |n_l d^l_{m,s}| ~ exp(-0.94 delta^1.5/(sqrt(m) cos(theta))), delta = m - m_t;
+// delta > 16 m^(1/3) puts the dropped values below exp(-60) ~ 1e-26 (checked against the oracle in
+// tests/test_legendre_gpu.py at lmax up to 2000).
+__device__ __forceinline__ bool ring_dead(int m, int s, int lmax, double sth)
+{
+	return (double)m - 16.0*cbrt((double)m) - s - 2 > (lmax + 0.5)*sth;
+}
+
+struct SeqConst {      // per-m constants of the start values
+	double pref; double sign_p, sign_q; int e, qc, qs, pc, ps;
+};
+
+__device__ __forceinline__ SeqConst seq_const(int m, int s, const double *pref)
+{
+	SeqConst c;
+	c.pref = pref[m];
+	c.sign_p = (m & 1) ? -1.0 : 1.0;
+	c.sign_q = (m >= s && ((m - s) & 1)) ? -1.0 : 1.0;
+	c.e = m > s ? m - s : 0;
+	if (m >= s) { c.qc = 2*s; c.qs = 0; c.pc = 0; c.ps = 2*s; }
+	else { c.qc = s + m; c.qs = s - m; c.pc = s - m; c.ps = s + m; }
+	return c;
+}
+
+// start values of q = n d^{l0}_{m,+s}, p = (-1)^s n d^{l0}_{m,-s} for one ring
+__device__ __forceinline__ bool init_pair(const PairInfo &pi, const SeqConst &c, int m, int s, int lmax,
+	double &x, double &p, int &sp, double &q, int &sq)
+{
+	x = pi.x;
+	double sth = 2.0*pi.sh*pi.ch;
+	if (pi.rn < 0 || ring_dead(m, s, lmax, sth)) { p = q = 0.0; sp = sq = 0; return false; }
+	double mant; int ex;
+	scaled_pow(sth, c.e, mant, ex);
+	double base = c.pref*mant;
+	init_scaled(c.sign_q*base*ipow(pi.ch, c.qc)*ipow(pi.sh, c.qs), ex, q, sq);
+	init_scaled(c.sign_p*base*ipow(pi.ch, c.pc)*ipow(pi.sh, c.ps), ex, p, sp);
+	return true;
+}
+
+// halving butterfly: on return v[0] of lane L holds the sum over all lanes of element idx(L), where
+// idx is built from the lane bits consumed while N > 1 (N = 32: idx = L; N = 16: idx = L >> 1).
+template<int N> __device__ __forceinline__ void bfly_reduce(double (&v)[N], int lane)
+{
+	int n = N;
+	#pragma unroll
+	for (int bit = 16; bit >= 1; bit >>= 1) {
+		if (n > 1) {
+			n >>= 1;
+			bool up = (lane & bit) != 0;
+			#pragma unroll
+			for (int i = 0; i < N/2; i++) if (i < n) {
+				double send = up ? v[i] : v[i + n];
+				double keep = up ? v[i + n] : v[i];
+				v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+			}
+		} else {
+			v[0] += __shfl_xor_sync(0xffffffffu, v[0], bit);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------ spin 0
+
+struct Tile0 { double ar, ai, a, pad; };            // alm*alpha (re, im), recurrence a_l
+
+// one window of 8 l values, MODE 0: recurrence only (nobody live), 1: masked + rescale, 2: plain
+template<int MODE, int R> __device__ __forceinline__ void synth0_window(const Tile0 *T,
+	const double (&x)[R], double (&g)[R], double (&gp)[R], int (&sc)[R], double (&acc)[R][2][2])
+{
+	#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const Tile0 t = T[j];
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (MODE != 0) {
+				double gv = (MODE == 1) ? (sc[r] == 0 ? g[r] : 0.0) : g[r];
+				acc[r][j & 1][0] = fma(gv, t.ar, acc[r][j & 1][0]);
+				acc[r][j & 1][1] = fma(gv, t.ai, acc[r][j & 1][1]);
+			}
+			double ng = fma(t.a*x[r], g[r], -gp[r]);
+			gp[r] = g[r]; g[r] = ng;
+			if (MODE != 2) rescale(g[r], gp[r], sc[r]);
+		}
+	}
+}
+
+template<int R, int NW> __global__ void __launch_bounds__(NW*32) k_synth0(LegArgs A)
+{
+	__shared__ __align__(16) Tile0 tiles[2][TL];
+	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int lmax = A.lmax, l0 = m;
+	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
+	const double *ta = A.ta + A.toff[m], *tal = A.talpha + A.toff[m];
+	const double2 *alm = A.alm0 + A.mstart[m];
+	const SeqConst sc0 = seq_const(m, 0, A.pref);
+	const int nchunk = A.npair_pad/(32*R);
+	double2 *leg = A.leg0 + (int64_t)m*A.leg_mstride;
+
+	for (int round = 0; round*NW < nchunk; round++) {
+		const int chunk = round*NW + warp;
+		double x[R], g[R], gp[R], acc[R][2][2]; int sc[R], rn[R], rs[R];
+		bool anyuse = false, use[R];
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			PairInfo pi; pi.rn = -1; pi.rs = -1; pi.x = 0; pi.sh = 0; pi.ch = 1;
+			if (chunk < nchunk) pi = A.pairs[(chunk*R + r)*32 + lane];
+			double dummy; int dsc;
+			use[r] = init_pair(pi, sc0, m, 0, lmax, x[r], dummy, dsc, g[r], sc[r]);
+			gp[r] = 0; rn[r] = pi.rn; rs[r] = pi.rs;
+			acc[r][0][0] = acc[r][0][1] = acc[r][1][0] = acc[r][1][1] = 0;
+			anyuse |= use[r];
+		}
+		// a round in which no ring of the CTA can contribute only has to write zeros
+		const bool wuse = __any_sync(0xffffffffu, anyuse);
+		if (__syncthreads_or(anyuse)) {
+			// tile 0 -> buffer 0
+			if (tid < TL) {
+				Tile0 t; t.ar = t.ai = t.a = t.pad = 0;
+				if (tid < nl) { double al = tal[tid]; double2 v = alm[(int64_t)(l0 + tid)*A.lstride]; t.ar = v.x*al; t.ai = v.y*al; t.a = ta[tid]; }
+				tiles[0][tid] = t;
+			}
+			__syncthreads();
+			for (int tile = 0; tile < ntile; tile++) {
+				const int buf = tile & 1;
+				Tile0 nxt; nxt.ar = nxt.ai = nxt.a = nxt.pad = 0;
+				if (tid < TL && tile + 1 < ntile) {
+					int i = (tile + 1)*TL + tid;
+					if (i < nl) { double al = tal[i]; double2 v = alm[(int64_t)(l0 + i)*A.lstride]; nxt.ar = v.x*al; nxt.ai = v.y*al; nxt.a = ta[i]; }
+				}
+				const int nwin = (min(TL, nl - tile*TL) + 7) >> 3;
+				for (int w = 0; wuse && w < nwin; w++) {
+					bool mylive = true, anylive = false;
+					#pragma unroll
+					for (int r = 0; r < R; r++) { mylive &= (sc[r] == 0); anylive |= (sc[r] == 0 && use[r]); }
+					const Tile0 *T = &tiles[buf][w*8];
+					if (__all_sync(0xffffffffu, mylive)) synth0_window<2, R>(T, x, g, gp, sc, acc);
+					else if (__any_sync(0xffffffffu, anylive)) synth0_window<1, R>(T, x, g, gp, sc, acc);
+					else synth0_window<0, R>(T, x, g, gp, sc, acc);
+				}
+				if (tid < TL) tiles[buf ^ 1][tid] = nxt;
+				__syncthreads();
+			}
+		}
+		// set 0 holds the l = l0, l0+2, ... terms (parity sigma0 = (-1)^(l0+m) = +1 for spin 0)
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (rn[r] >= 0) leg[rn[r]] = make_double2(acc[r][0][0] + acc[r][1][0], acc[r][0][1] + acc[r][1][1]);
+			if (rs[r] >= 0) leg[rs[r]] = make_double2(acc[r][0][0] - acc[r][1][0], acc[r][0][1] - acc[r][1][1]);
+		}
+	}
+}
+
+// adjoint, spin 0: window of 16 l values -> 32 partial sums (16 l x re/im) reduced over the warp
+template<int MODE, int R> __device__ __forceinline__ void adj0_window(const double *Ta,
+	const double (&x)[R], double (&g)[R], double (&gp)[R], int (&sc)[R],
+	const double (&in)[R][2][2], double (&v)[32])
+{
+	#pragma unroll
+	for (int j = 0; j < 16; j++) {
+		const double a = Ta[j];
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (MODE != 0) {
+				double gv = (MODE == 1) ? (sc[r] == 0 ? g[r] : 0.0) : g[r];
+				v[2*j]     = fma(gv, in[r][j & 1][0], v[2*j]);
+				v[2*j + 1] = fma(gv, in[r][j & 1][1], v[2*j + 1]);
+			}
+			double ng = fma(a*x[r], g[r], -gp[r]);
+			gp[r] = g[r]; g[r] = ng;
+			if (MODE != 2) rescale(g[r], gp[r], sc[r]);
+		}
+	}
+}
+
+template<int R, int NW> __global__ void __launch_bounds__(NW*32) k_adj0(LegArgs A)
+{
+	__shared__ double tiles[2][TL];
+	__shared__ double red[2][NW][64];
+	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int lmax = A.lmax, l0 = m;
+	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
+	const double *ta = A.ta + A.toff[m], *tal = A.talpha + A.toff[m];
+	double *almr = (double*)(A.alm0 + A.mstart[m]);
+	const SeqConst sc0 = seq_const(m, 0, A.pref);
+	const int nchunk = A.npair_pad/(32*R);
+	const double2 *leg = A.leg0 + (int64_t)m*A.leg_mstride;
+	bool first = true;
+
+	for (int round = 0; round*NW < nchunk; round++) {
+		const int chunk = round*NW + warp;
+		double x[R], g[R], gp[R], in[R][2][2]; int sc[R];
+		bool anyuse = false, use[R];
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			PairInfo pi; pi.rn = -1; pi.rs = -1; pi.x = 0; pi.sh = 0; pi.ch = 1;
+			if (chunk < nchunk) pi = A.pairs[(chunk*R + r)*32 + lane];
+			double dummy; int dsc;
+			use[r] = init_pair(pi, sc0, m, 0, lmax, x[r], dummy, dsc, g[r], sc[r]);
+			gp[r] = 0;
+			double2 gn = make_double2(0, 0), gs = make_double2(0, 0);
+			if (use[r]) { gn = leg[pi.rn]; if (pi.rs >= 0) gs = leg[pi.rs]; }
+			in[r][0][0] = gn.x + gs.x; in[r][0][1] = gn.y + gs.y;    // l - l0 even
+			in[r][1][0] = gn.x - gs.x; in[r][1][1] = gn.y - gs.y;    // l - l0 odd
+			anyuse |= use[r];
+		}
+		const bool wuse = __any_sync(0xffffffffu, anyuse);
+		if (!__syncthreads_or(anyuse)) continue;
+		if (tid < TL) tiles[0][tid] = tid < nl ? ta[tid] : 0.0;
+		__syncthreads();
+		for (int tile = 0; tile < ntile; tile++) {
+			const int buf = tile & 1;
+			double nxt = 0;
+			if (tid < TL && tile + 1 < ntile) { int i = (tile + 1)*TL + tid; if (i < nl) nxt = ta[i]; }
+			const int nwin = (min(TL, nl - tile*TL) + 15) >> 4;
+			#pragma unroll
+			for (int w = 0; w < 2; w++) {
+				double tot = 0;
+				if (wuse && w < nwin) {
+					double v[32];
+					#pragma unroll
+					for (int i = 0; i < 32; i++) v[i] = 0;
+					bool mylive = true, anylive = false;
+					#pragma unroll
+					for (int r = 0; r < R; r++) { mylive &= (sc[r] == 0); anylive |= (sc[r] == 0 && use[r]); }
+					const double *T = &tiles[buf][w*16];
+					if (__all_sync(0xffffffffu, mylive)) adj0_window<2, R>(T, x, g, gp, sc, in, v);
+					else if (__any_sync(0xffffffffu, anylive)) adj0_window<1, R>(T, x, g, gp, sc, in, v);
+					else adj0_window<0, R>(T, x, g, gp, sc, in, v);
+					bfly_reduce<32>(v, lane);
+					tot = v[0];
+				}
+				red[buf][warp][w*32 + lane] = tot;     // element (l = 16 w + lane/2, re/im = lane&1)
+			}
+			if (tid < TL) tiles[buf ^ 1][tid] = nxt;
+			__syncthreads();
+			if (tid < 64) {
+				double s = 0;
+				#pragma unroll
+				for (int w = 0; w < NW; w++) s += red[buf][w][tid];
+				int i = tile*TL + (tid >> 1);
+				if (i < nl) {
+					double *o = almr + 2*(int64_t)(l0 + i)*A.lstride + (tid & 1);
+					double val = s*tal[i];
+					*o = first ? val : *o + val;
+				}
+			}
+		}
+		first = false;
+	}
+	if (first) for (int i = tid; i < nl; i += NW*32) { double *o = almr + 2*(int64_t)(l0 + i)*A.lstride; o[0] = 0; o[1] = 0; }
+}
+
+// ------------------------------------------------------------------------------------ spin > 0
+
+struct Tile2 { double a, b, apr, api, amr, ami; };    // recurrence a,b; A+ = -(E+iB)alpha/2, A- = -(E-iB)alpha/2
+
+template<int MODE, int R> __device__ __forceinline__ void synth2_window(const Tile2 *T,
+	const double (&x)[R], double (&p)[R], double (&pp)[R], double (&q)[R], double (&qp)[R],
+	int (&sp)[R], int (&sq)[R], double (&acc)[R][2][8])
+{
+	#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const Tile2 t = T[j];
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (MODE != 0) {
+				double pv = (MODE == 1) ? (sp[r] == 0 ? p[r] : 0.0) : p[r];
+				double qv = (MODE == 1) ? (sq[r] == 0 ? q[r] : 0.0) : q[r];
+				double (&c)[8] = acc[r][j & 1];
+				c[0] = fma(pv, t.apr, c[0]); c[1] = fma(pv, t.api, c[1]);
+				c[2] = fma(pv, t.amr, c[2]); c[3] = fma(pv, t.ami, c[3]);
+				c[4] = fma(qv, t.apr, c[4]); c[5] = fma(qv, t.api, c[5]);
+				c[6] = fma(qv, t.amr, c[6]); c[7] = fma(qv, t.ami, c[7]);
+			}
+			double np = fma(fma(t.a, x[r],  t.b), p[r], -pp[r]);    // n = -s
+			double nq = fma(fma(t.a, x[r], -t.b), q[r], -qp[r]);    // n = +s
+			pp[r] = p[r]; p[r] = np; qp[r] = q[r]; q[r] = nq;
+			if (MODE != 2) { rescale(p[r], pp[r], sp[r]); rescale(q[r], qp[r], sq[r]); }
+		}
+	}
+}
+
+__device__ __forceinline__ Tile2 load_tile2_synth(const LegArgs &A, int m, int l0, int i, int nl,
+	const double *ta, const double *tb, const double *tal)
+{
+	Tile2 t; t.a = t.b = t.apr = t.api = t.amr = t.ami = 0;
+	if (i < nl) {
+		int l = l0 + i;
+		int64_t idx = A.mstart[m] + (int64_t)l*A.lstride;
+		double2 E = A.alm0[idx], B = make_double2(0, 0);
+		if (A.deriv1) { double f = sqrt((double)l*(l + 1.0)); E.x *= f; E.y *= f; }
+		else B = A.alm1[idx];
+		double h = -0.5*tal[i];
+		t.a = ta[i]; t.b = tb[i];
+		t.apr = h*(E.x - B.y); t.api = h*(E.y + B.x);
+		t.amr = h*(E.x + B.y); t.ami = h*(E.y - B.x);
+	}
+	return t;
+}
+
+template<int R, int NW> __global__ void __launch_bounds__(NW*32) k_synth2(LegArgs A)
+{
+	__shared__ __align__(16) Tile2 tiles[2][TL];
+	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int lmax = A.lmax, s = A.spin, l0 = m > s ? m : s;
+	double2 *legq = A.leg0 + (int64_t)m*A.leg_mstride, *legu = A.leg1 + (int64_t)m*A.leg_mstride;
+	const int nchunk = A.npair_pad/(32*R);
+	if (l0 > lmax) {      // nothing to sum: zero this m column
+		for (int i = tid; i < A.npair_pad; i += NW*32) {
+			PairInfo pi = A.pairs[i];
+			if (pi.rn >= 0) legq[pi.rn] = legu[pi.rn] = make_double2(0, 0);
+			if (pi.rs >= 0) legq[pi.rs] = legu[pi.rs] = make_double2(0, 0);
+		}
+		return;
+	}
+	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
+	const double *ta = A.ta + A.toff[m], *tb = A.tb + A.toff[m], *tal = A.talpha + A.toff[m];
+	const SeqConst sc0 = seq_const(m, s, A.pref);
+	const double sigma0 = ((l0 + m + s) & 1) ? -1.0 : 1.0;
+
+	for (int round = 0; round*NW < nchunk; round++) {
+		const int chunk = round*NW + warp;
+		double x[R], p[R], pp[R], q[R], qp[R], acc[R][2][8]; int sp[R], sq[R], rn[R], rs[R];
+		bool anyuse = false, use[R];
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			PairInfo pi; pi.rn = -1; pi.rs = -1; pi.x = 0; pi.sh = 0; pi.ch = 1;
+			if (chunk < nchunk) pi = A.pairs[(chunk*R + r)*32 + lane];
+			use[r] = init_pair(pi, sc0, m, s, lmax, x[r], p[r], sp[r], q[r], sq[r]);
+			pp[r] = qp[r] = 0; rn[r] = pi.rn; rs[r] = pi.rs;
+			#pragma unroll
+			for (int k = 0; k < 8; k++) acc[r][0][k] = acc[r][1][k] = 0;
+			anyuse |= use[r];
+		}
+		const bool wuse = __any_sync(0xffffffffu, anyuse);
+		if (__syncthreads_or(anyuse)) {
+			if (tid < TL) tiles[0][tid] = load_tile2_synth(A, m, l0, tid, nl, ta, tb, tal);
+			__syncthreads();
+			for (int tile = 0; tile < ntile; tile++) {
+				const int buf = tile & 1;
+				Tile2 nxt;
+				if (tid < TL) nxt = load_tile2_synth(A, m, l0, tile + 1 < ntile ? (tile + 1)*TL + tid : nl, nl, ta, tb, tal);
+				const int nwin = (min(TL, nl - tile*TL) + 7) >> 3;
+				for (int w = 0; wuse && w < nwin; w++) {
+					bool mylive = true, anylive = false;
+					#pragma unroll
+					for (int r = 0; r < R; r++) {
+						mylive &= (sp[r] == 0) & (sq[r] == 0);
+						anylive |= use[r] & ((sp[r] == 0) | (sq[r] == 0));
+					}
+					const Tile2 *T = &tiles[buf][w*8];
+					if (__all_sync(0xffffffffu, mylive)) synth2_window<2, R>(T, x, p, pp, q, qp, sp, sq, acc);
+					else if (__any_sync(0xffffffffu, anylive)) synth2_window<1, R>(T, x, p, pp, q, qp, sp, sq, acc);
+					else synth2_window<0, R>(T, x, p, pp, q, qp, sp, sq, acc);
+				}
+				if (tid < TL) tiles[buf ^ 1][tid] = nxt;
+				__syncthreads();
+			}
+		}
+		// Sp = sum p A+, Sq = sum q A-;  south: Sp' = sum sigma_l q A+, Sq' = sum sigma_l p A-
+		// Q = Sp + Sq, U = i (Sq - Sp)
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			const double (&c0)[8] = acc[r][0]; const double (&c1)[8] = acc[r][1];
+			if (rn[r] >= 0) {
+				double spr = c0[0] + c1[0], spi = c0[1] + c1[1], sqr = c0[6] + c1[6], sqi = c0[7] + c1[7];
+				legq[rn[r]] = make_double2(spr + sqr, spi + sqi);
+				legu[rn[r]] = make_double2(spi - sqi, sqr - spr);
+			}
+			if (rs[r] >= 0) {
+				double spr = sigma0*(c0[4] - c1[4]), spi = sigma0*(c0[5] - c1[5]);
+				double sqr = sigma0*(c0[2] - c1[2]), sqi = sigma0*(c0[3] - c1[3]);
+				legq[rs[r]] = make_double2(spr + sqr, spi + sqi);
+				legu[rs[r]] = make_double2(spi - sqi, sqr - spr);
+			}
+		}
+	}
+}
+
+// adjoint, spin > 0: window of 8 l values -> 32 partial sums (8 l x {A+re, A+im, A-re, A-im})
+//   A+_l = sum_pairs p Z+N + sigma_l q Z+S,  A-_l = sum_pairs q Z-N + sigma_l p Z-S,  Z+- = Q +- iU
+// zin[r][0..3] = Z+N (re,im), Z-N (re,im); zin[r][4..7] = sigma0 * (Z+S, Z-S)
+template<int MODE, int R> __device__ __forceinline__ void adj2_window(const double2 *Tab,
+	const double (&x)[R], double (&p)[R], double (&pp)[R], double (&q)[R], double (&qp)[R],
+	int (&sp)[R], int (&sq)[R], const double (&zin)[R][8], double (&v)[32])
+{
+	#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const double2 ab = Tab[j];
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (MODE != 0) {
+				double pv = (MODE == 1) ? (sp[r] == 0 ? p[r] : 0.0) : p[r];
+				double qv = (MODE == 1) ? (sq[r] == 0 ? q[r] : 0.0) : q[r];
+				// sigma_l alternates: fold the sign into the south products
+				double ps = (j & 1) ? -pv : pv, qs = (j & 1) ? -qv : qv;
+				v[4*j + 0] = fma(pv, zin[r][0], fma(qs, zin[r][4], v[4*j + 0]));
+				v[4*j + 1] = fma(pv, zin[r][1], fma(qs, zin[r][5], v[4*j + 1]));
+				v[4*j + 2] = fma(qv, zin[r][2], fma(ps, zin[r][6], v[4*j + 2]));
+				v[4*j + 3] = fma(qv, zin[r][3], fma(ps, zin[r][7], v[4*j + 3]));
+			}
+			double np = fma(fma(ab.x, x[r],  ab.y), p[r], -pp[r]);
+			double nq = fma(fma(ab.x, x[r], -ab.y), q[r], -qp[r]);
+			pp[r] = p[r]; p[r] = np; qp[r] = q[r]; q[r] = nq;
+			if (MODE != 2) { rescale(p[r], pp[r], sp[r]); rescale(q[r], qp[r], sq[r]); }
+		}
+	}
+}
+
+template<int R, int NW> __global__ void __launch_bounds__(NW*32) k_adj2(LegArgs A)
+{
+	__shared__ __align__(16) double2 tiles[2][TL];
+	__shared__ double red[2][NW][128];
+	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int lmax = A.lmax, s = A.spin, l0 = m > s ? m : s;
+	double *alme = (double*)A.alm0, *almb = (double*)A.alm1;
+	const int64_t ms = A.mstart[m];
+	// l < spin entries of the triangle are zero by definition
+	for (int l = m + tid; l < l0 && l <= lmax; l += NW*32) {
+		int64_t idx = 2*(ms + (int64_t)l*A.lstride);
+		alme[idx] = alme[idx + 1] = 0;
+		if (!A.deriv1) almb[idx] = almb[idx + 1] = 0;
+	}
+	if (l0 > lmax) return;
+	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
+	const double *ta = A.ta + A.toff[m], *tb = A.tb + A.toff[m], *tal = A.talpha + A.toff[m];
+	const SeqConst sc0 = seq_const(m, s, A.pref);
+	const double sigma0 = ((l0 + m + s) & 1) ? -1.0 : 1.0;
+	const double2 *legq = A.leg0 + (int64_t)m*A.leg_mstride, *legu = A.leg1 + (int64_t)m*A.leg_mstride;
+	const int nchunk = A.npair_pad/(32*R);
+	bool first = true;
+
+	for (int round = 0; round*NW < nchunk; round++) {
+		const int chunk = round*NW + warp;
+		double x[R], p[R], pp[R], q[R], qp[R], zin[R][8]; int sp[R], sq[R];
+		bool anyuse = false, use[R];
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			PairInfo pi; pi.rn = -1; pi.rs = -1; pi.x = 0; pi.sh = 0; pi.ch = 1;
+			if (chunk < nchunk) pi = A.pairs[(chunk*R + r)*32 + lane];
+			use[r] = init_pair(pi, sc0, m, s, lmax, x[r], p[r], sp[r], q[r], sq[r]);
+			pp[r] = qp[r] = 0;
+			double2 qn = make_double2(0, 0), un = qn, qs = qn, us = qn;
+			if (use[r]) { qn = legq[pi.rn]; un = legu[pi.rn]; if (pi.rs >= 0) { qs = legq[pi.rs]; us = legu[pi.rs]; } }
+			// Z+ = Q + iU = (Qr - Ui, Qi + Ur),  Z- = Q - iU = (Qr + Ui, Qi - Ur)
+			zin[r][0] = qn.x - un.y; zin[r][1] = qn.y + un.x; zin[r][2] = qn.x + un.y; zin[r][3] = qn.y - un.x;
+			zin[r][4] = sigma0*(qs.x - us.y); zin[r][5] = sigma0*(qs.y + us.x);
+			zin[r][6] = sigma0*(qs.x + us.y); zin[r][7] = sigma0*(qs.y - us.x);
+			anyuse |= use[r];
+		}
+		const bool wuse = __any_sync(0xffffffffu, anyuse);
+		if (!__syncthreads_or(anyuse)) continue;
+		if (tid < TL) tiles[0][tid] = tid < nl ? make_double2(ta[tid], tb[tid]) : make_double2(0, 0);
+		__syncthreads();
+		for (int tile = 0; tile < ntile; tile++) {
+			const int buf = tile & 1;
+			double2 nxt = make_double2(0, 0);
+			if (tid < TL && tile + 1 < ntile) { int i = (tile + 1)*TL + tid; if (i < nl) nxt = make_double2(ta[i], tb[i]); }
+			const int nwin = (min(TL, nl - tile*TL) + 7) >> 3;
+			#pragma unroll
+			for (int w = 0; w < 4; w++) {
+				double tot = 0;
+				if (wuse && w < nwin) {
+					double v[32];
+					#pragma unroll
+					for (int i = 0; i < 32; i++) v[i] = 0;
+					bool mylive = true, anylive = false;
+					#pragma unroll
+					for (int r = 0; r < R; r++) {
+						mylive &= (sp[r] == 0) & (sq[r] == 0);
+						anylive |= use[r] & ((sp[r] == 0) | (sq[r] == 0));
+					}
+					const double2 *T = &tiles[buf][w*8];
+					if (__all_sync(0xffffffffu, mylive)) adj2_window<2, R>(T, x, p, pp, q, qp, sp, sq, zin, v);
+					else if (__any_sync(0xffffffffu, anylive)) adj2_window<1, R>(T, x, p, pp, q, qp, sp, sq, zin, v);
+					else adj2_window<0, R>(T, x, p, pp, q, qp, sp, sq, zin, v);
+					bfly_reduce<32>(v, lane);
+					tot = v[0];
+				}
+				red[buf][warp][w*32 + lane] = tot;      // element (l = 8 w + lane/4, comp = lane&3)
+			}
+			if (tid < TL) tiles[buf ^ 1][tid] = nxt;
+			__syncthreads();
+			if (tid < 128) {
+				double c = 0;
+				#pragma unroll
+				for (int w = 0; w < NW; w++) c += red[buf][w][tid];
+				// gather the 4 components of this l from the neighbouring lanes
+				int base = lane & ~3, k = lane & 3;
+				double c0 = __shfl_sync(0xffffffffu, c, base), c1 = __shfl_sync(0xffffffffu, c, base + 1);
+				double c2 = __shfl_sync(0xffffffffu, c, base + 2), c3 = __shfl_sync(0xffffffffu, c, base + 3);
+				int i = tile*TL + 8*(tid >> 5) + (lane >> 2);
+				if (i < nl) {
+					int l = l0 + i;
+					double h = 0.5*tal[i];
+					// E = -(A+ + A-)/2, B = (i/2)(A+ - A-)
+					double val = k == 0 ? -h*(c0 + c2) : k == 1 ? -h*(c1 + c3) : k == 2 ? -h*(c1 - c3) : h*(c0 - c2);
+					int64_t idx = 2*(ms + (int64_t)l*A.lstride) + (k & 1);
+					if (A.deriv1) {
+						if (k < 2) { val *= sqrt((double)l*(l + 1.0)); alme[idx] = first ? val : alme[idx] + val; }
+					} else {
+						double *o = (k < 2 ? alme : almb) + idx;
+						*o = first ? val : *o + val;
+					}
+				}
+			}
+		}
+		first = false;
+	}
+	if (first) for (int i = tid; i < nl; i += NW*32) {
+		int64_t idx = 2*(ms + (int64_t)(l0 + i)*A.lstride);
+		alme[idx] = alme[idx + 1] = 0;
+		if (!A.deriv1) almb[idx] = almb[idx + 1] = 0;
+	}
+}
+
+// ------------------------------------------------------------------------------------ host entry points
+
+#define R0 4      // ring pairs per lane, spin 0
+#define R2 2      // ring pairs per lane, spin > 0
+#define NW0 8
+#define NW2 8
+
+static LegArgs make_args(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
+	double2 *alm, int64_t alm_cstride, double2 *leg)
+{
+	LegArgs A;
+	A.lmax = L.lmax; A.mmax = L.mmax; A.spin = T.spin; A.deriv1 = deriv1;
+	A.toff = T.toff.p; A.ta = T.a.p; A.tb = T.b.p; A.talpha = T.alpha.p; A.pref = T.pref.p;
+	A.pairs = G.pairs.p; A.npair_pad = G.npair_pad;
+	A.mstart = L.mstart_d; A.lstride = L.lstride;
+	A.alm0 = alm; A.alm1 = alm + alm_cstride;
+	A.leg_mstride = G.nring_pad;
+	A.leg0 = leg; A.leg1 = leg + (int64_t)(L.mmax + 1)*G.nring_pad;
+	return A;
+}
+
+static int check_args(const LegTables &T, const AlmLayout &L, int deriv1)
+{
+	B2_REQUIRE(T.lmax == L.lmax && T.mmax >= L.mmax, "Legendre tables do not match the alm layout");
+	B2_REQUIRE(!deriv1 || T.spin == 1, "DERIV1 mode needs spin-1 tables");
+	return 0;
+}
+
+int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
+	const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st)
+{
+	if (check_args(T, L, deriv1)) return 1;
+	LegArgs A = make_args(T, G, L, deriv1, (double2*)alm, alm_cstride, leg);
+	if (T.spin == 0) k_synth0<R0, NW0><<<L.mmax + 1, NW0*32, 0, st>>>(A);
+	else             k_synth2<R2, NW2><<<L.mmax + 1, NW2*32, 0, st>>>(A);
+	B2_LAUNCH_CHECK();
+	return 0;
+}
+
+int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
+	double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st)
+{
+	if (check_args(T, L, deriv1)) return 1;
+	LegArgs A = make_args(T, G, L, deriv1, alm, alm_cstride, (double2*)leg);
+	if (T.spin == 0) k_adj0<R0, NW0><<<L.mmax + 1, NW0*32, 0, st>>>(A);
+	else             k_adj2<R2, NW2><<<L.mmax + 1, NW2*32, 0, st>>>(A);
+	B2_LAUNCH_CHECK();
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------ DFMA peak
+
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters)
+{
+	double a0 = threadIdx.x*1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+	const double m = 1.0000001, c = 1e-9;
+	for (int i = 0; i < iters; i++) {
+		#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+			a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+		}
+	}
+	out[blockIdx.x*blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int dfma_peak_gflops(double *out)
+{
+	int dev; B2_CHECK(cudaGetDevice(&dev));
+	cudaDeviceProp pr; B2_CHECK(cudaGetDeviceProperties(&pr, dev));
+	int nb = pr.multiProcessorCount*8, nt = 256, iters = 4096;
+	DevBuf<double> buf; if (buf.alloc((size_t)nb*nt)) return 1;
+	cudaEvent_t e0, e1; B2_CHECK(cudaEventCreate(&e0)); B2_CHECK(cudaEventCreate(&e1));
+	double best = 0;
+	for (int rep = 0; rep < 4; rep++) {
+		B2_CHECK(cudaEventRecord(e0));
+		k_dfma_peak<<<nb, nt>>>(buf.p, iters);
+		B2_CHECK(cudaEventRecord(e1));
+		B2_CHECK(cudaEventSynchronize(e1));
+		float ms; B2_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+		double gf = 2.0*64.0*iters*(double)nb*nt/(ms*1e-3)/1e9;
+		if (rep > 0 && gf > best) best = gf;
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	*out = best;
+	return 0;
+}

@@ -1,0 +1,46 @@
+// legendre.cuh -- Legendre stage (K1 alm->leg, K2 leg->alm) of the B200 SHT engine.
+// Replaces the theta-dependent half of ducc0's synthesis / adjoint_synthesis
+// (call sites pixell/curvedsky.py:907-924, 936-960, 1068-1084).
+#pragma once
+#include "common.cuh"
+
+// one ring pair: a primary ring and (optionally) its mirror image theta -> pi-theta
+struct PairInfo {
+	double x;        // cos(theta) of the primary ring
+	double sh, ch;   // sin(theta/2), cos(theta/2)
+	int rn, rs;      // ring indices of the primary and the mirror ring (-1: absent)
+};
+
+// alpha-normalised recurrence tables for one (lmax, mmax, spin):
+//   G_{l+1} = (a_l x -+ b_l) G_l - G_{l-1},   n_l d^l_{m,+-s} = alpha_l G_l,   l = l0(m)..lmax, l0 = max(m,s)
+struct LegTables {
+	int lmax = -1, mmax = -1, spin = -1;
+	DevBuf<int64_t> toff;     // [mmax+2] offset of row m
+	DevBuf<double> a, b, alpha;
+	DevBuf<double> pref;      // [mmax+1] magnitude of the l0 start value without the theta powers
+	int build(int lmax, int mmax, int spin);
+	size_t bytes() const { return toff.bytes() + a.bytes() + b.bytes() + alpha.bytes() + pref.bytes(); }
+};
+
+struct LegGeom {
+	int nring = 0;            // rings (leg ring index = caller's ring index)
+	int npair = 0;
+	int64_t nring_pad = 0;    // leg row length (rings padded to a multiple of 32)
+	DevBuf<PairInfo> pairs;   // sorted pole -> equator, padded to a multiple of 256 pairs with rn = -1
+	int npair_pad = 0;
+	int build(int nring, const double *theta);
+	size_t bytes() const { return pairs.bytes(); }
+};
+
+struct AlmLayout {
+	int lmax, mmax;
+	const int64_t *mstart_d;  // device [mmax+1]
+	int64_t lstride;
+};
+
+// leg[ncomp_map][mmax+1][nring_pad] complex128; alm component c at alm + c*alm_cstride (complex elements)
+int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
+                const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st);
+int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
+                double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st);
+int dfma_peak_gflops(double *out);

@@ -1,0 +1,41 @@
+// plan.cuh -- the SHT plan object behind the C ABI (include/b200sht.h).
+#pragma once
+#include "legendre.cuh"
+#include "ringfft.cuh"
+#include "resample.cuh"
+#include <map>
+#include <memory>
+#include <string>
+
+struct b2_sht_plan {
+	int lmax = 0, mmax = 0;
+	int64_t lstride = 1;
+	int64_t alm_span = 0;              // elements of one alm component touched by the layout
+	DevBuf<int64_t> mstart;
+	std::vector<int64_t> mstart_h;
+	int nring = 0;
+	int64_t nphi = 0, npix = 0;
+	std::vector<int64_t> ringstart_h;
+	int64_t map_lo = 0, map_hi = 0;    // element range of one map component touched by the rings
+	int64_t row_pitch = 0;             // constant ring pitch (0: irregular)
+	LegGeom geom;
+	RingFft fft;
+	std::map<int, std::unique_ptr<LegTables>> tables;   // by spin
+	DevBuf<double2> leg;               // [2][mmax+1][nring_pad]
+	// 2d plans
+	bool is2d = false;
+	std::string geometry;
+	int ntheta = 0;
+	std::unique_ptr<ThetaResampler> resamp;   // exact analysis on grids with ntheta < 2 lmax + 2
+	DevBuf<double> w2d;                // direct quadrature weights / nphi (ring order of the plan)
+	// staging for host-memory calls
+	DevBuf<char> stage_alm, stage_map;
+	cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+	double timing[4] = {0, 0, 0, 0};
+	LegTables *get_tables(int spin);
+	size_t bytes() const;
+	~b2_sht_plan();
+};
+
+int gridweights_device(const char *geometry, int ntheta, double *out_host, double *out_dev);
+int grid_theta_host(const char *geometry, int ntheta, std::vector<double> &theta);

@@ -1,0 +1,223 @@
+// ringfft.cu -- K3 / K4: the per-ring FFT stage between leg[comp][m][ring] and the map rows.
+// Replaces the ring-FFT half of ducc0's synthesis / adjoint_synthesis (pixell/curvedsky.py:907-960)
+// including what pixell does around it on the host: the phi0 phase, x flips (as a conjugation),
+// cut rows (npix < nphi) and quadrature weights (curvedsky.py:852-868) are all fused here, so the
+// map is touched exactly once and no flipped/padded copy (map2buffer, :1384-1411) is ever made.
+//
+// One CTA per (ring, component); the ring lives in shared memory as a packed half-length complex
+// sequence (even nphi) or a full complex one (odd nphi); fft_smem.cuh does the passes.
+#include "ringfft.cuh"
+#include <algorithm>
+
+// ------------------------------------------------------------------------------------ tables
+
+bool FftTables::supported(int64_t n)
+{
+	if (n < 1) return false;
+	for (int p = 2; p <= FFT_MAX_RADIX && n > 1; p++) while (n % p == 0) n /= p;
+	return n == 1;
+}
+
+int FftTables::build(int n, int ntab)
+{
+	B2_REQUIRE(n >= 1 && ntab % n == 0, "bad FFT table request n=%d ntab=%d", n, ntab);
+	B2_REQUIRE(supported(n), "FFT length %d has a prime factor > %d (unsupported)", n, FFT_MAX_RADIX);
+	d.n = n; d.ntab = ntab; d.twmul = ntab/n; d.nfac = 0;
+	int rem = n;
+	while (rem % 4 == 0) { d.fac[d.nfac++] = 4; rem /= 4; }
+	for (int p = 2; p <= FFT_MAX_RADIX; p++) while (rem % p == 0) { B2_REQUIRE(d.nfac < FFT_MAX_FAC, "too many FFT factors"); d.fac[d.nfac++] = p; rem /= p; }
+	std::vector<double2> t(ntab);
+	const long double tau = 6.283185307179586476925286766559005768L;
+	for (int k = 0; k < ntab; k++) {
+		// exact octant symmetry is not needed: long double keeps the table at 0.5 ulp
+		long double a = tau*(long double)k/(long double)ntab;
+		t[k].x = (double)cosl(a); t[k].y = (double)-sinl(a);
+	}
+	std::vector<int> rv(n);
+	for (int k = 0; k < n; k++) {
+		int kk = k, pos = 0, len = n;
+		for (int f = 0; f < d.nfac; f++) { int r = d.fac[f]; len /= r; pos += (kk % r)*len; kk /= r; }
+		rv[k] = pos;
+	}
+	if (tw.upload(t) || rev.upload(rv)) return 1;
+	d.tw = tw.p; d.rev = rev.p;
+	return 0;
+}
+
+__global__ void k_phase(double2 *ph, int mmax, double phi0)
+{
+	int m = blockIdx.x*blockDim.x + threadIdx.x;
+	if (m > mmax) return;
+	double s, c; sincos((double)m*phi0, &s, &c);
+	ph[m] = make_double2(c, s);
+}
+
+int RingFft::build(int64_t nphi_, double phi0, int xdir_, int64_t npix_, int nring_, const int64_t *rs,
+	const double *w, int mmax_)
+{
+	nphi = nphi_; xdir = xdir_ < 0 ? -1 : 1; npix = npix_; nring = nring_; mmax = mmax_;
+	B2_REQUIRE(nphi >= 1 && npix >= 1 && npix <= nphi, "bad ring description: nphi=%lld npix=%lld", (long long)nphi, (long long)npix);
+	half = (nphi % 2 == 0) ? 1 : 0;
+	nfft = (int)(half ? nphi/2 : nphi);
+	smem = sizeof(double2)*(size_t)(nfft + 1);
+	B2_REQUIRE(smem <= 227*1024, "nphi=%lld needs %zu bytes of shared memory per ring (limit 227 KB)", (long long)nphi, smem);
+	if (tab.build(nfft, (int)nphi)) return 1;
+	if (phase.alloc(mmax + 1)) return 1;
+	k_phase<<<(mmax + 128)/128, 128>>>(phase.p, mmax, phi0);
+	B2_LAUNCH_CHECK();
+	std::vector<int64_t> r(rs, rs + nring);
+	if (ringstart.upload(r)) return 1;
+	if (w) { std::vector<double> ww(w, w + nring); if (weight.upload(ww)) return 1; }
+	threads = (int)std::min<int64_t>(512, std::max<int64_t>(64, b2_round_up(nfft/4, 32)));
+	B2_CHECK(cudaDeviceSynchronize());
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------ kernels
+
+struct RingArgs {
+	FftDesc d;
+	int half, nfft, mmax, xdir, nring;
+	int64_t nphi, npix, nring_pad;
+	const double2 *phase; const int64_t *ringstart; const double *weight;
+	double2 *leg; void *map; int64_t map_cstride;
+};
+
+__device__ __forceinline__ double2 leg_phase(const RingArgs &A, const double2 *legc, int m)
+{
+	double2 g = cmul(legc[(int64_t)m*A.nring_pad], A.phase[m]);
+	if (A.xdir < 0) g.y = -g.y;
+	return g;
+}
+
+template<typename MapT> __global__ void k_leg2map(RingArgs A)
+{
+	extern __shared__ __align__(16) double2 s[];
+	const int ring = blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+	const double2 *legc = A.leg + ((int64_t)comp*(A.mmax + 1))*A.nring_pad + ring;
+	MapT *row = (MapT*)A.map + (int64_t)comp*A.map_cstride + A.ringstart[ring];
+	const int n = (int)A.nphi, nf = A.nfft, mmax = A.mmax;
+	if (A.half) {
+		// half spectrum X[0..nf] of the real ring, |m| aliased mod nphi
+		for (int k = tid; k <= nf; k += T) {
+			double2 acc = make_double2(0, 0);
+			if (k == 0 || k == nf) {
+				for (int m = k; m <= mmax; m += n) { double2 g = leg_phase(A, legc, m); acc.x += (m == 0 ? 1.0 : 2.0)*g.x; }
+			} else {
+				for (int m = k; m <= mmax; m += n) acc = cadd(acc, leg_phase(A, legc, m));
+				for (int m = n - k; m <= mmax; m += n) acc = cadd(acc, cconj(leg_phase(A, legc, m)));
+			}
+			s[k] = acc;
+		}
+		__syncthreads();
+		// Z[k] = (X[k] + conj X[nf-k]) + i e^{+2 pi i k/n} (X[k] - conj X[nf-k]); z = IFFT(Z) packs (x_2j, x_2j+1)
+		for (int k = tid; 2*k <= nf; k += T) {
+			if (k == 0) { double x0 = s[0].x, xn = s[nf].x; s[0] = make_double2(x0 + xn, x0 - xn); }
+			else {
+				int kk = nf - k;
+				double2 a = s[k], b = s[kk];
+				double2 s1 = make_double2(a.x + b.x, a.y - b.y), d1 = make_double2(a.x - b.x, a.y + b.y);
+				double2 w = A.d.tw[k]; w.y = -w.y;
+				double2 wd = cmul(w, d1);
+				s[k] = make_double2(s1.x - wd.y, s1.y + wd.x);
+				if (kk != k) s[kk] = make_double2(s1.x + wd.y, -s1.y + wd.x);
+			}
+		}
+		__syncthreads();
+		fft_smem<true>(s, A.d, tid, T);
+		for (int64_t i = tid; i < A.npix; i += T) {
+			double2 z = s[A.d.rev[i >> 1]];
+			row[i] = (MapT)((i & 1) ? z.y : z.x);
+		}
+	} else {
+		for (int k = tid; k < n; k += T) {
+			double2 acc = make_double2(0, 0);
+			for (int m = k; m <= mmax; m += n) { double2 g = leg_phase(A, legc, m); if (m == 0) g.y = 0; acc = cadd(acc, g); }
+			for (int m = (k == 0 ? n : n - k); m <= mmax; m += n) acc = cadd(acc, cconj(leg_phase(A, legc, m)));
+			s[k] = acc;
+		}
+		__syncthreads();
+		fft_smem<true>(s, A.d, tid, T);
+		for (int64_t i = tid; i < A.npix; i += T) row[i] = (MapT)s[A.d.rev[i]].x;
+	}
+}
+
+template<typename MapT> __global__ void k_map2leg(RingArgs A)
+{
+	extern __shared__ __align__(16) double2 s[];
+	const int ring = blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+	double2 *legc = A.leg + ((int64_t)comp*(A.mmax + 1))*A.nring_pad + ring;
+	const MapT *row = (const MapT*)A.map + (int64_t)comp*A.map_cstride + A.ringstart[ring];
+	const int n = (int)A.nphi, nf = A.nfft, mmax = A.mmax;
+	const double wgt = A.weight ? A.weight[ring] : 1.0;
+	if (A.half) {
+		for (int j = tid; j < nf; j += T) {
+			int64_t i = 2*(int64_t)j;
+			double a = i < A.npix ? (double)row[i] : 0.0, b = i + 1 < A.npix ? (double)row[i + 1] : 0.0;
+			s[j] = make_double2(a, b);
+		}
+		__syncthreads();
+		fft_smem<false>(s, A.d, tid, T);
+		for (int m = tid; m <= mmax; m += T) {
+			int k = m % n; bool fold = k > nf; if (fold) k = n - k;
+			int k1 = k == nf ? 0 : k, k2 = k == 0 ? 0 : nf - k;
+			double2 zk = s[A.d.rev[k1]], zc = cconj(s[A.d.rev[k2]]);
+			double2 e = make_double2(0.5*(zk.x + zc.x), 0.5*(zk.y + zc.y));
+			double2 dd = make_double2(0.5*(zk.x - zc.x), 0.5*(zk.y - zc.y));
+			double2 o = make_double2(dd.y, -dd.x);
+			double2 x = cadd(e, cmul(A.d.tw[k], o));
+			if (fold) x.y = -x.y;
+			if (A.xdir < 0) x.y = -x.y;
+			legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, A.phase[m]), wgt);
+		}
+	} else {
+		for (int j = tid; j < n; j += T) s[j] = make_double2(j < A.npix ? (double)row[j] : 0.0, 0.0);
+		__syncthreads();
+		fft_smem<false>(s, A.d, tid, T);
+		for (int m = tid; m <= mmax; m += T) {
+			double2 x = s[A.d.rev[m % n]];
+			if (A.xdir < 0) x.y = -x.y;
+			legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, A.phase[m]), wgt);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------ host
+
+static RingArgs ring_args(const RingFft &F, const double2 *leg, int64_t nring_pad, const void *map, int64_t map_cstride, int use_weight)
+{
+	RingArgs A;
+	A.d = F.tab.d; A.half = F.half; A.nfft = F.nfft; A.mmax = F.mmax; A.xdir = F.xdir; A.nring = F.nring;
+	A.nphi = F.nphi; A.npix = F.npix; A.nring_pad = nring_pad;
+	A.phase = F.phase.p; A.ringstart = F.ringstart.p; A.weight = (use_weight && F.weight.n) ? F.weight.p : nullptr;
+	A.leg = (double2*)leg; A.map = (void*)map; A.map_cstride = map_cstride;
+	return A;
+}
+
+template<typename K> static int set_smem(K kern, size_t smem)
+{
+	if (smem > 48*1024) B2_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	return 0;
+}
+
+int ring_leg2map(const RingFft &F, int ncomp, const double2 *leg, int64_t nring_pad,
+	void *map, int64_t map_cstride, int dtype, cudaStream_t st)
+{
+	RingArgs A = ring_args(F, leg, nring_pad, map, map_cstride, 0);
+	dim3 grid(F.nring, ncomp);
+	if (dtype == 0) { if (set_smem(k_leg2map<double>, F.smem)) return 1; k_leg2map<double><<<grid, F.threads, F.smem, st>>>(A); }
+	else            { if (set_smem(k_leg2map<float>,  F.smem)) return 1; k_leg2map<float><<<grid, F.threads, F.smem, st>>>(A); }
+	B2_LAUNCH_CHECK();
+	return 0;
+}
+
+int ring_map2leg(const RingFft &F, int ncomp, double2 *leg, int64_t nring_pad,
+	const void *map, int64_t map_cstride, int dtype, int use_weight, cudaStream_t st)
+{
+	RingArgs A = ring_args(F, leg, nring_pad, map, map_cstride, use_weight);
+	dim3 grid(F.nring, ncomp);
+	if (dtype == 0) { if (set_smem(k_map2leg<double>, F.smem)) return 1; k_map2leg<double><<<grid, F.threads, F.smem, st>>>(A); }
+	else            { if (set_smem(k_map2leg<float>,  F.smem)) return 1; k_map2leg<float><<<grid, F.threads, F.smem, st>>>(A); }
+	B2_LAUNCH_CHECK();
+	return 0;
+}

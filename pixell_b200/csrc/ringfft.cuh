@@ -1,0 +1,28 @@
+// ringfft.cuh -- K3 (leg -> map, c2r ring FFT) and K4 (map -> leg, r2c ring FFT) of the SHT engine.
+#pragma once
+#include "fft_smem.cuh"
+
+struct RingFft {
+	int64_t nphi = 0;       // pixels per full circle
+	int half = 0;           // 1: even nphi handled as a packed complex transform of length nphi/2
+	int nfft = 0;           // complex transform length
+	int mmax = 0;
+	int xdir = 1;           // +1: phi grows with the pixel index, -1: decreases
+	int64_t npix = 0;       // stored pixels per ring (<= nphi)
+	int nring = 0;
+	FftTables tab;
+	DevBuf<double2> phase;  // exp(i m phi0), m = 0..mmax
+	DevBuf<int64_t> ringstart;
+	DevBuf<double> weight;  // empty: no weights
+	int threads = 256;
+	size_t smem = 0;
+	int build(int64_t nphi, double phi0, int xdir, int64_t npix, int nring, const int64_t *ringstart,
+	          const double *weight, int mmax);
+	size_t bytes() const { return tab.bytes() + phase.bytes() + ringstart.bytes() + weight.bytes(); }
+};
+
+// leg: [ncomp][mmax+1][nring_pad] complex128 (device); map component c at map + c*map_cstride (elements of MapT)
+int ring_leg2map(const RingFft &F, int ncomp, const double2 *leg, int64_t nring_pad,
+                 void *map, int64_t map_cstride, int dtype, cudaStream_t st);
+int ring_map2leg(const RingFft &F, int ncomp, double2 *leg, int64_t nring_pad,
+                 const void *map, int64_t map_cstride, int dtype, int use_weight, cudaStream_t st);

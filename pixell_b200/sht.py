@@ -1,0 +1,209 @@
+"""pixell_b200.sht -- drop-in for the ducc0.sht.experimental functions pixell's curvedsky calls
+(reference pixell/curvedsky.py:328-329, 398-399, 501, 531-555, 855, 907-924, 936-960, 1032-1046,
+1068-1084), backed by the CUDA engine in libb200sht.so.  Same keyword-only signatures, same
+in-place-and-return behaviour.  Inputs may be numpy arrays (host memory: staged through the GPU)
+or torch CUDA tensors (zero-copy).  `nthreads` is accepted and ignored.
+
+Limits (outside the hot path of SURVEY.md section 8): rings must share nphi and phi0 (CAR maps;
+HEALPix ring sets are refused), and lstride/pixstride other than what pixell uses are refused.
+"""
+import collections, ctypes
+import numpy as np
+from . import _lib as L
+
+_MODES = {"STANDARD": L.MODE_STANDARD, "DERIV1": L.MODE_DERIV1}
+
+# ------------------------------------------------------------------ plans (cached)
+
+class Plan:
+	def __init__(self, handle): self.handle = handle
+	def __del__(self):
+		try:
+			if self.handle: L.lib().b2_sht_plan_destroy(self.handle); self.handle = None
+		except Exception: pass
+	@property
+	def nbytes(self): return L.lib().b2_sht_plan_bytes(self.handle)
+	def last_timing(self):
+		"""device milliseconds of the last transform: dict(legendre, ringfft, resample, copies)"""
+		out = (ctypes.c_double*4)()
+		L.check(L.lib().b2_sht_last_timing(self.handle, out))
+		return dict(legendre=out[0], ringfft=out[1], resample=out[2], copies=out[3])
+
+_plans = collections.OrderedDict()
+PLAN_CACHE_SIZE = 4
+
+def _cached(key, make):
+	dev = L.init()
+	key = (dev,)+key
+	p = _plans.get(key)
+	if p is None:
+		while len(_plans) >= PLAN_CACHE_SIZE: _plans.popitem(last=False)
+		p = make(); _plans[key] = p
+	else: _plans.move_to_end(key)
+	return p
+
+def clear_plans(): _plans.clear()
+
+def default_mstart(lmax, mmax):
+	m = np.arange(mmax+1, dtype=np.int64)
+	return m*(2*lmax+1-m)//2
+
+def _layout(lmax, mmax, mstart, lstride):
+	if mmax is None: mmax = lmax
+	mstart = default_mstart(lmax, mmax) if mstart is None else L.as_i64(mstart)[:mmax+1]
+	if len(mstart) != mmax+1: raise ValueError("mstart must have mmax+1 entries")
+	return int(lmax), int(mmax), mstart, int(lstride)
+
+def plan_rings(theta, nphi, phi0, ringstart, lmax, mmax=None, mstart=None, lstride=1, weight=None, xdir=1, npix=None):
+	theta = np.ascontiguousarray(theta, dtype=np.float64)
+	nphi_a = np.atleast_1d(np.asarray(nphi)).astype(np.int64); phi0_a = np.atleast_1d(np.asarray(phi0, dtype=np.float64))
+	if np.any(nphi_a != nphi_a[0]) or np.any(phi0_a != phi0_a[0]):
+		raise NotImplementedError("pixell_b200: rings must share nphi and phi0 (cylindrical maps only)")
+	nphi0, phi00 = int(nphi_a[0]), float(phi0_a[0])
+	ringstart = L.as_i64(ringstart)
+	lmax, mmax, mstart, lstride = _layout(lmax, mmax, mstart, lstride)
+	npix = nphi0 if npix is None else int(npix)
+	w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+	key = ("rings", theta.tobytes(), nphi0, phi00, int(xdir), npix, ringstart.tobytes(),
+		None if w is None else w.tobytes(), lmax, mmax, mstart.tobytes(), lstride)
+	def make():
+		h = ctypes.c_void_p()
+		L.check(L.lib().b2_sht_plan_rings(ctypes.byref(h), len(theta), L.p_dbl(theta), nphi0, phi00, int(xdir), npix,
+			L.p_i64(ringstart), None if w is None else L.p_dbl(w), lmax, mmax, L.p_i64(mstart), lstride), ValueError)
+		return Plan(h)
+	return _cached(key, make)
+
+def plan_2d(geometry, ntheta, nphi, phi0, lmax, mmax=None, mstart=None, lstride=1, flip_y=False, flip_x=False):
+	lmax, mmax, mstart, lstride = _layout(lmax, mmax, mstart, lstride)
+	key = ("2d", geometry, int(ntheta), int(nphi), float(phi0), bool(flip_y), bool(flip_x), lmax, mmax, mstart.tobytes(), lstride)
+	def make():
+		h = ctypes.c_void_p()
+		L.check(L.lib().b2_sht_plan_2d(ctypes.byref(h), geometry.encode(), int(ntheta), int(nphi), float(phi0),
+			int(bool(flip_y)), int(bool(flip_x)), lmax, mmax, L.p_i64(mstart), lstride), ValueError)
+		return Plan(h)
+	return _cached(key, make)
+
+# ------------------------------------------------------------------ execution helpers
+
+def _empty_like(ref, shape, dtype):
+	if L.is_torch(ref):
+		import torch
+		td = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
+			np.dtype(np.complex128): torch.complex128, np.dtype(np.complex64): torch.complex64}[np.dtype(dtype)]
+		return torch.zeros(shape, dtype=td, device=ref.device)
+	return np.zeros(shape, dtype)
+
+def _check_last_contig(a, name, nlast=1):
+	st = L.strides_elems(a)
+	want = 1
+	for i in range(1, nlast+1):
+		if a.shape[-i] != 1 and st[-i] != want: raise ValueError("%s must be C-contiguous in its last %d axes" % (name, nlast))
+		want *= a.shape[-i]
+
+def _run(fn, plan, spin, mode, alm, map, nmapdim, has_mode=True):
+	"""alm [nca, nalm], map [ncm, npix] or [ncm, ny, nx]"""
+	pa, mema, dta = L.buffer_info(alm); pm, memm, dtm = L.buffer_info(map)
+	if mema != memm: raise ValueError("alm and map must both be host arrays or both be CUDA tensors")
+	if dta == np.complex128 and dtm == np.float64: dtype = L.F64
+	elif dta == np.complex64 and dtm == np.float32: dtype = L.F32
+	else: raise ValueError("alm/map dtypes must be (complex128, float64) or (complex64, float32), got (%s, %s)" % (dta, dtm))
+	ncm = 1 if spin == 0 else 2
+	nca = 1 if (spin == 0 or mode == L.MODE_DERIV1) else 2
+	if alm.ndim != 2 or alm.shape[0] != nca: raise ValueError("alm must have shape [%d, nalm] for spin %d" % (nca, spin))
+	if map.ndim != 1+nmapdim or map.shape[0] != ncm: raise ValueError("map must have %d components for spin %d" % (ncm, spin))
+	_check_last_contig(alm, "alm", 1); _check_last_contig(map, "map", nmapdim)
+	acs = L.strides_elems(alm)[0] if nca > 1 else 0
+	mcs = L.strides_elems(map)[0] if ncm > 1 else 0
+	stream = L.current_stream(map)
+	args = [plan.handle, int(spin)] + ([mode] if has_mode else []) + [dtype, 1, pa, acs, 0, pm, mcs, 0, mema, stream]
+	L.check(fn(*args))
+
+def _alm_len(mstart, lmax, lstride): return int(np.max(mstart) + lmax*lstride + 1)
+
+# ------------------------------------------------------------------ ducc0.sht.experimental look-alikes
+
+def synthesis(*, alm, theta, nphi, phi0, ringstart, spin, lmax, mmax=None, mstart=None, lstride=1, pixstride=1,
+		map=None, mode="STANDARD", nthreads=0, weight=None, xdir=1, npix=None, **kw):
+	"""ducc0.sht.experimental.synthesis: alm[nca, nalm] -> map[ncm, npix_total] (filled in place and returned)."""
+	if pixstride != 1: raise NotImplementedError("pixstride != 1")
+	plan = plan_rings(theta, nphi, phi0, ringstart, lmax, mmax, mstart, lstride, weight, xdir, npix)
+	md = _MODES[mode]
+	if map is None:
+		ncm = 1 if spin == 0 else 2
+		n = int(np.max(np.asarray(ringstart)) + (np.atleast_1d(nphi)[0] if npix is None else npix))
+		map = _empty_like(alm, (ncm, n), np.float64 if L.buffer_info(alm)[2] == np.complex128 else np.float32)
+	_run(L.lib().b2_synthesis, plan, spin, md, alm, map, 1)
+	return map
+
+def adjoint_synthesis(*, map, theta, nphi, phi0, ringstart, spin, lmax, mmax=None, mstart=None, lstride=1, pixstride=1,
+		alm=None, mode="STANDARD", nthreads=0, weight=None, xdir=1, npix=None, **kw):
+	"""ducc0.sht.experimental.adjoint_synthesis: map -> alm = Y^T (w map)."""
+	if pixstride != 1: raise NotImplementedError("pixstride != 1")
+	plan = plan_rings(theta, nphi, phi0, ringstart, lmax, mmax, mstart, lstride, weight, xdir, npix)
+	md = _MODES[mode]
+	if alm is None:
+		lm, mm, ms, ls = _layout(lmax, mmax, mstart, lstride)
+		nca = 1 if (spin == 0 or md == L.MODE_DERIV1) else 2
+		alm = _empty_like(map, (nca, _alm_len(ms, lm, ls)), np.complex128 if L.buffer_info(map)[2] == np.float64 else np.complex64)
+	_run(L.lib().b2_adjoint_synthesis, plan, spin, md, alm, map, 1)
+	return alm
+
+def _plan_for_2d(map, ntheta, nphi, geometry, phi0, lmax, mmax, mstart, lstride, flip_y, flip_x):
+	if map is not None: ntheta, nphi = map.shape[-2:]
+	if ntheta is None or nphi is None: raise ValueError("need map or ntheta/nphi")
+	return plan_2d(geometry, ntheta, nphi, phi0, lmax, mmax, mstart, lstride, flip_y, flip_x), int(ntheta), int(nphi)
+
+def synthesis_2d(*, alm, spin, lmax, geometry, ntheta=None, nphi=None, mmax=None, mstart=None, lstride=1,
+		phi0=0.0, map=None, mode="STANDARD", nthreads=0, flip_y=False, flip_x=False, **kw):
+	"""ducc0.sht.experimental.synthesis_2d (pixell/curvedsky.py:908)."""
+	plan, ntheta, nphi = _plan_for_2d(map, ntheta, nphi, geometry, phi0, lmax, mmax, mstart, lstride, flip_y, flip_x)
+	if map is None:
+		map = _empty_like(alm, (1 if spin == 0 else 2, ntheta, nphi), np.float64 if L.buffer_info(alm)[2] == np.complex128 else np.float32)
+	_run(L.lib().b2_synthesis, plan, spin, _MODES[mode], alm, map, 2)
+	return map
+
+def adjoint_synthesis_2d(*, map, spin, lmax, geometry, mmax=None, mstart=None, lstride=1, phi0=0.0, alm=None,
+		mode="STANDARD", nthreads=0, flip_y=False, flip_x=False, **kw):
+	"""ducc0.sht.experimental.adjoint_synthesis_2d (pixell/curvedsky.py:907)."""
+	plan, ntheta, nphi = _plan_for_2d(map, None, None, geometry, phi0, lmax, mmax, mstart, lstride, flip_y, flip_x)
+	md = _MODES[mode]
+	if alm is None:
+		lm, mm, ms, ls = _layout(lmax, mmax, mstart, lstride)
+		nca = 1 if (spin == 0 or md == L.MODE_DERIV1) else 2
+		alm = _empty_like(map, (nca, _alm_len(ms, lm, ls)), np.complex128 if L.buffer_info(map)[2] == np.float64 else np.complex64)
+	_run(L.lib().b2_adjoint_synthesis, plan, spin, md, alm, map, 2)
+	return alm
+
+def analysis_2d(*, map, spin, lmax, geometry, mmax=None, mstart=None, lstride=1, phi0=0.0, alm=None,
+		nthreads=0, flip_y=False, flip_x=False, **kw):
+	"""ducc0.sht.experimental.analysis_2d (pixell/curvedsky.py:1033): exact inverse of synthesis_2d
+	for band-limited maps."""
+	plan, ntheta, nphi = _plan_for_2d(map, None, None, geometry, phi0, lmax, mmax, mstart, lstride, flip_y, flip_x)
+	if alm is None:
+		lm, mm, ms, ls = _layout(lmax, mmax, mstart, lstride)
+		alm = _empty_like(map, (1 if spin == 0 else 2, _alm_len(ms, lm, ls)), np.complex128 if L.buffer_info(map)[2] == np.float64 else np.complex64)
+	_run(L.lib().b2_analysis_2d, plan, spin, L.MODE_STANDARD, alm, map, 2, has_mode=False)
+	return alm
+
+def adjoint_analysis_2d(*, alm, spin, lmax, geometry, ntheta=None, nphi=None, mmax=None, mstart=None, lstride=1,
+		phi0=0.0, map=None, nthreads=0, flip_y=False, flip_x=False, **kw):
+	"""ducc0.sht.experimental.adjoint_analysis_2d (pixell/curvedsky.py:1032)."""
+	plan, ntheta, nphi = _plan_for_2d(map, ntheta, nphi, geometry, phi0, lmax, mmax, mstart, lstride, flip_y, flip_x)
+	if map is None:
+		map = _empty_like(alm, (1 if spin == 0 else 2, ntheta, nphi), np.float64 if L.buffer_info(alm)[2] == np.complex128 else np.float32)
+	_run(L.lib().b2_adjoint_analysis_2d, plan, spin, L.MODE_STANDARD, alm, map, 2, has_mode=False)
+	return map
+
+def get_gridweights(geometry, ntheta):
+	"""ducc0.sht.experimental.get_gridweights (pixell/curvedsky.py:501, 531, 855)."""
+	L.init()
+	out = np.zeros(int(ntheta), np.float64)
+	L.check(L.lib().b2_gridweights(geometry.encode(), int(ntheta), L.p_dbl(out)), ValueError)
+	return out
+
+def maxlmax(geometry, ny):
+	"""pixell/curvedsky.py:1349-1353 (get_ducc_maxlmax)"""
+	if   geometry == "CC": return ny-2
+	elif geometry == "DH": return (ny-2)//2
+	elif geometry == "F2": return (ny-1)//2
+	else:                  return ny-1
