@@ -37,6 +37,8 @@ int         b2_init(int device);              /* select the CUDA device for this
 const char *b2_last_error(void);
 int         b2_version(void);
 int         b2_device_synchronize(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t     b2_launch_count(void);
 /* measured peak FP64 FMA rate of the current device in GFLOP/s (microbenchmark; the roofline
  * denominator for the Legendre kernels) */
 int         b2_dfma_peak_gflops(double *out);

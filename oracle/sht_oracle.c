@@ -34,6 +34,9 @@
 #include <omp.h>
 
 #define VL 8            /* rings processed together (lets gcc vectorise the inner loops) */
+/* bench.py's bounded CPU-baseline sample: process only every g_mstride-th m (default: all) */
+static int g_mstride = 1;
+void orc_set_mstride(int s) { g_mstride = s > 0 ? s : 1; }
 #define RS_BITS 256     /* renormalisation step (binary exponent) */
 
 typedef struct { double c0, c1, c2; } rec_t;   /* F_{l+1} = (c0*cos(theta) - c1) F_l - c2 F_{l-1} */
@@ -170,7 +173,7 @@ int orc_alm2leg(int spin, int deriv1, int lmax, int mmax, const int64_t *mstart,
 		double *P = malloc(sizeof(double)*VL*ldo), *Q = malloc(sizeof(double)*VL*ldo);
 		double *a0 = malloc(sizeof(double)*2*(lmax+1)), *a1 = malloc(sizeof(double)*2*(lmax+1));
 		#pragma omp for schedule(dynamic,1)
-		for (int m = 0; m <= mmax; m++) {
+		for (int m = 0; m <= mmax; m += g_mstride) {
 			int l0 = m > spin ? m : spin;
 			if (l0 > lmax) continue;
 			/* gather this m's coefficients */
@@ -260,7 +263,7 @@ int orc_leg2alm(int spin, int deriv1, int lmax, int mmax, const int64_t *mstart,
 		double *P = malloc(sizeof(double)*VL*ldo), *Q = malloc(sizeof(double)*VL*ldo);
 		double *a0 = malloc(sizeof(double)*2*(lmax+1)), *a1 = malloc(sizeof(double)*2*(lmax+1));
 		#pragma omp for schedule(dynamic,1)
-		for (int m = 0; m <= mmax; m++) {
+		for (int m = 0; m <= mmax; m += g_mstride) {
 			int l0 = m > spin ? m : spin;
 			/* spin>0: l < spin entries are zero by definition */
 			for (int l = m; l < l0 && l <= lmax; l++) {

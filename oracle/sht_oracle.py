@@ -46,6 +46,10 @@ def _load():
 def nthreads():
 	return _load().orc_num_threads()
 
+def set_mstride(s):
+	"""bench.py only: restrict the Legendre stage to every s-th m (bounded CPU-baseline sample)"""
+	_load().orc_set_mstride(int(s))
+
 def _dp(a): return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 def _ip(a): return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
 

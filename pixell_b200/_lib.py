@@ -22,6 +22,7 @@ _PROTOS = {
 	"b2_last_error": ([], c_cp),
 	"b2_version": ([], c_int),
 	"b2_device_synchronize": ([], c_int),
+	"b2_launch_count": ([], c_i64),
 	"b2_dfma_peak_gflops": ([_dblp], c_int),
 	"b2_sht_plan_rings": ([ctypes.POINTER(c_vp), c_int, _dblp, c_i64, c_dbl, c_int, c_i64, _i64p, _dblp, c_int, c_int, _i64p, c_i64], c_int),
 	"b2_sht_plan_2d": ([ctypes.POINTER(c_vp), c_cp, c_int, c_i64, c_dbl, c_int, c_int, c_int, c_int, _i64p, c_i64], c_int),

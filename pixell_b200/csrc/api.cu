@@ -14,6 +14,8 @@ void b2_set_error(const char *fmt, ...)
 }
 extern "C" const char *b2_last_error(void) { return g_err; }
 extern "C" int b2_version(void) { return 100; }
+long long g_b2_launches = 0;
+extern "C" int64_t b2_launch_count(void) { return g_b2_launches; }
 
 extern "C" int b2_init(int device)
 {
@@ -147,6 +149,11 @@ static int plan_common(b2_sht_plan *p, int nring, const double *theta, int64_t n
 	for (int m = 0; m <= mmax; m++) {
 		B2_REQUIRE(mstart[m] + (int64_t)m*lstride >= 0, "plan: negative alm index for m=%d", m);
 		p->alm_span = std::max(p->alm_span, mstart[m] + (int64_t)lmax*lstride + 1);
+	}
+	{
+		int64_t owned = 0;
+		for (int m = 0; m <= mmax; m++) owned += lmax - m + 1;
+		p->alm_dense = (lstride == 1 && owned == p->alm_span);
 	}
 	if (p->mstart.upload(p->mstart_h)) return 1;
 	p->nring = nring; p->nphi = nphi; p->npix = npix;
@@ -290,6 +297,7 @@ static int run_one(Exec &E, void *alm, int64_t alm_cstride, void *map, int64_t m
 		// the input direction needs the values; the output direction needs them too so that entries the
 		// transform does not own survive the round trip
 		for (int c = 0; c < E.nca; c++) {
+			if (!to_map && p->alm_dense) break;      // every entry of the span is overwritten
 			char *src = (char*)alm + (size_t)c*alm_cstride*E.asz;
 			if (E.dtype == B2_F64) B2_CHECK(cudaMemcpyAsync(dalm + c*dalm_cs, src, p->alm_span*16, cudaMemcpyDefault, E.st));
 			else {

@@ -12,7 +12,8 @@ void b2_set_error(const char *fmt, ...);
 #define B2_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
 	b2_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return 1; } } while (0)
 #define B2_REQUIRE(cond, ...) do { if (!(cond)) { b2_set_error(__VA_ARGS__); return 1; } } while (0)
-#define B2_LAUNCH_CHECK() B2_CHECK(cudaGetLastError())
+extern long long g_b2_launches;
+#define B2_LAUNCH_CHECK() do { g_b2_launches++; B2_CHECK(cudaGetLastError()); } while (0)
 
 static inline int64_t b2_round_up(int64_t a, int64_t b) { return (a + b - 1)/b*b; }
 

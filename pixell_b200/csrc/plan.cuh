@@ -11,6 +11,7 @@ struct b2_sht_plan {
 	int lmax = 0, mmax = 0;
 	int64_t lstride = 1;
 	int64_t alm_span = 0;              // elements of one alm component touched by the layout
+	bool alm_dense = false;            // the transform owns every element of the span
 	DevBuf<int64_t> mstart;
 	std::vector<int64_t> mstart_h;
 	int nring = 0;

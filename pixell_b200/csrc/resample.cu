@@ -51,10 +51,10 @@ template<int STAGE> __global__ void k_resamp(ResampArgs R)
 			else if (STAGE == 4) v = B[idx];
 			else v = A[idx];
 			int e = (q*p) % P;
-			if (e) v = cmul(v, twid<INV>(R.d, (2*N/P)*e));
+			if (e) v = cmul(v, cj(R.d.tw[(2*N/P)*e], INV));
 			acc = cadd(acc, v);
 		}
-		if (p) acc = cmul(acc, twid<INV>(R.d, 2*j*p));
+		if (p) acc = cmul(acc, cj(R.d.tw[2*j*p], INV));
 		s[j] = acc;
 	}
 	__syncthreads();
@@ -124,13 +124,13 @@ int ThetaResampler::build(const std::string &g, int ntheta, int64_t nphi_, int l
 		if (mir[k] == pos[k]) mu[k] = 1.0; else sr[mir[k]] = k | 0x40000000;
 	}
 	P = 1;
-	while ((size_t)(N/P)*sizeof(double2) > 200*1024 || !FftTables::supported(N/P)) {
+	while ((size_t)FftTables::smem_len(N/P)*sizeof(double2) > 200*1024) {
 		int np = P*2;
-		B2_REQUIRE(np <= 8 && N % np == 0, "cannot factor the theta transform of length %d", N);
+		B2_REQUIRE(np <= 8 && N % np == 0, "theta transform of length %d does not fit in shared memory", N);
 		P = np;
 	}
 	if (tab.build(N/P, 2*N)) return 1;
-	smem = sizeof(double2)*(size_t)(N/P);
+	smem = sizeof(double2)*(size_t)FftTables::smem_len(N/P);
 	threads = (int)std::min<int64_t>(512, std::max<int64_t>(64, b2_round_up(N/P/4, 32)));
 	if (src.upload(sr) || mult.upload(mu) || wfine.alloc(2*(size_t)N)) return 1;
 	k_wfine<<<(N + 128)/128, 128>>>(wfine.p, N, 4.0*M_PI/(2.0*N)/(double)nphi);

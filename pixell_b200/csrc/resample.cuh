@@ -5,8 +5,7 @@
 
 // Applies, to every (component, m) column of leg[.][m][ring] on a CC / F1 / MW / MWflip grid with
 // fewer than 2 lmax + 2 rings, the operator that ducc0's analysis_2d realises by upsampling to a
-// Clenshaw-Curtis grid and weighting there (pixell/curvedsky.py:1033-1046; oracle/sht_oracle.py
-// resample_to_cc + get_gridweights) -- but folded back onto the ORIGINAL rings: the weighted fine
+// Clenshaw-Curtis grid and weighting there (pixell/curvedsky.py:1033-1046) -- but folded back onto the ORIGINAL rings: the weighted fine
 // samples are low-passed to |k| <= lmax and re-evaluated on the coarse grid, which leaves every
 // a_lm unchanged (lambda_lm has bandwidth lmax) and lets the Legendre stage run on ntheta rings
 // instead of 2 lmax + 2.  See DESIGN.md "theta weighting".

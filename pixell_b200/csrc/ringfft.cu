@@ -8,39 +8,115 @@
 // sequence (even nphi) or a full complex one (odd nphi); fft_smem.cuh does the passes.
 #include "ringfft.cuh"
 #include <algorithm>
+#include <complex>
 
 // ------------------------------------------------------------------------------------ tables
 
-bool FftTables::supported(int64_t n)
+bool FftTables::smooth(int64_t n)
 {
 	if (n < 1) return false;
 	for (int p = 2; p <= FFT_MAX_RADIX && n > 1; p++) while (n % p == 0) n /= p;
 	return n == 1;
 }
 
-int FftTables::build(int n, int ntab)
+int FftTables::bluestein_len(int n)
 {
-	B2_REQUIRE(n >= 1 && ntab % n == 0, "bad FFT table request n=%d ntab=%d", n, ntab);
-	B2_REQUIRE(supported(n), "FFT length %d has a prime factor > %d (unsupported)", n, FFT_MAX_RADIX);
-	d.n = n; d.ntab = ntab; d.twmul = ntab/n; d.nfac = 0;
-	int rem = n;
-	while (rem % 4 == 0) { d.fac[d.nfac++] = 4; rem /= 4; }
-	for (int p = 2; p <= FFT_MAX_RADIX; p++) while (rem % p == 0) { B2_REQUIRE(d.nfac < FFT_MAX_FAC, "too many FFT factors"); d.fac[d.nfac++] = p; rem /= p; }
-	std::vector<double2> t(ntab);
-	const long double tau = 6.283185307179586476925286766559005768L;
-	for (int k = 0; k < ntab; k++) {
-		// exact octant symmetry is not needed: long double keeps the table at 0.5 ulp
-		long double a = tau*(long double)k/(long double)ntab;
-		t[k].x = (double)cosl(a); t[k].y = (double)-sinl(a);
+	for (int M = 2*n - 1; ; M++) {
+		int r = M;
+		while (r % 2 == 0) r /= 2;
+		while (r % 3 == 0) r /= 3;
+		while (r % 5 == 0) r /= 5;
+		if (r == 1) return M;
 	}
+}
+
+typedef std::complex<long double> cld;
+static const long double TAU = 6.283185307179586476925286766559005768L;
+
+// plain recursive mixed-radix FFT in long double (host, plan time only)
+static void host_fft(std::vector<cld> &x)
+{
+	size_t n = x.size();
+	if (n <= 1) return;
+	size_t r = n;
+	for (size_t p = 2; p*p <= n; p++) if (n % p == 0) { r = p; break; }
+	size_t m = n/r;
+	std::vector<std::vector<cld>> sub(r, std::vector<cld>(m));
+	for (size_t q = 0; q < r; q++) { for (size_t j = 0; j < m; j++) sub[q][j] = x[j*r + q]; host_fft(sub[q]); }
+	for (size_t k = 0; k < n; k++) {
+		cld acc = 0;
+		for (size_t q = 0; q < r; q++) {
+			long double a = -TAU*(long double)((q*k) % n)/(long double)n;
+			acc += sub[q][k % m]*cld(cosl(a), sinl(a));
+		}
+		x[k] = acc;
+	}
+}
+
+static void factorize(int n, int *fac, int &nfac)
+{
+	nfac = 0;
+	int rem = n;
+	while (rem % 4 == 0) { fac[nfac++] = 4; rem /= 4; }
+	for (int p = 2; p <= FFT_MAX_RADIX; p++) while (rem % p == 0) { fac[nfac++] = p; rem /= p; }
+}
+
+static std::vector<int> digit_reversal(int n, const int *fac, int nfac)
+{
 	std::vector<int> rv(n);
 	for (int k = 0; k < n; k++) {
 		int kk = k, pos = 0, len = n;
-		for (int f = 0; f < d.nfac; f++) { int r = d.fac[f]; len /= r; pos += (kk % r)*len; kk /= r; }
+		for (int f = 0; f < nfac; f++) { int r = fac[f]; len /= r; pos += (kk % r)*len; kk /= r; }
 		rv[k] = pos;
 	}
-	if (tw.upload(t) || rev.upload(rv)) return 1;
-	d.tw = tw.p; d.rev = rev.p;
+	return rv;
+}
+
+static std::vector<double2> twiddles(int n)
+{
+	std::vector<double2> t(n);
+	for (int k = 0; k < n; k++) {
+		long double a = TAU*(long double)k/(long double)n;
+		t[k].x = (double)cosl(a); t[k].y = (double)-sinl(a);
+	}
+	return t;
+}
+
+int FftTables::build(int n, int ntab)
+{
+	B2_REQUIRE(n >= 1 && ntab % n == 0, "bad FFT table request n=%d ntab=%d", n, ntab);
+	d.n = n; d.ntab = ntab; d.twmul = ntab/n;
+	if (tw.upload(twiddles(ntab))) return 1;
+	d.tw = tw.p;
+	if (smooth(n)) {
+		d.bluestein = 0; d.nt = n; d.nsmem = n;
+		factorize(n, d.fac, d.nfac);
+		B2_REQUIRE(d.nfac <= FFT_MAX_FAC, "too many FFT factors");
+		if (rev.upload(digit_reversal(n, d.fac, d.nfac))) return 1;
+		d.rev = rev.p; d.btw = nullptr; d.chirp = nullptr; d.bhat = nullptr;
+		return 0;
+	}
+	// Bluestein: chirp c_k = exp(-i pi k^2/n); X = c .* IFFT_M(FFT_M(x .* c) .* FFT_M(conj c wrapped))
+	const int M = bluestein_len(n);
+	d.bluestein = 1; d.nt = M; d.nsmem = M;
+	factorize(M, d.fac, d.nfac);
+	std::vector<int> rv = digit_reversal(M, d.fac, d.nfac);
+	std::vector<double2> ch(n);
+	std::vector<cld> b(M, cld(0, 0));
+	for (int k = 0; k < n; k++) {
+		long long k2 = ((long long)k*k) % (2LL*n);
+		long double a = TAU*(long double)k2/(2.0L*n);
+		ch[k].x = (double)cosl(a); ch[k].y = (double)-sinl(a);
+		cld bc(cosl(a), sinl(a));
+		b[k] = bc; if (k) b[M - k] = bc;
+	}
+	host_fft(b);
+	std::vector<double2> bh(M);
+	for (int k = 0; k < M; k++) { bh[rv[k]].x = (double)(b[k].real()/M); bh[rv[k]].y = (double)(b[k].imag()/M); }
+	std::vector<int> ident(n);
+	for (int k = 0; k < n; k++) ident[k] = k;
+	if (btw.upload(twiddles(M)) || chirp.upload(ch) || bhat.upload(bh) || rev.upload(ident)) return 1;
+	d.btw = btw.p; d.chirp = chirp.p; d.bhat = bhat.p; d.rev = rev.p;
 	return 0;
 }
 
@@ -59,7 +135,7 @@ int RingFft::build(int64_t nphi_, double phi0, int xdir_, int64_t npix_, int nri
 	B2_REQUIRE(nphi >= 1 && npix >= 1 && npix <= nphi, "bad ring description: nphi=%lld npix=%lld", (long long)nphi, (long long)npix);
 	half = (nphi % 2 == 0) ? 1 : 0;
 	nfft = (int)(half ? nphi/2 : nphi);
-	smem = sizeof(double2)*(size_t)(nfft + 1);
+	smem = sizeof(double2)*(size_t)std::max<int64_t>(nfft + 1, FftTables::smem_len(nfft));
 	B2_REQUIRE(smem <= 227*1024, "nphi=%lld needs %zu bytes of shared memory per ring (limit 227 KB)", (long long)nphi, smem);
 	if (tab.build(nfft, (int)nphi)) return 1;
 	if (phase.alloc(mmax + 1)) return 1;
