@@ -17,8 +17,13 @@
 #include "legendre.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
-#define TL 32                 // l values per shared-memory tile
+#define B2_DEF_SYNTH0 0
+#define B2_DEF_ADJ0 0
+#define B2_DEF_SYNTH2 0
+#define B2_DEF_ADJ2 0
+
 #define BIGV   0x1p256
 #define SMALLV 0x1p-512
 
@@ -116,7 +121,7 @@ int LegGeom::build(int nring_, const double *theta)
 	// pole -> equator: chunks of neighbouring pairs become live at similar l
 	std::stable_sort(pr.begin(), pr.end(), [](const PairInfo &a, const PairInfo &b) { return a.sh*a.ch < b.sh*b.ch; });
 	npair = (int)pr.size();
-	npair_pad = (int)b2_round_up(npair, 128);
+	npair_pad = (int)b2_round_up(npair, 256);
 	PairInfo dead; dead.x = 0; dead.sh = 0; dead.ch = 1; dead.rn = -1; dead.rs = -1;
 	pr.resize(npair_pad, dead);
 	return pairs.upload(pr);
@@ -254,7 +259,7 @@ template<int MODE, int R> __device__ __forceinline__ void synth0_window(const Ti
 	}
 }
 
-template<int R, int NW> __global__ void __launch_bounds__(NW*32) k_synth0(LegArgs A)
+template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*32, MINB) k_synth0(LegArgs A)
 {
 	__shared__ __align__(16) Tile0 tiles[2][TL];
 	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -320,13 +325,14 @@ template<int R, int NW> __global__ void __launch_bounds__(NW*32) k_synth0(LegArg
 	}
 }
 
-// adjoint, spin 0: window of 16 l values -> 32 partial sums (16 l x re/im) reduced over the warp
-template<int MODE, int R> __device__ __forceinline__ void adj0_window(const double *Ta,
+// adjoint, spin 0: a window of W l values -> NV = 2W partial sums (W l x re/im) reduced over the warp;
+// after bfly_reduce lane L holds element L >> log2(32/NV)
+template<int MODE, int R, int W> __device__ __forceinline__ void adj0_window(const double *Ta,
 	const double (&x)[R], double (&g)[R], double (&gp)[R], int (&sc)[R],
-	const double (&in)[R][2][2], double (&v)[32])
+	const double (&in)[R][2][2], double (&v)[2*W])
 {
 	#pragma unroll
-	for (int j = 0; j < 16; j++) {
+	for (int j = 0; j < W; j++) {
 		const double a = Ta[j];
 		#pragma unroll
 		for (int r = 0; r < R; r++) {
@@ -342,10 +348,12 @@ template<int MODE, int R> __device__ __forceinline__ void adj0_window(const doub
 	}
 }
 
-template<int R, int NW> __global__ void __launch_bounds__(NW*32) k_adj0(LegArgs A)
+template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds__(NW*32, MINB) k_adj0(LegArgs A)
 {
+	constexpr int NV = 2*W, SH = (NV == 32 ? 0 : NV == 16 ? 1 : NV == 8 ? 2 : 3), NOUT = 2*TL;
+	constexpr int NT = NW*32, NH = (NOUT + NT - 1)/NT;
 	__shared__ double tiles[2][TL];
-	__shared__ double red[2][NW][64];
+	__shared__ double red[2][NW][NOUT];
 	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, l0 = m;
 	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
@@ -381,37 +389,45 @@ template<int R, int NW> __global__ void __launch_bounds__(NW*32) k_adj0(LegArgs 
 			const int buf = tile & 1;
 			double nxt = 0;
 			if (tid < TL && tile + 1 < ntile) { int i = (tile + 1)*TL + tid; if (i < nl) nxt = ta[i]; }
-			const int nwin = (min(TL, nl - tile*TL) + 15) >> 4;
+			const int nwin = (min(TL, nl - tile*TL) + W - 1)/W;
+			// output threads fetch the running sum early so the read-modify-write latency hides behind the tile
+			double oldv[NH], alv[NH];
 			#pragma unroll
-			for (int w = 0; w < 2; w++) {
+			for (int h = 0; h < NH; h++) {
+				oldv[h] = 0; alv[h] = 0;
+				int e = tid + h*NT, i = tile*TL + (e >> 1);
+				if (e < NOUT && i < nl) { alv[h] = tal[i]; if (!first) oldv[h] = almr[2*(int64_t)(l0 + i)*A.lstride + (e & 1)]; }
+			}
+			#pragma unroll
+			for (int w = 0; w < TL/W; w++) {
 				double tot = 0;
 				if (wuse && w < nwin) {
-					double v[32];
+					double v[NV];
 					#pragma unroll
-					for (int i = 0; i < 32; i++) v[i] = 0;
+					for (int i = 0; i < NV; i++) v[i] = 0;
 					bool mylive = true, anylive = false;
 					#pragma unroll
 					for (int r = 0; r < R; r++) { mylive &= (sc[r] == 0); anylive |= (sc[r] == 0 && use[r]); }
-					const double *T = &tiles[buf][w*16];
-					if (__all_sync(0xffffffffu, mylive)) adj0_window<2, R>(T, x, g, gp, sc, in, v);
-					else if (__any_sync(0xffffffffu, anylive)) adj0_window<1, R>(T, x, g, gp, sc, in, v);
-					else adj0_window<0, R>(T, x, g, gp, sc, in, v);
-					bfly_reduce<32>(v, lane);
+					const double *T = &tiles[buf][w*W];
+					if (__all_sync(0xffffffffu, mylive)) adj0_window<2, R, W>(T, x, g, gp, sc, in, v);
+					else if (__any_sync(0xffffffffu, anylive)) adj0_window<1, R, W>(T, x, g, gp, sc, in, v);
+					else adj0_window<0, R, W>(T, x, g, gp, sc, in, v);
+					bfly_reduce<NV>(v, lane);
 					tot = v[0];
 				}
-				red[buf][warp][w*32 + lane] = tot;     // element (l = 16 w + lane/2, re/im = lane&1)
+				// element (l = w W + (lane >> SH)/2, re/im = (lane >> SH) & 1); duplicates write the same value
+				red[buf][warp][w*NV + (lane >> SH)] = tot;
 			}
 			if (tid < TL) tiles[buf ^ 1][tid] = nxt;
 			__syncthreads();
-			if (tid < 64) {
-				double s = 0;
-				#pragma unroll
-				for (int w = 0; w < NW; w++) s += red[buf][w][tid];
-				int i = tile*TL + (tid >> 1);
-				if (i < nl) {
-					double *o = almr + 2*(int64_t)(l0 + i)*A.lstride + (tid & 1);
-					double val = s*tal[i];
-					*o = first ? val : *o + val;
+			#pragma unroll
+			for (int h = 0; h < NH; h++) {
+				int e = tid + h*NT, i = tile*TL + (e >> 1);
+				if (e < NOUT && i < nl) {
+					double s = 0;
+					#pragma unroll
+					for (int w = 0; w < NW; w++) s += red[buf][w][e];
+					almr[2*(int64_t)(l0 + i)*A.lstride + (e & 1)] = oldv[h] + s*alv[h];
 				}
 			}
 		}
@@ -468,7 +484,7 @@ __device__ __forceinline__ Tile2 load_tile2_synth(const LegArgs &A, int m, int l
 	return t;
 }
 
-template<int R, int NW> __global__ void __launch_bounds__(NW*32) k_synth2(LegArgs A)
+template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*32, MINB) k_synth2(LegArgs A)
 {
 	__shared__ __align__(16) Tile2 tiles[2][TL];
 	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -547,15 +563,15 @@ template<int R, int NW> __global__ void __launch_bounds__(NW*32) k_synth2(LegArg
 	}
 }
 
-// adjoint, spin > 0: window of 8 l values -> 32 partial sums (8 l x {A+re, A+im, A-re, A-im})
+// adjoint, spin > 0: a window of W l values -> NV = 4W partial sums (W l x {A+re, A+im, A-re, A-im})
 //   A+_l = sum_pairs p Z+N + sigma_l q Z+S,  A-_l = sum_pairs q Z-N + sigma_l p Z-S,  Z+- = Q +- iU
 // zin[r][0..3] = Z+N (re,im), Z-N (re,im); zin[r][4..7] = sigma0 * (Z+S, Z-S)
-template<int MODE, int R> __device__ __forceinline__ void adj2_window(const double2 *Tab,
+template<int MODE, int R, int W> __device__ __forceinline__ void adj2_window(const double2 *Tab,
 	const double (&x)[R], double (&p)[R], double (&pp)[R], double (&q)[R], double (&qp)[R],
-	int (&sp)[R], int (&sq)[R], const double (&zin)[R][8], double (&v)[32])
+	int (&sp)[R], int (&sq)[R], const double (&zin)[R][8], double (&v)[4*W])
 {
 	#pragma unroll
-	for (int j = 0; j < 8; j++) {
+	for (int j = 0; j < W; j++) {
 		const double2 ab = Tab[j];
 		#pragma unroll
 		for (int r = 0; r < R; r++) {
@@ -577,10 +593,12 @@ template<int MODE, int R> __device__ __forceinline__ void adj2_window(const doub
 	}
 }
 
-template<int R, int NW> __global__ void __launch_bounds__(NW*32) k_adj2(LegArgs A)
+template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds__(NW*32, MINB) k_adj2(LegArgs A)
 {
+	constexpr int NV = 4*W, SH = (NV == 32 ? 0 : NV == 16 ? 1 : NV == 8 ? 2 : 3), NOUT = 4*TL;
+	constexpr int NT = NW*32, NH = (NOUT + NT - 1)/NT;
 	__shared__ __align__(16) double2 tiles[2][TL];
-	__shared__ double red[2][NW][128];
+	__shared__ double red[2][NW][NOUT];
 	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, s = A.spin, l0 = m > s ? m : s;
 	double *alme = (double*)A.alm0, *almb = (double*)A.alm1;
@@ -626,52 +644,63 @@ template<int R, int NW> __global__ void __launch_bounds__(NW*32) k_adj2(LegArgs 
 			const int buf = tile & 1;
 			double2 nxt = make_double2(0, 0);
 			if (tid < TL && tile + 1 < ntile) { int i = (tile + 1)*TL + tid; if (i < nl) nxt = make_double2(ta[i], tb[i]); }
-			const int nwin = (min(TL, nl - tile*TL) + 7) >> 3;
+			const int nwin = (min(TL, nl - tile*TL) + W - 1)/W;
+			// output threads: element e -> (l offset e >> 2, component e & 3); fetch the running sum early
+			double oldv[NH], alv[NH];
 			#pragma unroll
-			for (int w = 0; w < 4; w++) {
+			for (int h = 0; h < NH; h++) {
+				oldv[h] = 0; alv[h] = 0;
+				int e = tid + h*NT, i = tile*TL + (e >> 2), k = e & 3;
+				if (e < NOUT && i < nl) {
+					alv[h] = tal[i];
+					int64_t idx = 2*(ms + (int64_t)(l0 + i)*A.lstride) + (k & 1);
+					if (!first && !(A.deriv1 && k >= 2)) oldv[h] = (k < 2 ? alme : almb)[idx];
+				}
+			}
+			#pragma unroll
+			for (int w = 0; w < TL/W; w++) {
 				double tot = 0;
 				if (wuse && w < nwin) {
-					double v[32];
+					double v[NV];
 					#pragma unroll
-					for (int i = 0; i < 32; i++) v[i] = 0;
+					for (int i = 0; i < NV; i++) v[i] = 0;
 					bool mylive = true, anylive = false;
 					#pragma unroll
 					for (int r = 0; r < R; r++) {
 						mylive &= (sp[r] == 0) & (sq[r] == 0);
 						anylive |= use[r] & ((sp[r] == 0) | (sq[r] == 0));
 					}
-					const double2 *T = &tiles[buf][w*8];
-					if (__all_sync(0xffffffffu, mylive)) adj2_window<2, R>(T, x, p, pp, q, qp, sp, sq, zin, v);
-					else if (__any_sync(0xffffffffu, anylive)) adj2_window<1, R>(T, x, p, pp, q, qp, sp, sq, zin, v);
-					else adj2_window<0, R>(T, x, p, pp, q, qp, sp, sq, zin, v);
-					bfly_reduce<32>(v, lane);
+					const double2 *T = &tiles[buf][w*W];
+					if (__all_sync(0xffffffffu, mylive)) adj2_window<2, R, W>(T, x, p, pp, q, qp, sp, sq, zin, v);
+					else if (__any_sync(0xffffffffu, anylive)) adj2_window<1, R, W>(T, x, p, pp, q, qp, sp, sq, zin, v);
+					else adj2_window<0, R, W>(T, x, p, pp, q, qp, sp, sq, zin, v);
+					bfly_reduce<NV>(v, lane);
 					tot = v[0];
 				}
-				red[buf][warp][w*32 + lane] = tot;      // element (l = 8 w + lane/4, comp = lane&3)
+				red[buf][warp][w*NV + (lane >> SH)] = tot;      // element (l = w W + (lane>>SH)/4, comp = (lane>>SH)&3)
 			}
 			if (tid < TL) tiles[buf ^ 1][tid] = nxt;
 			__syncthreads();
-			if (tid < 128) {
+			#pragma unroll
+			for (int h = 0; h < NH; h++) {
+				int e = tid + h*NT, i = tile*TL + (e >> 2), k = e & 3;
 				double c = 0;
-				#pragma unroll
-				for (int w = 0; w < NW; w++) c += red[buf][w][tid];
-				// gather the 4 components of this l from the neighbouring lanes
-				int base = lane & ~3, k = lane & 3;
+				if (e < NOUT) {
+					#pragma unroll
+					for (int w = 0; w < NW; w++) c += red[buf][w][e];
+				}
+				// the 4 components of one l sit in 4 neighbouring lanes (NT and NOUT are multiples of 32)
+				int base = lane & ~3;
 				double c0 = __shfl_sync(0xffffffffu, c, base), c1 = __shfl_sync(0xffffffffu, c, base + 1);
 				double c2 = __shfl_sync(0xffffffffu, c, base + 2), c3 = __shfl_sync(0xffffffffu, c, base + 3);
-				int i = tile*TL + 8*(tid >> 5) + (lane >> 2);
-				if (i < nl) {
+				if (e < NOUT && i < nl) {
 					int l = l0 + i;
-					double h = 0.5*tal[i];
+					double hh = 0.5*alv[h];
 					// E = -(A+ + A-)/2, B = (i/2)(A+ - A-)
-					double val = k == 0 ? -h*(c0 + c2) : k == 1 ? -h*(c1 + c3) : k == 2 ? -h*(c1 - c3) : h*(c0 - c2);
+					double val = k == 0 ? -hh*(c0 + c2) : k == 1 ? -hh*(c1 + c3) : k == 2 ? -hh*(c1 - c3) : hh*(c0 - c2);
 					int64_t idx = 2*(ms + (int64_t)l*A.lstride) + (k & 1);
-					if (A.deriv1) {
-						if (k < 2) { val *= sqrt((double)l*(l + 1.0)); alme[idx] = first ? val : alme[idx] + val; }
-					} else {
-						double *o = (k < 2 ? alme : almb) + idx;
-						*o = first ? val : *o + val;
-					}
+					if (A.deriv1) { if (k < 2) alme[idx] = oldv[h] + val*sqrt((double)l*(l + 1.0)); }
+					else (k < 2 ? alme : almb)[idx] = oldv[h] + val;
 				}
 			}
 		}
@@ -686,10 +715,20 @@ template<int R, int NW> __global__ void __launch_bounds__(NW*32) k_adj2(LegArgs 
 
 // ------------------------------------------------------------------------------------ host entry points
 
-#define R0 4      // ring pairs per lane, spin 0
-#define R2 2      // ring pairs per lane, spin > 0
-#define NW0 8
-#define NW2 8
+// Kernel variants: R ring pairs per lane, NW warps per CTA, MINB resident CTAs per SM the register
+// allocation is tuned for, TL l-values per shared-memory tile.  The default is the fastest measured
+// on B200 (profiles/); B2_LEG_VARIANT=<synth0>,<adj0>,<synth2>,<adj2> selects others for tuning runs.
+static int variant_of(int which)
+{
+	static int v[4] = {-1, -1, -1, -1};
+	if (v[0] < 0) {
+		int d[4] = {B2_DEF_SYNTH0, B2_DEF_ADJ0, B2_DEF_SYNTH2, B2_DEF_ADJ2};
+		const char *e = getenv("B2_LEG_VARIANT");
+		if (e) sscanf(e, "%d,%d,%d,%d", &d[0], &d[1], &d[2], &d[3]);
+		for (int i = 0; i < 4; i++) v[i] = d[i];
+	}
+	return v[which];
+}
 
 static LegArgs make_args(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
 	double2 *alm, int64_t alm_cstride, double2 *leg)
@@ -712,13 +751,30 @@ static int check_args(const LegTables &T, const AlmLayout &L, int deriv1)
 	return 0;
 }
 
+#define LAUNCH(K, ...) K<__VA_ARGS__><<<L.mmax + 1, launch_threads<__VA_ARGS__>(), 0, st>>>(A)
+template<int R, int NW, int... REST> constexpr int launch_threads() { return NW*32; }
+
 int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
 	const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st)
 {
 	if (check_args(T, L, deriv1)) return 1;
 	LegArgs A = make_args(T, G, L, deriv1, (double2*)alm, alm_cstride, leg);
-	if (T.spin == 0) k_synth0<R0, NW0><<<L.mmax + 1, NW0*32, 0, st>>>(A);
-	else             k_synth2<R2, NW2><<<L.mmax + 1, NW2*32, 0, st>>>(A);
+	// template arguments: R, NW, MINB, TL
+	if (T.spin == 0) switch (variant_of(0)) {
+		case 0: LAUNCH(k_synth0, 2, 8, 3, 64); break;
+		case 1: LAUNCH(k_synth0, 4, 4, 4, 64); break;
+		case 2: LAUNCH(k_synth0, 2, 4, 6, 64); break;
+		case 3: LAUNCH(k_synth0, 2, 2, 12, 64); break;
+		case 4: LAUNCH(k_synth0, 2, 1, 24, 32); break;
+		default: B2_REQUIRE(0, "unknown k_synth0 variant");
+	} else switch (variant_of(2)) {
+		case 0: LAUNCH(k_synth2, 2, 4, 3, 64); break;
+		case 1: LAUNCH(k_synth2, 2, 2, 6, 64); break;
+		case 2: LAUNCH(k_synth2, 2, 1, 12, 32); break;
+		case 3: LAUNCH(k_synth2, 2, 8, 1, 32); break;
+		case 4: LAUNCH(k_synth2, 1, 4, 6, 64); break;
+		default: B2_REQUIRE(0, "unknown k_synth2 variant");
+	}
 	B2_LAUNCH_CHECK();
 	return 0;
 }
@@ -728,8 +784,22 @@ int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 {
 	if (check_args(T, L, deriv1)) return 1;
 	LegArgs A = make_args(T, G, L, deriv1, alm, alm_cstride, (double2*)leg);
-	if (T.spin == 0) k_adj0<R0, NW0><<<L.mmax + 1, NW0*32, 0, st>>>(A);
-	else             k_adj2<R2, NW2><<<L.mmax + 1, NW2*32, 0, st>>>(A);
+	// template arguments: R, NW, MINB, TL, W
+	if (T.spin == 0) switch (variant_of(1)) {
+		case 0: LAUNCH(k_adj0, 4, 8, 1, 32, 16); break;
+		case 1: LAUNCH(k_adj0, 8, 8, 1, 32, 8); break;
+		case 2: LAUNCH(k_adj0, 8, 8, 1, 64, 8); break;
+		case 3: LAUNCH(k_adj0, 8, 4, 2, 64, 8); break;
+		case 4: LAUNCH(k_adj0, 4, 8, 1, 64, 16); break;
+		default: B2_REQUIRE(0, "unknown k_adj0 variant");
+	} else switch (variant_of(3)) {
+		case 0: LAUNCH(k_adj2, 2, 8, 1, 32, 8); break;
+		case 1: LAUNCH(k_adj2, 4, 8, 1, 32, 4); break;
+		case 2: LAUNCH(k_adj2, 4, 8, 1, 64, 4); break;
+		case 3: LAUNCH(k_adj2, 4, 4, 2, 64, 4); break;
+		case 4: LAUNCH(k_adj2, 2, 8, 1, 64, 8); break;
+		default: B2_REQUIRE(0, "unknown k_adj2 variant");
+	}
 	B2_LAUNCH_CHECK();
 	return 0;
 }

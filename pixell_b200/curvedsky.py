@@ -72,10 +72,11 @@ def _flipped(shape, wcs, flip):
 	return geometry.CarWCS(w.crval, cdelt, crpix)
 
 def _is_cyl(wcs):
+	"""plate carree with the equator as reference latitude: the only separable projection whose rows are
+	equidistant in declination (what the ring kernels assume); anything else is the reference's "general" case"""
 	ctype = getattr(wcs.wcs, "ctype", None)
-	if ctype is None: return True
-	proj = str(ctype[0])[-3:].upper()
-	return proj in ("CAR", "CEA", "") and abs(wcs.wcs.crval[1]) < 1e-12 if proj == "CAR" else proj in ("CEA", "")
+	proj = "CAR" if ctype is None else str(ctype[0])[-3:].upper()
+	return proj in ("CAR", "") and abs(wcs.wcs.crval[1]) < 1e-12
 
 def get_ducc_geo(wcs, shape, tol=1e-6):
 	"""pixell/curvedsky.py:1308-1347 on an already flipped (north-first, ra increasing) geometry."""
@@ -334,33 +335,44 @@ def map2alm(map, alm=None, lmax=None, spin=[0,2], deriv=False, adjoint=False, co
 	wring = _ring_weights(map.shape, wcs, minfo) if weights is None else np.asarray(weights, dtype=np.float64)
 	wrow = wring[::-1] if minfo.flip[0] else wring                             # caller's row order
 	pk = _plan_kwargs(map.shape, wcs, minfo, "cyl", ainfo, ainfo.lmax, ainfo.mmax, weights=np.ascontiguousarray(wrow))
-	pk_now = dict(pk, weight=None)
+	ny, nx = map.shape[-2:]
+	nphi = pk["nphi"]
+	# The Jacobi iteration runs on full rings: the reference pads cut rows with zeros (xpad, :864-868), so the
+	# residual Y(x) - y also lives on the pixels outside the patch.  Full-width temporaries reproduce that.
+	pkf = dict(pk, npix=nphi, ringstart=np.arange(ny, dtype=np.int64)*nphi)
+	pkf_now = dict(pkf, weight=None)
 	def wmul(m):
 		if L.is_torch(m):
 			import torch
-			return m*torch.as_tensor(wrow, device=m.device, dtype=m.dtype)[:, None]
+			return m*torch.as_tensor(np.ascontiguousarray(wrow), device=m.device, dtype=m.dtype)[:, None]
 		return m*wrow.astype(m.dtype)[:, None]
+	def widen(m):
+		if nx == nphi: return m
+		out = _zeros_like_kind(m, tuple(m.shape[:-1])+(nphi,), rdt); out[..., :nx] = m; return out
 	for I in np.ndindex(*map_full.shape[:-3]):
 		for s, j1, j2 in spin_helper(spin, alm_full.shape[-2]):
 			a, acopied = _comp_block(alm_full[I], j1, j2, 1)
 			m, mcopied = _comp_block(map_full[I], j1, j2, 2)
+			if niter == 0 and not adjoint:
+				_synth(pk, a, m, s, adjoint=True)
+				if acopied: alm_full[I][j1:j2] = a
+				continue
+			fshape = tuple(m.shape[:-1])+(nphi,)
 			def Y(x):
-				out = _zeros_like_kind(m, m.shape, rdt); _synth(pk_now, x, out, s); return out
+				out = _zeros_like_kind(m, fshape, rdt); _synth(pkf_now, x, out, s); return out
 			def YT(y):
-				out = _zeros_like_kind(a, a.shape, _ctype_of(rdt)); _synth(pk_now, out, y, s, adjoint=True); return out
+				out = _zeros_like_kind(a, a.shape, _ctype_of(rdt)); _synth(pkf_now, out, y, s, adjoint=True); return out
 			def YTW(y):
-				out = _zeros_like_kind(a, a.shape, _ctype_of(rdt)); _synth(pk, out, y, s, adjoint=True); return out
+				out = _zeros_like_kind(a, a.shape, _ctype_of(rdt)); _synth(pkf, out, y, s, adjoint=True); return out
 			def WY(x): return wmul(Y(x))
 			if adjoint:
 				x = WY(a)
 				for it in range(niter): x -= WY(YT(x)-a)
-				map_full[I][j1:j2] = x
-			elif niter == 0:
-				_synth(pk, a, m, s, adjoint=True)
-				if acopied: alm_full[I][j1:j2] = a
+				map_full[I][j1:j2] = x[..., :nx]
 			else:
-				x = YTW(m)
-				for it in range(niter): x -= YTW(Y(x)-m)
+				y = widen(m)
+				x = YTW(y)
+				for it in range(niter): x -= YTW(Y(x)-y)
 				_assign(a, x)
 				if acopied: alm_full[I][j1:j2] = a
 	return map if adjoint else alm
@@ -484,7 +496,7 @@ def rand_alm_healpy(ps, lmax=None, seed=None, dtype=np.complex128):
 		ainfo = alm_info(lmax)
 		re = np.random.standard_normal(ainfo.nelem); im = np.random.standard_normal(ainfo.nelem)
 		alm = (re + 1j*im).astype(dtype)
-		cl = pad_spectrum(ps, lmax)[:lmax+1]
+		cl = np.zeros(lmax+1); n = min(lmax+1, ps.shape[-1]); cl[:n] = ps[:n]
 		alm = ainfo.lmul(alm, np.sqrt(cl/2).astype(alm.real.dtype), alm)
 		alm[:lmax+1] = re[:lmax+1]*np.sqrt(cl)
 		return alm

@@ -58,35 +58,43 @@ def test_alm_conversion(cs, geom):
 	with pytest.raises(ValueError):
 		cs.map2alm(omap, alm=np.zeros(ainfo.nelem, np.complex64), spin=0)
 
-def _dense(cs, fun_alm2map, ainfo, shape, wcs, ncomp, spin, rdt):
-	"""matrix of a linear alm -> map function in the real alm basis (reference helpers map_bash/alm_bash)"""
-	from pixell_b200 import geometry
-	cols = []
-	nreal = ncomp*2*ainfo.nelem
-	for k in range(nreal):
-		alm = np.zeros((ncomp, ainfo.nelem), np.result_type(rdt, 0j))
-		alm.view(rdt).reshape(-1)[k] = 1
-		m = geometry.zeros((ncomp,)+shape, wcs, rdt)
-		cols.append(np.array(fun_alm2map(alm, m)).reshape(-1))
-	return np.array(cols).T
+def _zip_alm(alm, ainfo):
+	"""real orthonormal alm basis of the reference's adjointness helpers (tests/test_pixell.py:218-230):
+	m = 0 real parts, then sqrt(2) (re, im) of the m > 0 entries"""
+	n = int(ainfo.lm2ind(1, 1))
+	return np.concatenate([alm[..., :n].real, alm[..., n:].view(np.float64)*2**0.5], -1)
+
+def _unzip_alm(zalm, ainfo):
+	n = int(ainfo.lm2ind(1, 1))
+	oalm = np.zeros(zalm.shape[:-1]+(ainfo.nelem,), np.complex128)
+	oalm[..., :n] = zalm[..., :n]
+	oalm[..., n:] = zalm[..., n:].view(np.complex128)/2**0.5
+	return oalm
 
 @pytest.mark.parametrize("variant,ny,nx", [("fejer1", 6, 12), ("cc", 7, 12)])
 @pytest.mark.parametrize("ncomp", [1, 3])
 def test_adjointness(cs, geom, variant, ny, nx, ncomp):
-	"""reference tests/test_pixell.py:1051-1085 (full-sky geometries): alm2map_adjoint == alm2map^T"""
-	lmax = 4
+	"""reference tests/test_pixell.py:1051-1085 (full-sky geometries): alm2map_adjoint == alm2map^T in the
+	zipped real alm basis (alm_bash / map_bash)"""
 	shape, wcs = geom.fullsky_geometry(shape=(ny, nx), variant=variant)
+	lmax = 5
 	ainfo = cs.alm_info(lmax)
-	rdt = np.float64
-	A = _dense(cs, lambda a, m: cs.alm2map(a, m, spin=[0, 2] if ncomp == 3 else [0]), ainfo, shape, wcs, ncomp, None, rdt)
-	cols = []
-	for k in range(ncomp*ny*nx):
-		m = geom.zeros((ncomp,)+shape, wcs, rdt); m.reshape(-1)[k] = 1
-		a = cs.alm2map_adjoint(m, spin=[0, 2] if ncomp == 3 else [0], ainfo=ainfo)
-		cols.append(a.view(rdt).reshape(-1).copy())
-	AT = np.array(cols).T
-	# entries of alm the transform does not own (imag of m=0 never reaches the map; l<2 for spin 2) are zero on both sides
-	np.testing.assert_array_almost_equal(AT, A.T, decimal=10)
+	nz = 2*ainfo.nelem - int(ainfo.lm2ind(1, 1))
+	spin = [0, 2] if ncomp == 3 else [0]
+	mat1 = np.zeros((ncomp, nz, ncomp)+shape)
+	for ci in range(ncomp):
+		for i in range(nz):
+			z = np.zeros((ncomp, nz)); z[ci, i] = 1
+			omap = geom.zeros((ncomp,)+shape, wcs)
+			cs.alm2map(_unzip_alm(z, ainfo), omap, spin=spin, ainfo=ainfo)
+			mat1[ci, i] = omap
+	mat2 = np.zeros((ncomp, nz, ncomp)+shape)
+	for I in np.ndindex(*((ncomp,)+shape)):
+		umap = geom.zeros((ncomp,)+shape, wcs); umap[I] = 1
+		oalm = np.zeros((ncomp, ainfo.nelem), np.complex128)
+		cs.alm2map_adjoint(umap, alm=oalm, spin=spin, ainfo=ainfo)
+		mat2[(slice(None), slice(None))+I] = _zip_alm(oalm, ainfo)
+	np.testing.assert_array_almost_equal(mat1, mat2, decimal=12)
 
 def test_cyl_band_and_cut_sky(cs, geom):
 	"""method 'cyl': a declination band (full rows) and a cut-sky patch (partial rows), both spins, with the

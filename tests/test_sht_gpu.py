@@ -192,7 +192,7 @@ def test_golden_unlensed_fits(sht):
 	stored south-first with ra decreasing; flips handled in place by the engine."""
 	g = np.load(os.path.join(GOLDEN, "unlensed_071123.npz"))
 	ps = np.load(os.path.join(GOLDEN, "lens_ps_400.npy"))
-	alm = ao.rand_alm(ps, 400, 1)[1:]
+	alm = np.ascontiguousarray(ao.rand_alm(ps, 400, 1)[1:])
 	ny, nx = int(g["shape"][1]), int(g["shape"][2])
 	geo = pr.Geo((ny, nx), g["crval"], g["cdelt"], g["crpix"])
 	ai = ao.AlmInfo(400)
