@@ -98,6 +98,9 @@ int b2_sht_last_timing(b2_sht_plan *plan, double out[4]);
 /* test hooks: run only the Legendre stage on device-resident leg[ncomp][mmax+1][nring] (ring order = plan order) */
 int b2_alm2leg(b2_sht_plan *plan, int spin, int mode, const void *alm_dev, int64_t alm_cstride, void *leg_dev, void *stream);
 int b2_leg2alm(b2_sht_plan *plan, int spin, int mode, void *alm_dev, int64_t alm_cstride, const void *leg_dev, void *stream);
+/* tuning hook: choose the kernel variant (launch shape) of Legendre kernel `which` (0 synth spin 0, 1 adjoint spin 0,
+ * 2 synth spin>0, 3 adjoint spin>0); results are identical across variants */
+int b2_set_leg_variant(int which, int variant);
 
 /* ducc0.sht.experimental.get_gridweights(name, ntheta) (curvedsky.py:501, 531, 855): ring
  * quadrature weights, sum = 4*pi.  Host computation into out[ntheta]. */

@@ -35,6 +35,7 @@ _PROTOS = {
 	"b2_sht_last_timing": ([c_vp, _dblp], c_int),
 	"b2_alm2leg": ([c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_vp], c_int),
 	"b2_leg2alm": ([c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_vp], c_int),
+	"b2_set_leg_variant": ([c_int, c_int], c_int),
 	"b2_gridweights": ([c_cp, c_int, _dblp], c_int),
 	"b2_alm2cl": ([c_int, c_int, _i64p, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp], c_int),
 	"b2_lmul": ([c_int, c_int, _i64p, c_int, c_vp, c_int, c_vp, c_int, c_vp], c_int),

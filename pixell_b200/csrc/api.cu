@@ -28,6 +28,7 @@ extern "C" int b2_init(int device)
 }
 extern "C" int b2_device_synchronize(void) { B2_CHECK(cudaDeviceSynchronize()); return 0; }
 extern "C" int b2_dfma_peak_gflops(double *out) { return dfma_peak_gflops(out); }
+extern "C" int b2_set_leg_variant(int which, int v) { return leg_set_variant(which, v); }
 
 // ------------------------------------------------------------------------------------ grids
 

@@ -10,7 +10,7 @@
 //     (2 DFMA per step and sequence), accumulation in the +- basis with north/south parity split;
 //   * start values in extended-exponent form (binary powering), a rescaling pre-phase (window
 //     variants A/B) and a check-free main phase (variant C); rings beyond the evanescent tail are
-//     skipped (Airy-tail bound, see ring_dead());
+//     skipped (Airy-tail bound, see SeqConst::dead_sth);
 //   * K2 reduces over rings with a halving warp-shuffle butterfly (about one 64-bit exchange per
 //     output value and l), then across warps through shared memory, and accumulates into alm in
 //     a fixed order: results are bit-reproducible run to run.
@@ -19,10 +19,10 @@
 #include <cmath>
 #include <cstdlib>
 
-#define B2_DEF_SYNTH0 0
-#define B2_DEF_ADJ0 0
-#define B2_DEF_SYNTH2 0
-#define B2_DEF_ADJ2 0
+#define B2_DEF_SYNTH0 4
+#define B2_DEF_ADJ0 2
+#define B2_DEF_SYNTH2 5
+#define B2_DEF_ADJ2 7
 
 #define BIGV   0x1p256
 #define SMALLV 0x1p-512
@@ -130,7 +130,7 @@ int LegGeom::build(int nring_, const double *theta)
 // ------------------------------------------------------------------------------------ device helpers
 
 struct LegArgs {
-	int lmax, mmax, spin, deriv1;
+	int lmax, mmax, spin, deriv1, npair;
 	const int64_t *toff; const double *ta, *tb, *talpha, *pref;
 	const PairInfo *pairs; int npair_pad;
 	const int64_t *mstart; int64_t lstride;
@@ -167,25 +167,25 @@ __device__ __forceinline__ void init_scaled(double t, int ex, double &v, int &sc
 	else { int k = (-256 - E + 511)/512; v = ldexp(t, ex + 512*k); sc = -k; }
 }
 
+// Once per window of <= 16 l: bring a scaled sequence back into range.  The test reads the exponent field
+// with integer instructions (the FP64 pipe is the bottleneck of these kernels).  Within 16 steps a sequence
+// grows by less than 2^100 (|a_l x| <= sqrt(2 lmax + 1)), so values stay far below overflow between tests,
+// and a lane whose value passes 2^-256 inside a window joins the sums at the next window (it misses < 2^-190).
 __device__ __forceinline__ void rescale(double &v, double &vp, int &sc)
 {
-	if (sc < 0 && fabs(v) >= BIGV) { v *= SMALLV; vp *= SMALLV; sc++; }
+	if (sc < 0 && (__double2hiint(v) & 0x7ff00000) >= ((1023 + 256) << 20)) { v *= SMALLV; vp *= SMALLV; sc++; }
 }
 
 // A ring contributes nothing for this m when m lies beyond the evanescent tail of the turning point
 // m_t = (lmax+1/2) sin(theta): |n_l d^l_{m,s}| ~ exp(-0.94 delta^1.5/(sqrt(m) cos(theta))), delta = m - m_t;
 // delta > 16 m^(1/3) puts the dropped values below exp(-60) ~ 1e-26 (checked against the oracle in
-// tests/test_legendre_gpu.py at lmax up to 2000).
-__device__ __forceinline__ bool ring_dead(int m, int s, int lmax, double sth)
-{
-	return (double)m - 16.0*cbrt((double)m) - s - 2 > (lmax + 0.5)*sth;
-}
-
+// tests/test_legendre_gpu.py at lmax up to 2000).  The threshold on sin(theta) is SeqConst::dead_sth.
 struct SeqConst {      // per-m constants of the start values
 	double pref; double sign_p, sign_q; int e, qc, qs, pc, ps;
+	double dead_sth;    // rings with sin(theta) below this contribute nothing for this m
 };
 
-__device__ __forceinline__ SeqConst seq_const(int m, int s, const double *pref)
+__device__ __forceinline__ SeqConst seq_const(int m, int s, int lmax, const double *pref)
 {
 	SeqConst c;
 	c.pref = pref[m];
@@ -194,7 +194,20 @@ __device__ __forceinline__ SeqConst seq_const(int m, int s, const double *pref)
 	c.e = m > s ? m - s : 0;
 	if (m >= s) { c.qc = 2*s; c.qs = 0; c.pc = 0; c.ps = 2*s; }
 	else { c.qc = s + m; c.qs = s - m; c.pc = s - m; c.ps = s + m; }
+	c.dead_sth = ((double)m - 16.0*cbrt((double)m) - s - 2)/(lmax + 0.5);
 	return c;
+}
+
+// pairs are sorted by sin(theta), so the rings that are dead for this m form a prefix: index of the first live pair
+__device__ __forceinline__ int first_live_pair(const PairInfo *pairs, int npair, double dead_sth)
+{
+	int lo = 0, hi = npair;
+	while (lo < hi) {
+		int mid = (lo + hi) >> 1;
+		PairInfo pi = pairs[mid];
+		if (2.0*pi.sh*pi.ch < dead_sth) lo = mid + 1; else hi = mid;
+	}
+	return lo;
 }
 
 // start values of q = n d^{l0}_{m,+s}, p = (-1)^s n d^{l0}_{m,-s} for one ring
@@ -203,7 +216,7 @@ __device__ __forceinline__ bool init_pair(const PairInfo &pi, const SeqConst &c,
 {
 	x = pi.x;
 	double sth = 2.0*pi.sh*pi.ch;
-	if (pi.rn < 0 || ring_dead(m, s, lmax, sth)) { p = q = 0.0; sp = sq = 0; return false; }
+	if (pi.rn < 0 || sth < c.dead_sth) { p = q = 0.0; sp = sq = 0; return false; }
 	double mant; int ex;
 	scaled_pow(sth, c.e, mant, ex);
 	double base = c.pref*mant;
@@ -212,18 +225,33 @@ __device__ __forceinline__ bool init_pair(const PairInfo &pi, const SeqConst &c,
 	return true;
 }
 
-// halving butterfly: on return v[0] of lane L holds the sum over all lanes of element idx(L), where
-// idx is built from the lane bits consumed while N > 1 (N = 32: idx = L; N = 16: idx = L >> 1).
-template<int N> __device__ __forceinline__ void bfly_reduce(double (&v)[N], int lane)
+// Warp reduction of the adjoint kernels.  Every lane holds NC*W partial sums v[slot*W + j] (NC component
+// slots x W consecutive l); on return v[0] of lane L is the sum over all 32 lanes of one (component, j):
+//   NC = 4: component (L >> 3) & 3, j = (L & 7) >> (3 - log2 W);   NC = 2: component (L >> 4) & 1, j = (L & 15) >> (4 - log2 W).
+// Halving butterfly (each level sends one half of the values to the partner lane and keeps the other, about
+// one 64-bit exchange per value in total).  The component levels need no register selects because the lanes
+// store their slots permuted: slot s of lane L holds component s ^ ((L >> 3) & 3) (NC = 4) or s ^ (L >> 4)
+// (NC = 2) -- the kernels arrange that by permuting each lane's ring inputs once per round.
+template<int NC, int W> __device__ __forceinline__ void bfly_reduce(double (&v)[NC*W], int lane)
 {
-	int n = N;
+	static_assert((NC == 4 && W <= 8) || (NC == 2 && W <= 16), "window too long for the lane bits");
+	if (NC == 4) {
+		#pragma unroll
+		for (int i = 0; i < 2*W; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i + 2*W], 16);
+		#pragma unroll
+		for (int i = 0; i < W; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i + W], 8);
+	} else {
+		#pragma unroll
+		for (int i = 0; i < W; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i + W], 16);
+	}
+	int n = W;
 	#pragma unroll
-	for (int bit = 16; bit >= 1; bit >>= 1) {
+	for (int bit = (NC == 4 ? 4 : 8); bit >= 1; bit >>= 1) {
 		if (n > 1) {
 			n >>= 1;
-			bool up = (lane & bit) != 0;
+			const bool up = (lane & bit) != 0;
 			#pragma unroll
-			for (int i = 0; i < N/2; i++) if (i < n) {
+			for (int i = 0; i < W/2; i++) if (i < n) {
 				double send = up ? v[i] : v[i + n];
 				double keep = up ? v[i + n] : v[i];
 				v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
@@ -233,6 +261,31 @@ template<int N> __device__ __forceinline__ void bfly_reduce(double (&v)[N], int 
 		}
 	}
 }
+// index (in the order [j][component]) of the element lane L holds after bfly_reduce
+template<int NC, int W> __device__ __forceinline__ int bfly_element(int lane)
+{
+	constexpr int LW = (W == 1 ? 0 : W == 2 ? 1 : W == 4 ? 2 : W == 8 ? 3 : 4);
+	constexpr int S4 = LW <= 3 ? 3 - LW : 0, S2 = 4 - LW;
+	if (NC == 4) return NC*((lane & 7) >> S4) + ((lane >> 3) & 3);
+	return NC*((lane & 15) >> S2) + ((lane >> 4) & 1);
+}
+
+// cp.async (LDGSTS): the next l tile travels global -> shared while the FP64 pipe works on the current
+// one, without holding registers and without a load-to-use stall in the instruction stream
+__device__ __forceinline__ void cp_async8(void *sm, const void *g)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(sm)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *sm, const void *g)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(sm)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// CTAs of one warp (NW = 1) are fully warp-synchronous: no block barriers at all
+template<int NW> __device__ __forceinline__ void cta_sync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
+template<int NW> __device__ __forceinline__ bool cta_or(bool v) { return NW == 1 ? __any_sync(0xffffffffu, v) : (__syncthreads_or(v) != 0); }
 
 // ------------------------------------------------------------------------------------ spin 0
 
@@ -254,24 +307,36 @@ template<int MODE, int R> __device__ __forceinline__ void synth0_window(const Ti
 			}
 			double ng = fma(t.a*x[r], g[r], -gp[r]);
 			gp[r] = g[r]; g[r] = ng;
-			if (MODE != 2) rescale(g[r], gp[r], sc[r]);
 		}
+	}
+	if (MODE != 2) {
+		#pragma unroll
+		for (int r = 0; r < R; r++) rescale(g[r], gp[r], sc[r]);
 	}
 }
 
 template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*32, MINB) k_synth0(LegArgs A)
 {
 	__shared__ __align__(16) Tile0 tiles[2][TL];
+	__shared__ __align__(16) double2 raw_alm[TL];       // cp.async staging: alm, (alpha, a)
+	__shared__ __align__(16) double raw_al[TL], raw_a[TL];
 	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, l0 = m;
 	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
 	const double *ta = A.ta + A.toff[m], *tal = A.talpha + A.toff[m];
 	const double2 *alm = A.alm0 + A.mstart[m];
-	const SeqConst sc0 = seq_const(m, 0, A.pref);
+	const SeqConst sc0 = seq_const(m, 0, lmax, A.pref);
 	const int nchunk = A.npair_pad/(32*R);
 	double2 *leg = A.leg0 + (int64_t)m*A.leg_mstride;
+	// rounds made of dead rings only write zeros
+	const int round0 = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R*NW);
+	for (int i = tid; i < round0*32*R*NW; i += NW*32) {
+		PairInfo pi = A.pairs[i];
+		if (pi.rn >= 0) leg[pi.rn] = make_double2(0, 0);
+		if (pi.rs >= 0) leg[pi.rs] = make_double2(0, 0);
+	}
 
-	for (int round = 0; round*NW < nchunk; round++) {
+	for (int round = round0; round*NW < nchunk; round++) {
 		const int chunk = round*NW + warp;
 		double x[R], g[R], gp[R], acc[R][2][2]; int sc[R], rn[R], rs[R];
 		bool anyuse = false, use[R];
@@ -287,33 +352,46 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 		}
 		// a round in which no ring of the CTA can contribute only has to write zeros
 		const bool wuse = __any_sync(0xffffffffu, anyuse);
-		if (__syncthreads_or(anyuse)) {
-			// tile 0 -> buffer 0
-			if (tid < TL) {
-				Tile0 t; t.ar = t.ai = t.a = t.pad = 0;
-				if (tid < nl) { double al = tal[tid]; double2 v = alm[(int64_t)(l0 + tid)*A.lstride]; t.ar = v.x*al; t.ai = v.y*al; t.a = ta[tid]; }
-				tiles[0][tid] = t;
-			}
-			__syncthreads();
+		int phase = 0;
+		if (cta_or<NW>(anyuse)) {
+			// each of the first TL threads fetches one l of the next tile (issue), later scales it into the tile (finish)
+			auto issue = [&](int tile) {
+				int i = tile*TL + tid;
+				if (tid < TL && i < nl) {
+					cp_async16(&raw_alm[tid], &alm[(int64_t)(l0 + i)*A.lstride]);
+					cp_async8(&raw_al[tid], &tal[i]); cp_async8(&raw_a[tid], &ta[i]);
+				}
+				cp_async_commit();
+			};
+			auto finish = [&](int tile, int buf) {
+				cp_async_wait_all();
+				int i = tile*TL + tid;
+				if (tid < TL) {
+					Tile0 t; t.ar = t.ai = t.a = t.pad = 0;
+					if (i < nl) { double al = raw_al[tid]; double2 v = raw_alm[tid]; t.ar = v.x*al; t.ai = v.y*al; t.a = raw_a[tid]; }
+					tiles[buf][tid] = t;
+				}
+			};
+			issue(0); finish(0, 0);
+			cta_sync<NW>();
 			for (int tile = 0; tile < ntile; tile++) {
 				const int buf = tile & 1;
-				Tile0 nxt; nxt.ar = nxt.ai = nxt.a = nxt.pad = 0;
-				if (tid < TL && tile + 1 < ntile) {
-					int i = (tile + 1)*TL + tid;
-					if (i < nl) { double al = tal[i]; double2 v = alm[(int64_t)(l0 + i)*A.lstride]; nxt.ar = v.x*al; nxt.ai = v.y*al; nxt.a = ta[i]; }
-				}
+				if (tile + 1 < ntile) issue(tile + 1);
 				const int nwin = (min(TL, nl - tile*TL) + 7) >> 3;
 				for (int w = 0; wuse && w < nwin; w++) {
-					bool mylive = true, anylive = false;
-					#pragma unroll
-					for (int r = 0; r < R; r++) { mylive &= (sc[r] == 0); anylive |= (sc[r] == 0 && use[r]); }
+					if (phase < 2) {      // liveness only grows: once every lane is live no more votes are needed
+						bool mylive = true, anylive = false;
+						#pragma unroll
+						for (int r = 0; r < R; r++) { mylive &= (sc[r] == 0); anylive |= (sc[r] == 0 && use[r]); }
+						phase = __all_sync(0xffffffffu, mylive) ? 2 : __any_sync(0xffffffffu, anylive) ? 1 : 0;
+					}
 					const Tile0 *T = &tiles[buf][w*8];
-					if (__all_sync(0xffffffffu, mylive)) synth0_window<2, R>(T, x, g, gp, sc, acc);
-					else if (__any_sync(0xffffffffu, anylive)) synth0_window<1, R>(T, x, g, gp, sc, acc);
+					if (phase == 2) synth0_window<2, R>(T, x, g, gp, sc, acc);
+					else if (phase == 1) synth0_window<1, R>(T, x, g, gp, sc, acc);
 					else synth0_window<0, R>(T, x, g, gp, sc, acc);
 				}
-				if (tid < TL) tiles[buf ^ 1][tid] = nxt;
-				__syncthreads();
+				if (tile + 1 < ntile) finish(tile + 1, buf ^ 1);
+				cta_sync<NW>();
 			}
 		}
 		// set 0 holds the l = l0, l0+2, ... terms (parity sigma0 = (-1)^(l0+m) = +1 for spin 0)
@@ -325,8 +403,8 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 	}
 }
 
-// adjoint, spin 0: a window of W l values -> NV = 2W partial sums (W l x re/im) reduced over the warp;
-// after bfly_reduce lane L holds element L >> log2(32/NV)
+// adjoint, spin 0: a window of W l values -> NV = 2W partial sums v[slot*W + j] (slots: re, im) reduced over
+// the warp by bfly_reduce<2, W>
 template<int MODE, int R, int W> __device__ __forceinline__ void adj0_window(const double *Ta,
 	const double (&x)[R], double (&g)[R], double (&gp)[R], int (&sc)[R],
 	const double (&in)[R][2][2], double (&v)[2*W])
@@ -338,33 +416,38 @@ template<int MODE, int R, int W> __device__ __forceinline__ void adj0_window(con
 		for (int r = 0; r < R; r++) {
 			if (MODE != 0) {
 				double gv = (MODE == 1) ? (sc[r] == 0 ? g[r] : 0.0) : g[r];
-				v[2*j]     = fma(gv, in[r][j & 1][0], v[2*j]);
-				v[2*j + 1] = fma(gv, in[r][j & 1][1], v[2*j + 1]);
+				v[j]     = fma(gv, in[r][j & 1][0], v[j]);
+				v[W + j] = fma(gv, in[r][j & 1][1], v[W + j]);
 			}
 			double ng = fma(a*x[r], g[r], -gp[r]);
 			gp[r] = g[r]; g[r] = ng;
-			if (MODE != 2) rescale(g[r], gp[r], sc[r]);
 		}
+	}
+	if (MODE != 2) {
+		#pragma unroll
+		for (int r = 0; r < R; r++) rescale(g[r], gp[r], sc[r]);
 	}
 }
 
 template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds__(NW*32, MINB) k_adj0(LegArgs A)
 {
-	constexpr int NV = 2*W, SH = (NV == 32 ? 0 : NV == 16 ? 1 : NV == 8 ? 2 : 3), NOUT = 2*TL;
+	constexpr int NV = 2*W, NOUT = 2*TL;
 	constexpr int NT = NW*32, NH = (NOUT + NT - 1)/NT;
 	__shared__ double tiles[2][TL];
 	__shared__ double red[2][NW][NOUT];
+	__shared__ __align__(16) double olds[NOUT], alvs[NOUT];      // running sums and alpha_l of the tile's outputs (cp.async)
 	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, l0 = m;
 	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
 	const double *ta = A.ta + A.toff[m], *tal = A.talpha + A.toff[m];
 	double *almr = (double*)(A.alm0 + A.mstart[m]);
-	const SeqConst sc0 = seq_const(m, 0, A.pref);
+	const SeqConst sc0 = seq_const(m, 0, lmax, A.pref);
 	const int nchunk = A.npair_pad/(32*R);
 	const double2 *leg = A.leg0 + (int64_t)m*A.leg_mstride;
 	bool first = true;
+	const int round0 = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R*NW);
 
-	for (int round = 0; round*NW < nchunk; round++) {
+	for (int round = round0; round*NW < nchunk; round++) {
 		const int chunk = round*NW + warp;
 		double x[R], g[R], gp[R], in[R][2][2]; int sc[R];
 		bool anyuse = false, use[R];
@@ -377,49 +460,60 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 			gp[r] = 0;
 			double2 gn = make_double2(0, 0), gs = make_double2(0, 0);
 			if (use[r]) { gn = leg[pi.rn]; if (pi.rs >= 0) gs = leg[pi.rs]; }
+			if (lane & 16) { gn = make_double2(gn.y, gn.x); gs = make_double2(gs.y, gs.x); }    // slot permutation of bfly_reduce
 			in[r][0][0] = gn.x + gs.x; in[r][0][1] = gn.y + gs.y;    // l - l0 even
 			in[r][1][0] = gn.x - gs.x; in[r][1][1] = gn.y - gs.y;    // l - l0 odd
 			anyuse |= use[r];
 		}
 		const bool wuse = __any_sync(0xffffffffu, anyuse);
-		if (!__syncthreads_or(anyuse)) continue;
-		if (tid < TL) tiles[0][tid] = tid < nl ? ta[tid] : 0.0;
-		__syncthreads();
+		int phase = 0;
+		if (!cta_or<NW>(anyuse)) continue;
+		// recurrence coefficients of a tile travel global -> shared with cp.async, one tile ahead
+		auto issue = [&](int tile, int buf) {
+			int i = tile*TL + tid;
+			if (tid < TL) { if (i < nl) cp_async8(&tiles[buf][tid], &ta[i]); else tiles[buf][tid] = 0.0; }
+			cp_async_commit();
+		};
+		issue(0, 0); cp_async_wait_all();
+		cta_sync<NW>();
 		for (int tile = 0; tile < ntile; tile++) {
 			const int buf = tile & 1;
-			double nxt = 0;
-			if (tid < TL && tile + 1 < ntile) { int i = (tile + 1)*TL + tid; if (i < nl) nxt = ta[i]; }
+			if (tile + 1 < ntile) issue(tile + 1, buf ^ 1);
 			const int nwin = (min(TL, nl - tile*TL) + W - 1)/W;
-			// output threads fetch the running sum early so the read-modify-write latency hides behind the tile
-			double oldv[NH], alv[NH];
+			// output threads fetch the running sum early (cp.async) so the read-modify-write latency hides behind the tile
 			#pragma unroll
 			for (int h = 0; h < NH; h++) {
-				oldv[h] = 0; alv[h] = 0;
 				int e = tid + h*NT, i = tile*TL + (e >> 1);
-				if (e < NOUT && i < nl) { alv[h] = tal[i]; if (!first) oldv[h] = almr[2*(int64_t)(l0 + i)*A.lstride + (e & 1)]; }
+				if (e < NOUT && i < nl) {
+					cp_async8(&alvs[e], &tal[i]);
+					if (!first) cp_async8(&olds[e], &almr[2*(int64_t)(l0 + i)*A.lstride + (e & 1)]);
+				}
 			}
-			#pragma unroll
+			cp_async_commit();
+			#pragma unroll 1
 			for (int w = 0; w < TL/W; w++) {
 				double tot = 0;
 				if (wuse && w < nwin) {
 					double v[NV];
 					#pragma unroll
 					for (int i = 0; i < NV; i++) v[i] = 0;
-					bool mylive = true, anylive = false;
-					#pragma unroll
-					for (int r = 0; r < R; r++) { mylive &= (sc[r] == 0); anylive |= (sc[r] == 0 && use[r]); }
+					if (phase < 2) {
+						bool mylive = true, anylive = false;
+						#pragma unroll
+						for (int r = 0; r < R; r++) { mylive &= (sc[r] == 0); anylive |= (sc[r] == 0 && use[r]); }
+						phase = __all_sync(0xffffffffu, mylive) ? 2 : __any_sync(0xffffffffu, anylive) ? 1 : 0;
+					}
 					const double *T = &tiles[buf][w*W];
-					if (__all_sync(0xffffffffu, mylive)) adj0_window<2, R, W>(T, x, g, gp, sc, in, v);
-					else if (__any_sync(0xffffffffu, anylive)) adj0_window<1, R, W>(T, x, g, gp, sc, in, v);
+					if (phase == 2) adj0_window<2, R, W>(T, x, g, gp, sc, in, v);
+					else if (phase == 1) adj0_window<1, R, W>(T, x, g, gp, sc, in, v);
 					else adj0_window<0, R, W>(T, x, g, gp, sc, in, v);
-					bfly_reduce<NV>(v, lane);
-					tot = v[0];
+					if (phase != 0) { bfly_reduce<2, W>(v, lane); tot = v[0]; }
 				}
-				// element (l = w W + (lane >> SH)/2, re/im = (lane >> SH) & 1); duplicates write the same value
-				red[buf][warp][w*NV + (lane >> SH)] = tot;
+				// element 2 (l - l_window) + re/im; lanes holding the same element write the same value
+				red[buf][warp][w*NV + bfly_element<2, W>(lane)] = tot;
 			}
-			if (tid < TL) tiles[buf ^ 1][tid] = nxt;
-			__syncthreads();
+			cp_async_wait_all();
+			cta_sync<NW>();
 			#pragma unroll
 			for (int h = 0; h < NH; h++) {
 				int e = tid + h*NT, i = tile*TL + (e >> 1);
@@ -427,7 +521,7 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 					double s = 0;
 					#pragma unroll
 					for (int w = 0; w < NW; w++) s += red[buf][w][e];
-					almr[2*(int64_t)(l0 + i)*A.lstride + (e & 1)] = oldv[h] + s*alv[h];
+					almr[2*(int64_t)(l0 + i)*A.lstride + (e & 1)] = (first ? 0.0 : olds[e]) + s*alvs[e];
 				}
 			}
 		}
@@ -440,9 +534,11 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 
 struct Tile2 { double a, b, apr, api, amr, ami; };    // recurrence a,b; A+ = -(E+iB)alpha/2, A- = -(E-iB)alpha/2
 
+// north sums need sum_l p A+ and sum_l q A-, south sums sum_l sigma_l q A+ and sum_l sigma_l p A-: eight
+// accumulators per ring pair, one DFMA each per l; sigma_l alternates and is folded into the operand sign
 template<int MODE, int R> __device__ __forceinline__ void synth2_window(const Tile2 *T,
 	const double (&x)[R], double (&p)[R], double (&pp)[R], double (&q)[R], double (&qp)[R],
-	int (&sp)[R], int (&sq)[R], double (&acc)[R][2][8])
+	int (&sp)[R], int (&sq)[R], double (&acc)[R][8])
 {
 	#pragma unroll
 	for (int j = 0; j < 8; j++) {
@@ -452,41 +548,29 @@ template<int MODE, int R> __device__ __forceinline__ void synth2_window(const Ti
 			if (MODE != 0) {
 				double pv = (MODE == 1) ? (sp[r] == 0 ? p[r] : 0.0) : p[r];
 				double qv = (MODE == 1) ? (sq[r] == 0 ? q[r] : 0.0) : q[r];
-				double (&c)[8] = acc[r][j & 1];
+				double ps = (j & 1) ? -pv : pv, qs = (j & 1) ? -qv : qv;
+				double (&c)[8] = acc[r];
 				c[0] = fma(pv, t.apr, c[0]); c[1] = fma(pv, t.api, c[1]);
-				c[2] = fma(pv, t.amr, c[2]); c[3] = fma(pv, t.ami, c[3]);
-				c[4] = fma(qv, t.apr, c[4]); c[5] = fma(qv, t.api, c[5]);
+				c[2] = fma(ps, t.amr, c[2]); c[3] = fma(ps, t.ami, c[3]);
+				c[4] = fma(qs, t.apr, c[4]); c[5] = fma(qs, t.api, c[5]);
 				c[6] = fma(qv, t.amr, c[6]); c[7] = fma(qv, t.ami, c[7]);
 			}
 			double np = fma(fma(t.a, x[r],  t.b), p[r], -pp[r]);    // n = -s
 			double nq = fma(fma(t.a, x[r], -t.b), q[r], -qp[r]);    // n = +s
 			pp[r] = p[r]; p[r] = np; qp[r] = q[r]; q[r] = nq;
-			if (MODE != 2) { rescale(p[r], pp[r], sp[r]); rescale(q[r], qp[r], sq[r]); }
 		}
 	}
-}
-
-__device__ __forceinline__ Tile2 load_tile2_synth(const LegArgs &A, int m, int l0, int i, int nl,
-	const double *ta, const double *tb, const double *tal)
-{
-	Tile2 t; t.a = t.b = t.apr = t.api = t.amr = t.ami = 0;
-	if (i < nl) {
-		int l = l0 + i;
-		int64_t idx = A.mstart[m] + (int64_t)l*A.lstride;
-		double2 E = A.alm0[idx], B = make_double2(0, 0);
-		if (A.deriv1) { double f = sqrt((double)l*(l + 1.0)); E.x *= f; E.y *= f; }
-		else B = A.alm1[idx];
-		double h = -0.5*tal[i];
-		t.a = ta[i]; t.b = tb[i];
-		t.apr = h*(E.x - B.y); t.api = h*(E.y + B.x);
-		t.amr = h*(E.x + B.y); t.ami = h*(E.y - B.x);
+	if (MODE != 2) {
+		#pragma unroll
+		for (int r = 0; r < R; r++) { rescale(p[r], pp[r], sp[r]); rescale(q[r], qp[r], sq[r]); }
 	}
-	return t;
 }
 
 template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*32, MINB) k_synth2(LegArgs A)
 {
 	__shared__ __align__(16) Tile2 tiles[2][TL];
+	__shared__ __align__(16) double2 raw_e[TL], raw_b[TL];       // cp.async staging: E, B, (a, b, alpha)
+	__shared__ __align__(16) double raw_ta[TL], raw_tb[TL], raw_al[TL];
 	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, s = A.spin, l0 = m > s ? m : s;
 	double2 *legq = A.leg0 + (int64_t)m*A.leg_mstride, *legu = A.leg1 + (int64_t)m*A.leg_mstride;
@@ -501,12 +585,19 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 	}
 	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
 	const double *ta = A.ta + A.toff[m], *tb = A.tb + A.toff[m], *tal = A.talpha + A.toff[m];
-	const SeqConst sc0 = seq_const(m, s, A.pref);
+	const SeqConst sc0 = seq_const(m, s, lmax, A.pref);
 	const double sigma0 = ((l0 + m + s) & 1) ? -1.0 : 1.0;
+	const int64_t ms = A.mstart[m];
+	const int round0 = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R*NW);
+	for (int i = tid; i < round0*32*R*NW; i += NW*32) {
+		PairInfo pi = A.pairs[i];
+		if (pi.rn >= 0) legq[pi.rn] = legu[pi.rn] = make_double2(0, 0);
+		if (pi.rs >= 0) legq[pi.rs] = legu[pi.rs] = make_double2(0, 0);
+	}
 
-	for (int round = 0; round*NW < nchunk; round++) {
+	for (int round = round0; round*NW < nchunk; round++) {
 		const int chunk = round*NW + warp;
-		double x[R], p[R], pp[R], q[R], qp[R], acc[R][2][8]; int sp[R], sq[R], rn[R], rs[R];
+		double x[R], p[R], pp[R], q[R], qp[R], acc[R][8]; int sp[R], sq[R], rn[R], rs[R];
 		bool anyuse = false, use[R];
 		#pragma unroll
 		for (int r = 0; r < R; r++) {
@@ -515,47 +606,77 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 			use[r] = init_pair(pi, sc0, m, s, lmax, x[r], p[r], sp[r], q[r], sq[r]);
 			pp[r] = qp[r] = 0; rn[r] = pi.rn; rs[r] = pi.rs;
 			#pragma unroll
-			for (int k = 0; k < 8; k++) acc[r][0][k] = acc[r][1][k] = 0;
+			for (int k = 0; k < 8; k++) acc[r][k] = 0;
 			anyuse |= use[r];
 		}
 		const bool wuse = __any_sync(0xffffffffu, anyuse);
-		if (__syncthreads_or(anyuse)) {
-			if (tid < TL) tiles[0][tid] = load_tile2_synth(A, m, l0, tid, nl, ta, tb, tal);
-			__syncthreads();
+		int phase = 0;
+		if (cta_or<NW>(anyuse)) {
+			auto issue = [&](int tile) {
+				int i = tile*TL + tid;
+				if (tid < TL && i < nl) {
+					int64_t idx = ms + (int64_t)(l0 + i)*A.lstride;
+					cp_async16(&raw_e[tid], &A.alm0[idx]);
+					if (!A.deriv1) cp_async16(&raw_b[tid], &A.alm1[idx]);
+					cp_async8(&raw_ta[tid], &ta[i]); cp_async8(&raw_tb[tid], &tb[i]); cp_async8(&raw_al[tid], &tal[i]);
+				}
+				cp_async_commit();
+			};
+			auto finish = [&](int tile, int buf) {
+				cp_async_wait_all();
+				int i = tile*TL + tid;
+				if (tid < TL) {
+					Tile2 t; t.a = t.b = t.apr = t.api = t.amr = t.ami = 0;
+					if (i < nl) {
+						int l = l0 + i;
+						double2 E = raw_e[tid], B = make_double2(0, 0);
+						if (A.deriv1) { double f = sqrt((double)l*(l + 1.0)); E.x *= f; E.y *= f; }
+						else B = raw_b[tid];
+						double h = -0.5*raw_al[tid];
+						t.a = raw_ta[tid]; t.b = raw_tb[tid];
+						t.apr = h*(E.x - B.y); t.api = h*(E.y + B.x);
+						t.amr = h*(E.x + B.y); t.ami = h*(E.y - B.x);
+					}
+					tiles[buf][tid] = t;
+				}
+			};
+			issue(0); finish(0, 0);
+			cta_sync<NW>();
 			for (int tile = 0; tile < ntile; tile++) {
 				const int buf = tile & 1;
-				Tile2 nxt;
-				if (tid < TL) nxt = load_tile2_synth(A, m, l0, tile + 1 < ntile ? (tile + 1)*TL + tid : nl, nl, ta, tb, tal);
+				if (tile + 1 < ntile) issue(tile + 1);
 				const int nwin = (min(TL, nl - tile*TL) + 7) >> 3;
 				for (int w = 0; wuse && w < nwin; w++) {
-					bool mylive = true, anylive = false;
-					#pragma unroll
-					for (int r = 0; r < R; r++) {
-						mylive &= (sp[r] == 0) & (sq[r] == 0);
-						anylive |= use[r] & ((sp[r] == 0) | (sq[r] == 0));
+					if (phase < 2) {
+						bool mylive = true, anylive = false;
+						#pragma unroll
+						for (int r = 0; r < R; r++) {
+							mylive &= (sp[r] == 0) & (sq[r] == 0);
+							anylive |= use[r] & ((sp[r] == 0) | (sq[r] == 0));
+						}
+						phase = __all_sync(0xffffffffu, mylive) ? 2 : __any_sync(0xffffffffu, anylive) ? 1 : 0;
 					}
 					const Tile2 *T = &tiles[buf][w*8];
-					if (__all_sync(0xffffffffu, mylive)) synth2_window<2, R>(T, x, p, pp, q, qp, sp, sq, acc);
-					else if (__any_sync(0xffffffffu, anylive)) synth2_window<1, R>(T, x, p, pp, q, qp, sp, sq, acc);
+					if (phase == 2) synth2_window<2, R>(T, x, p, pp, q, qp, sp, sq, acc);
+					else if (phase == 1) synth2_window<1, R>(T, x, p, pp, q, qp, sp, sq, acc);
 					else synth2_window<0, R>(T, x, p, pp, q, qp, sp, sq, acc);
 				}
-				if (tid < TL) tiles[buf ^ 1][tid] = nxt;
-				__syncthreads();
+				if (tile + 1 < ntile) finish(tile + 1, buf ^ 1);
+				cta_sync<NW>();
 			}
 		}
 		// Sp = sum p A+, Sq = sum q A-;  south: Sp' = sum sigma_l q A+, Sq' = sum sigma_l p A-
 		// Q = Sp + Sq, U = i (Sq - Sp)
 		#pragma unroll
 		for (int r = 0; r < R; r++) {
-			const double (&c0)[8] = acc[r][0]; const double (&c1)[8] = acc[r][1];
+			const double (&c)[8] = acc[r];
 			if (rn[r] >= 0) {
-				double spr = c0[0] + c1[0], spi = c0[1] + c1[1], sqr = c0[6] + c1[6], sqi = c0[7] + c1[7];
+				double spr = c[0], spi = c[1], sqr = c[6], sqi = c[7];
 				legq[rn[r]] = make_double2(spr + sqr, spi + sqi);
 				legu[rn[r]] = make_double2(spi - sqi, sqr - spr);
 			}
 			if (rs[r] >= 0) {
-				double spr = sigma0*(c0[4] - c1[4]), spi = sigma0*(c0[5] - c1[5]);
-				double sqr = sigma0*(c0[2] - c1[2]), sqi = sigma0*(c0[3] - c1[3]);
+				double spr = sigma0*c[4], spi = sigma0*c[5], sqr = sigma0*c[2], sqi = sigma0*c[3];
 				legq[rs[r]] = make_double2(spr + sqr, spi + sqi);
 				legu[rs[r]] = make_double2(spi - sqi, sqr - spr);
 			}
@@ -563,16 +684,21 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 	}
 }
 
-// adjoint, spin > 0: a window of W l values -> NV = 4W partial sums (W l x {A+re, A+im, A-re, A-im})
+// adjoint, spin > 0: a window of W l values -> NV = 4W partial sums v[slot*W + j], slots {A+re, A+im, A-re, A-im}:
 //   A+_l = sum_pairs p Z+N + sigma_l q Z+S,  A-_l = sum_pairs q Z-N + sigma_l p Z-S,  Z+- = Q +- iU
-// zin[r][0..3] = Z+N (re,im), Z-N (re,im); zin[r][4..7] = sigma0 * (Z+S, Z-S)
+// zin[r][0..3] = Z+N (re,im), Z-N (re,im); zin[r][4..7] = sigma0 * (Z+S, Z-S).
+// Slot permutation for bfly_reduce<4, W>: lanes with bit 3 set swap re <-> im of every Z; lanes with bit 4 set
+// swap the roles of the two sequences (their "p" registers carry q and vice versa, Z+ <-> Z-), which only
+// flips the sign of b_l in the recurrence: the tile stores (a, b, a, -b) and such lanes read the second pair.
+struct TileAB { double a, b, a2, nb; };
+
 template<int MODE, int R, int W> __device__ __forceinline__ void adj2_window(const double2 *Tab,
 	const double (&x)[R], double (&p)[R], double (&pp)[R], double (&q)[R], double (&qp)[R],
 	int (&sp)[R], int (&sq)[R], const double (&zin)[R][8], double (&v)[4*W])
 {
 	#pragma unroll
 	for (int j = 0; j < W; j++) {
-		const double2 ab = Tab[j];
+		const double2 ab = Tab[2*j];      // (a, b) or (a, -b), chosen by the caller's pointer offset
 		#pragma unroll
 		for (int r = 0; r < R; r++) {
 			if (MODE != 0) {
@@ -580,25 +706,29 @@ template<int MODE, int R, int W> __device__ __forceinline__ void adj2_window(con
 				double qv = (MODE == 1) ? (sq[r] == 0 ? q[r] : 0.0) : q[r];
 				// sigma_l alternates: fold the sign into the south products
 				double ps = (j & 1) ? -pv : pv, qs = (j & 1) ? -qv : qv;
-				v[4*j + 0] = fma(pv, zin[r][0], fma(qs, zin[r][4], v[4*j + 0]));
-				v[4*j + 1] = fma(pv, zin[r][1], fma(qs, zin[r][5], v[4*j + 1]));
-				v[4*j + 2] = fma(qv, zin[r][2], fma(ps, zin[r][6], v[4*j + 2]));
-				v[4*j + 3] = fma(qv, zin[r][3], fma(ps, zin[r][7], v[4*j + 3]));
+				v[j]       = fma(pv, zin[r][0], fma(qs, zin[r][4], v[j]));
+				v[W + j]   = fma(pv, zin[r][1], fma(qs, zin[r][5], v[W + j]));
+				v[2*W + j] = fma(qv, zin[r][2], fma(ps, zin[r][6], v[2*W + j]));
+				v[3*W + j] = fma(qv, zin[r][3], fma(ps, zin[r][7], v[3*W + j]));
 			}
 			double np = fma(fma(ab.x, x[r],  ab.y), p[r], -pp[r]);
 			double nq = fma(fma(ab.x, x[r], -ab.y), q[r], -qp[r]);
 			pp[r] = p[r]; p[r] = np; qp[r] = q[r]; q[r] = nq;
-			if (MODE != 2) { rescale(p[r], pp[r], sp[r]); rescale(q[r], qp[r], sq[r]); }
 		}
+	}
+	if (MODE != 2) {
+		#pragma unroll
+		for (int r = 0; r < R; r++) { rescale(p[r], pp[r], sp[r]); rescale(q[r], qp[r], sq[r]); }
 	}
 }
 
 template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds__(NW*32, MINB) k_adj2(LegArgs A)
 {
-	constexpr int NV = 4*W, SH = (NV == 32 ? 0 : NV == 16 ? 1 : NV == 8 ? 2 : 3), NOUT = 4*TL;
+	constexpr int NV = 4*W, NOUT = 4*TL;
 	constexpr int NT = NW*32, NH = (NOUT + NT - 1)/NT;
-	__shared__ __align__(16) double2 tiles[2][TL];
+	__shared__ __align__(16) TileAB tiles[2][TL];
 	__shared__ double red[2][NW][NOUT];
+	__shared__ __align__(16) double olds[NOUT], alvs[NOUT];      // running sums and alpha_l of the tile's outputs (cp.async)
 	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, s = A.spin, l0 = m > s ? m : s;
 	double *alme = (double*)A.alm0, *almb = (double*)A.alm1;
@@ -612,13 +742,14 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 	if (l0 > lmax) return;
 	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
 	const double *ta = A.ta + A.toff[m], *tb = A.tb + A.toff[m], *tal = A.talpha + A.toff[m];
-	const SeqConst sc0 = seq_const(m, s, A.pref);
+	const SeqConst sc0 = seq_const(m, s, lmax, A.pref);
 	const double sigma0 = ((l0 + m + s) & 1) ? -1.0 : 1.0;
 	const double2 *legq = A.leg0 + (int64_t)m*A.leg_mstride, *legu = A.leg1 + (int64_t)m*A.leg_mstride;
 	const int nchunk = A.npair_pad/(32*R);
 	bool first = true;
+	const int round0 = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R*NW);
 
-	for (int round = 0; round*NW < nchunk; round++) {
+	for (int round = round0; round*NW < nchunk; round++) {
 		const int chunk = round*NW + warp;
 		double x[R], p[R], pp[R], q[R], qp[R], zin[R][8]; int sp[R], sq[R];
 		bool anyuse = false, use[R];
@@ -634,53 +765,80 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 			zin[r][0] = qn.x - un.y; zin[r][1] = qn.y + un.x; zin[r][2] = qn.x + un.y; zin[r][3] = qn.y - un.x;
 			zin[r][4] = sigma0*(qs.x - us.y); zin[r][5] = sigma0*(qs.y + us.x);
 			zin[r][6] = sigma0*(qs.x + us.y); zin[r][7] = sigma0*(qs.y - us.x);
+			// slot permutation of bfly_reduce (see adj2_window)
+			if (lane & 8) {
+				#pragma unroll
+				for (int k = 0; k < 8; k += 2) { double t = zin[r][k]; zin[r][k] = zin[r][k + 1]; zin[r][k + 1] = t; }
+			}
+			if (lane & 16) {
+				#pragma unroll
+				for (int k = 0; k < 2; k++) {
+					double t = zin[r][k]; zin[r][k] = zin[r][k + 2]; zin[r][k + 2] = t;
+					t = zin[r][k + 4]; zin[r][k + 4] = zin[r][k + 6]; zin[r][k + 6] = t;
+				}
+				double t = p[r]; p[r] = q[r]; q[r] = t;
+				int ti = sp[r]; sp[r] = sq[r]; sq[r] = ti;
+			}
 			anyuse |= use[r];
 		}
 		const bool wuse = __any_sync(0xffffffffu, anyuse);
-		if (!__syncthreads_or(anyuse)) continue;
-		if (tid < TL) tiles[0][tid] = tid < nl ? make_double2(ta[tid], tb[tid]) : make_double2(0, 0);
-		__syncthreads();
+		int phase = 0;
+		if (!cta_or<NW>(anyuse)) continue;
+		auto issue = [&](int tile, int buf) {
+			int i = tile*TL + tid;
+			if (tid < TL) {
+				if (i < nl) { cp_async8(&tiles[buf][tid].a, &ta[i]); cp_async8(&tiles[buf][tid].b, &tb[i]); }
+				else tiles[buf][tid].a = tiles[buf][tid].b = 0;
+			}
+			cp_async_commit();
+		};
+		auto finish = [&](int buf) {      // the issuing thread completes its entry: (a, b, a, -b)
+			if (tid < TL) { TileAB &t = tiles[buf][tid]; t.a2 = t.a; t.nb = -t.b; }
+		};
+		issue(0, 0); cp_async_wait_all(); finish(0);
+		cta_sync<NW>();
 		for (int tile = 0; tile < ntile; tile++) {
 			const int buf = tile & 1;
-			double2 nxt = make_double2(0, 0);
-			if (tid < TL && tile + 1 < ntile) { int i = (tile + 1)*TL + tid; if (i < nl) nxt = make_double2(ta[i], tb[i]); }
+			if (tile + 1 < ntile) issue(tile + 1, buf ^ 1);
 			const int nwin = (min(TL, nl - tile*TL) + W - 1)/W;
-			// output threads: element e -> (l offset e >> 2, component e & 3); fetch the running sum early
-			double oldv[NH], alv[NH];
+			// output threads: element e -> (l offset e >> 2, component e & 3); fetch the running sum early (cp.async)
 			#pragma unroll
 			for (int h = 0; h < NH; h++) {
-				oldv[h] = 0; alv[h] = 0;
 				int e = tid + h*NT, i = tile*TL + (e >> 2), k = e & 3;
 				if (e < NOUT && i < nl) {
-					alv[h] = tal[i];
+					cp_async8(&alvs[e], &tal[i]);
 					int64_t idx = 2*(ms + (int64_t)(l0 + i)*A.lstride) + (k & 1);
-					if (!first && !(A.deriv1 && k >= 2)) oldv[h] = (k < 2 ? alme : almb)[idx];
+					if (!first && !(A.deriv1 && k >= 2)) cp_async8(&olds[e], &(k < 2 ? alme : almb)[idx]);
 				}
 			}
-			#pragma unroll
+			cp_async_commit();
+			#pragma unroll 1
 			for (int w = 0; w < TL/W; w++) {
 				double tot = 0;
 				if (wuse && w < nwin) {
 					double v[NV];
 					#pragma unroll
 					for (int i = 0; i < NV; i++) v[i] = 0;
-					bool mylive = true, anylive = false;
-					#pragma unroll
-					for (int r = 0; r < R; r++) {
-						mylive &= (sp[r] == 0) & (sq[r] == 0);
-						anylive |= use[r] & ((sp[r] == 0) | (sq[r] == 0));
+					if (phase < 2) {
+						bool mylive = true, anylive = false;
+						#pragma unroll
+						for (int r = 0; r < R; r++) {
+							mylive &= (sp[r] == 0) & (sq[r] == 0);
+							anylive |= use[r] & ((sp[r] == 0) | (sq[r] == 0));
+						}
+						phase = __all_sync(0xffffffffu, mylive) ? 2 : __any_sync(0xffffffffu, anylive) ? 1 : 0;
 					}
-					const double2 *T = &tiles[buf][w*W];
-					if (__all_sync(0xffffffffu, mylive)) adj2_window<2, R, W>(T, x, p, pp, q, qp, sp, sq, zin, v);
-					else if (__any_sync(0xffffffffu, anylive)) adj2_window<1, R, W>(T, x, p, pp, q, qp, sp, sq, zin, v);
+					const double2 *T = (const double2*)&tiles[buf][w*W] + ((lane >> 4) & 1);
+					if (phase == 2) adj2_window<2, R, W>(T, x, p, pp, q, qp, sp, sq, zin, v);
+					else if (phase == 1) adj2_window<1, R, W>(T, x, p, pp, q, qp, sp, sq, zin, v);
 					else adj2_window<0, R, W>(T, x, p, pp, q, qp, sp, sq, zin, v);
-					bfly_reduce<NV>(v, lane);
-					tot = v[0];
+					if (phase != 0) { bfly_reduce<4, W>(v, lane); tot = v[0]; }
 				}
-				red[buf][warp][w*NV + (lane >> SH)] = tot;      // element (l = w W + (lane>>SH)/4, comp = (lane>>SH)&3)
+				red[buf][warp][w*NV + bfly_element<4, W>(lane)] = tot;      // element 4 (l - l_window) + component
 			}
-			if (tid < TL) tiles[buf ^ 1][tid] = nxt;
-			__syncthreads();
+			cp_async_wait_all();
+			if (tile + 1 < ntile) finish(buf ^ 1);
+			cta_sync<NW>();
 			#pragma unroll
 			for (int h = 0; h < NH; h++) {
 				int e = tid + h*NT, i = tile*TL + (e >> 2), k = e & 3;
@@ -695,12 +853,12 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 				double c2 = __shfl_sync(0xffffffffu, c, base + 2), c3 = __shfl_sync(0xffffffffu, c, base + 3);
 				if (e < NOUT && i < nl) {
 					int l = l0 + i;
-					double hh = 0.5*alv[h];
+					double hh = 0.5*alvs[e], oldv = first ? 0.0 : olds[e];
 					// E = -(A+ + A-)/2, B = (i/2)(A+ - A-)
 					double val = k == 0 ? -hh*(c0 + c2) : k == 1 ? -hh*(c1 + c3) : k == 2 ? -hh*(c1 - c3) : hh*(c0 - c2);
 					int64_t idx = 2*(ms + (int64_t)l*A.lstride) + (k & 1);
-					if (A.deriv1) { if (k < 2) alme[idx] = oldv[h] + val*sqrt((double)l*(l + 1.0)); }
-					else (k < 2 ? alme : almb)[idx] = oldv[h] + val;
+					if (A.deriv1) { if (k < 2) alme[idx] = oldv + val*sqrt((double)l*(l + 1.0)); }
+					else (k < 2 ? alme : almb)[idx] = oldv + val;
 				}
 			}
 		}
@@ -718,17 +876,23 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 // Kernel variants: R ring pairs per lane, NW warps per CTA, MINB resident CTAs per SM the register
 // allocation is tuned for, TL l-values per shared-memory tile.  The default is the fastest measured
 // on B200 (profiles/); B2_LEG_VARIANT=<synth0>,<adj0>,<synth2>,<adj2> selects others for tuning runs.
-static int variant_of(int which)
+static int g_variant[4] = {-1, -1, -1, -1};
+static void variant_init()
 {
-	static int v[4] = {-1, -1, -1, -1};
-	if (v[0] < 0) {
-		int d[4] = {B2_DEF_SYNTH0, B2_DEF_ADJ0, B2_DEF_SYNTH2, B2_DEF_ADJ2};
-		const char *e = getenv("B2_LEG_VARIANT");
-		if (e) sscanf(e, "%d,%d,%d,%d", &d[0], &d[1], &d[2], &d[3]);
-		for (int i = 0; i < 4; i++) v[i] = d[i];
-	}
-	return v[which];
+	if (g_variant[0] >= 0) return;
+	int d[4] = {B2_DEF_SYNTH0, B2_DEF_ADJ0, B2_DEF_SYNTH2, B2_DEF_ADJ2};
+	const char *e = getenv("B2_LEG_VARIANT");
+	if (e) sscanf(e, "%d,%d,%d,%d", &d[0], &d[1], &d[2], &d[3]);
+	for (int i = 0; i < 4; i++) g_variant[i] = d[i];
 }
+int leg_set_variant(int which, int v)
+{
+	B2_REQUIRE(which >= 0 && which < 4 && v >= 0, "leg_set_variant: argument out of range");
+	variant_init();
+	g_variant[which] = v;
+	return 0;
+}
+static int variant_of(int which) { variant_init(); return g_variant[which]; }
 
 static LegArgs make_args(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
 	double2 *alm, int64_t alm_cstride, double2 *leg)
@@ -736,7 +900,7 @@ static LegArgs make_args(const LegTables &T, const LegGeom &G, const AlmLayout &
 	LegArgs A;
 	A.lmax = L.lmax; A.mmax = L.mmax; A.spin = T.spin; A.deriv1 = deriv1;
 	A.toff = T.toff.p; A.ta = T.a.p; A.tb = T.b.p; A.talpha = T.alpha.p; A.pref = T.pref.p;
-	A.pairs = G.pairs.p; A.npair_pad = G.npair_pad;
+	A.pairs = G.pairs.p; A.npair_pad = G.npair_pad; A.npair = G.npair;
 	A.mstart = L.mstart_d; A.lstride = L.lstride;
 	A.alm0 = alm; A.alm1 = alm + alm_cstride;
 	A.leg_mstride = G.nring_pad;
@@ -761,18 +925,19 @@ int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 	LegArgs A = make_args(T, G, L, deriv1, (double2*)alm, alm_cstride, leg);
 	// template arguments: R, NW, MINB, TL
 	if (T.spin == 0) switch (variant_of(0)) {
-		case 0: LAUNCH(k_synth0, 2, 8, 3, 64); break;
+		case 0: LAUNCH(k_synth0, 2, 4, 6, 64); break;
 		case 1: LAUNCH(k_synth0, 4, 4, 4, 64); break;
-		case 2: LAUNCH(k_synth0, 2, 4, 6, 64); break;
-		case 3: LAUNCH(k_synth0, 2, 2, 12, 64); break;
-		case 4: LAUNCH(k_synth0, 2, 1, 24, 32); break;
+		case 2: LAUNCH(k_synth0, 4, 1, 16, 32); break;
+		case 3: LAUNCH(k_synth0, 2, 1, 24, 32); break;
+		case 4: LAUNCH(k_synth0, 4, 2, 8, 64); break;
 		default: B2_REQUIRE(0, "unknown k_synth0 variant");
 	} else switch (variant_of(2)) {
 		case 0: LAUNCH(k_synth2, 2, 4, 3, 64); break;
 		case 1: LAUNCH(k_synth2, 2, 2, 6, 64); break;
-		case 2: LAUNCH(k_synth2, 2, 1, 12, 32); break;
-		case 3: LAUNCH(k_synth2, 2, 8, 1, 32); break;
-		case 4: LAUNCH(k_synth2, 1, 4, 6, 64); break;
+		case 2: LAUNCH(k_synth2, 4, 4, 3, 64); break;
+		case 3: LAUNCH(k_synth2, 4, 1, 12, 32); break;
+		case 4: LAUNCH(k_synth2, 2, 1, 16, 32); break;
+		case 5: LAUNCH(k_synth2, 4, 2, 6, 64); break;
 		default: B2_REQUIRE(0, "unknown k_synth2 variant");
 	}
 	B2_LAUNCH_CHECK();
@@ -787,17 +952,25 @@ int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 	// template arguments: R, NW, MINB, TL, W
 	if (T.spin == 0) switch (variant_of(1)) {
 		case 0: LAUNCH(k_adj0, 4, 8, 1, 32, 16); break;
-		case 1: LAUNCH(k_adj0, 8, 8, 1, 32, 8); break;
-		case 2: LAUNCH(k_adj0, 8, 8, 1, 64, 8); break;
-		case 3: LAUNCH(k_adj0, 8, 4, 2, 64, 8); break;
-		case 4: LAUNCH(k_adj0, 4, 8, 1, 64, 16); break;
+		case 1: LAUNCH(k_adj0, 4, 1, 12, 32, 8); break;
+		case 2: LAUNCH(k_adj0, 8, 1, 8, 32, 8); break;
+		case 3: LAUNCH(k_adj0, 4, 4, 3, 64, 8); break;
+		case 4: LAUNCH(k_adj0, 4, 1, 8, 32, 16); break;
+		case 5: LAUNCH(k_adj0, 8, 1, 10, 32, 4); break;
+		case 6: LAUNCH(k_adj0, 8, 1, 12, 32, 4); break;
+		case 7: LAUNCH(k_adj0, 4, 1, 16, 32, 4); break;
 		default: B2_REQUIRE(0, "unknown k_adj0 variant");
 	} else switch (variant_of(3)) {
 		case 0: LAUNCH(k_adj2, 2, 8, 1, 32, 8); break;
-		case 1: LAUNCH(k_adj2, 4, 8, 1, 32, 4); break;
-		case 2: LAUNCH(k_adj2, 4, 8, 1, 64, 4); break;
-		case 3: LAUNCH(k_adj2, 4, 4, 2, 64, 4); break;
-		case 4: LAUNCH(k_adj2, 2, 8, 1, 64, 8); break;
+		case 1: LAUNCH(k_adj2, 2, 1, 12, 32, 8); break;
+		case 2: LAUNCH(k_adj2, 4, 1, 8, 32, 4); break;
+		case 3: LAUNCH(k_adj2, 2, 4, 3, 64, 4); break;
+		case 4: LAUNCH(k_adj2, 2, 1, 16, 32, 4); break;
+		case 5: LAUNCH(k_adj2, 2, 4, 3, 32, 8); break;
+		case 6: LAUNCH(k_adj2, 4, 1, 12, 32, 2); break;
+		case 7: LAUNCH(k_adj2, 4, 1, 10, 32, 4); break;
+		case 8: LAUNCH(k_adj2, 4, 1, 10, 32, 2); break;
+		case 9: LAUNCH(k_adj2, 2, 1, 16, 32, 2); break;
 		default: B2_REQUIRE(0, "unknown k_adj2 variant");
 	}
 	B2_LAUNCH_CHECK();

@@ -44,3 +44,4 @@ int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
                 double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st);
 int dfma_peak_gflops(double *out);
+int leg_set_variant(int which, int v);

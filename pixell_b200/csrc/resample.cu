@@ -4,7 +4,11 @@
 //   S2  A -> IFFT -> x weight at the shifted nodes       B = W(theta_{k+1/2}) F(theta_{k+1/2})
 //   S3  W(theta_k) ext -> FFT, keep |f| <= lmax          A = a_f
 //   S4  B -> FFT, combine                                A = (a_f + e^{-i pi f/N} b_f)/2, |f| <= lmax
-//   S5  A -> IFFT -> leg = 2 mult g(theta_k)
+//   S5  A -> IFFT -> A = g on the circle;   S6  leg = 2 mult g(theta_k)
+// Two columns share every transform: neighbouring m of one component have opposite parity under
+// theta -> 2 pi - theta, sigma = (-1)^(m+s), and every operator above commutes with that mirror map, so the
+// pipeline runs on z = ext(col m) + ext(col m+1) and S6 separates the results again by parity,
+//   g_m = (z + sigma z o mirror)/2,  g_{m+1} = (z - sigma z o mirror)/2  (half the FFT work per column).
 // The two polyphase halves {theta_k}, {theta_{k+1/2}} together are the Clenshaw-Curtis circle grid
 // with 2N points on which the weight function W is exact for band limit 2 lmax + 1.
 // Transforms longer than the shared-memory capacity are split decimation-in-frequency over P CTAs
@@ -14,20 +18,31 @@
 
 struct ResampArgs {
 	FftDesc d;
-	int N, P, o2, n, L, nm, spin;
+	int N, P, o2, n, L, nm, npc, spin;
 	int64_t nring_pad;
-	const int *src; const double *wfine; const double *mult;
+	const int *src, *pos, *mir; const double *wfine; const double *mult;
 	double2 *leg, *A, *B;
-	int64_t col0;
+	int64_t col0;          // first column pair of this batch (pair index = comp*npc + i, columns m = 2i, 2i+1)
 };
 
-__device__ __forceinline__ double2 ext_load(const ResampArgs &R, const double2 *legcol, int j, double sigma)
+// the two leg columns of pair `pidx` (the second is null for the unpaired last m) and the parity of the first
+__device__ __forceinline__ void pair_cols(const ResampArgs &R, int64_t pidx, double2 *&ca, double2 *&cb, double &sigma)
+{
+	int comp = (int)(pidx / R.npc), i = (int)(pidx % R.npc), m = 2*i;
+	ca = R.leg + ((int64_t)comp*R.nm + m)*R.nring_pad;
+	cb = (m + 1 < R.nm) ? ca + R.nring_pad : nullptr;
+	sigma = ((m + R.spin) & 1) ? -1.0 : 1.0;
+}
+
+// sample j of z = ext(col a) + ext(col b) on the circle
+__device__ __forceinline__ double2 ext_load(const ResampArgs &R, const double2 *ca, const double2 *cb, int j, double sigma)
 {
 	int sidx = R.src[j];
 	if (sidx < 0) return make_double2(0, 0);
-	double2 v = legcol[sidx & 0x3fffffff];
-	if (sidx & 0x40000000) { v.x *= sigma; v.y *= sigma; }
-	return v;
+	int r = sidx & 0x3fffffff;
+	double2 a = ca[r], b = cb ? cb[r] : make_double2(0, 0);
+	if (sidx & 0x40000000) return make_double2(sigma*(a.x - b.x), sigma*(a.y - b.y));
+	return make_double2(a.x + b.x, a.y + b.y);
 }
 
 template<int STAGE> __global__ void k_resamp(ResampArgs R)
@@ -36,18 +51,16 @@ template<int STAGE> __global__ void k_resamp(ResampArgs R)
 	constexpr bool INV = (STAGE == 2 || STAGE == 5);
 	const int tid = threadIdx.x, T = blockDim.x, c = blockIdx.x, p = blockIdx.y;
 	const int N = R.N, P = R.P, Nl = N/P;
-	const int64_t col = R.col0 + c;
-	const int m = (int)(col % R.nm);
-	const double sigma = ((m + R.spin) & 1) ? -1.0 : 1.0;
-	double2 *legcol = R.leg + col*R.nring_pad;
+	double2 *ca, *cb; double sigma;
+	pair_cols(R, R.col0 + c, ca, cb, sigma);
 	double2 *A = R.A + (int64_t)c*N, *B = R.B + (int64_t)c*N;
 	for (int j = tid; j < Nl; j += T) {
 		double2 acc = make_double2(0, 0);
 		for (int q = 0; q < P; q++) {
 			int idx = j + q*Nl;
 			double2 v;
-			if (STAGE == 1) v = ext_load(R, legcol, idx, sigma);
-			else if (STAGE == 3) v = cscale(ext_load(R, legcol, idx, sigma), R.wfine[(2*idx + R.o2) % (2*N)]);
+			if (STAGE == 1) v = ext_load(R, ca, cb, idx, sigma);
+			else if (STAGE == 3) v = cscale(ext_load(R, ca, cb, idx, sigma), R.wfine[(2*idx + R.o2) % (2*N)]);
 			else if (STAGE == 4) v = B[idx];
 			else v = A[idx];
 			int e = (q*p) % P;
@@ -79,9 +92,22 @@ template<int STAGE> __global__ void k_resamp(ResampArgs R)
 				A[k] = make_double2(0.5*(a.x + b.x), 0.5*(a.y + b.y));
 			}
 		} else {
-			int sidx = R.src[k];
-			if (sidx >= 0 && !(sidx & 0x40000000)) legcol[sidx] = cscale(x, 2.0*R.mult[sidx]);
+			A[k] = x;
 		}
+	}
+}
+
+// S6: separate the two columns of each pair by parity and scale: leg = 2 mult g(theta_k)
+__global__ void k_resamp_split(ResampArgs R)
+{
+	double2 *ca, *cb; double sigma;
+	pair_cols(R, R.col0 + blockIdx.x, ca, cb, sigma);
+	const double2 *A = R.A + (int64_t)blockIdx.x*R.N;
+	for (int r = threadIdx.x; r < R.n; r += blockDim.x) {
+		double2 zp = A[R.pos[r]], zm = A[R.mir[r]];
+		double mu = R.mult[r];
+		ca[r] = make_double2(mu*(zp.x + sigma*zm.x), mu*(zp.y + sigma*zm.y));
+		if (cb) cb[r] = make_double2(mu*(zp.x - sigma*zm.x), mu*(zp.y - sigma*zm.y));
 	}
 }
 
@@ -110,7 +136,7 @@ bool ThetaResampler::needed(const std::string &g, int ntheta, int lmax)
 
 int ThetaResampler::build(const std::string &g, int ntheta, int64_t nphi_, int lmax_, int mmax, int64_t nring_pad_)
 {
-	n = ntheta; lmax = lmax_; nm = mmax + 1; nring_pad = nring_pad_; nphi = nphi_;
+	n = ntheta; lmax = lmax_; nm = mmax + 1; npc = (nm + 1)/2; nring_pad = nring_pad_; nphi = nphi_;
 	std::vector<int> pos(n), mir(n); std::vector<double> mu(n, 2.0);
 	if (g == "CC")          { N = 2*(n - 1); o2 = 0; for (int k = 0; k < n; k++) { pos[k] = k; mir[k] = (N - k) % N; } }
 	else if (g == "F1")     { N = 2*n;       o2 = 1; for (int k = 0; k < n; k++) { pos[k] = k; mir[k] = N - 1 - k; } }
@@ -132,10 +158,10 @@ int ThetaResampler::build(const std::string &g, int ntheta, int64_t nphi_, int l
 	if (tab.build(N/P, 2*N)) return 1;
 	smem = sizeof(double2)*(size_t)FftTables::smem_len(N/P);
 	threads = (int)std::min<int64_t>(512, std::max<int64_t>(64, b2_round_up(N/P/4, 32)));
-	if (src.upload(sr) || mult.upload(mu) || wfine.alloc(2*(size_t)N)) return 1;
+	if (src.upload(sr) || mult.upload(mu) || wfine.alloc(2*(size_t)N) || dpos.upload(pos) || dmir.upload(mir)) return 1;
 	k_wfine<<<(N + 128)/128, 128>>>(wfine.p, N, 4.0*M_PI/(2.0*N)/(double)nphi);
 	B2_LAUNCH_CHECK();
-	cb = std::max<int64_t>(1, std::min<int64_t>((int64_t)nm*2, (int64_t)(1 << 26)/N));
+	cb = std::max<int64_t>(1, std::min<int64_t>((int64_t)npc*2, (int64_t)(1 << 26)/N));
 	if (A.alloc((size_t)cb*N) || B.alloc((size_t)cb*N)) return 1;
 	B2_CHECK(cudaDeviceSynchronize());
 	return 0;
@@ -152,10 +178,10 @@ template<int STAGE> static int launch_stage(const ResampArgs &R, int ncols, int 
 int ThetaResampler::apply(double2 *leg, int ncomp, int spin, cudaStream_t st)
 {
 	ResampArgs R;
-	R.d = tab.d; R.N = N; R.P = P; R.o2 = o2; R.n = n; R.L = lmax; R.nm = nm; R.spin = spin;
-	R.nring_pad = nring_pad; R.src = src.p; R.wfine = wfine.p; R.mult = mult.p;
+	R.d = tab.d; R.N = N; R.P = P; R.o2 = o2; R.n = n; R.L = lmax; R.nm = nm; R.npc = npc; R.spin = spin;
+	R.nring_pad = nring_pad; R.src = src.p; R.pos = dpos.p; R.mir = dmir.p; R.wfine = wfine.p; R.mult = mult.p;
 	R.leg = leg; R.A = A.p; R.B = B.p;
-	int64_t ncol = (int64_t)ncomp*nm;
+	int64_t ncol = (int64_t)ncomp*npc;
 	for (int64_t c0 = 0; c0 < ncol; c0 += cb) {
 		int nc = (int)std::min<int64_t>(cb, ncol - c0);
 		R.col0 = c0;
@@ -164,6 +190,8 @@ int ThetaResampler::apply(double2 *leg, int ncomp, int spin, cudaStream_t st)
 		if (launch_stage<3>(R, nc, threads, smem, st)) return 1;
 		if (launch_stage<4>(R, nc, threads, smem, st)) return 1;
 		if (launch_stage<5>(R, nc, threads, smem, st)) return 1;
+		k_resamp_split<<<nc, 256, 0, st>>>(R);
+		B2_LAUNCH_CHECK();
 	}
 	return 0;
 }

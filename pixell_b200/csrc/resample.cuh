@@ -10,18 +10,19 @@
 // a_lm unchanged (lambda_lm has bandwidth lmax) and lets the Legendre stage run on ntheta rings
 // instead of 2 lmax + 2.  See DESIGN.md "theta weighting".
 struct ThetaResampler {
-	int n = 0, N = 0, o2 = 0, P = 1, lmax = 0, nm = 0;
+	int n = 0, N = 0, o2 = 0, P = 1, lmax = 0, nm = 0, npc = 0;   // npc: column pairs per component
 	int64_t nring_pad = 0, nphi = 0;
 	FftTables tab;             // length N/P, twiddle table of 2N entries
 	DevBuf<int> src;           // [N] circle slot -> ring index, bit 30 = mirrored copy, -1 = empty
+	DevBuf<int> dpos, dmir;    // [n] ring -> its circle slot and the slot of its mirror image
 	DevBuf<double> wfine;      // [2N] quadrature weight function on the fine circle / nphi
 	DevBuf<double> mult;       // [n] 2 (interior ring) or 1 (pole ring)
 	DevBuf<double2> A, B;      // scratch [cb][N]
-	int64_t cb = 0;            // columns per batch
+	int64_t cb = 0;            // column pairs per batch
 	int threads = 256; size_t smem = 0;
 	static bool needed(const std::string &geom, int ntheta, int lmax);
 	int build(const std::string &geom, int ntheta, int64_t nphi, int lmax, int mmax, int64_t nring_pad);
 	// in place on leg[ncomp][nm][nring_pad]
 	int apply(double2 *leg, int ncomp, int spin, cudaStream_t st);
-	size_t bytes() const { return tab.bytes() + src.bytes() + wfine.bytes() + mult.bytes() + A.bytes() + B.bytes(); }
+	size_t bytes() const { return tab.bytes() + src.bytes() + dpos.bytes() + dmir.bytes() + wfine.bytes() + mult.bytes() + A.bytes() + B.bytes(); }
 };

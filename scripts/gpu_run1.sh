@@ -1,0 +1,9 @@
+set -x
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt
+python scripts/tune_legendre.py c3 5 0123 > gpurun_out/tune_c3.txt 2>&1
+cat gpurun_out/tune_c3.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.txt 2>&1; tail -3 gpurun_out/pytest_gpu.txt
+B2_LEG_VARIANT=0,0,0,1 ncu --set full --clock-control none --import-source on -k regex:k_adj2 -s 1 -c 1 -o gpurun_out/r1b_adj2_v1 python scripts/tune_legendre.py c3 0 3 > gpurun_out/ncu_adj2.log 2>&1
+B2_LEG_VARIANT=0,0,0,0 ncu --set full --clock-control none --import-source on -k regex:k_synth2 -s 1 -c 1 -o gpurun_out/r1b_synth2_v0 python scripts/tune_legendre.py c3 0 2 > gpurun_out/ncu_synth2.log 2>&1
+ls -la gpurun_out
