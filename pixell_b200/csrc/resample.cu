@@ -4,7 +4,7 @@
 //   S2  A -> IFFT -> x weight at the shifted nodes       B = W(theta_{k+1/2}) F(theta_{k+1/2})
 //   S3  W(theta_k) ext -> FFT, keep |f| <= lmax          A = a_f
 //   S4  B -> FFT, combine                                A = (a_f + e^{-i pi f/N} b_f)/2, |f| <= lmax
-//   S5  A -> IFFT -> A = g on the circle;   S6  leg = 2 mult g(theta_k)
+//   S5  A -> IFFT -> B = g on the circle;   S6  leg = 2 mult g(theta_k)
 // Two columns share every transform: neighbouring m of one component have opposite parity under
 // theta -> 2 pi - theta, sigma = (-1)^(m+s), and every operator above commutes with that mirror map, so the
 // pipeline runs on z = ext(col m) + ext(col m+1) and S6 separates the results again by parity,
@@ -92,7 +92,7 @@ template<int STAGE> __global__ void k_resamp(ResampArgs R)
 				A[k] = make_double2(0.5*(a.x + b.x), 0.5*(a.y + b.y));
 			}
 		} else {
-			A[k] = x;
+			B[k] = x;      // not A: with P > 1 the other CTAs of this column are still reading A
 		}
 	}
 }
@@ -102,7 +102,7 @@ __global__ void k_resamp_split(ResampArgs R)
 {
 	double2 *ca, *cb; double sigma;
 	pair_cols(R, R.col0 + blockIdx.x, ca, cb, sigma);
-	const double2 *A = R.A + (int64_t)blockIdx.x*R.N;
+	const double2 *A = R.B + (int64_t)blockIdx.x*R.N;
 	for (int r = threadIdx.x; r < R.n; r += blockDim.x) {
 		double2 zp = A[R.pos[r]], zm = A[R.mir[r]];
 		double mu = R.mult[r];

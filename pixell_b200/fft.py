@@ -1,0 +1,183 @@
+"""pixell_b200.fft -- the pixell.fft interface (reference pixell/fft.py) on the B200 FFT engine.
+
+Two layers, both backed by b2_fft_plan_create / b2_fft_execute of libb200sht.so:
+  * `engine`: an object with the plug-in shape the reference's `fft.engines` registry expects
+    (pixell/fft.py:8-113): `engine.FFTW(a, b, axes=(-1,), direction='FFTW_FORWARD', threads=1, flags=...)`
+    returns a plan object; calling it (`plan(normalise_idft=False)`) fills `b` in place;
+    `engine.empty_aligned(shape, dtype, n=None)`.  Register it with
+        pixell.fft.engines["b200"] = pixell_b200.fft.engine; pixell.fft.set_engine("b200")
+    (INTEGRATION.md).  The transform kind is inferred from shapes and dtypes exactly as the reference's
+    numpy / ducc engines do: equal shapes -> c2c, else r2c (forward) / c2r (backward).
+  * `fft, ifft, rfft, irfft` with the reference's signatures and conventions (:133-209): forward
+    unnormalised, backward unnormalised unless normalize=True, output allocated when not given.
+Arrays may be numpy arrays (host; staged through the GPU, strided views allowed) or torch CUDA tensors
+(zero-copy).  nthread / flags are accepted and ignored.  There is no CPU fallback.
+"""
+import collections, ctypes
+import numpy as np
+from . import _lib as L
+
+_plans = collections.OrderedDict()
+PLAN_CACHE_SIZE = 8
+
+class _Plan:
+	def __init__(self, handle): self.handle = handle
+	def __del__(self):
+		try:
+			if self.handle: L.lib().b2_fft_plan_destroy(self.handle); self.handle = None
+		except Exception: pass
+
+def clear_plans(): _plans.clear()
+
+def _get_plan(shape, istride, ostride, axes, kind, dtype):
+	dev = L.init()
+	key = (dev, tuple(shape), tuple(istride), tuple(ostride), tuple(axes), kind, dtype)
+	p = _plans.get(key)
+	if p is None:
+		while len(_plans) >= PLAN_CACHE_SIZE: _plans.popitem(last=False)
+		h = ctypes.c_void_p()
+		sh, ist, ost = L.as_i64(shape), L.as_i64(istride), L.as_i64(ostride)
+		ax = np.ascontiguousarray(np.asarray(axes, dtype=np.int32))
+		L.check(L.lib().b2_fft_plan_create(ctypes.byref(h), len(shape), L.p_i64(sh), L.p_i64(ist), L.p_i64(ost),
+			len(axes), ax.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), kind, dtype), ValueError)
+		p = _Plan(h); _plans[key] = p
+	else: _plans.move_to_end(key)
+	return p
+
+def _collapse(shape, ist, ost, axes):
+	"""Merge leading non-transform dimensions until at most 4 remain (the engine's limit) when their strides allow it."""
+	shape, ist, ost, axes = list(shape), list(ist), list(ost), sorted(axes)
+	d = 0
+	while len(shape) > 4 and d+1 < len(shape):
+		if d not in axes and d+1 not in axes and ist[d] == ist[d+1]*shape[d+1] and ost[d] == ost[d+1]*shape[d+1]:
+			shape[d+1] *= shape[d]; del shape[d], ist[d], ost[d]
+			axes = [a-1 if a > d else a for a in axes]
+		else: d += 1
+	return shape, ist, ost, axes
+
+def transform(a, b, axes, forward, scale=1.0):
+	"""b = DFT(a) over `axes` (kind inferred like the reference engines).  a, b: numpy arrays or torch CUDA tensors."""
+	pa, mema, dta = L.buffer_info(a); pb, memb, dtb = L.buffer_info(b)
+	if mema != memb: raise ValueError("fft: input and output must both be host arrays or both be CUDA tensors")
+	nd = a.ndim
+	if nd == 0: raise ValueError("fft: zero-dimensional input")
+	axes = [ax+nd if ax < 0 else ax for ax in (list(axes) if np.ndim(axes) else [axes])]
+	if len(axes) > 2: raise NotImplementedError("pixell_b200.fft transforms at most two axes at a time")
+	ca, cb = dta.kind == "c", dtb.kind == "c"
+	if tuple(a.shape) == tuple(b.shape) and ca and cb: kind, full = L.FFT_C2C, a.shape
+	elif not ca and cb and forward: kind, full = L.FFT_R2C, a.shape
+	elif ca and not cb and not forward: kind, full = L.FFT_C2R, b.shape
+	else: raise ValueError("fft: cannot infer the transform from shapes %s -> %s and dtypes %s -> %s" % (a.shape, b.shape, dta, dtb))
+	half = list(full); half[axes[-1]] = full[axes[-1]]//2+1
+	if kind == L.FFT_R2C and tuple(b.shape) != tuple(half): raise ValueError("fft: r2c output must have shape %s" % (tuple(half),))
+	if kind == L.FFT_C2R and tuple(a.shape) != tuple(half): raise ValueError("fft: c2r input must have shape %s" % (tuple(half),))
+	prec = {8: L.F64, 4: L.F32}[dta.itemsize//(2 if ca else 1)]
+	if dtb.itemsize//(2 if cb else 1) != dta.itemsize//(2 if ca else 1): raise ValueError("fft: input and output precision differ")
+	ist, ost = L.strides_elems(a), L.strides_elems(b)
+	if any(s < 0 for s in ist) or any(s < 0 for s in ost): raise ValueError("fft: negative strides are not supported")
+	shape, ist, ost, axes2 = _collapse(full, ist, ost, axes)
+	if len(shape) > 4: raise NotImplementedError("fft: more than 4 non-mergeable dimensions")
+	# keep the caller's axis order (the last listed axis is the real one)
+	order = [sorted(axes).index(ax) for ax in axes]
+	axes2 = [axes2[i] for i in order]
+	plan = _get_plan(shape, ist, ost, axes2, kind, prec)
+	stream = L.current_stream(b)
+	L.check(L.lib().b2_fft_execute(plan.handle, pa, pb, 1 if forward else 0, float(scale), mema, stream))
+	return b
+
+# ------------------------------------------------------------------ engine plug-in (pixell/fft.py:8-113)
+
+class FFTW:
+	"""Plan object with the call shape of pyfftw.FFTW / the reference's numpy_FFTW and ducc_FFTW classes."""
+	def __init__(self, a, b, axes=(-1,), direction="FFTW_FORWARD", threads=1, flags=None, *args, **kwargs):
+		self.a, self.b = a, b
+		self.axes = tuple(axes) if np.ndim(axes) else (axes,)
+		if not isinstance(direction, str): raise NotImplementedError("pixell_b200.fft: r2r (DCT/DST) transforms are not provided")
+		if direction not in ("FFTW_FORWARD", "FFTW_BACKWARD"): raise ValueError("unknown direction %s" % direction)
+		self.direction = direction
+	def __call__(self, normalise_idft=False):
+		fwd = self.direction == "FFTW_FORWARD"
+		scale = 1.0
+		if not fwd and normalise_idft:
+			out_shape = self.b.shape
+			scale = 1.0/np.prod([out_shape[ax] for ax in self.axes])
+		transform(self.a, self.b, self.axes, fwd, scale)
+		return self.b
+
+def empty_aligned(shape, dtype, n=None):
+	return np.empty(shape, dtype)
+
+class _Engine: pass
+engine = _Engine()
+engine.FFTW = FFTW
+engine.empty_aligned = empty_aligned
+
+def register(pixell_fft_module, name="b200", select=True):
+	"""pixell.fft.engines[name] = engine (and select it): the whole integration on the reference side."""
+	pixell_fft_module.engines[name] = engine
+	if select: pixell_fft_module.set_engine(name)
+
+# ------------------------------------------------------------------ pixell.fft functions (:133-209)
+
+def _astuple(x): return tuple(x) if np.ndim(x) else (x,)
+
+def _asfc(a):
+	if L.is_torch(a): return a
+	a = np.asarray(a)
+	return np.asarray(a, np.result_type(a, 0.0))
+
+def _empty_like(ref, shape, dtype):
+	if L.is_torch(ref):
+		import torch
+		td = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
+			np.dtype(np.complex128): torch.complex128, np.dtype(np.complex64): torch.complex64}[np.dtype(dtype)]
+		return torch.empty(tuple(shape), dtype=td, device=ref.device)
+	return np.empty(tuple(shape), dtype)
+
+def _dtype(a): return L.buffer_info(a)[2]
+def _size(a): return int(np.prod(a.shape))
+
+def fft(tod, ft=None, nthread=0, axes=[-1], flags=None, _direction="FFTW_FORWARD", engine="auto"):
+	"""pixell/fft.py:133-160"""
+	tod = _asfc(tod)
+	axes = _astuple(-1 if axes is None else axes)
+	if _size(tod) == 0: return
+	if ft is None:
+		otype = np.result_type(_dtype(tod), 0j)
+		ft = _empty_like(tod, tod.shape, otype)
+		tod = tod.to(ft.dtype) if L.is_torch(tod) else tod.astype(otype, copy=False)
+	return transform(tod, ft, axes, _direction == "FFTW_FORWARD")
+
+def ifft(ft, tod=None, nthread=0, normalize=False, axes=[-1], flags=None, engine="auto"):
+	"""pixell/fft.py:162-187 (normalisation is fused into the last pass instead of a separate division)"""
+	ft = _asfc(ft)
+	axes = _astuple(-1 if axes is None else axes)
+	if _size(ft) == 0: return
+	if tod is None: tod = _empty_like(ft, ft.shape, _dtype(ft))
+	scale = 1.0/np.prod([tod.shape[i] for i in axes]) if normalize else 1.0
+	return transform(ft, tod, axes, False, scale)
+
+def rfft_shape(ishape, axes=[-1]):
+	oshape = list(ishape); oshape[axes[-1]] = oshape[axes[-1]]//2+1
+	return oshape
+
+def irfft_shape(ishape, n=None, axes=[-1]):
+	oshape = list(ishape); oshape[axes[-1]] = (oshape[axes[-1]]-1)*2 if n is None else n
+	return oshape
+
+def rfft(tod, ft=None, nthread=0, axes=[-1], flags=None, engine="auto"):
+	"""pixell/fft.py:189-198"""
+	tod = _asfc(tod)
+	axes = _astuple(-1 if axes is None else axes)
+	if ft is None: ft = _empty_like(tod, rfft_shape(tod.shape, axes=axes), np.result_type(_dtype(tod), 0j))
+	return fft(tod, ft, nthread, axes, flags=flags)
+
+def irfft(ft, tod=None, n=None, nthread=0, normalize=False, axes=[-1], flags=None, engine="auto"):
+	"""pixell/fft.py:200-213"""
+	ft = _asfc(ft)
+	axes = _astuple(-1 if axes is None else axes)
+	if tod is None: tod = _empty_like(ft, irfft_shape(ft.shape, axes=axes, n=n), np.zeros([], _dtype(ft)).real.dtype)
+	return ifft(ft, tod, nthread, normalize, axes, flags=flags)
+
+def fftfreq(n, d=1.0, dtype=np.float64): return np.fft.fftfreq(n, d=d).astype(dtype, copy=False)
+def rfftfreq(n, d=1.0, dtype=np.float64): return np.arange(n//2+1, dtype=dtype)/(n*d)

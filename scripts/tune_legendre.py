@@ -45,6 +45,7 @@ def main():
 				e0.record(); run(); e1.record(); torch.cuda.synchronize()
 				best = min(best, e0.elapsed_time(e1))
 			res = (leg if k % 2 == 0 else out)[: (1 if spin == 0 else 2)].clone()
+			(leg if k % 2 == 0 else out).fill_(float('nan'))      # a variant that skips outputs must not inherit them
 			if ref is None: ref = res
 			diff = (res-ref).abs().max().item()
 			print("%-7s variant %d: %9.3f ms   maxdiff vs v0 %.3e" % (names[k], v, best, diff), flush=True)

@@ -1,0 +1,142 @@
+"""GPU parity tests of the FFT engine (K7; C ABI b2_fft_* through pixell_b200.fft / pixell_b200.enmap)
+against numpy's pocketfft (the same algorithm family ducc0.fft ships; reference pixell/fft.py:33-60).
+Tolerance: 1e-12 relative to the largest output element for float64, 2e-6 for float32."""
+import numpy as np, pytest
+
+pytestmark = pytest.mark.gpu
+
+@pytest.fixture(scope="module")
+def F():
+	from pixell_b200 import fft
+	return fft
+
+def rel(a, b): return np.abs(a-b).max()/max(np.abs(b).max(), 1e-300)
+
+def cdata(shape, seed=0, dtype=np.complex128):
+	rng = np.random.default_rng(seed)
+	return (rng.standard_normal(shape) + 1j*rng.standard_normal(shape)).astype(dtype)
+
+# last-axis lengths: powers of two, smooth, primes (Bluestein), longer than one CTA's shared memory (split lines)
+@pytest.mark.parametrize("shape", [(7, 64), (3, 1000), (5, 61), (2, 4099), (2, 2160), (2, 20000), (1, 32768), (1, 43200)])
+def test_c2c_last_axis(F, shape):
+	a = cdata(shape)
+	got = F.fft(a, axes=[-1])
+	assert rel(got, np.fft.fft(a, axis=-1)) < 1e-12
+	back = F.ifft(got, axes=[-1], normalize=True)
+	assert rel(back, a) < 1e-12
+
+@pytest.mark.parametrize("shape", [(64, 33), (1000, 7), (61, 5), (20000, 3), (16384, 2)])
+def test_c2c_strided_axis(F, shape):
+	a = cdata(shape, 1)
+	got = F.fft(a, axes=[0])
+	assert rel(got, np.fft.fft(a, axis=0)) < 1e-12
+	back = F.ifft(got, axes=[0])
+	assert rel(back, a*shape[0]) < 1e-12
+
+@pytest.mark.parametrize("shape", [(3, 48, 80), (2, 33, 45), (1, 128, 4099), (2, 4, 6, 10)])
+def test_c2c_2d(F, shape):
+	a = cdata(shape, 2)
+	got = F.fft(a, axes=[-2, -1])
+	assert rel(got, np.fft.fft2(a)) < 1e-12
+	# in place
+	b = a.copy()
+	F.fft(b, b, axes=[-2, -1])
+	assert rel(b, np.fft.fft2(a)) < 1e-12
+	back = F.ifft(got, axes=[-2, -1], normalize=True)
+	assert rel(back, a) < 1e-12
+
+def test_strided_views(F):
+	"""non-contiguous input and output views (reference tests/test_pixell.py:412-422)"""
+	big = cdata((4, 40, 70), 3)
+	a = big[1:3, 4:36, 3:67]
+	obig = np.full((2, 50, 80), 7+7j)
+	o = obig[:, 10:42, 8:72]
+	F.fft(a, o, axes=[-2, -1])
+	assert rel(o, np.fft.fft2(a)) < 1e-12
+	assert np.all(obig[:, :10] == 7+7j) and np.all(obig[:, :, 72:] == 7+7j)      # untouched outside the view
+	t = a.transpose(0, 2, 1)              # transform axes with swapped strides
+	assert rel(F.fft(t, axes=[-2, -1]), np.fft.fft2(t)) < 1e-12
+
+@pytest.mark.parametrize("shape", [(4, 100), (4, 101), (3, 61), (2, 20000), (1, 32768)])
+def test_r2c_c2r_1d(F, shape):
+	rng = np.random.default_rng(4)
+	a = rng.standard_normal(shape)
+	ft = F.rfft(a)
+	assert ft.shape == shape[:-1]+(shape[-1]//2+1,)
+	assert rel(ft, np.fft.rfft(a, axis=-1)) < 1e-12
+	back = F.irfft(ft, n=shape[-1], normalize=True)
+	assert rel(back, a) < 1e-12
+
+@pytest.mark.parametrize("shape", [(3, 50, 64), (2, 33, 45), (1, 64, 4100), (2, 1000, 18)])
+def test_r2c_c2r_2d(F, shape):
+	rng = np.random.default_rng(5)
+	a = rng.standard_normal(shape)
+	ft = F.rfft(a, axes=[-2, -1])
+	assert rel(ft, np.fft.rfft2(a)) < 1e-12
+	back = F.irfft(ft, n=shape[-1], axes=[-2, -1])
+	assert rel(back, a*shape[-1]*shape[-2]) < 1e-12
+
+def test_float32(F):
+	a = cdata((3, 32, 96), 6, np.complex64)
+	got = F.fft(a, axes=[-2, -1])
+	assert got.dtype == np.complex64
+	assert rel(got, np.fft.fft2(a.astype(np.complex128))) < 2e-6
+	r = np.random.default_rng(7).standard_normal((2, 40, 50)).astype(np.float32)
+	ft = F.rfft(r, axes=[-2, -1])
+	assert ft.dtype == np.complex64 and rel(ft, np.fft.rfft2(r.astype(np.float64))) < 2e-6
+	assert rel(F.irfft(ft, n=50, axes=[-2, -1], normalize=True), r) < 2e-6
+
+def test_engine_object(F):
+	"""the plug-in shape pixell.fft.engines expects (reference pixell/fft.py:8-60, 126-131)"""
+	a = cdata((2, 30, 24), 8); b = np.empty_like(a)
+	plan = F.engine.FFTW(a, b, axes=(-2, -1), direction="FFTW_FORWARD", threads=4, flags=["FFTW_ESTIMATE"])
+	plan()
+	assert rel(b, np.fft.fft2(a)) < 1e-12
+	c = np.empty_like(a)
+	F.engine.FFTW(b, c, axes=(-2, -1), direction="FFTW_BACKWARD")(normalise_idft=True)
+	assert rel(c, a) < 1e-12
+	r = np.random.default_rng(9).standard_normal((3, 90)); fr = np.empty((3, 46), complex)
+	F.engine.FFTW(r, fr, axes=(-1,), direction="FFTW_FORWARD")()
+	assert rel(fr, np.fft.rfft(r)) < 1e-12
+	rr = F.engine.empty_aligned((3, 90), np.float64)
+	F.engine.FFTW(fr, rr, axes=(-1,), direction="FFTW_BACKWARD")()
+	assert rel(rr, r*90) < 1e-12
+	with pytest.raises(NotImplementedError): F.engine.FFTW(r, rr, direction=["FFTW_REDFT00"])
+
+def test_errors(F):
+	a = cdata((4, 8));
+	with pytest.raises(ValueError): F.transform(a, np.empty((4, 7), complex), [-1], True)
+	with pytest.raises(ValueError): F.transform(a, np.empty((4, 8), np.complex64), [-1], True)
+	with pytest.raises(ValueError): F.transform(a[:, ::-1], np.empty((4, 8), complex), [-1], True)
+
+def test_torch_device(F):
+	import torch
+	a = cdata((3, 64, 80), 10)
+	ta = torch.from_numpy(a).cuda()
+	got = F.fft(ta, axes=[-2, -1])
+	assert got.is_cuda and rel(got.cpu().numpy(), np.fft.fft2(a)) < 1e-12
+	r = torch.randn((2, 100, 128), dtype=torch.float64, device="cuda")
+	ft = F.rfft(r, axes=[-2, -1])
+	assert rel(ft.cpu().numpy(), np.fft.rfft2(r.cpu().numpy())) < 1e-12
+	back = F.irfft(ft, n=128, axes=[-2, -1], normalize=True)
+	assert rel(back.cpu().numpy(), r.cpu().numpy()) < 1e-12
+
+def test_enmap_fft_roundtrip():
+	"""enmap.fft / ifft normalisation conventions (reference pixell/enmap.py:1307-1337; tests/test_pixell.py test_fft*)"""
+	from pixell_b200 import enmap, geometry
+	shape, wcs = geometry.slice_geometry(*geometry.fullsky_geometry(res=np.deg2rad(0.5)), 100, 164, 200, 296)
+	rng = np.random.default_rng(11)
+	m = geometry.ndmap(rng.standard_normal((3,)+shape), wcs)
+	f = enmap.fft(m)
+	assert rel(f, np.fft.fft2(m)/np.sqrt(m.shape[-1]*m.shape[-2])) < 1e-12
+	assert rel(enmap.ifft(f).real, m) < 1e-12
+	fp = enmap.fft(m, normalize="phys")
+	assert rel(fp, np.asarray(f)*enmap.pixsize(shape, wcs)**0.5) < 1e-12
+	assert rel(enmap.ifft(fp, normalize="phys").real, m) < 1e-12
+	# Parseval with the symmetric normalisation
+	assert abs(np.sum(np.abs(f)**2)/np.sum(np.asarray(m)**2) - 1) < 1e-12
+	# harmonic Gaussian smoothing against its numpy restatement
+	sigma = np.deg2rad(1.0)
+	ly, lx = enmap.laxes(shape, wcs)
+	want = np.fft.ifft2(np.fft.fft2(m)*np.exp(-0.5*sigma**2*(ly[:, None]**2+lx[None, :]**2))).real
+	assert rel(enmap.smooth_gauss(m, sigma), want) < 1e-12

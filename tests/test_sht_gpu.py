@@ -204,3 +204,16 @@ def test_golden_unlensed_fits(sht):
 	got, want = out[:, g["rows"]], g["map"]
 	assert np.abs(got[0]-want[0]).max() < 5e-10
 	assert np.abs(got[1:]-want[1:]).max() < 5e-11
+
+@pytest.mark.parametrize("spin", [0, 2])
+def test_analysis_2d_split_theta_transform(sht, spin):
+	"""exact analysis on a grid whose theta circle (2 x 6500 rings) exceeds one CTA's shared memory, so the theta
+	weighting runs split over two CTAs per column pair (size-independent property: analysis inverts synthesis)"""
+	ny, nx, lmax, mmax = 6500, 64, 6400, 24
+	nc = 1 if spin == 0 else 2
+	alm, ai = rand_alm(lmax, nc, 11, spin, mmax)
+	alm[:, ~used_mask(ai, spin)] = 0
+	kw = dict(spin=spin, lmax=lmax, mmax=mmax, mstart=ai.mstart, geometry="F1", phi0=0.0)
+	m = sht.synthesis_2d(alm=alm, ntheta=ny, nphi=nx, **kw)
+	back = sht.analysis_2d(map=m, **kw)
+	assert relerr(back, alm) < 1e-11
