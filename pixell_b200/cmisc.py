@@ -88,7 +88,7 @@ def lmul(ainfo, alm, lfun, out=None):
 	if lfun.ndim == 3 and alm.ndim == 2:
 		N, M = lfun.shape[:2]
 		if M != alm.shape[0]: raise ValueError("lmul: matrix and alm component counts differ")
-		if out is None: out = xp.zeros_like(alm[:1]).repeat(N, 0) if tor else np.zeros((N,)+alm.shape[1:], alm.dtype)
+		if out is None: out = xp.zeros((N,)+tuple(alm.shape[1:]), dtype=alm.dtype, device=alm.device) if tor else np.zeros((N,)+alm.shape[1:], alm.dtype)
 		lf = lfun.contiguous() if tor else np.ascontiguousarray(lfun)
 		pa, mem, _ = L.buffer_info(alm); po = L.buffer_info(out)[0]; pf = L.buffer_info(lf)[0]
 		acs = L.strides_elems(alm)[0] if M > 1 else alm.shape[-1]

@@ -1,0 +1,120 @@
+"""pixell_b200.mc -- batches of curvedsky.rand_map realisations sharded over the GPUs of one box.
+
+The reference draws realisations one at a time (pixell/curvedsky.py:17-36 -> rand_alm_healpy / rand_alm
+:44-77 -> alm2map) and leaves any parallelism to the caller (MPI scripts).  The units are independent,
+so the multi-GPU form is plain sharding: one process per GPU (torchrun), realisations
+block-partitioned over ranks, the input C_l broadcast from rank 0 (NCCL through torch.distributed; gloo
+in the CPU tests), maps and alm never leave their GPU.  Optionally the per-realisation power spectra are
+gathered.  Nothing here is a data-path collective.
+
+Random streams:
+  rng="reference"  numpy's legacy global stream on the host, seeded per realisation, exactly as the reference
+                   (curvedsky.rand_alm / rand_alm_healpy): bit-identical alm for a given seed, host-RNG bound.
+  rng="device"     torch's Philox generator on the GPU, seeded per realisation: same statistics, different
+                   numbers; colouring (symmetric square root of C_l, lmatmul kernel) and the m = 0 fix-up
+                   follow curvedsky.rand_alm :61-77.
+"""
+import numpy as np
+from . import _lib as L, curvedsky, geometry
+
+def world():
+	"""(rank, world_size) of the torch.distributed job, (0, 1) outside one"""
+	try:
+		import torch.distributed as dist
+		if dist.is_available() and dist.is_initialized(): return dist.get_rank(), dist.get_world_size()
+	except ImportError: pass
+	return 0, 1
+
+def partition(n, nrank=None, rank=None):
+	"""Block partition of n units: the half-open index range of `rank` (first n % nrank ranks get one extra)."""
+	if nrank is None or rank is None:
+		r, w = world(); rank = r if rank is None else rank; nrank = w if nrank is None else nrank
+	base, extra = divmod(int(n), int(nrank))
+	lo = rank*base + min(rank, extra)
+	return range(lo, lo + base + (1 if rank < extra else 0))
+
+def broadcast_ps(ps, src=0, device=None):
+	"""The input spectrum is known on rank `src` only (e.g. read from disk there): every rank gets a copy.
+	ps may be None on the other ranks; the shape travels first."""
+	rank, nrank = world()
+	if nrank == 1: return np.asarray(ps, dtype=np.float64)
+	import torch, torch.distributed as dist
+	dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
+	hdr = torch.zeros(5, dtype=torch.int64, device=dev)
+	if rank == src:
+		ps = np.ascontiguousarray(ps, dtype=np.float64)
+		hdr[0] = ps.ndim; hdr[1:1+ps.ndim] = torch.tensor(ps.shape, dtype=torch.int64)
+	dist.broadcast(hdr, src)
+	shape = tuple(int(v) for v in hdr[1:1+int(hdr[0])].tolist())
+	buf = torch.from_numpy(ps).to(dev) if rank == src else torch.empty(shape, dtype=torch.float64, device=dev)
+	dist.broadcast(buf, src)
+	return buf.cpu().numpy()
+
+def gather_rows(local, counts=None):
+	"""All ranks get the concatenation (rank order) of every rank's rows: used for the small per-realisation
+	results (spectra), never for maps.  local: numpy [nlocal, ...]."""
+	rank, nrank = world()
+	if nrank == 1: return np.asarray(local)
+	import torch, torch.distributed as dist
+	dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+	local = np.ascontiguousarray(local)
+	n = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+	ns = [torch.zeros_like(n) for _ in range(nrank)]
+	dist.all_gather(ns, n)
+	ns = [int(v.item()) for v in ns]
+	nmax = max(ns)
+	pad = np.zeros((nmax,)+local.shape[1:], local.dtype); pad[:local.shape[0]] = local
+	bufs = [torch.empty(pad.shape, dtype=torch.from_numpy(pad).dtype, device=dev) for _ in range(nrank)]
+	dist.all_gather(bufs, torch.from_numpy(pad).to(dev))
+	return np.concatenate([b.cpu().numpy()[:k] for b, k in zip(bufs, ns)], 0)
+
+def _wps(ps, ncomp, lmax):
+	ps = np.asarray(ps, dtype=np.float64)
+	if ps.ndim == 1: ps = ps[None, None]
+	elif ps.ndim == 2: ps = curvedsky.sym_expand(ps)
+	ps = ps[:ncomp, :ncomp]
+	if ps.shape[-1] < lmax+1: ps = curvedsky.pad_spectrum(ps, lmax)
+	return ps[..., :lmax+1]
+
+def rand_alm_device(ps12, ainfo, seed, device, dtype=None):
+	"""Coloured Gaussian alm on the GPU: white alm from torch's generator, alm <- ps^(1/2)/sqrt(2) alm (lmatmul
+	kernel), m = 0 made real with the sqrt(2) restored (curvedsky.rand_alm :61-77, device stream)."""
+	import torch
+	ncomp = ps12.shape[0]
+	g = torch.Generator(device=device); g.manual_seed(int(seed))
+	alm = torch.randn((ncomp, ainfo.nelem), dtype=torch.complex128 if dtype is None else dtype, device=device, generator=g)
+	# torch's complex normal has unit total variance; the reference fills re and im with unit variance each
+	alm *= 2**0.5
+	out = ainfo.lmul(alm, ps12/2**0.5)
+	m0 = out[:, :ainfo.lmax+1]
+	out[:, :ainfo.lmax+1] = (m0.real*2**0.5).to(out.dtype)
+	return out
+
+def rand_maps(shape, wcs, ps, seeds, lmax=None, spin=[0, 2], rng="reference", device=None, out=None, return_alm=False):
+	"""This rank's share of the realisations `seeds` (block partition): a torch CUDA tensor
+	[nlocal, ncomp, ny, nx] of maps (float64), realisation i of the share = seed seeds[partition[i]].
+	ps: [ncomp,ncomp,nl], [nspec,nl] or [nl], already present on every rank (see broadcast_ps)."""
+	import torch
+	L.init()
+	if device is None: device = torch.device("cuda", torch.cuda.current_device())
+	seeds = list(seeds)
+	mine = partition(len(seeds))
+	ncomp = 1 if len(shape) == 2 else shape[-3]
+	ny, nx = shape[-2:]
+	if lmax is None: lmax = np.asarray(ps).shape[-1]-1
+	wps = _wps(ps, ncomp, lmax)
+	ainfo = curvedsky.alm_info(lmax)
+	if out is None: out = torch.empty((len(mine), ncomp, ny, nx), dtype=torch.float64, device=device)
+	ps12 = None
+	alms = []
+	for i, k in enumerate(mine):
+		if rng == "reference":
+			a = curvedsky.rand_alm_healpy(wps[0, 0] if ncomp == 1 else wps, lmax=lmax, seed=seeds[k])
+			alm = torch.from_numpy(np.atleast_2d(a)).to(device)
+		elif rng == "device":
+			if ps12 is None: ps12 = torch.as_tensor(curvedsky.multi_pow_half(wps), device=device)
+			alm = rand_alm_device(ps12, ainfo, seeds[k], device)
+		else: raise ValueError("rng must be 'reference' or 'device'")
+		curvedsky.alm2map(alm, out[i], spin=spin, ainfo=ainfo, wcs=wcs)
+		if return_alm: alms.append(alm)
+	return (out, alms) if return_alm else out

@@ -8,9 +8,14 @@ import csv, subprocess, sys, re, collections
 def main():
 	path = sys.argv[1]; ntop = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 	out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-	rows = list(csv.reader(out.splitlines()))
-	hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
-	H = rows[hi]; data = rows[hi+1:]
+	allrows = list(csv.reader(out.splitlines()))
+	heads = [i for i, r in enumerate(allrows) if r and r[0] == "Address"]
+	for n, hi in enumerate(heads):       # one section per captured launch
+		end = heads[n+1]-1 if n+1 < len(heads) else len(allrows)
+		if hi > 0 and allrows[hi-1] and allrows[hi-1][0] == "Kernel Name": print("==== %s" % allrows[hi-1][1])
+		section(allrows[hi], allrows[hi+1:end], ntop)
+
+def section(H, data, ntop):
 	c_src, c_smp, c_exec = H.index("Source"), H.index("# Samples"), H.index("Instructions Executed")
 	stall_cols = [(i, h) for i, h in enumerate(H) if h.startswith("stall_") and "Not Issued" not in h]
 	regions = []; cur = []
