@@ -251,86 +251,105 @@ __global__ void k_scale_rows(double2 *leg, const double *w, int nring, int64_t n
 enum { OP_SYNTH, OP_ADJ_SYNTH, OP_ANALYSIS, OP_ADJ_ANALYSIS };
 
 struct Exec {
-	b2_sht_plan *p; int op, spin, mode, dtype, mem; cudaStream_t st;
+	b2_sht_plan *p; int op, spin, mode, dtype, mem; cudaStream_t st;      // st: compute stream
+	cudaStream_t s_in, s_out;                                             // copy streams (host-memory calls)
 	int nca, ncm;              // alm / map components
 	size_t asz, msz;           // bytes per complex alm element / real map element
 };
 
-static int copy_map(Exec &E, void *host, void *dev, bool to_dev)
+// one spin group in flight: where its operands live on the device
+struct GroupCtx {
+	void *alm; int64_t alm_cs; void *map; int64_t map_cs;      // caller's operands
+	double2 *dalm; int64_t dalm_cs; float2 *tmp32;             // complex128 alm on the device (+ complex64 scratch)
+	void *dmap; int64_t dmap_cs; char *dmap_base;              // map on the device (element offsets as in the caller's array)
+	bool alm_direct;
+	cudaEvent_t ev_in, ev_done;
+};
+
+static int copy_map(Exec &E, void *host, void *dev, bool to_dev, cudaStream_t st)
 {
 	b2_sht_plan *p = E.p;
 	// host component pointer `host` addresses element 0; the rings occupy [map_lo, map_hi)
 	char *h = (char*)host + p->map_lo*E.msz; char *d = (char*)dev;
 	cudaMemcpyKind kind = to_dev ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
 	if (p->row_pitch == p->npix || p->row_pitch == -p->npix || p->nring == 1) {
-		if (to_dev) B2_CHECK(cudaMemcpyAsync(d, h, (p->map_hi - p->map_lo)*E.msz, kind, E.st));
-		else        B2_CHECK(cudaMemcpyAsync(h, d, (p->map_hi - p->map_lo)*E.msz, kind, E.st));
+		if (to_dev) B2_CHECK(cudaMemcpyAsync(d, h, (p->map_hi - p->map_lo)*E.msz, kind, st));
+		else        B2_CHECK(cudaMemcpyAsync(h, d, (p->map_hi - p->map_lo)*E.msz, kind, st));
 	} else {
 		// only the ring pixels move (rows with gaps between them)
 		for (int r = 0; r < p->nring; r++) {
 			size_t off = (p->ringstart_h[r] - p->map_lo)*E.msz;
-			if (to_dev) B2_CHECK(cudaMemcpyAsync(d + off, h + off, p->npix*E.msz, kind, E.st));
-			else        B2_CHECK(cudaMemcpyAsync(h + off, d + off, p->npix*E.msz, kind, E.st));
+			if (to_dev) B2_CHECK(cudaMemcpyAsync(d + off, h + off, p->npix*E.msz, kind, st));
+			else        B2_CHECK(cudaMemcpyAsync(h + off, d + off, p->npix*E.msz, kind, st));
 		}
 	}
 	return 0;
 }
 
-static int run_one(Exec &E, void *alm, int64_t alm_cstride, void *map, int64_t map_cstride)
+static inline bool to_map_op(int op) { return op == OP_SYNTH || op == OP_ADJ_ANALYSIS; }
+static size_t group_alm_bytes(const Exec &E) { return (size_t)E.nca*E.p->alm_span*16 + (E.dtype == B2_F32 ? (size_t)E.nca*E.p->alm_span*8 : 0); }
+static size_t group_map_bytes(const Exec &E) { return (size_t)E.ncm*(size_t)(E.p->map_hi - E.p->map_lo)*E.msz; }
+
+// phase 1: operands to the device (copy stream); salm / smap: this group's staging areas
+static int group_stage_in(Exec &E, GroupCtx &G, char *salm, char *smap)
 {
 	b2_sht_plan *p = E.p;
-	const bool to_map = (E.op == OP_SYNTH || E.op == OP_ADJ_ANALYSIS);
+	const bool to_map = to_map_op(E.op);
+	G.alm_direct = (E.mem == B2_MEM_DEVICE && E.dtype == B2_F64);
+	G.tmp32 = nullptr;
+	if (G.alm_direct) { G.dalm = (double2*)G.alm; G.dalm_cs = G.alm_cs; }
+	else {
+		G.dalm = (double2*)salm; G.dalm_cs = p->alm_span;
+		G.tmp32 = (float2*)(salm + (size_t)E.nca*p->alm_span*16);
+		// the input direction needs the values; the output direction needs them too so that entries the
+		// transform does not own survive the round trip
+		for (int c = 0; c < E.nca; c++) {
+			if (!to_map && p->alm_dense) break;      // every entry of the span is overwritten
+			char *src = (char*)G.alm + (size_t)c*G.alm_cs*E.asz;
+			if (E.dtype == B2_F64) B2_CHECK(cudaMemcpyAsync(G.dalm + c*G.dalm_cs, src, p->alm_span*16, cudaMemcpyDefault, E.s_in));
+			else if (E.mem == B2_MEM_HOST) B2_CHECK(cudaMemcpyAsync(G.tmp32 + c*p->alm_span, src, p->alm_span*8, cudaMemcpyHostToDevice, E.s_in));
+		}
+	}
+	G.dmap = G.map; G.dmap_cs = G.map_cs; G.dmap_base = nullptr;
+	if (E.mem == B2_MEM_HOST) {
+		size_t span = (size_t)(p->map_hi - p->map_lo);
+		G.dmap_cs = (int64_t)span; G.dmap_base = smap;
+		G.dmap = smap - p->map_lo*E.msz;      // so that element offsets keep their meaning
+		if (!to_map) for (int c = 0; c < E.ncm; c++)
+			if (copy_map(E, (char*)G.map + (size_t)c*G.map_cs*E.msz, smap + (size_t)c*span*E.msz, true, E.s_in)) return 1;
+	}
+	if (E.s_in != E.st) B2_CHECK(cudaEventRecord(G.ev_in, E.s_in));
+	return 0;
+}
+
+// phase 2: the transform (compute stream)
+static int group_compute(Exec &E, GroupCtx &G)
+{
+	b2_sht_plan *p = E.p;
+	const bool to_map = to_map_op(E.op);
 	LegTables *T = p->get_tables(E.spin);
 	if (!T) return 1;
 	AlmLayout L; L.lmax = p->lmax; L.mmax = p->mmax; L.mstart_d = p->mstart.p; L.lstride = p->lstride;
 	const int deriv1 = E.mode == B2_MODE_DERIV1;
 	B2_CHECK(cudaEventRecord(p->ev[0], E.st));
-
-	// ---- stage alm on the device as complex128
-	double2 *dalm = nullptr; int64_t dalm_cs = alm_cstride;
-	const bool alm_direct = (E.mem == B2_MEM_DEVICE && E.dtype == B2_F64);
-	if (alm_direct) dalm = (double2*)alm;
-	else {
-		size_t need = (size_t)E.nca*p->alm_span*16 + (E.dtype == B2_F32 ? (size_t)E.nca*p->alm_span*8 : 0);
-		if (p->stage_alm.n < need && p->stage_alm.alloc(need)) return 1;
-		dalm = (double2*)p->stage_alm.p; dalm_cs = p->alm_span;
-		float2 *tmp32 = (float2*)(p->stage_alm.p + (size_t)E.nca*p->alm_span*16);
-		// the input direction needs the values; the output direction needs them too so that entries the
-		// transform does not own survive the round trip
+	if (E.s_in != E.st) B2_CHECK(cudaStreamWaitEvent(E.st, G.ev_in, 0));
+	if (!G.alm_direct && E.dtype == B2_F32 && !(!to_map && p->alm_dense)) {
 		for (int c = 0; c < E.nca; c++) {
-			if (!to_map && p->alm_dense) break;      // every entry of the span is overwritten
-			char *src = (char*)alm + (size_t)c*alm_cstride*E.asz;
-			if (E.dtype == B2_F64) B2_CHECK(cudaMemcpyAsync(dalm + c*dalm_cs, src, p->alm_span*16, cudaMemcpyDefault, E.st));
-			else {
-				const float2 *s32 = (const float2*)src;
-				if (E.mem == B2_MEM_HOST) { B2_CHECK(cudaMemcpyAsync(tmp32 + c*p->alm_span, src, p->alm_span*8, cudaMemcpyHostToDevice, E.st)); s32 = tmp32 + c*p->alm_span; }
-				k_c64_to_c128<<<(unsigned)((p->alm_span + 255)/256), 256, 0, E.st>>>(s32, dalm + c*dalm_cs, p->alm_span);
-				B2_LAUNCH_CHECK();
-			}
+			const float2 *s32 = E.mem == B2_MEM_HOST ? G.tmp32 + c*p->alm_span : (const float2*)((char*)G.alm + (size_t)c*G.alm_cs*E.asz);
+			k_c64_to_c128<<<(unsigned)((p->alm_span + 255)/256), 256, 0, E.st>>>(s32, G.dalm + c*G.dalm_cs, p->alm_span);
+			B2_LAUNCH_CHECK();
 		}
 	}
-	// ---- stage the map
-	void *dmap = map; int64_t dmap_cs = map_cstride;
-	if (E.mem == B2_MEM_HOST) {
-		size_t span = (size_t)(p->map_hi - p->map_lo);
-		size_t need = (size_t)E.ncm*span*E.msz;
-		if (p->stage_map.n < need && p->stage_map.alloc(need)) return 1;
-		dmap_cs = (int64_t)span;
-		dmap = p->stage_map.p - p->map_lo*E.msz;      // so that element offsets keep their meaning
-		if (!to_map) for (int c = 0; c < E.ncm; c++)
-			if (copy_map(E, (char*)map + (size_t)c*map_cstride*E.msz, p->stage_map.p + (size_t)c*span*E.msz, true)) return 1;
-	}
 	B2_CHECK(cudaEventRecord(p->ev[1], E.st));
-
 	if (to_map) {
-		if (leg_alm2leg(*T, p->geom, L, deriv1, dalm, dalm_cs, p->leg.p, E.st)) return 1;
+		if (leg_alm2leg(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st)) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[2], E.st));
 		if (E.op == OP_ADJ_ANALYSIS) { b2_set_error("adjoint_analysis_2d is not implemented yet"); return 1; }
 		B2_CHECK(cudaEventRecord(p->ev[3], E.st));
-		if (ring_leg2map(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, dmap, dmap_cs, E.dtype, E.st)) return 1;
+		if (ring_leg2map(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.st)) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[4], E.st));
 	} else {
-		if (ring_map2leg(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, dmap, dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, E.st)) return 1;
+		if (ring_map2leg(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, E.st)) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[2], E.st));
 		if (E.op == OP_ANALYSIS) {
 			if (p->resamp) { if (p->resamp->apply(p->leg.p, E.ncm, E.spin, E.st)) return 1; }
@@ -341,31 +360,100 @@ static int run_one(Exec &E, void *alm, int64_t alm_cstride, void *map, int64_t m
 			}
 		}
 		B2_CHECK(cudaEventRecord(p->ev[3], E.st));
-		if (leg_leg2alm(*T, p->geom, L, deriv1, dalm, dalm_cs, p->leg.p, E.st)) return 1;
+		if (leg_leg2alm(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st)) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[4], E.st));
-	}
-
-	// ---- results back
-	if (to_map) {
-		if (E.mem == B2_MEM_HOST) {
-			size_t span = (size_t)(p->map_hi - p->map_lo);
-			for (int c = 0; c < E.ncm; c++)
-				if (copy_map(E, (char*)map + (size_t)c*map_cstride*E.msz, p->stage_map.p + (size_t)c*span*E.msz, false)) return 1;
-		}
-	} else if (!alm_direct) {
-		float2 *tmp32 = (float2*)(p->stage_alm.p + (size_t)E.nca*p->alm_span*16);
-		for (int c = 0; c < E.nca; c++) {
-			char *dst = (char*)alm + (size_t)c*alm_cstride*E.asz;
-			if (E.dtype == B2_F64) B2_CHECK(cudaMemcpyAsync(dst, dalm + c*dalm_cs, p->alm_span*16, cudaMemcpyDefault, E.st));
-			else {
-				float2 *d32 = E.mem == B2_MEM_HOST ? tmp32 + c*p->alm_span : (float2*)dst;
-				k_c128_to_c64<<<(unsigned)((p->alm_span + 255)/256), 256, 0, E.st>>>(dalm + c*dalm_cs, d32, p->alm_span);
+		if (!G.alm_direct && E.dtype == B2_F32) {
+			for (int c = 0; c < E.nca; c++) {
+				float2 *d32 = E.mem == B2_MEM_HOST ? G.tmp32 + c*p->alm_span : (float2*)((char*)G.alm + (size_t)c*G.alm_cs*E.asz);
+				k_c128_to_c64<<<(unsigned)((p->alm_span + 255)/256), 256, 0, E.st>>>(G.dalm + c*G.dalm_cs, d32, p->alm_span);
 				B2_LAUNCH_CHECK();
-				if (E.mem == B2_MEM_HOST) B2_CHECK(cudaMemcpyAsync(dst, d32, p->alm_span*8, cudaMemcpyDeviceToHost, E.st));
 			}
 		}
 	}
 	p->timing[0] = to_map ? 1 : -1;
+	if (E.s_out != E.st) B2_CHECK(cudaEventRecord(G.ev_done, E.st));
+	return 0;
+}
+
+// phase 3: results back to the caller (copy stream)
+static int group_stage_out(Exec &E, GroupCtx &G)
+{
+	b2_sht_plan *p = E.p;
+	const bool to_map = to_map_op(E.op);
+	if (E.s_out != E.st) B2_CHECK(cudaStreamWaitEvent(E.s_out, G.ev_done, 0));
+	if (to_map) {
+		if (E.mem == B2_MEM_HOST) {
+			size_t span = (size_t)(p->map_hi - p->map_lo);
+			for (int c = 0; c < E.ncm; c++)
+				if (copy_map(E, (char*)G.map + (size_t)c*G.map_cs*E.msz, G.dmap_base + (size_t)c*span*E.msz, false, E.s_out)) return 1;
+		}
+	} else if (!G.alm_direct) {
+		for (int c = 0; c < E.nca; c++) {
+			char *dst = (char*)G.alm + (size_t)c*G.alm_cs*E.asz;
+			if (E.dtype == B2_F64) B2_CHECK(cudaMemcpyAsync(dst, G.dalm + c*G.dalm_cs, p->alm_span*16, cudaMemcpyDefault, E.s_out));
+			else if (E.mem == B2_MEM_HOST) B2_CHECK(cudaMemcpyAsync(dst, G.tmp32 + c*p->alm_span, p->alm_span*8, cudaMemcpyDeviceToHost, E.s_out));
+		}
+	}
+	return 0;
+}
+
+static int check_exec_args(b2_sht_plan *plan, int op, int spin, int mode, int dtype, int mem)
+{
+	B2_REQUIRE(spin >= 0 && spin <= 32, "transform: spin %d out of range", spin);
+	B2_REQUIRE(dtype == B2_F64 || dtype == B2_F32, "transform: bad dtype");
+	B2_REQUIRE(mem == B2_MEM_HOST || mem == B2_MEM_DEVICE, "transform: bad memory kind");
+	B2_REQUIRE(mode == B2_MODE_STANDARD || (mode == B2_MODE_DERIV1 && spin == 1), "transform: DERIV1 needs spin=1");
+	if (op == OP_ANALYSIS || op == OP_ADJ_ANALYSIS) {
+		B2_REQUIRE(plan->is2d, "analysis_2d needs a plan made by b2_sht_plan_2d");
+		B2_REQUIRE(plan->resamp || plan->w2d.n, "lmax=%d too large for geometry %s with %d rings", plan->lmax, plan->geometry.c_str(), plan->ntheta);
+	}
+	return 0;
+}
+
+// Runs a list of spin groups.  Device memory: everything on the caller's stream, in order.  Host memory: three
+// streams -- the H2D copies of group g+1 and the D2H copies of group g-1 overlap the kernels of group g.
+static int execute_groups(b2_sht_plan *plan, int op, int ngroups, const int *spins, int mode, int dtype,
+	void *const *alms, const int64_t *alm_cs, void *const *maps, const int64_t *map_cs, int mem, void *stream)
+{
+	B2_REQUIRE(plan && ngroups >= 1 && ngroups <= B2_MAX_GROUPS, "transform: bad group count");
+	Exec E; E.p = plan; E.op = op; E.mode = mode; E.dtype = dtype; E.mem = mem; E.st = (cudaStream_t)stream;
+	E.asz = dtype == B2_F64 ? 16 : 8; E.msz = dtype == B2_F64 ? 8 : 4;
+	E.s_in = E.s_out = E.st;
+	const bool pipelined = (mem == B2_MEM_HOST);
+	if (pipelined) {
+		if (!plan->s_in) { B2_CHECK(cudaStreamCreateWithFlags(&plan->s_in, cudaStreamNonBlocking)); B2_CHECK(cudaStreamCreateWithFlags(&plan->s_out, cudaStreamNonBlocking)); }
+		if (!plan->s_comp) B2_CHECK(cudaStreamCreateWithFlags(&plan->s_comp, cudaStreamNonBlocking));
+		E.s_in = plan->s_in; E.s_out = plan->s_out;
+		if (!E.st) E.st = plan->s_comp;      // never the legacy stream: it would serialise with the copy streams' neighbours
+	}
+	GroupCtx G[B2_MAX_GROUPS];
+	size_t off_a[B2_MAX_GROUPS + 1] = {0}, off_m[B2_MAX_GROUPS + 1] = {0};
+	for (int g = 0; g < ngroups; g++) {
+		B2_REQUIRE(alms[g] && maps[g], "transform: null argument");
+		if (check_exec_args(plan, op, spins[g], mode, dtype, mem)) return 1;
+		E.spin = spins[g]; E.ncm = E.spin == 0 ? 1 : 2; E.nca = (E.spin == 0 || mode == B2_MODE_DERIV1) ? 1 : 2;
+		const bool direct = (mem == B2_MEM_DEVICE && dtype == B2_F64);
+		off_a[g + 1] = off_a[g] + (direct ? 0 : b2_round_up((int64_t)group_alm_bytes(E), 256));
+		off_m[g + 1] = off_m[g] + (mem == B2_MEM_HOST ? b2_round_up((int64_t)group_map_bytes(E), 256) : 0);
+	}
+	if (plan->stage_alm.n < off_a[ngroups] && plan->stage_alm.alloc(off_a[ngroups])) return 1;
+	if (plan->stage_map.n < off_m[ngroups] && plan->stage_map.alloc(off_m[ngroups])) return 1;
+	if (pipelined) for (int g = 0; g < ngroups; g++) {
+		if (!plan->gev[2*g]) { B2_CHECK(cudaEventCreateWithFlags(&plan->gev[2*g], cudaEventDisableTiming)); B2_CHECK(cudaEventCreateWithFlags(&plan->gev[2*g + 1], cudaEventDisableTiming)); }
+	}
+	auto setup = [&](int g) {
+		E.spin = spins[g]; E.ncm = E.spin == 0 ? 1 : 2; E.nca = (E.spin == 0 || mode == B2_MODE_DERIV1) ? 1 : 2;
+		G[g].alm = alms[g]; G[g].alm_cs = alm_cs[g]; G[g].map = maps[g]; G[g].map_cs = map_cs[g];
+		G[g].ev_in = plan->gev[2*g]; G[g].ev_done = plan->gev[2*g + 1];
+	};
+	// all copies in are queued first (they run back to back on the copy stream), then each group's kernels and copies out
+	for (int g = 0; g < ngroups; g++) { setup(g); if (group_stage_in(E, G[g], plan->stage_alm.p + off_a[g], plan->stage_map.p + off_m[g])) return 1; }
+	for (int g = 0; g < ngroups; g++) {
+		setup(g);
+		if (group_compute(E, G[g])) return 1;
+		if (group_stage_out(E, G[g])) return 1;
+	}
+	if (mem == B2_MEM_HOST) { B2_CHECK(cudaStreamSynchronize(E.s_out)); B2_CHECK(cudaStreamSynchronize(E.st)); }
 	return 0;
 }
 
@@ -374,24 +462,28 @@ static int execute(b2_sht_plan *plan, int op, int spin, int mode, int dtype, int
 	int mem, void *stream)
 {
 	B2_REQUIRE(plan && alm && map, "transform: null argument");
-	B2_REQUIRE(spin >= 0 && spin <= 32, "transform: spin %d out of range", spin);
-	B2_REQUIRE(dtype == B2_F64 || dtype == B2_F32, "transform: bad dtype");
-	B2_REQUIRE(mem == B2_MEM_HOST || mem == B2_MEM_DEVICE, "transform: bad memory kind");
-	B2_REQUIRE(mode == B2_MODE_STANDARD || (mode == B2_MODE_DERIV1 && spin == 1), "transform: DERIV1 needs spin=1");
 	B2_REQUIRE(nbatch >= 1, "transform: nbatch must be >= 1");
-	if (op == OP_ANALYSIS || op == OP_ADJ_ANALYSIS) {
-		B2_REQUIRE(plan->is2d, "analysis_2d needs a plan made by b2_sht_plan_2d");
-		B2_REQUIRE(plan->resamp || plan->w2d.n, "lmax=%d too large for geometry %s with %d rings", plan->lmax, plan->geometry.c_str(), plan->ntheta);
+	if (check_exec_args(plan, op, spin, mode, dtype, mem)) return 1;
+	const size_t asz = dtype == B2_F64 ? 16 : 8, msz = dtype == B2_F64 ? 8 : 4;
+	// batches run as groups of the same spin, B2_MAX_GROUPS at a time
+	for (int b0 = 0; b0 < nbatch; b0 += B2_MAX_GROUPS) {
+		int ng = std::min(B2_MAX_GROUPS, nbatch - b0);
+		int spins[B2_MAX_GROUPS]; void *alms[B2_MAX_GROUPS], *maps[B2_MAX_GROUPS]; int64_t acs[B2_MAX_GROUPS], mcs[B2_MAX_GROUPS];
+		for (int g = 0; g < ng; g++) {
+			spins[g] = spin; acs[g] = alm_cstride; mcs[g] = map_cstride;
+			alms[g] = (char*)alm + (size_t)(b0 + g)*alm_bstride*asz; maps[g] = (char*)map + (size_t)(b0 + g)*map_bstride*msz;
+		}
+		if (execute_groups(plan, op, ng, spins, mode, dtype, alms, acs, maps, mcs, mem, stream)) return 1;
 	}
-	Exec E; E.p = plan; E.op = op; E.spin = spin; E.mode = mode; E.dtype = dtype; E.mem = mem; E.st = (cudaStream_t)stream;
-	E.ncm = spin == 0 ? 1 : 2;
-	E.nca = (spin == 0 || mode == B2_MODE_DERIV1) ? 1 : 2;
-	E.asz = dtype == B2_F64 ? 16 : 8; E.msz = dtype == B2_F64 ? 8 : 4;
-	for (int b = 0; b < nbatch; b++) {
-		if (run_one(E, (char*)alm + (size_t)b*alm_bstride*E.asz, alm_cstride, (char*)map + (size_t)b*map_bstride*E.msz, map_cstride)) return 1;
-	}
-	if (mem == B2_MEM_HOST) B2_CHECK(cudaStreamSynchronize(E.st));
 	return 0;
+}
+
+extern "C" int b2_sht_execute_groups(b2_sht_plan *plan, int op, int ngroups, const int *spins, int mode, int dtype,
+	void *const *alm, const int64_t *alm_cstride, void *const *map, const int64_t *map_cstride, int mem, void *stream)
+{
+	B2_REQUIRE(plan && spins && alm && alm_cstride && map && map_cstride, "execute_groups: null argument");
+	B2_REQUIRE(op >= OP_SYNTH && op <= OP_ADJ_ANALYSIS, "execute_groups: bad operation");
+	return execute_groups(plan, op, ngroups, spins, mode, dtype, alm, alm_cstride, map, map_cstride, mem, stream);
 }
 
 extern "C" int b2_synthesis(b2_sht_plan *plan, int spin, int mode, int dtype, int nbatch,

@@ -19,7 +19,7 @@ enum { SK_C128, SK_C64, SK_HC128, SK_HC64, SK_F64, SK_F32 };
 
 struct AxisArgs {
 	FftDesc d;
-	int n, P, nl, nb, jfast, lk, sk, lstride;   // lstride: shared-memory elements per line
+	int n, P, nl, nb, jfast, lk, sk, lstride, twoff;   // lstride: shared-memory elements per line; twoff: twiddle tables
 	int64_t n_in, n_o1, n_o2;                    // lines are enumerated by (inner, outer1, outer2) indices
 	int64_t is_t, is_in, is_o1, is_o2;           // input strides in elements of the input type
 	int64_t os_t, os_in, os_o1, os_o2;
@@ -68,6 +68,8 @@ template<bool INV> __global__ void k_fft_axis(AxisArgs A)
 	const int nbv = (int)min((int64_t)nb, A.n_in - i0);
 	const int64_t bin = o1*A.is_o1 + o2*A.is_o2 + i0*A.is_in, bout = o1*A.os_o1 + o2*A.os_o2 + i0*A.os_in;
 	const int tot = nb*nl;
+	const double2 *twsm = s + A.twoff;
+	fft_load_tw(s + A.twoff, A.d, tid, T);
 	for (int idx = tid; idx < tot; idx += T) {
 		int line, j;
 		if (A.jfast) { line = idx/nl; j = idx - line*nl; } else { j = idx/nb; line = idx - j*nb; }
@@ -85,14 +87,14 @@ template<bool INV> __global__ void k_fft_axis(AxisArgs A)
 				if (p) acc = cmul(acc, cj(A.d.tw[j*p], INV));
 			}
 		}
-		s[line*ls + j] = acc;
+		s[line*ls + fft_pad(A.d, j)] = acc;
 	}
 	__syncthreads();
-	fft_smem<INV>(s, A.d, tid, T, nb);
+	fft_smem<INV>(s, A.d, tid, T, nb, twsm);
 	for (int idx = tid; idx < tot; idx += T) {
 		int line, kk;
 		if (A.jfast) { line = idx/nl; kk = idx - line*nl; } else { kk = idx/nb; line = idx - kk*nb; }
-		if (line < nbv) fft_st(A, bout + line*A.os_in, p + P*kk, s[line*ls + A.d.rev[kk]]);
+		if (line < nbv) fft_st(A, bout + line*A.os_in, p + P*kk, s[line*ls + fft_pad(A.d, A.d.rev[kk])]);
 	}
 }
 
@@ -121,7 +123,7 @@ static int setup_pass(AxisPass &ps, int axis, int n, bool can_batch)
 {
 	ps.axis = axis; ps.n = n;
 	int P = 1;
-	while ((size_t)FftTables::smem_len(n/P)*sizeof(double2) > FFT_SMEM_MAX) {
+	while ((size_t)(FftTables::smem_len(n/P) + n/FFT_TWLO + FFT_TWLO + 1)*sizeof(double2) > FFT_SMEM_MAX) {
 		int np = P + 1;
 		while (np <= 64 && n % np) np++;
 		B2_REQUIRE(np <= 64, "fft: a transform of length %d does not fit in shared memory (no usable split)", n);
@@ -130,7 +132,7 @@ static int setup_pass(AxisPass &ps, int axis, int n, bool can_batch)
 	ps.P = P; ps.nl = n/P;
 	if (ps.tab.build(ps.nl, n)) return 1;
 	ps.nb = 1;
-	if (can_batch && FftTables::smooth(ps.nl)) ps.nb = (int)std::max<size_t>(1, FFT_TILE_ELEMS/ps.nl);
+	if (can_batch && FftTables::smooth(ps.nl)) ps.nb = (int)std::max<size_t>(1, FFT_TILE_ELEMS/FftTables::smem_len(ps.nl));
 	return 0;
 }
 
@@ -196,8 +198,9 @@ static int run_pass(b2_fft_plan *p, AxisPass &ps, const int64_t *dims, const voi
 	A.os_t = ds[ps.axis]; A.os_in = sout[0]; A.os_o1 = sout[1]; A.os_o2 = sout[2];
 	A.jfast = (A.n_in == 1 || A.is_t <= A.is_in) ? 1 : 0;
 	A.nb = (int)std::min<int64_t>(ps.nb, A.n_in);
-	A.lstride = A.nb > 1 ? ps.nl : ps.tab.d.nsmem;
-	size_t smem = sizeof(double2)*(size_t)std::max(A.nb*ps.nl, ps.tab.d.nsmem);
+	A.lstride = ps.tab.d.nsmem;
+	A.twoff = A.nb*ps.tab.d.nsmem;
+	size_t smem = sizeof(double2)*(size_t)(A.twoff + ps.tab.twsm_len());
 	int threads = (int)std::min<int64_t>(512, std::max<int64_t>(64, b2_round_up((int64_t)A.nb*ps.nl/4, 32)));
 	int64_t ntile = (A.n_in + A.nb - 1)/A.nb;
 	int64_t nblk = ntile*A.n_o1*A.n_o2;

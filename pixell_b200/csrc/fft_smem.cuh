@@ -15,6 +15,7 @@
 
 #define FFT_MAX_FAC 20
 #define FFT_MAX_RADIX 64
+#define FFT_TWLO 128       // fine twiddle table: tw[0..128); coarse table: tw[128 i]
 
 struct FftDesc {
 	int n;                 // transform length seen by the caller
@@ -25,7 +26,12 @@ struct FftDesc {
 	int twmul;             // stride of w_nt in the twiddle table tw
 	int ntab;
 	const double2 *tw;     // tw[k] = exp(-2 pi i k / ntab), ntab a multiple of n (caller-visible table)
-	const int *rev;        // position of X[k] after fft_smem (identity for Bluestein)
+	const int *rev;        // position of X[k] after fft_smem (identity for Bluestein); apply fft_pad() to it
+	// fast path (all factors in {2,3,4,5,8,16}): register butterflies, padded shared memory, two-level
+	// twiddle tables in shared memory (no global loads inside the passes)
+	int fast;
+	int pad_shift;         // element i lives at s[i + (i >> pad_shift)] (31: no padding)
+	int ntw_hi;            // entries of the coarse twiddle table (ceil(ntab / FFT_TWLO))
 	// Bluestein only
 	int bluestein;
 	const double2 *btw;    // exp(-2 pi i k / M), k < M
@@ -41,8 +47,12 @@ struct FftTables {
 	int build(int n, int ntab);
 	static bool smooth(int64_t n);
 	static int bluestein_len(int n);
-	// shared-memory elements a transform of length n needs
-	static int64_t smem_len(int64_t n) { return smooth(n) ? n : bluestein_len((int)n); }
+	// shared-memory elements a transform of length n needs (padding included; twiddle tables not included)
+	static int64_t smem_len(int64_t n);
+	static bool fast_ok(int64_t n);
+	static int pad_shift_of(int64_t n);
+	// shared-memory elements of the twiddle tables of this plan (0 on the slow path)
+	int twsm_len() const { return d.fast ? d.ntw_hi + FFT_TWLO : 0; }
 	size_t bytes() const { return tw.bytes() + rev.bytes() + btw.bytes() + chirp.bytes() + bhat.bytes(); }
 };
 
@@ -140,11 +150,182 @@ template<bool INV, bool DIT> __device__ void fft_passes(double2 *s, int nt, int 
 	}
 }
 
+
+// ------------------------------------------------------------------------------------ fast path
+
+__device__ __forceinline__ int fft_pad(const FftDesc &d, int i) { return i + (i >> d.pad_shift); }
+
+// copy the two-level twiddle tables into shared memory (twsm: d.ntw_hi + FFT_TWLO elements); the caller
+// synchronises before the first fft_smem call
+__device__ __forceinline__ void fft_load_tw(double2 *twsm, const FftDesc &d, int tid, int nthreads)
+{
+	if (!d.fast) return;
+	for (int i = tid; i < d.ntw_hi; i += nthreads) twsm[i] = d.tw[i*FFT_TWLO];
+	for (int i = tid; i < FFT_TWLO; i += nthreads) twsm[d.ntw_hi + i] = d.tw[i < d.ntab ? i : 0];
+}
+
+// exp(-2 pi i e / ntab) (conjugated for INV) from the tables: one complex product
+template<bool INV> __device__ __forceinline__ double2 fft_tw(const double2 *twsm, int nhi, int e)
+{
+	double2 a = twsm[e >> 7], b = twsm[nhi + (e & (FFT_TWLO - 1))];
+	double2 w = make_double2(fma(a.x, b.x, -a.y*b.y), fma(a.x, b.y, a.y*b.x));
+	if (INV) w.y = -w.y;
+	return w;
+}
+
+template<bool INV> __device__ __forceinline__ void r4(double2 &a, double2 &b, double2 &c, double2 &d)
+{
+	double2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = mul_mi<INV>(csub(b, d));
+	a = cadd(t0, t2); b = cadd(t1, t3); c = csub(t0, t2); d = csub(t1, t3);
+}
+// multiply by exp(-+ 2 pi i k / 16), k = 1, 2, 3 (forward sign for INV = false)
+template<bool INV, int K> __device__ __forceinline__ double2 mul_w16(double2 a)
+{
+	const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+	double wr = K == 1 ? c1 : K == 2 ? h : s1, wi = K == 1 ? s1 : K == 2 ? h : c1;      // w = wr - i wi (forward)
+	if (INV) return make_double2(fma(a.x, wr, -a.y*wi), fma(a.y, wr, a.x*wi));
+	return make_double2(fma(a.x, wr, a.y*wi), fma(a.y, wr, -a.x*wi));
+}
+
+// in-register DFTs: natural order in, natural order out
+template<bool INV> __device__ __forceinline__ void dft8(double2 (&u)[8])
+{
+	r4<INV>(u[0], u[2], u[4], u[6]);      // even samples -> E[k], k = 0..3 in u[0], u[2], u[4], u[6]
+	r4<INV>(u[1], u[3], u[5], u[7]);      // odd samples  -> O[k]
+	u[3] = mul_w16<INV, 2>(u[3]);         // O[1] w8
+	u[5] = mul_mi<INV>(u[5]);             // O[2] w8^2 = -+i
+	u[7] = mul_mi<INV>(mul_w16<INV, 2>(u[7]));      // O[3] w8^3
+	double2 y[8];
+	#pragma unroll
+	for (int k = 0; k < 4; k++) { y[k] = cadd(u[2*k], u[2*k + 1]); y[k + 4] = csub(u[2*k], u[2*k + 1]); }
+	#pragma unroll
+	for (int k = 0; k < 8; k++) u[k] = y[k];
+}
+
+template<bool INV> __device__ __forceinline__ void dft16(double2 (&u)[16])
+{
+	// x[4 a + b]: DFT over a for each b, twiddle w16^(b k1), DFT over b; X[k1 + 4 k2]
+	#pragma unroll
+	for (int b = 0; b < 4; b++) r4<INV>(u[b], u[4 + b], u[8 + b], u[12 + b]);      // u[4 k1 + b] = T[b][k1]
+	u[5]  = mul_w16<INV, 1>(u[5]);  u[6]  = mul_w16<INV, 2>(u[6]);  u[7]  = mul_w16<INV, 3>(u[7]);
+	u[9]  = mul_w16<INV, 2>(u[9]);  u[10] = mul_mi<INV>(u[10]);     u[11] = mul_mi<INV>(mul_w16<INV, 2>(u[11]));
+	u[13] = mul_w16<INV, 3>(u[13]); u[14] = mul_mi<INV>(mul_w16<INV, 2>(u[14]));
+	{ double2 t = mul_w16<INV, 1>(u[15]); u[15] = make_double2(-t.x, -t.y); }      // w16^9 = -w16
+	double2 y[16];
+	#pragma unroll
+	for (int k1 = 0; k1 < 4; k1++) {
+		double2 a = u[4*k1], b = u[4*k1 + 1], c = u[4*k1 + 2], d = u[4*k1 + 3];
+		r4<INV>(a, b, c, d);
+		y[k1] = a; y[k1 + 4] = b; y[k1 + 8] = c; y[k1 + 12] = d;
+	}
+	#pragma unroll
+	for (int k = 0; k < 16; k++) u[k] = y[k];
+}
+
+template<bool INV> __device__ __forceinline__ void dft3(double2 (&u)[3])
+{
+	const double s3 = 0.86602540378443864676;
+	double2 t = cadd(u[1], u[2]), dd = csub(u[1], u[2]);
+	double2 a = make_double2(u[0].x - 0.5*t.x, u[0].y - 0.5*t.y), bb = cscale(mul_mi<INV>(dd), s3);
+	u[0] = cadd(u[0], t); u[1] = cadd(a, bb); u[2] = csub(a, bb);
+}
+
+template<bool INV> __device__ __forceinline__ void dft5(double2 (&u)[5])
+{
+	const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
+	const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
+	double2 a1 = cadd(u[1], u[4]), b1 = csub(u[1], u[4]), a2 = cadd(u[2], u[3]), b2 = csub(u[2], u[3]);
+	double2 e1 = make_double2(u[0].x + c1*a1.x + c2*a2.x, u[0].y + c1*a1.y + c2*a2.y);
+	double2 e2 = make_double2(u[0].x + c2*a1.x + c1*a2.x, u[0].y + c2*a1.y + c1*a2.y);
+	double2 o1 = mul_mi<INV>(make_double2(s1*b1.x + s2*b2.x, s1*b1.y + s2*b2.y));
+	double2 o2 = mul_mi<INV>(make_double2(s2*b1.x - s1*b2.x, s2*b1.y - s1*b2.y));
+	u[0] = make_double2(u[0].x + a1.x + a2.x, u[0].y + a1.y + a2.y);
+	u[1] = cadd(e1, o1); u[4] = csub(e1, o1); u[2] = cadd(e2, o2); u[3] = csub(e2, o2);
+}
+
+template<int R, bool INV> __device__ __forceinline__ void dft_small(double2 (&u)[R])
+{
+	if constexpr (R == 2) { double2 a = u[0]; u[0] = cadd(a, u[1]); u[1] = csub(a, u[1]); }
+	else if constexpr (R == 3) dft3<INV>(u);
+	else if constexpr (R == 4) r4<INV>(u[0], u[1], u[2], u[3]);
+	else if constexpr (R == 5) dft5<INV>(u);
+	else if constexpr (R == 8) dft8<INV>(u);
+	else dft16<INV>(u);
+}
+
+// one decimation-in-frequency pass of radix R over blocks of length Ls (all threads; ends with __syncthreads())
+template<int R, bool INV> __device__ __forceinline__ void fft_pass_fast(double2 *s, const FftDesc &d, int Ls,
+	int tid, int nthreads, int nbatch, const double2 *twsm)
+{
+	const int m = Ls/R, nbf = d.nt/R, total = nbf*nbatch, tws = d.twmul*(d.nt/Ls), nhi = d.ntw_hi;
+	for (int b = tid; b < total; b += nthreads) {
+		const int line = b/nbf, bb = b - line*nbf;
+		const int blk = bb/m, j = bb - blk*m;
+		double2 *S = s + (int64_t)line*d.nsmem;
+		const int base = blk*Ls + j;
+		double2 u[R];
+		#pragma unroll
+		for (int q = 0; q < R; q++) u[q] = S[fft_pad(d, base + q*m)];
+		dft_small<R, INV>(u);
+		if (j) {
+			// u[k] *= w^k, w = exp(-+ 2 pi i j / Ls); the powers are built by products of depth <= 4
+			double2 w1 = fft_tw<INV>(twsm, nhi, tws*j);
+			u[1] = cmul(u[1], w1);
+			if constexpr (R > 2) {
+				double2 w2 = cmul(w1, w1);
+				u[2] = cmul(u[2], w2);
+				if constexpr (R > 3) {
+					double2 w3 = cmul(w2, w1);
+					u[3] = cmul(u[3], w3);
+					if constexpr (R > 4) {
+						double2 w4 = cmul(w2, w2);
+						u[4] = cmul(u[4], w4);
+						if constexpr (R > 5) {
+							double2 w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+							u[5] = cmul(u[5], w5); u[6] = cmul(u[6], w6); u[7] = cmul(u[7], w7);
+							if constexpr (R > 8) {
+								double2 w8 = cmul(w4, w4);
+								u[8] = cmul(u[8], w8);
+								u[9] = cmul(u[9], cmul(w8, w1)); u[10] = cmul(u[10], cmul(w8, w2)); u[11] = cmul(u[11], cmul(w8, w3));
+								u[12] = cmul(u[12], cmul(w8, w4)); u[13] = cmul(u[13], cmul(w8, w5)); u[14] = cmul(u[14], cmul(w8, w6));
+								u[15] = cmul(u[15], cmul(w8, w7));
+							}
+						}
+					}
+				}
+			}
+		}
+		#pragma unroll
+		for (int q = 0; q < R; q++) S[fft_pad(d, base + q*m)] = u[q];
+	}
+	__syncthreads();
+}
+
+template<bool INV> __device__ void fft_fast(double2 *s, const FftDesc &d, int tid, int nthreads, int nbatch, const double2 *twsm)
+{
+	int Ls = d.nt;
+	for (int f = 0; f < d.nfac; f++) {
+		const int r = d.fac[f];
+		switch (r) {
+			case 2:  fft_pass_fast<2, INV>(s, d, Ls, tid, nthreads, nbatch, twsm); break;
+			case 3:  fft_pass_fast<3, INV>(s, d, Ls, tid, nthreads, nbatch, twsm); break;
+			case 4:  fft_pass_fast<4, INV>(s, d, Ls, tid, nthreads, nbatch, twsm); break;
+			case 5:  fft_pass_fast<5, INV>(s, d, Ls, tid, nthreads, nbatch, twsm); break;
+			case 8:  fft_pass_fast<8, INV>(s, d, Ls, tid, nthreads, nbatch, twsm); break;
+			default: fft_pass_fast<16, INV>(s, d, Ls, tid, nthreads, nbatch, twsm); break;
+		}
+		Ls /= r;
+	}
+}
+
 // In-place FFT of s[0..n) by all `nthreads` threads of the CTA (ends with __syncthreads()); the caller
 // must have synchronised after filling s and must provide d.nsmem elements per transform.
 // Result X[k] is at s[d.rev[k]].  nbatch > 1 (smooth lengths only): transforms back to back in s.
-template<bool INV> __device__ void fft_smem(double2 *s, const FftDesc &d, int tid, int nthreads, int nbatch = 1)
+// Fast plans (d.fast): element i of transform b lives at s[b*d.nsmem + fft_pad(d, i)] and twsm must point at the
+// twiddle tables filled by fft_load_tw; other plans ignore twsm and use no padding.
+template<bool INV> __device__ void fft_smem(double2 *s, const FftDesc &d, int tid, int nthreads, int nbatch = 1, const double2 *twsm = nullptr)
 {
+	if (d.fast) { fft_fast<INV>(s, d, tid, nthreads, nbatch, twsm); return; }
 	if (!d.bluestein) {
 		fft_passes<INV, false>(s, d.nt, d.nfac, d.fac, d.tw, d.twmul, d.ntab, tid, nthreads, nbatch);
 		return;

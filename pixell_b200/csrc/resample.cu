@@ -18,7 +18,7 @@
 
 struct ResampArgs {
 	FftDesc d;
-	int N, P, o2, n, L, nm, npc, spin;
+	int N, P, o2, n, L, nm, npc, spin, twoff;
 	int64_t nring_pad;
 	const int *src, *pos, *mir; const double *wfine; const double *mult;
 	double2 *leg, *A, *B;
@@ -54,6 +54,8 @@ template<int STAGE> __global__ void k_resamp(ResampArgs R)
 	double2 *ca, *cb; double sigma;
 	pair_cols(R, R.col0 + c, ca, cb, sigma);
 	double2 *A = R.A + (int64_t)c*N, *B = R.B + (int64_t)c*N;
+	const double2 *twsm = s + R.twoff;
+	fft_load_tw(s + R.twoff, R.d, tid, T);
 	for (int j = tid; j < Nl; j += T) {
 		double2 acc = make_double2(0, 0);
 		for (int q = 0; q < P; q++) {
@@ -68,14 +70,14 @@ template<int STAGE> __global__ void k_resamp(ResampArgs R)
 			acc = cadd(acc, v);
 		}
 		if (p) acc = cmul(acc, cj(R.d.tw[2*j*p], INV));
-		s[j] = acc;
+		s[fft_pad(R.d, j)] = acc;
 	}
 	__syncthreads();
-	fft_smem<INV>(s, R.d, tid, T);
+	fft_smem<INV>(s, R.d, tid, T, 1, twsm);
 	const double inv = 1.0/N;
 	for (int kk = tid; kk < Nl; kk += T) {
 		const int k = p + P*kk;
-		double2 x = s[R.d.rev[kk]];
+		double2 x = s[fft_pad(R.d, R.d.rev[kk])];
 		const int f = (2*k <= N) ? k : k - N;
 		const bool nyq = (2*k == N);
 		if (STAGE == 1) {
@@ -150,13 +152,14 @@ int ThetaResampler::build(const std::string &g, int ntheta, int64_t nphi_, int l
 		if (mir[k] == pos[k]) mu[k] = 1.0; else sr[mir[k]] = k | 0x40000000;
 	}
 	P = 1;
-	while ((size_t)FftTables::smem_len(N/P)*sizeof(double2) > 200*1024) {
+	while ((size_t)(FftTables::smem_len(N/P) + 2*N/FFT_TWLO + FFT_TWLO + 1)*sizeof(double2) > 210*1024) {
 		int np = P*2;
 		B2_REQUIRE(np <= 8 && N % np == 0, "theta transform of length %d does not fit in shared memory", N);
 		P = np;
 	}
 	if (tab.build(N/P, 2*N)) return 1;
-	smem = sizeof(double2)*(size_t)FftTables::smem_len(N/P);
+	twoff = (int)FftTables::smem_len(N/P);
+	smem = sizeof(double2)*(size_t)(twoff + tab.twsm_len());
 	threads = (int)std::min<int64_t>(512, std::max<int64_t>(64, b2_round_up(N/P/4, 32)));
 	if (src.upload(sr) || mult.upload(mu) || wfine.alloc(2*(size_t)N) || dpos.upload(pos) || dmir.upload(mir)) return 1;
 	k_wfine<<<(N + 128)/128, 128>>>(wfine.p, N, 4.0*M_PI/(2.0*N)/(double)nphi);
@@ -178,7 +181,7 @@ template<int STAGE> static int launch_stage(const ResampArgs &R, int ncols, int 
 int ThetaResampler::apply(double2 *leg, int ncomp, int spin, cudaStream_t st)
 {
 	ResampArgs R;
-	R.d = tab.d; R.N = N; R.P = P; R.o2 = o2; R.n = n; R.L = lmax; R.nm = nm; R.npc = npc; R.spin = spin;
+	R.d = tab.d; R.twoff = twoff; R.N = N; R.P = P; R.o2 = o2; R.n = n; R.L = lmax; R.nm = nm; R.npc = npc; R.spin = spin;
 	R.nring_pad = nring_pad; R.src = src.p; R.pos = dpos.p; R.mir = dmir.p; R.wfine = wfine.p; R.mult = mult.p;
 	R.leg = leg; R.A = A.p; R.B = B.p;
 	int64_t ncol = (int64_t)ncomp*npc;

@@ -19,7 +19,7 @@ struct ThetaResampler {
 	DevBuf<double> mult;       // [n] 2 (interior ring) or 1 (pole ring)
 	DevBuf<double2> A, B;      // scratch [cb][N]
 	int64_t cb = 0;            // column pairs per batch
-	int threads = 256; size_t smem = 0;
+	int threads = 256; size_t smem = 0; int twoff = 0;
 	static bool needed(const std::string &geom, int ntheta, int lmax);
 	int build(const std::string &geom, int ntheta, int64_t nphi, int lmax, int mmax, int64_t nring_pad);
 	// in place on leg[ncomp][nm][nring_pad]

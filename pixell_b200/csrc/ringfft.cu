@@ -61,6 +61,49 @@ static void factorize(int n, int *fac, int &nfac)
 	for (int p = 2; p <= FFT_MAX_RADIX; p++) while (rem % p == 0) { fac[nfac++] = p; rem /= p; }
 }
 
+bool FftTables::fast_ok(int64_t n)
+{
+	if (n < 2) return false;
+	while (n % 2 == 0) n /= 2;
+	while (n % 3 == 0) n /= 3;
+	while (n % 5 == 0) n /= 5;
+	return n == 1;
+}
+
+// fast path: odd radices first (long strides), then a leftover 2 or 4, then 16s, then 8s; the last radix sets the padding
+static void factorize_fast(int n, int *fac, int &nfac)
+{
+	nfac = 0;
+	int rem = n, a = 0;
+	while (rem % 5 == 0) { fac[nfac++] = 5; rem /= 5; }
+	while (rem % 3 == 0) { fac[nfac++] = 3; rem /= 3; }
+	while (rem % 2 == 0) { a++; rem /= 2; }
+	if (a == 1) fac[nfac++] = 2;
+	else if (a == 2) fac[nfac++] = 4;
+	else if (a == 5) { fac[nfac++] = 4; fac[nfac++] = 8; }
+	else if (a > 0) {
+		int y = 0;
+		while ((a - 3*y) % 4 != 0) y++;
+		for (int i = 0; i < (a - 3*y)/4; i++) fac[nfac++] = 16;
+		for (int i = 0; i < y; i++) fac[nfac++] = 8;
+	}
+}
+
+int FftTables::pad_shift_of(int64_t n)
+{
+	if (!fast_ok(n)) return 31;
+	int fac[FFT_MAX_FAC], nfac;
+	factorize_fast((int)n, fac, nfac);
+	int last = fac[nfac - 1];
+	return last == 16 ? 4 : last == 8 ? 3 : last == 4 ? 2 : 31;
+}
+
+int64_t FftTables::smem_len(int64_t n)
+{
+	if (fast_ok(n)) return n + (n >> pad_shift_of(n));
+	return smooth(n) ? n : bluestein_len((int)n);
+}
+
 static std::vector<int> digit_reversal(int n, const int *fac, int nfac)
 {
 	std::vector<int> rv(n);
@@ -88,6 +131,15 @@ int FftTables::build(int n, int ntab)
 	d.n = n; d.ntab = ntab; d.twmul = ntab/n;
 	if (tw.upload(twiddles(ntab))) return 1;
 	d.tw = tw.p;
+	d.fast = 0; d.pad_shift = 31; d.ntw_hi = 0;
+	if (fast_ok(n)) {
+		d.bluestein = 0; d.nt = n; d.fast = 1;
+		factorize_fast(n, d.fac, d.nfac);
+		d.pad_shift = pad_shift_of(n); d.nsmem = (int)smem_len(n); d.ntw_hi = (ntab + FFT_TWLO - 1)/FFT_TWLO;
+		if (rev.upload(digit_reversal(n, d.fac, d.nfac))) return 1;
+		d.rev = rev.p; d.btw = nullptr; d.chirp = nullptr; d.bhat = nullptr;
+		return 0;
+	}
 	if (smooth(n)) {
 		d.bluestein = 0; d.nt = n; d.nsmem = n;
 		factorize(n, d.fac, d.nfac);
@@ -135,9 +187,10 @@ int RingFft::build(int64_t nphi_, double phi0, int xdir_, int64_t npix_, int nri
 	B2_REQUIRE(nphi >= 1 && npix >= 1 && npix <= nphi, "bad ring description: nphi=%lld npix=%lld", (long long)nphi, (long long)npix);
 	half = (nphi % 2 == 0) ? 1 : 0;
 	nfft = (int)(half ? nphi/2 : nphi);
-	smem = sizeof(double2)*(size_t)std::max<int64_t>(nfft + 1, FftTables::smem_len(nfft));
-	B2_REQUIRE(smem <= 227*1024, "nphi=%lld needs %zu bytes of shared memory per ring (limit 227 KB)", (long long)nphi, smem);
 	if (tab.build(nfft, (int)nphi)) return 1;
+	twoff = (int)FftTables::smem_len(nfft) + 1;      // data (one extra element for the packed real transform), then twiddle tables
+	smem = sizeof(double2)*(size_t)(twoff + tab.twsm_len());
+	B2_REQUIRE(smem <= 227*1024, "nphi=%lld needs %zu bytes of shared memory per ring (limit 227 KB)", (long long)nphi, smem);
 	if (phase.alloc(mmax + 1)) return 1;
 	k_phase<<<(mmax + 128)/128, 128>>>(phase.p, mmax, phi0);
 	B2_LAUNCH_CHECK();
@@ -153,7 +206,7 @@ int RingFft::build(int64_t nphi_, double phi0, int xdir_, int64_t npix_, int nri
 
 struct RingArgs {
 	FftDesc d;
-	int half, nfft, mmax, xdir, nring;
+	int half, nfft, mmax, xdir, nring, twoff;
 	int64_t nphi, npix, nring_pad;
 	const double2 *phase; const int64_t *ringstart; const double *weight;
 	double2 *leg; void *map; int64_t map_cstride;
@@ -173,6 +226,9 @@ template<typename MapT> __global__ void k_leg2map(RingArgs A)
 	const double2 *legc = A.leg + ((int64_t)comp*(A.mmax + 1))*A.nring_pad + ring;
 	MapT *row = (MapT*)A.map + (int64_t)comp*A.map_cstride + A.ringstart[ring];
 	const int n = (int)A.nphi, nf = A.nfft, mmax = A.mmax;
+	#define SI(i) fft_pad(A.d, (i))
+	const double2 *twsm = s + A.twoff;
+	fft_load_tw(s + A.twoff, A.d, tid, T);
 	if (A.half) {
 		// half spectrum X[0..nf] of the real ring, |m| aliased mod nphi
 		for (int k = tid; k <= nf; k += T) {
@@ -183,26 +239,26 @@ template<typename MapT> __global__ void k_leg2map(RingArgs A)
 				for (int m = k; m <= mmax; m += n) acc = cadd(acc, leg_phase(A, legc, m));
 				for (int m = n - k; m <= mmax; m += n) acc = cadd(acc, cconj(leg_phase(A, legc, m)));
 			}
-			s[k] = acc;
+			s[SI(k)] = acc;
 		}
 		__syncthreads();
 		// Z[k] = (X[k] + conj X[nf-k]) + i e^{+2 pi i k/n} (X[k] - conj X[nf-k]); z = IFFT(Z) packs (x_2j, x_2j+1)
 		for (int k = tid; 2*k <= nf; k += T) {
-			if (k == 0) { double x0 = s[0].x, xn = s[nf].x; s[0] = make_double2(x0 + xn, x0 - xn); }
+			if (k == 0) { double x0 = s[0].x, xn = s[SI(nf)].x; s[0] = make_double2(x0 + xn, x0 - xn); }
 			else {
 				int kk = nf - k;
-				double2 a = s[k], b = s[kk];
+				double2 a = s[SI(k)], b = s[SI(kk)];
 				double2 s1 = make_double2(a.x + b.x, a.y - b.y), d1 = make_double2(a.x - b.x, a.y + b.y);
 				double2 w = A.d.tw[k]; w.y = -w.y;
 				double2 wd = cmul(w, d1);
-				s[k] = make_double2(s1.x - wd.y, s1.y + wd.x);
-				if (kk != k) s[kk] = make_double2(s1.x + wd.y, -s1.y + wd.x);
+				s[SI(k)] = make_double2(s1.x - wd.y, s1.y + wd.x);
+				if (kk != k) s[SI(kk)] = make_double2(s1.x + wd.y, -s1.y + wd.x);
 			}
 		}
 		__syncthreads();
-		fft_smem<true>(s, A.d, tid, T);
+		fft_smem<true>(s, A.d, tid, T, 1, twsm);
 		for (int64_t i = tid; i < A.npix; i += T) {
-			double2 z = s[A.d.rev[i >> 1]];
+			double2 z = s[SI(A.d.rev[i >> 1])];
 			row[i] = (MapT)((i & 1) ? z.y : z.x);
 		}
 	} else {
@@ -210,11 +266,11 @@ template<typename MapT> __global__ void k_leg2map(RingArgs A)
 			double2 acc = make_double2(0, 0);
 			for (int m = k; m <= mmax; m += n) { double2 g = leg_phase(A, legc, m); if (m == 0) g.y = 0; acc = cadd(acc, g); }
 			for (int m = (k == 0 ? n : n - k); m <= mmax; m += n) acc = cadd(acc, cconj(leg_phase(A, legc, m)));
-			s[k] = acc;
+			s[SI(k)] = acc;
 		}
 		__syncthreads();
-		fft_smem<true>(s, A.d, tid, T);
-		for (int64_t i = tid; i < A.npix; i += T) row[i] = (MapT)s[A.d.rev[i]].x;
+		fft_smem<true>(s, A.d, tid, T, 1, twsm);
+		for (int64_t i = tid; i < A.npix; i += T) row[i] = (MapT)s[SI(A.d.rev[i])].x;
 	}
 }
 
@@ -226,18 +282,20 @@ template<typename MapT> __global__ void k_map2leg(RingArgs A)
 	const MapT *row = (const MapT*)A.map + (int64_t)comp*A.map_cstride + A.ringstart[ring];
 	const int n = (int)A.nphi, nf = A.nfft, mmax = A.mmax;
 	const double wgt = A.weight ? A.weight[ring] : 1.0;
+	const double2 *twsm = s + A.twoff;
+	fft_load_tw(s + A.twoff, A.d, tid, T);
 	if (A.half) {
 		for (int j = tid; j < nf; j += T) {
 			int64_t i = 2*(int64_t)j;
 			double a = i < A.npix ? (double)row[i] : 0.0, b = i + 1 < A.npix ? (double)row[i + 1] : 0.0;
-			s[j] = make_double2(a, b);
+			s[SI(j)] = make_double2(a, b);
 		}
 		__syncthreads();
-		fft_smem<false>(s, A.d, tid, T);
+		fft_smem<false>(s, A.d, tid, T, 1, twsm);
 		for (int m = tid; m <= mmax; m += T) {
 			int k = m % n; bool fold = k > nf; if (fold) k = n - k;
 			int k1 = k == nf ? 0 : k, k2 = k == 0 ? 0 : nf - k;
-			double2 zk = s[A.d.rev[k1]], zc = cconj(s[A.d.rev[k2]]);
+			double2 zk = s[SI(A.d.rev[k1])], zc = cconj(s[SI(A.d.rev[k2])]);
 			double2 e = make_double2(0.5*(zk.x + zc.x), 0.5*(zk.y + zc.y));
 			double2 dd = make_double2(0.5*(zk.x - zc.x), 0.5*(zk.y - zc.y));
 			double2 o = make_double2(dd.y, -dd.x);
@@ -247,11 +305,11 @@ template<typename MapT> __global__ void k_map2leg(RingArgs A)
 			legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, A.phase[m]), wgt);
 		}
 	} else {
-		for (int j = tid; j < n; j += T) s[j] = make_double2(j < A.npix ? (double)row[j] : 0.0, 0.0);
+		for (int j = tid; j < n; j += T) s[SI(j)] = make_double2(j < A.npix ? (double)row[j] : 0.0, 0.0);
 		__syncthreads();
-		fft_smem<false>(s, A.d, tid, T);
+		fft_smem<false>(s, A.d, tid, T, 1, twsm);
 		for (int m = tid; m <= mmax; m += T) {
-			double2 x = s[A.d.rev[m % n]];
+			double2 x = s[SI(A.d.rev[m % n])];
 			if (A.xdir < 0) x.y = -x.y;
 			legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, A.phase[m]), wgt);
 		}
@@ -263,7 +321,7 @@ template<typename MapT> __global__ void k_map2leg(RingArgs A)
 static RingArgs ring_args(const RingFft &F, const double2 *leg, int64_t nring_pad, const void *map, int64_t map_cstride, int use_weight)
 {
 	RingArgs A;
-	A.d = F.tab.d; A.half = F.half; A.nfft = F.nfft; A.mmax = F.mmax; A.xdir = F.xdir; A.nring = F.nring;
+	A.d = F.tab.d; A.twoff = F.twoff; A.half = F.half; A.nfft = F.nfft; A.mmax = F.mmax; A.xdir = F.xdir; A.nring = F.nring;
 	A.nphi = F.nphi; A.npix = F.npix; A.nring_pad = nring_pad;
 	A.phase = F.phase.p; A.ringstart = F.ringstart.p; A.weight = (use_weight && F.weight.n) ? F.weight.p : nullptr;
 	A.leg = (double2*)leg; A.map = (void*)map; A.map_cstride = map_cstride;

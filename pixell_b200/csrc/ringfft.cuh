@@ -16,6 +16,7 @@ struct RingFft {
 	DevBuf<double> weight;  // empty: no weights
 	int threads = 256;
 	size_t smem = 0;
+	int twoff = 0;          // offset (elements) of the twiddle tables inside the dynamic shared memory
 	int build(int64_t nphi, double phi0, int xdir, int64_t npix, int nring, const int64_t *ringstart,
 	          const double *weight, int mmax);
 	size_t bytes() const { return tab.bytes() + phase.bytes() + ringstart.bytes() + weight.bytes(); }
