@@ -92,12 +92,24 @@ int b2_analysis_2d(b2_sht_plan *plan, int spin, int dtype, int nbatch,
 int b2_adjoint_analysis_2d(b2_sht_plan *plan, int spin, int dtype, int nbatch,
                  const void *alm, int64_t alm_cstride, int64_t alm_bstride,
                  void *map, int64_t map_cstride, int64_t map_bstride, int mem, void *stream);
+/* Several spin groups of one map (e.g. T with spin 0 and Q,U with spin 2: what pixell's curvedsky loops over at
+ * curvedsky.py:922, 1064) in one call.  op: 0 synthesis, 1 adjoint_synthesis, 2 analysis_2d, 3 adjoint_analysis_2d.
+ * Group g transforms alm[g] (component stride alm_cstride[g]) <-> map[g] (component stride map_cstride[g]) with
+ * spin spins[g].  With B2_MEM_HOST the groups are pipelined over three streams: the host-to-device copies of
+ * group g+1 and the device-to-host copies of group g-1 overlap the kernels of group g (pinned host memory is
+ * needed for the overlap, not for correctness).  At most 8 groups. */
+int b2_sht_execute_groups(b2_sht_plan *plan, int op, int ngroups, const int *spins, int mode, int dtype,
+                 void *const *alm, const int64_t *alm_cstride, void *const *map, const int64_t *map_cstride,
+                 int mem, void *stream);
 /* per-stage device times (ms) of the last transform executed on this plan:
  * out[0] = Legendre, out[1] = ring FFT, out[2] = theta resampling, out[3] = staging copies */
 int b2_sht_last_timing(b2_sht_plan *plan, double out[4]);
 /* test hooks: run only the Legendre stage on device-resident leg[ncomp][mmax+1][nring] (ring order = plan order) */
 int b2_alm2leg(b2_sht_plan *plan, int spin, int mode, const void *alm_dev, int64_t alm_cstride, void *leg_dev, void *stream);
 int b2_leg2alm(b2_sht_plan *plan, int spin, int mode, void *alm_dev, int64_t alm_cstride, const void *leg_dev, void *stream);
+/* test hook: the theta-weighting operator of analysis_2d (adjoint = 0) or its conjugate transpose (adjoint = 1) alone,
+ * in place on device-resident leg[ncomp][mmax+1][nring_pad] (nring_pad = rings rounded up to a multiple of 32) */
+int b2_theta_weighting(b2_sht_plan *plan, int spin, int ncomp, int adjoint, void *leg_dev, void *stream);
 /* tuning hook: choose the kernel variant (launch shape) of Legendre kernel `which` (0 synth spin 0, 1 adjoint spin 0,
  * 2 synth spin>0, 3 adjoint spin>0); results are identical across variants */
 int b2_set_leg_variant(int which, int variant);

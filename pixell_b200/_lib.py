@@ -32,9 +32,11 @@ _PROTOS = {
 	"b2_adjoint_synthesis": ([c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_vp], c_int),
 	"b2_analysis_2d": ([c_vp, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_vp], c_int),
 	"b2_adjoint_analysis_2d": ([c_vp, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_vp], c_int),
+	"b2_sht_execute_groups": ([c_vp, c_int, c_int, _intp, c_int, c_int, ctypes.POINTER(c_vp), _i64p, ctypes.POINTER(c_vp), _i64p, c_int, c_vp], c_int),
 	"b2_sht_last_timing": ([c_vp, _dblp], c_int),
 	"b2_alm2leg": ([c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_vp], c_int),
 	"b2_leg2alm": ([c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_vp], c_int),
+	"b2_theta_weighting": ([c_vp, c_int, c_int, c_int, c_vp, c_vp], c_int),
 	"b2_set_leg_variant": ([c_int, c_int], c_int),
 	"b2_gridweights": ([c_cp, c_int, _dblp], c_int),
 	"b2_alm2cl": ([c_int, c_int, _i64p, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp], c_int),

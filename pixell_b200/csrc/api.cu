@@ -113,7 +113,14 @@ extern "C" int b2_gridweights(const char *geometry, int ntheta, double *out)
 
 // ------------------------------------------------------------------------------------ plans
 
-b2_sht_plan::~b2_sht_plan() { for (auto &e : ev) if (e) cudaEventDestroy(e); }
+b2_sht_plan::~b2_sht_plan()
+{
+	for (auto &e : ev) if (e) cudaEventDestroy(e);
+	for (auto &e : gev) if (e) cudaEventDestroy(e);
+	if (s_in) cudaStreamDestroy(s_in);
+	if (s_out) cudaStreamDestroy(s_out);
+	if (s_comp) cudaStreamDestroy(s_comp);
+}
 
 size_t b2_sht_plan::bytes() const
 {
@@ -344,7 +351,14 @@ static int group_compute(Exec &E, GroupCtx &G)
 	if (to_map) {
 		if (leg_alm2leg(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st)) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[2], E.st));
-		if (E.op == OP_ADJ_ANALYSIS) { b2_set_error("adjoint_analysis_2d is not implemented yet"); return 1; }
+		if (E.op == OP_ADJ_ANALYSIS) {
+			if (p->resamp) { if (p->resamp->apply(p->leg.p, E.ncm, E.spin, E.st, true)) return 1; }
+			else {
+				int64_t nrow = (int64_t)E.ncm*(p->mmax + 1);
+				k_scale_rows<<<(unsigned)((nrow*p->geom.nring_pad + 255)/256), 256, 0, E.st>>>(p->leg.p, p->w2d.p, p->nring, p->geom.nring_pad, nrow);
+				B2_LAUNCH_CHECK();
+			}
+		}
 		B2_CHECK(cudaEventRecord(p->ev[3], E.st));
 		if (ring_leg2map(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.st)) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[4], E.st));
@@ -522,6 +536,13 @@ extern "C" int b2_alm2leg(b2_sht_plan *p, int spin, int mode, const void *alm_de
 	LegTables *T = p->get_tables(spin); if (!T) return 1;
 	AlmLayout L; L.lmax = p->lmax; L.mmax = p->mmax; L.mstart_d = p->mstart.p; L.lstride = p->lstride;
 	return leg_alm2leg(*T, p->geom, L, mode == B2_MODE_DERIV1, (const double2*)alm_dev, acs, (double2*)leg_dev, (cudaStream_t)stream);
+}
+
+extern "C" int b2_theta_weighting(b2_sht_plan *p, int spin, int ncomp, int adjoint, void *leg_dev, void *stream)
+{
+	B2_REQUIRE(p && leg_dev, "theta_weighting: null argument");
+	B2_REQUIRE(p->resamp, "theta_weighting: this plan integrates with plain ring weights");
+	return p->resamp->apply((double2*)leg_dev, ncomp, spin, (cudaStream_t)stream, adjoint != 0);
 }
 
 extern "C" int b2_leg2alm(b2_sht_plan *p, int spin, int mode, void *alm_dev, int64_t acs, const void *leg_dev, void *stream)

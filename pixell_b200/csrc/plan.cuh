@@ -7,6 +7,8 @@
 #include <memory>
 #include <string>
 
+#define B2_MAX_GROUPS 8
+
 struct b2_sht_plan {
 	int lmax = 0, mmax = 0;
 	int64_t lstride = 1;
@@ -32,6 +34,9 @@ struct b2_sht_plan {
 	// staging for host-memory calls
 	DevBuf<char> stage_alm, stage_map;
 	cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+	// host-memory calls are pipelined over three streams (copies in, kernels, copies out)
+	cudaStream_t s_in = nullptr, s_out = nullptr, s_comp = nullptr;
+	cudaEvent_t gev[2*B2_MAX_GROUPS] = {};      // per group: operands on the device, results ready
 	double timing[4] = {0, 0, 0, 0};
 	LegTables *get_tables(int spin);
 	size_t bytes() const;

@@ -18,11 +18,13 @@ struct ThetaResampler {
 	DevBuf<double> wfine;      // [2N] quadrature weight function on the fine circle / nphi
 	DevBuf<double> mult;       // [n] 2 (interior ring) or 1 (pole ring)
 	DevBuf<double2> A, B;      // scratch [cb][N]
+	DevBuf<double2> C;         // third scratch array, allocated by the first adjoint call
 	int64_t cb = 0;            // column pairs per batch
 	int threads = 256; size_t smem = 0; int twoff = 0;
+	int M0 = 0;                // the mirror image of ring r sits in circle slot M0 - r
 	static bool needed(const std::string &geom, int ntheta, int lmax);
 	int build(const std::string &geom, int ntheta, int64_t nphi, int lmax, int mmax, int64_t nring_pad);
-	// in place on leg[ncomp][nm][nring_pad]
-	int apply(double2 *leg, int ncomp, int spin, cudaStream_t st);
-	size_t bytes() const { return tab.bytes() + src.bytes() + dpos.bytes() + dmir.bytes() + wfine.bytes() + mult.bytes() + A.bytes() + B.bytes(); }
+	// in place on leg[ncomp][nm][nring_pad]; adjoint = true applies the conjugate-transposed operator (adjoint_analysis_2d)
+	int apply(double2 *leg, int ncomp, int spin, cudaStream_t st, bool adjoint = false);
+	size_t bytes() const { return tab.bytes() + src.bytes() + dpos.bytes() + dmir.bytes() + wfine.bytes() + mult.bytes() + A.bytes() + B.bytes() + C.bytes(); }
 };

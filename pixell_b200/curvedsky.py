@@ -216,7 +216,7 @@ def _plan_kwargs(shape, wcs, minfo, method, ainfo, lmax, mmax, weights=None):
 	if method == "2d":
 		dg = minfo.ducc_geo
 		return dict(kind="2d", geometry=dg.name, phi0=minfo.phi0_user, flip_y=minfo.flip[0], flip_x=minfo.flip[1],
-			lmax=lmax, mmax=mmax, mstart=np.asarray(ainfo.mstart)[:mmax+1], lstride=ainfo.stride)
+			lmax=lmax, mmax=mmax, mstart=np.asarray(ainfo.mstart)[:mmax+1], lstride=ainfo.stride, ntheta=shape[-2], nphi=shape[-1])
 	ri = get_ring_info(shape, wcs, minfo)
 	return dict(kind="rings", theta=ri.theta, nphi=ri.nphi, phi0=ri.phi0, ringstart=ri.offsets, xdir=ri.xdir, npix=ri.npix,
 		lmax=lmax, mmax=mmax, mstart=np.asarray(ainfo.mstart)[:mmax+1], lstride=ainfo.stride, weight=weights)
@@ -232,6 +232,22 @@ def _synth(pk, alm, map, spin, mode="STANDARD", adjoint=False):
 		flat = map.reshape(map.shape[0], -1)
 		if adjoint: sht.adjoint_synthesis(map=flat, alm=alm, spin=spin, mode=mode, weight=pk.get("weight"), **kw)
 		else:       sht.synthesis(alm=alm, map=flat, spin=spin, mode=mode, **kw)
+
+def _plan_of(pk):
+	if pk["kind"] == "2d":
+		return sht.plan_2d(pk["geometry"], pk["ntheta"], pk["nphi"], pk["phi0"], pk["lmax"], pk["mmax"], pk["mstart"], pk["lstride"], pk["flip_y"], pk["flip_x"])
+	return sht.plan_rings(pk["theta"], pk["nphi"], pk["phi0"], pk["ringstart"], pk["lmax"], pk["mmax"], pk["mstart"], pk["lstride"],
+		pk.get("weight"), pk["xdir"], pk["npix"])
+
+def _grouped(pk, op, groups, alm2, map3):
+	"""All spin groups of one [ncomp, nalm] / [ncomp, ny, nx] pair in a single engine call when no copies are
+	needed (the usual case): lets the engine overlap host<->device copies of one group with the kernels of the
+	next.  Returns False when the arrays need the per-group path."""
+	if len(groups) < 2 or len(groups) > 8: return False
+	sa, sm = L.strides_elems(alm2), L.strides_elems(map3)
+	if sa[-1] != 1 or sm[-1] != 1 or sm[-2] != map3.shape[-1]: return False
+	sht.run_groups(_plan_of(pk), op, groups, alm2, map3)
+	return True
 
 def _check_method(method, minfo, shape):
 	if method == "general": raise NotImplementedError("pixell_b200 implements the '2d' and 'cyl' methods only (cylindrical maps)")
@@ -320,7 +336,9 @@ def map2alm(map, alm=None, lmax=None, spin=[0,2], deriv=False, adjoint=False, co
 		pk = _plan_kwargs(map.shape, wcs, minfo, "2d", ainfo, lm, mm)
 		kw = {k: pk[k] for k in ("geometry", "phi0", "flip_y", "flip_x", "lmax", "mmax", "mstart", "lstride")}
 		for I in np.ndindex(*map_full.shape[:-3]):
-			for s, j1, j2 in spin_helper(spin, alm_full.shape[-2]):
+			groups = list(spin_helper(spin, alm_full.shape[-2]))
+			if _grouped(pk, "adjoint_analysis_2d" if adjoint else "analysis_2d", groups, alm_full[I], map_full[I]): continue
+			for s, j1, j2 in groups:
 				a, acopied = _comp_block(alm_full[I], j1, j2, 1)
 				m, mcopied = _comp_block(map_full[I], j1, j2, 2)
 				if adjoint:

@@ -118,6 +118,25 @@ def _run(fn, plan, spin, mode, alm, map, nmapdim, has_mode=True):
 	args = [plan.handle, int(spin)] + ([mode] if has_mode else []) + [dtype, 1, pa, acs, 0, pm, mcs, 0, mema, stream]
 	L.check(fn(*args))
 
+OPS = {"synthesis": 0, "adjoint_synthesis": 1, "analysis_2d": 2, "adjoint_analysis_2d": 3}
+
+def run_groups(plan, op, groups, alm, map, mode=L.MODE_STANDARD):
+	"""Several spin groups of one component-stacked alm [ncomp, nalm] / map [ncomp, ...] pair in one engine call
+	(b2_sht_execute_groups): groups = [(spin, j1, j2), ...] as enmap.spin_helper yields them.  Host arrays are
+	pipelined (copies of one group overlap the kernels of the next).  The caller guarantees contiguous trailing axes."""
+	pa, mema, dta = L.buffer_info(alm); pm, memm, dtm = L.buffer_info(map)
+	if mema != memm: raise ValueError("alm and map must both be host arrays or both be CUDA tensors")
+	if dta == np.complex128 and dtm == np.float64: dtype = L.F64
+	elif dta == np.complex64 and dtm == np.float32: dtype = L.F32
+	else: raise ValueError("alm/map dtypes must be (complex128, float64) or (complex64, float32), got (%s, %s)" % (dta, dtm))
+	acs, mcs = L.strides_elems(alm)[0], L.strides_elems(map)[0]
+	n = len(groups)
+	spins = (ctypes.c_int*n)(*[int(g[0]) for g in groups])
+	alms = (ctypes.c_void_p*n)(*[int(pa) + int(g[1])*int(acs)*int(dta.itemsize) for g in groups])
+	maps = (ctypes.c_void_p*n)(*[int(pm) + int(g[1])*int(mcs)*int(dtm.itemsize) for g in groups])
+	a_cs = (ctypes.c_int64*n)(*[int(acs)]*n); m_cs = (ctypes.c_int64*n)(*[int(mcs)]*n)
+	L.check(L.lib().b2_sht_execute_groups(plan.handle, OPS[op], n, spins, mode, dtype, alms, a_cs, maps, m_cs, mema, L.current_stream(map)))
+
 def _alm_len(mstart, lmax, lstride): return int(np.max(mstart) + lmax*lstride + 1)
 
 # ------------------------------------------------------------------ ducc0.sht.experimental look-alikes

@@ -217,3 +217,100 @@ def test_analysis_2d_split_theta_transform(sht, spin):
 	m = sht.synthesis_2d(alm=alm, ntheta=ny, nphi=nx, **kw)
 	back = sht.analysis_2d(map=m, **kw)
 	assert relerr(back, alm) < 1e-11
+
+@pytest.mark.parametrize("spin", [0, 1, 2])
+@pytest.mark.parametrize("name,ny,nx,lmax,mmax", [c for c in CASES_2D if c[3] <= so.maxlmax(c[0], c[1])])
+def test_adjoint_analysis_2d(sht, spin, name, ny, nx, lmax, mmax):
+	"""adjoint_analysis_2d (pixell/curvedsky.py:1032) as the exact transpose of analysis_2d:
+	<analysis(m), a> = <m, adjoint_analysis(a)> with the real inner products pixell's adjointness test uses
+	(reference tests/test_pixell.py test_adjointness).  On grids that need the theta weighting the operator is
+	only pinned on band-limited maps, so the oracle comparison is restricted to the other grids."""
+	nc = 1 if spin == 0 else 2
+	alm, ai = rand_alm(lmax, nc, 21, spin, mmax)
+	alm[:, ~used_mask(ai, spin)] = 0
+	kw = dict(spin=spin, lmax=lmax, mmax=mmax, mstart=ai.mstart, geometry=name, phi0=0.4)
+	got = sht.adjoint_analysis_2d(alm=alm, ntheta=ny, nphi=nx, **kw)
+	if not so._needs_resample(name, ny, lmax):
+		want = so.adjoint_analysis_2d(alm=alm, ntheta=ny, nphi=nx, **kw)
+		assert relerr(got, want) < 1e-11
+	rng = np.random.default_rng(22)
+	m = rng.standard_normal((nc, ny, nx))
+	a2 = sht.analysis_2d(map=m, **kw)
+	wgt = np.full(ai.nelem, 2.0); wgt[ai.mstart[0] + np.arange(lmax+1)] = 1.0      # m > 0 stands for +-m
+	lhs = np.sum(wgt*(a2.real*alm.real + a2.imag*alm.imag))
+	rhs = np.sum(m*got)
+	assert abs(lhs-rhs) < 1e-10*max(abs(lhs), abs(rhs), 1.0)
+
+def test_adjoint_analysis_2d_split(sht):
+	"""the adjoint theta operator with its transforms split over two CTAs (see test_analysis_2d_split_theta_transform)"""
+	ny, nx, lmax, mmax, spin = 6500, 64, 6400, 24, 2
+	alm, ai = rand_alm(lmax, 2, 23, spin, mmax)
+	alm[:, ~used_mask(ai, spin)] = 0
+	kw = dict(spin=spin, lmax=lmax, mmax=mmax, mstart=ai.mstart, geometry="F1", phi0=0.0)
+	got = sht.adjoint_analysis_2d(alm=alm, ntheta=ny, nphi=nx, **kw)
+	rng = np.random.default_rng(24)
+	m = rng.standard_normal((2, ny, nx))
+	a2 = sht.analysis_2d(map=m, **kw)
+	wgt = np.full(ai.nelem, 2.0); wgt[ai.mstart[0] + np.arange(lmax+1)] = 1.0
+	lhs = np.sum(wgt*(a2.real*alm.real + a2.imag*alm.imag)); rhs = np.sum(m*got)
+	assert abs(lhs-rhs) < 1e-9*max(abs(lhs), abs(rhs), 1.0)
+
+def _theta_model(g, n, L):
+	"""numpy restatement of the theta-weighting operator K on one column pair:
+	returns (fwd, adj) acting on (xa, xb, sigma)"""
+	if g == "CC": N = 2*(n-1); o2 = 0; pos = np.arange(n); mir = (N-np.arange(n)) % N
+	elif g == "F1": N = 2*n; o2 = 1; pos = np.arange(n); mir = N-1-np.arange(n)
+	else: N = 2*n-1; o2 = 1; pos = np.arange(n); mir = N-1-np.arange(n)          # MW
+	mult = np.where(mir == pos, 1.0, 2.0); nm = mir != pos
+	j = np.arange(1, N//2+1); c = np.where(2*j == N, 1.0, 2.0)
+	wf = np.array([1-np.sum(c*np.cos(2*j*t*np.pi/N)/(4.0*j*j-1)) for t in range(N+1)])
+	w = np.zeros(2*N); w[:N+1] = wf; w[N+1:] = wf[1:N][::-1]
+	k = np.arange(N); f = np.where(2*k <= N, k, k-N); nyq = 2*k == N
+	D = np.exp(1j*np.pi*f/N); LP = (np.abs(f) <= L) & ~nyq
+	Wo = w[(2*k+o2) % (2*N)]; Wh = w[(2*k+o2+1) % (2*N)]
+	def fwd(xa, xb, sig):
+		z = np.zeros(N, complex); z[pos] = np.where(nm, xa+xb, xa if sig > 0 else xb); z[mir[nm]] = sig*(xa-xb)[nm]
+		A = np.where(nyq, 0, D*np.fft.fft(z)/N)
+		B = Wh*(np.fft.ifft(A)*N)
+		A3 = np.where(LP, np.fft.fft(Wo*z)/N, 0)
+		A4 = np.where(LP, 0.5*(A3+np.fft.fft(B)/N/D), A3)
+		gz = np.fft.ifft(A4)*N
+		return mult*(gz[pos]+sig*gz[mir]), mult*(gz[pos]-sig*gz[mir])
+	def adj(ya, yb, sig):
+		wv = np.zeros(N, complex)
+		np.add.at(wv, pos, mult*(ya+yb)); np.add.at(wv, mir[nm], (mult*sig*(ya-yb))[nm])
+		wv[pos[~nm]] += (sig*(ya-yb))[~nm]
+		A = np.where(LP, 0.5*np.fft.fft(wv), 0)
+		B = Wh*np.fft.ifft(D*A)
+		C = np.where(nyq, 0, np.fft.fft(B)/D/N)
+		u = np.fft.ifft(C)*N + Wo*np.fft.ifft(A)
+		return np.where(nm, u[pos]+sig*u[mir], u[pos] if sig > 0 else 0), np.where(nm, u[pos]-sig*u[mir], 0 if sig > 0 else u[pos])
+	return fwd, adj, (4*np.pi/(2*N))
+
+@pytest.mark.parametrize("name,n,L", [("F1", 32, 30), ("CC", 33, 30), ("MW", 31, 30), ("CC", 258, 256)])
+@pytest.mark.parametrize("spin", [0, 1])
+def test_theta_weighting_operator(sht, name, n, L, spin):
+	"""the K5 kernels alone (test hook b2_theta_weighting) against a numpy restatement, forward and adjoint, on
+	arbitrary (not band-limited) columns"""
+	import torch, ctypes
+	from pixell_b200 import _lib as Lb
+	nphi = 2*L+2
+	plan = sht.plan_2d(name, n, nphi, 0.0, L)
+	nm, npad = L+1, (n+31)//32*32
+	rng = np.random.default_rng(31)
+	x = rng.standard_normal((1, nm, n)) + 1j*rng.standard_normal((1, nm, n))
+	fwd, adj, scale = _theta_model(name, n, L)
+	for adjoint, op in ((0, fwd), (1, adj)):
+		leg = torch.zeros((1, nm, npad), dtype=torch.complex128, device="cuda")
+		leg[:, :, :n] = torch.from_numpy(x).cuda()
+		Lb.check(Lb.lib().b2_theta_weighting(plan.handle, spin, 1, adjoint, leg.data_ptr(), None))
+		got = leg.cpu().numpy()[0, :, :n]
+		want = np.zeros_like(got)
+		for i in range((nm+1)//2):
+			sig = -1.0 if (2*i+spin) & 1 else 1.0
+			xb = x[0, 2*i+1] if 2*i+1 < nm else np.zeros(n, complex)
+			ya, yb = op(x[0, 2*i], xb, sig)
+			want[2*i] = ya
+			if 2*i+1 < nm: want[2*i+1] = yb
+		want *= scale/nphi
+		assert relerr(got, want) < 1e-12, (name, adjoint)
