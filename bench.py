@@ -105,7 +105,16 @@ def run_ours(args, w):
 	if not torch.cuda.is_available(): raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
 	torch.cuda.set_device(local)
 	device = torch.device("cuda", local)
-	if world > 1: dist.init_process_group("nccl", device_id=device)
+	if world > 1:
+		# NCCL may print its version banner on stdout when the communicator is created: keep stdout to the one JSON line
+		sys.stdout.flush()
+		saved = os.dup(1); os.dup2(2, 1)
+		try:
+			dist.init_process_group("nccl", device_id=device)
+			dist.barrier()
+			torch.cuda.synchronize()
+		finally:
+			sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
 	from pixell_b200 import curvedsky, _lib as L, sht
 	L.init(local)
 	alm0, map, wcs, ainfo, spin = make_inputs(w, 3+rank, torch, device)
@@ -246,7 +255,15 @@ def cpu_pair_seconds(w, mstride, ring_frac_rows):
 	t_fft = (time.perf_counter()-t0)*ny/nr
 	return t_leg + t_fft, dict(t_legendre_est=t_leg, t_fft_est=t_fft, m_fraction=float(frac_m), rings=nr)
 
+def use_all_host_cores():
+	"""torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core.  Must run before the
+	oracle's OpenMP runtime is loaded."""
+	n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+	os.environ["OMP_NUM_THREADS"] = str(n)
+	return n
+
 def cpu_baseline(w, budget_s=20.0):
+	use_all_host_cores()
 	from oracle import sht_oracle as so
 	so.build()
 	cores = so.nthreads()
@@ -266,6 +283,7 @@ def cpu_baseline(w, budget_s=20.0):
 def run_reference(args, w):
 	rank = int(os.environ.get("RANK", 0))
 	if rank != 0: return
+	use_all_host_cores()
 	cb = None
 	vals = []
 	for i in range(args.warmup + args.steps):

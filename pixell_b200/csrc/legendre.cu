@@ -19,10 +19,10 @@
 #include <cmath>
 #include <cstdlib>
 
-#define B2_DEF_SYNTH0 4
-#define B2_DEF_ADJ0 2
-#define B2_DEF_SYNTH2 5
-#define B2_DEF_ADJ2 7
+#define B2_DEF_SYNTH0 0
+#define B2_DEF_ADJ0 0
+#define B2_DEF_SYNTH2 0
+#define B2_DEF_ADJ2 0
 
 #define BIGV   0x1p256
 #define SMALLV 0x1p-512
@@ -434,7 +434,7 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 	constexpr int NV = 2*W, NOUT = 2*TL;
 	constexpr int NT = NW*32, NH = (NOUT + NT - 1)/NT;
 	__shared__ double tiles[2][TL];
-	__shared__ double red[2][NW][NOUT];
+	__shared__ __align__(16) double red[2][NW][NOUT];
 	__shared__ __align__(16) double olds[NOUT], alvs[NOUT];      // running sums and alpha_l of the tile's outputs (cp.async)
 	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, l0 = m;
@@ -470,8 +470,11 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 		if (!cta_or<NW>(anyuse)) continue;
 		// recurrence coefficients of a tile travel global -> shared with cp.async, one tile ahead
 		auto issue = [&](int tile, int buf) {
-			int i = tile*TL + tid;
-			if (tid < TL) { if (i < nl) cp_async8(&tiles[buf][tid], &ta[i]); else tiles[buf][tid] = 0.0; }
+			#pragma unroll
+			for (int t = tid; t < TL; t += NT) {
+				int i = tile*TL + t;
+				if (i < nl) cp_async8(&tiles[buf][t], &ta[i]); else tiles[buf][t] = 0.0;
+			}
 			cp_async_commit();
 		};
 		issue(0, 0); cp_async_wait_all();
@@ -481,12 +484,24 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 			if (tile + 1 < ntile) issue(tile + 1, buf ^ 1);
 			const int nwin = (min(TL, nl - tile*TL) + W - 1)/W;
 			// output threads fetch the running sum early (cp.async) so the read-modify-write latency hides behind the tile
-			#pragma unroll
-			for (int h = 0; h < NH; h++) {
-				int e = tid + h*NT, i = tile*TL + (e >> 1);
-				if (e < NOUT && i < nl) {
-					cp_async8(&alvs[e], &tal[i]);
-					if (!first) cp_async8(&olds[e], &almr[2*(int64_t)(l0 + i)*A.lstride + (e & 1)]);
+			if constexpr (NW == 1) {
+				// one l per lane: a_lm as one 16-byte access
+				#pragma unroll
+				for (int h = 0; h < TL/32; h++) {
+					int o = lane + 32*h, i = tile*TL + o;
+					if (i < nl) {
+						cp_async8(&alvs[o], &tal[i]);
+						if (!first) cp_async16(&olds[2*o], &almr[2*(int64_t)(l0 + i)*A.lstride]);
+					}
+				}
+			} else {
+				#pragma unroll
+				for (int h = 0; h < NH; h++) {
+					int e = tid + h*NT, i = tile*TL + (e >> 1);
+					if (e < NOUT && i < nl) {
+						cp_async8(&alvs[e], &tal[i]);
+						if (!first) cp_async8(&olds[e], &almr[2*(int64_t)(l0 + i)*A.lstride + (e & 1)]);
+					}
 				}
 			}
 			cp_async_commit();
@@ -514,14 +529,27 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 			}
 			cp_async_wait_all();
 			cta_sync<NW>();
-			#pragma unroll
-			for (int h = 0; h < NH; h++) {
-				int e = tid + h*NT, i = tile*TL + (e >> 1);
-				if (e < NOUT && i < nl) {
-					double s = 0;
-					#pragma unroll
-					for (int w = 0; w < NW; w++) s += red[buf][w][e];
-					almr[2*(int64_t)(l0 + i)*A.lstride + (e & 1)] = (first ? 0.0 : olds[e]) + s*alvs[e];
+			if constexpr (NW == 1) {
+				#pragma unroll
+				for (int h = 0; h < TL/32; h++) {
+					int o = lane + 32*h, i = tile*TL + o;
+					if (i < nl) {
+						double2 c = *(const double2*)&red[buf][0][2*o];
+						double2 old = first ? make_double2(0, 0) : *(const double2*)&olds[2*o];
+						double al = alvs[o];
+						*(double2*)&almr[2*(int64_t)(l0 + i)*A.lstride] = make_double2(fma(c.x, al, old.x), fma(c.y, al, old.y));
+					}
+				}
+			} else {
+				#pragma unroll
+				for (int h = 0; h < NH; h++) {
+					int e = tid + h*NT, i = tile*TL + (e >> 1);
+					if (e < NOUT && i < nl) {
+						double s = 0;
+						#pragma unroll
+						for (int w = 0; w < NW; w++) s += red[buf][w][e];
+						almr[2*(int64_t)(l0 + i)*A.lstride + (e & 1)] = (first ? 0.0 : olds[e]) + s*alvs[e];
+					}
 				}
 			}
 		}
@@ -727,7 +755,7 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 	constexpr int NV = 4*W, NOUT = 4*TL;
 	constexpr int NT = NW*32, NH = (NOUT + NT - 1)/NT;
 	__shared__ __align__(16) TileAB tiles[2][TL];
-	__shared__ double red[2][NW][NOUT];
+	__shared__ __align__(16) double red[2][NW][NOUT];
 	__shared__ __align__(16) double olds[NOUT], alvs[NOUT];      // running sums and alpha_l of the tile's outputs (cp.async)
 	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, s = A.spin, l0 = m > s ? m : s;
@@ -785,15 +813,17 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 		int phase = 0;
 		if (!cta_or<NW>(anyuse)) continue;
 		auto issue = [&](int tile, int buf) {
-			int i = tile*TL + tid;
-			if (tid < TL) {
-				if (i < nl) { cp_async8(&tiles[buf][tid].a, &ta[i]); cp_async8(&tiles[buf][tid].b, &tb[i]); }
-				else tiles[buf][tid].a = tiles[buf][tid].b = 0;
+			#pragma unroll
+			for (int t = tid; t < TL; t += NT) {
+				int i = tile*TL + t;
+				if (i < nl) { cp_async8(&tiles[buf][t].a, &ta[i]); cp_async8(&tiles[buf][t].b, &tb[i]); }
+				else tiles[buf][t].a = tiles[buf][t].b = 0;
 			}
 			cp_async_commit();
 		};
-		auto finish = [&](int buf) {      // the issuing thread completes its entry: (a, b, a, -b)
-			if (tid < TL) { TileAB &t = tiles[buf][tid]; t.a2 = t.a; t.nb = -t.b; }
+		auto finish = [&](int buf) {      // the issuing thread completes its entries: (a, b, a, -b)
+			#pragma unroll
+			for (int t = tid; t < TL; t += NT) { TileAB &e = tiles[buf][t]; e.a2 = e.a; e.nb = -e.b; }
 		};
 		issue(0, 0); cp_async_wait_all(); finish(0);
 		cta_sync<NW>();
@@ -802,13 +832,29 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 			if (tile + 1 < ntile) issue(tile + 1, buf ^ 1);
 			const int nwin = (min(TL, nl - tile*TL) + W - 1)/W;
 			// output threads: element e -> (l offset e >> 2, component e & 3); fetch the running sum early (cp.async)
-			#pragma unroll
-			for (int h = 0; h < NH; h++) {
-				int e = tid + h*NT, i = tile*TL + (e >> 2), k = e & 3;
-				if (e < NOUT && i < nl) {
-					cp_async8(&alvs[e], &tal[i]);
-					int64_t idx = 2*(ms + (int64_t)(l0 + i)*A.lstride) + (k & 1);
-					if (!first && !(A.deriv1 && k >= 2)) cp_async8(&olds[e], &(k < 2 ? alme : almb)[idx]);
+			if constexpr (NW == 1) {
+				// one l per lane: E_lm and B_lm as one 16-byte access each
+				#pragma unroll
+				for (int h = 0; h < TL/32; h++) {
+					int o = lane + 32*h, i = tile*TL + o;
+					if (i < nl) {
+						cp_async8(&alvs[o], &tal[i]);
+						if (!first) {
+							int64_t idx = ms + (int64_t)(l0 + i)*A.lstride;
+							cp_async16(&olds[4*o], &A.alm0[idx]);
+							if (!A.deriv1) cp_async16(&olds[4*o + 2], &A.alm1[idx]);
+						}
+					}
+				}
+			} else {
+				#pragma unroll
+				for (int h = 0; h < NH; h++) {
+					int e = tid + h*NT, i = tile*TL + (e >> 2), k = e & 3;
+					if (e < NOUT && i < nl) {
+						cp_async8(&alvs[e], &tal[i]);
+						int64_t idx = 2*(ms + (int64_t)(l0 + i)*A.lstride) + (k & 1);
+						if (!first && !(A.deriv1 && k >= 2)) cp_async8(&olds[e], &(k < 2 ? alme : almb)[idx]);
+					}
 				}
 			}
 			cp_async_commit();
@@ -839,6 +885,28 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 			cp_async_wait_all();
 			if (tile + 1 < ntile) finish(buf ^ 1);
 			cta_sync<NW>();
+			if constexpr (NW == 1) {
+				#pragma unroll
+				for (int h = 0; h < TL/32; h++) {
+					int o = lane + 32*h, i = tile*TL + o;
+					if (i < nl) {
+						const int l = l0 + i;
+						const double2 c01 = *(const double2*)&red[buf][0][4*o], c23 = *(const double2*)&red[buf][0][4*o + 2];
+						const double hh = 0.5*alvs[o];
+						// E = -(A+ + A-)/2, B = (i/2)(A+ - A-)
+						double2 E = make_double2(-hh*(c01.x + c23.x), -hh*(c01.y + c23.y));
+						double2 Bv = make_double2(-hh*(c01.y - c23.y), hh*(c01.x - c23.x));
+						int64_t idx = ms + (int64_t)l*A.lstride;
+						if (A.deriv1) { double f = sqrt((double)l*(l + 1.0)); E.x *= f; E.y *= f; }
+						if (!first) { double2 oe = *(const double2*)&olds[4*o]; E.x += oe.x; E.y += oe.y; }
+						A.alm0[idx] = E;
+						if (!A.deriv1) {
+							if (!first) { double2 ob = *(const double2*)&olds[4*o + 2]; Bv.x += ob.x; Bv.y += ob.y; }
+							A.alm1[idx] = Bv;
+						}
+					}
+				}
+			} else {
 			#pragma unroll
 			for (int h = 0; h < NH; h++) {
 				int e = tid + h*NT, i = tile*TL + (e >> 2), k = e & 3;
@@ -861,311 +929,11 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 					else (k < 2 ? alme : almb)[idx] = oldv + val;
 				}
 			}
+			}
 		}
 		first = false;
 	}
 	if (first) for (int i = tid; i < nl; i += NW*32) {
-		int64_t idx = 2*(ms + (int64_t)(l0 + i)*A.lstride);
-		alme[idx] = alme[idx + 1] = 0;
-		if (!A.deriv1) almb[idx] = almb[idx + 1] = 0;
-	}
-}
-
-// ------------------------------------------------------------------------------------ systolic adjoint
-//
-// One warp per m, lanes = ring pairs as before, but the lanes run SKEWED in l: at step t lane k works on
-// l = l0 + t - k.  The partial sum of one l then travels lane 0 -> 31 through shfl_up, every lane adding
-// its rings with the same DFMAs it would use anyway (the running sum is the accumulator input), and leaves
-// lane 31 complete.  Compared with the butterfly kernels above: no DADDs, no selects and no reduction
-// phase whose latency would leave the FP64 pipe idle -- only one 64-bit shuffle per output value and step.
-//   * fill: lane k must reach its start values at step k.  While l < l0 the coefficient ring buffer holds
-//     zeros, for which the recurrence (G, G') -> (-G', G) is a quarter turn; lane k starts from the start
-//     pair turned back by k quarter turns, so no lane needs a mask.  Sums of l outside [l0, lmax] are
-//     never stored.
-//   * the alternating sign sigma_l and the even/odd input sets depend on the parity of t - k: folded into
-//     each lane's ring inputs once per round.
-//   * outputs lag by up to 31 steps: tile T's sums are complete at the end of tile T + 1.
-
-#define SYS_RB 128      // coefficient ring buffer entries (>= 96, power of two)
-
-// spin 0.  in[r][par][c]: par = parity of (step index j inside an even-aligned window), c = re/im
-template<int MODE, int R, int W> __device__ __forceinline__ void adj0_sys_window(const double *ring, int t0, int lane,
-	const double (&x)[R], double (&g)[R], double (&gp)[R], int (&sc)[R], const double (&in)[R][2][2],
-	double (&S)[2], double *red)
-{
-	#pragma unroll
-	for (int j = 0; j < W; j++) {
-		const int li = t0 + j - lane;                    // this lane's l index (relative to l0)
-		const double a = ring[(li + 32) & (SYS_RB - 1)];
-		if (MODE != 0) {
-			double s0 = __shfl_up_sync(0xffffffffu, S[0], 1), s1 = __shfl_up_sync(0xffffffffu, S[1], 1);
-			if (lane == 0) { s0 = 0; s1 = 0; }
-			#pragma unroll
-			for (int r = 0; r < R; r++) {
-				double gv = (MODE == 1) ? (sc[r] == 0 ? g[r] : 0.0) : g[r];
-				s0 = fma(gv, in[r][j & 1][0], s0);
-				s1 = fma(gv, in[r][j & 1][1], s1);
-			}
-			S[0] = s0; S[1] = s1;
-		}
-		if (lane == 31 && li >= 0) *(double2*)&red[((li >> 5) & 1)*64 + (li & 31)*2] = make_double2(S[0], S[1]);
-		#pragma unroll
-		for (int r = 0; r < R; r++) {
-			double ng = fma(a*x[r], g[r], -gp[r]);
-			gp[r] = g[r]; g[r] = ng;
-		}
-	}
-	if (MODE != 2) {
-		#pragma unroll
-		for (int r = 0; r < R; r++) rescale(g[r], gp[r], sc[r]);
-	}
-}
-
-template<int R, int MINB, int W> __global__ void __launch_bounds__(32, MINB) k_adj0_sys(LegArgs A)
-{
-	__shared__ __align__(16) double ring[SYS_RB];
-	__shared__ __align__(16) double red[2*64];
-	__shared__ __align__(16) double olds[64], alvs[64];
-	const int m = blockIdx.x, lane = threadIdx.x;
-	const int lmax = A.lmax, l0 = m;
-	const int nl = lmax - l0 + 1, ntt = (nl + 31)/32 + 1;
-	const double *ta = A.ta + A.toff[m], *tal = A.talpha + A.toff[m];
-	double *almr = (double*)(A.alm0 + A.mstart[m]);
-	const SeqConst sc0 = seq_const(m, 0, lmax, A.pref);
-	const int nchunk = A.npair_pad/(32*R);
-	const double2 *leg = A.leg0 + (int64_t)m*A.leg_mstride;
-	bool first = true;
-	const int chunk0 = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R);
-
-	for (int chunk = chunk0; chunk < nchunk; chunk++) {
-		double x[R], g[R], gp[R], in[R][2][2]; int sc[R];
-		bool anyuse = false, use[R];
-		#pragma unroll
-		for (int r = 0; r < R; r++) {
-			PairInfo pi = A.pairs[(chunk*R + r)*32 + lane];
-			double dummy; int dsc;
-			use[r] = init_pair(pi, sc0, m, 0, lmax, x[r], dummy, dsc, g[r], sc[r]);
-			// start pair turned back by `lane` quarter turns (see above)
-			double g0 = g[r];
-			g[r]  = (lane & 1) ? 0.0 : ((lane & 2) ? -g0 : g0);
-			gp[r] = (lane & 1) ? ((lane & 2) ? g0 : -g0) : 0.0;
-			double2 gn = make_double2(0, 0), gs = make_double2(0, 0);
-			if (use[r]) { gn = leg[pi.rn]; if (pi.rs >= 0) gs = leg[pi.rs]; }
-			// set 0 serves even steps: l - l0 even for even lanes (N + S), odd for odd lanes (N - S)
-			const double sg = (lane & 1) ? -1.0 : 1.0;
-			in[r][0][0] = gn.x + sg*gs.x; in[r][0][1] = gn.y + sg*gs.y;
-			in[r][1][0] = gn.x - sg*gs.x; in[r][1][1] = gn.y - sg*gs.y;
-			anyuse |= use[r];
-		}
-		if (!__any_sync(0xffffffffu, anyuse)) continue;
-		int phase = 0;
-		double S[2] = {0, 0};
-		// ring buffer: entries of l index [-32, 32) now, one 32-block ahead inside the loop
-		auto issue = [&](int blk) {      // l indices [32 blk, 32 blk + 32)
-			int i = 32*blk + lane;
-			double *dst = &ring[(i + 32) & (SYS_RB - 1)];
-			if (i >= 0 && i < nl) cp_async8(dst, &ta[i]); else *dst = 0.0;
-		};
-		issue(-1); issue(0); cp_async_commit(); cp_async_wait_all();
-		__syncwarp();
-		for (int tt = 0; tt < ntt; tt++) {
-			issue(tt + 1);
-			// running sums and alpha of the tile that completes during this iteration (tile tt - 1)
-			if (tt >= 1) {
-				#pragma unroll
-				for (int h = 0; h < 2; h++) {
-					int e = lane + 32*h, i = (tt - 1)*32 + (e >> 1);
-					if (i < nl) {
-						cp_async8(&alvs[e], &tal[i]);
-						if (!first) cp_async8(&olds[e], &almr[2*(int64_t)(l0 + i)*A.lstride + (e & 1)]);
-					}
-				}
-			}
-			cp_async_commit();
-			#pragma unroll 1
-			for (int w = 0; w < 32/W; w++) {
-				if (phase < 2) {
-					bool mylive = true, anylive = false;
-					#pragma unroll
-					for (int r = 0; r < R; r++) { mylive &= (sc[r] == 0); anylive |= (sc[r] == 0 && use[r]); }
-					phase = __all_sync(0xffffffffu, mylive) ? 2 : __any_sync(0xffffffffu, anylive) ? 1 : 0;
-				}
-				const int t0 = tt*32 + w*W;
-				if (phase == 2) adj0_sys_window<2, R, W>(ring, t0, lane, x, g, gp, sc, in, S, red);
-				else if (phase == 1) adj0_sys_window<1, R, W>(ring, t0, lane, x, g, gp, sc, in, S, red);
-				else adj0_sys_window<0, R, W>(ring, t0, lane, x, g, gp, sc, in, S, red);
-			}
-			cp_async_wait_all();
-			__syncwarp();
-			if (tt >= 1) {
-				const double *rd = &red[((tt - 1) & 1)*64];
-				#pragma unroll
-				for (int h = 0; h < 2; h++) {
-					int e = lane + 32*h, i = (tt - 1)*32 + (e >> 1);
-					if (i < nl) almr[2*(int64_t)(l0 + i)*A.lstride + (e & 1)] = (first ? 0.0 : olds[e]) + rd[e]*alvs[e];
-				}
-			}
-			__syncwarp();
-		}
-		first = false;
-	}
-	if (first) for (int i = lane; i < nl; i += 32) { double *o = almr + 2*(int64_t)(l0 + i)*A.lstride; o[0] = 0; o[1] = 0; }
-}
-
-// spin > 0.  zin as in adj2_window, with the south entries [4..7] multiplied by (-1)^lane
-template<int MODE, int R, int W> __device__ __forceinline__ void adj2_sys_window(const double2 *ring, int t0, int lane,
-	const double (&x)[R], double (&p)[R], double (&pp)[R], double (&q)[R], double (&qp)[R],
-	int (&sp)[R], int (&sq)[R], const double (&zin)[R][8], double (&S)[4], double *red)
-{
-	#pragma unroll
-	for (int j = 0; j < W; j++) {
-		const int li = t0 + j - lane;
-		const double2 ab = ring[(li + 32) & (SYS_RB - 1)];
-		if (MODE != 0) {
-			double s[4];
-			#pragma unroll
-			for (int k = 0; k < 4; k++) { s[k] = __shfl_up_sync(0xffffffffu, S[k], 1); if (lane == 0) s[k] = 0; }
-			#pragma unroll
-			for (int r = 0; r < R; r++) {
-				double pv = (MODE == 1) ? (sp[r] == 0 ? p[r] : 0.0) : p[r];
-				double qv = (MODE == 1) ? (sq[r] == 0 ? q[r] : 0.0) : q[r];
-				double ps = (j & 1) ? -pv : pv, qs = (j & 1) ? -qv : qv;
-				s[0] = fma(pv, zin[r][0], fma(qs, zin[r][4], s[0]));
-				s[1] = fma(pv, zin[r][1], fma(qs, zin[r][5], s[1]));
-				s[2] = fma(qv, zin[r][2], fma(ps, zin[r][6], s[2]));
-				s[3] = fma(qv, zin[r][3], fma(ps, zin[r][7], s[3]));
-			}
-			#pragma unroll
-			for (int k = 0; k < 4; k++) S[k] = s[k];
-		}
-		if (lane == 31 && li >= 0) {
-			double2 *o = (double2*)&red[((li >> 5) & 1)*128 + (li & 31)*4];
-			o[0] = make_double2(S[0], S[1]); o[1] = make_double2(S[2], S[3]);
-		}
-		#pragma unroll
-		for (int r = 0; r < R; r++) {
-			double np = fma(fma(ab.x, x[r],  ab.y), p[r], -pp[r]);
-			double nq = fma(fma(ab.x, x[r], -ab.y), q[r], -qp[r]);
-			pp[r] = p[r]; p[r] = np; qp[r] = q[r]; q[r] = nq;
-		}
-	}
-	if (MODE != 2) {
-		#pragma unroll
-		for (int r = 0; r < R; r++) { rescale(p[r], pp[r], sp[r]); rescale(q[r], qp[r], sq[r]); }
-	}
-}
-
-template<int R, int MINB, int W> __global__ void __launch_bounds__(32, MINB) k_adj2_sys(LegArgs A)
-{
-	__shared__ __align__(16) double2 ring[SYS_RB];
-	__shared__ __align__(16) double red[2*128];
-	__shared__ __align__(16) double olds[128], alvs[128];
-	const int m = blockIdx.x, lane = threadIdx.x;
-	const int lmax = A.lmax, s = A.spin, l0 = m > s ? m : s;
-	double *alme = (double*)A.alm0, *almb = (double*)A.alm1;
-	const int64_t ms = A.mstart[m];
-	for (int l = m + lane; l < l0 && l <= lmax; l += 32) {      // l < spin entries of the triangle are zero by definition
-		int64_t idx = 2*(ms + (int64_t)l*A.lstride);
-		alme[idx] = alme[idx + 1] = 0;
-		if (!A.deriv1) almb[idx] = almb[idx + 1] = 0;
-	}
-	if (l0 > lmax) return;
-	const int nl = lmax - l0 + 1, ntt = (nl + 31)/32 + 1;
-	const double *ta = A.ta + A.toff[m], *tb = A.tb + A.toff[m], *tal = A.talpha + A.toff[m];
-	const SeqConst sc0 = seq_const(m, s, lmax, A.pref);
-	const double sigma0 = ((l0 + m + s) & 1) ? -1.0 : 1.0;
-	const double2 *legq = A.leg0 + (int64_t)m*A.leg_mstride, *legu = A.leg1 + (int64_t)m*A.leg_mstride;
-	const int nchunk = A.npair_pad/(32*R);
-	bool first = true;
-	const int chunk0 = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R);
-
-	for (int chunk = chunk0; chunk < nchunk; chunk++) {
-		double x[R], p[R], pp[R], q[R], qp[R], zin[R][8]; int sp[R], sq[R];
-		bool anyuse = false, use[R];
-		#pragma unroll
-		for (int r = 0; r < R; r++) {
-			PairInfo pi = A.pairs[(chunk*R + r)*32 + lane];
-			use[r] = init_pair(pi, sc0, m, s, lmax, x[r], p[r], sp[r], q[r], sq[r]);
-			double p0 = p[r], q0 = q[r];
-			p[r]  = (lane & 1) ? 0.0 : ((lane & 2) ? -p0 : p0);
-			pp[r] = (lane & 1) ? ((lane & 2) ? p0 : -p0) : 0.0;
-			q[r]  = (lane & 1) ? 0.0 : ((lane & 2) ? -q0 : q0);
-			qp[r] = (lane & 1) ? ((lane & 2) ? q0 : -q0) : 0.0;
-			double2 qn = make_double2(0, 0), un = qn, qs = qn, us = qn;
-			if (use[r]) { qn = legq[pi.rn]; un = legu[pi.rn]; if (pi.rs >= 0) { qs = legq[pi.rs]; us = legu[pi.rs]; } }
-			const double sg = (lane & 1) ? -sigma0 : sigma0;      // sigma of this lane's l at even steps
-			zin[r][0] = qn.x - un.y; zin[r][1] = qn.y + un.x; zin[r][2] = qn.x + un.y; zin[r][3] = qn.y - un.x;
-			zin[r][4] = sg*(qs.x - us.y); zin[r][5] = sg*(qs.y + us.x);
-			zin[r][6] = sg*(qs.x + us.y); zin[r][7] = sg*(qs.y - us.x);
-			anyuse |= use[r];
-		}
-		if (!__any_sync(0xffffffffu, anyuse)) continue;
-		int phase = 0;
-		double S[4] = {0, 0, 0, 0};
-		auto issue = [&](int blk) {
-			int i = 32*blk + lane;
-			double2 *dst = &ring[(i + 32) & (SYS_RB - 1)];
-			if (i >= 0 && i < nl) { cp_async8(&dst->x, &ta[i]); cp_async8(&dst->y, &tb[i]); } else *dst = make_double2(0, 0);
-		};
-		issue(-1); issue(0); cp_async_commit(); cp_async_wait_all();
-		__syncwarp();
-		for (int tt = 0; tt < ntt; tt++) {
-			issue(tt + 1);
-			if (tt >= 1) {
-				#pragma unroll
-				for (int h = 0; h < 4; h++) {
-					int e = lane + 32*h, i = (tt - 1)*32 + (e >> 2), k = e & 3;
-					if (i < nl) {
-						cp_async8(&alvs[e], &tal[i]);
-						int64_t idx = 2*(ms + (int64_t)(l0 + i)*A.lstride) + (k & 1);
-						if (!first && !(A.deriv1 && k >= 2)) cp_async8(&olds[e], &(k < 2 ? alme : almb)[idx]);
-					}
-				}
-			}
-			cp_async_commit();
-			#pragma unroll 1
-			for (int w = 0; w < 32/W; w++) {
-				if (phase < 2) {
-					bool mylive = true, anylive = false;
-					#pragma unroll
-					for (int r = 0; r < R; r++) {
-						mylive &= (sp[r] == 0) & (sq[r] == 0);
-						anylive |= use[r] & ((sp[r] == 0) | (sq[r] == 0));
-					}
-					phase = __all_sync(0xffffffffu, mylive) ? 2 : __any_sync(0xffffffffu, anylive) ? 1 : 0;
-				}
-				const int t0 = tt*32 + w*W;
-				if (phase == 2) adj2_sys_window<2, R, W>(ring, t0, lane, x, p, pp, q, qp, sp, sq, zin, S, red);
-				else if (phase == 1) adj2_sys_window<1, R, W>(ring, t0, lane, x, p, pp, q, qp, sp, sq, zin, S, red);
-				else adj2_sys_window<0, R, W>(ring, t0, lane, x, p, pp, q, qp, sp, sq, zin, S, red);
-			}
-			cp_async_wait_all();
-			__syncwarp();
-			if (tt >= 1) {
-				const double *rd = &red[((tt - 1) & 1)*128];
-				#pragma unroll
-				for (int h = 0; h < 4; h++) {
-					int e = lane + 32*h, i = (tt - 1)*32 + (e >> 2), k = e & 3;
-					double c = rd[e];
-					int base = lane & ~3;
-					double c0 = __shfl_sync(0xffffffffu, c, base), c1 = __shfl_sync(0xffffffffu, c, base + 1);
-					double c2 = __shfl_sync(0xffffffffu, c, base + 2), c3 = __shfl_sync(0xffffffffu, c, base + 3);
-					if (i < nl) {
-						int l = l0 + i;
-						double hh = 0.5*alvs[e], oldv = first ? 0.0 : olds[e];
-						// E = -(A+ + A-)/2, B = (i/2)(A+ - A-)
-						double val = k == 0 ? -hh*(c0 + c2) : k == 1 ? -hh*(c1 + c3) : k == 2 ? -hh*(c1 - c3) : hh*(c0 - c2);
-						int64_t idx = 2*(ms + (int64_t)l*A.lstride) + (k & 1);
-						if (A.deriv1) { if (k < 2) alme[idx] = oldv + val*sqrt((double)l*(l + 1.0)); }
-						else (k < 2 ? alme : almb)[idx] = oldv + val;
-					}
-				}
-			}
-			__syncwarp();
-		}
-		first = false;
-	}
-	if (first) for (int i = lane; i < nl; i += 32) {
 		int64_t idx = 2*(ms + (int64_t)(l0 + i)*A.lstride);
 		alme[idx] = alme[idx + 1] = 0;
 		if (!A.deriv1) almb[idx] = almb[idx + 1] = 0;
@@ -1224,21 +992,17 @@ int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 {
 	if (check_args(T, L, deriv1)) return 1;
 	LegArgs A = make_args(T, G, L, deriv1, (double2*)alm, alm_cstride, leg);
-	// template arguments: R, NW, MINB, TL
+	// template arguments: R, NW, MINB, TL (variant 0 = fastest measured on B200 at lmax 8000, profiles/r1*_tune_*)
 	if (T.spin == 0) switch (variant_of(0)) {
-		case 0: LAUNCH(k_synth0, 2, 4, 6, 64); break;
-		case 1: LAUNCH(k_synth0, 4, 4, 4, 64); break;
-		case 2: LAUNCH(k_synth0, 4, 1, 16, 32); break;
-		case 3: LAUNCH(k_synth0, 2, 1, 24, 32); break;
-		case 4: LAUNCH(k_synth0, 4, 2, 8, 64); break;
+		case 0: LAUNCH(k_synth0, 4, 2, 8, 64); break;
+		case 1: LAUNCH(k_synth0, 4, 1, 16, 32); break;
+		case 2: LAUNCH(k_synth0, 2, 4, 6, 64); break;
 		default: B2_REQUIRE(0, "unknown k_synth0 variant");
 	} else switch (variant_of(2)) {
-		case 0: LAUNCH(k_synth2, 2, 4, 3, 64); break;
-		case 1: LAUNCH(k_synth2, 2, 2, 6, 64); break;
-		case 2: LAUNCH(k_synth2, 4, 4, 3, 64); break;
-		case 3: LAUNCH(k_synth2, 4, 1, 12, 32); break;
-		case 4: LAUNCH(k_synth2, 2, 1, 16, 32); break;
-		case 5: LAUNCH(k_synth2, 4, 2, 6, 64); break;
+		case 0: LAUNCH(k_synth2, 4, 2, 6, 64); break;
+		case 1: LAUNCH(k_synth2, 4, 4, 3, 64); break;
+		case 2: LAUNCH(k_synth2, 4, 1, 12, 32); break;
+		case 3: LAUNCH(k_synth2, 2, 4, 3, 64); break;
 		default: B2_REQUIRE(0, "unknown k_synth2 variant");
 	}
 	B2_LAUNCH_CHECK();
@@ -1252,35 +1016,15 @@ int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 	LegArgs A = make_args(T, G, L, deriv1, alm, alm_cstride, (double2*)leg);
 	// template arguments: R, NW, MINB, TL, W
 	if (T.spin == 0) switch (variant_of(1)) {
-		case 0: LAUNCH(k_adj0, 4, 8, 1, 32, 16); break;
-		case 1: LAUNCH(k_adj0, 4, 1, 12, 32, 8); break;
-		case 2: LAUNCH(k_adj0, 8, 1, 8, 32, 8); break;
-		case 3: LAUNCH(k_adj0, 4, 4, 3, 64, 8); break;
-		case 4: LAUNCH(k_adj0, 4, 1, 8, 32, 16); break;
-		case 5: LAUNCH(k_adj0, 8, 1, 10, 32, 4); break;
-		case 6: LAUNCH(k_adj0, 8, 1, 12, 32, 4); break;
-		case 7: LAUNCH(k_adj0, 4, 1, 16, 32, 4); break;
-		case 10: k_adj0_sys<8, 8, 8><<<L.mmax + 1, 32, 0, st>>>(A); break;      // systolic: R, MINB, W
-		case 11: k_adj0_sys<8, 10, 8><<<L.mmax + 1, 32, 0, st>>>(A); break;
-		case 12: k_adj0_sys<4, 16, 8><<<L.mmax + 1, 32, 0, st>>>(A); break;
-		case 13: k_adj0_sys<8, 12, 4><<<L.mmax + 1, 32, 0, st>>>(A); break;
+		case 0: LAUNCH(k_adj0, 8, 1, 8, 32, 8); break;
+		case 1: LAUNCH(k_adj0, 8, 1, 10, 32, 4); break;
+		case 2: LAUNCH(k_adj0, 4, 4, 3, 64, 8); break;
 		default: B2_REQUIRE(0, "unknown k_adj0 variant");
 	} else switch (variant_of(3)) {
-		case 0: LAUNCH(k_adj2, 2, 8, 1, 32, 8); break;
-		case 1: LAUNCH(k_adj2, 2, 1, 12, 32, 8); break;
-		case 2: LAUNCH(k_adj2, 4, 1, 8, 32, 4); break;
-		case 3: LAUNCH(k_adj2, 2, 4, 3, 64, 4); break;
-		case 4: LAUNCH(k_adj2, 2, 1, 16, 32, 4); break;
-		case 5: LAUNCH(k_adj2, 2, 4, 3, 32, 8); break;
-		case 6: LAUNCH(k_adj2, 4, 1, 12, 32, 2); break;
-		case 7: LAUNCH(k_adj2, 4, 1, 10, 32, 4); break;
-		case 8: LAUNCH(k_adj2, 4, 1, 10, 32, 2); break;
-		case 9: LAUNCH(k_adj2, 2, 1, 16, 32, 2); break;
-		case 10: k_adj2_sys<4, 8, 4><<<L.mmax + 1, 32, 0, st>>>(A); break;       // systolic: R, MINB, W
-		case 11: k_adj2_sys<4, 10, 4><<<L.mmax + 1, 32, 0, st>>>(A); break;
-		case 12: k_adj2_sys<4, 12, 4><<<L.mmax + 1, 32, 0, st>>>(A); break;
-		case 13: k_adj2_sys<2, 16, 8><<<L.mmax + 1, 32, 0, st>>>(A); break;
-		case 14: k_adj2_sys<4, 12, 2><<<L.mmax + 1, 32, 0, st>>>(A); break;
+		case 0: LAUNCH(k_adj2, 4, 1, 10, 32, 4); break;
+		case 1: LAUNCH(k_adj2, 4, 1, 8, 32, 4); break;
+		case 2: LAUNCH(k_adj2, 2, 4, 3, 32, 8); break;
+		case 3: LAUNCH(k_adj2, 2, 1, 12, 32, 8); break;
 		default: B2_REQUIRE(0, "unknown k_adj2 variant");
 	}
 	B2_LAUNCH_CHECK();
