@@ -37,6 +37,14 @@ def peaks():
 	except Exception:
 		return {"hbm_gbs": 6650.0}, "fallback"
 
+def recorded_traffic(kernel):
+	"""dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
+	--set full capture (profiles/roofline_traffic.json); None if there is no capture for this kernel"""
+	try:
+		with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f: t = json.load(f)
+		return t.get(kernel)
+	except Exception: return None
+
 def algorithmic_bytes(w):
 	nalm = (w["lmax"]+1)*(w["lmax"]+2)//2
 	one = 16*w["ncomp"]*nalm + 8*w["ncomp"]*w["ny"]*w["nx"]
@@ -199,7 +207,7 @@ def run_ours(args, w):
 				"d2h_bytes_per_step": int(mapbytes+almbytes), "roundtrip_rel_err": err_e2e, "host_memory": "pinned"},
 			"roofline": {"kernel": "k_adj2 (Legendre adjoint, spin 2)" if w["ncomp"] == 3 else "k_adj0 (Legendre adjoint, spin 0)",
 				"bound": "hbm", "achieved": kbytes/(kms*1e-3)/1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-				"frac": kbytes/(kms*1e-3)/1e9/pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
+				"frac": kbytes/(kms*1e-3)/1e9/pk["hbm_gbs"], "traffic": recorded_traffic("k_adj2" if w["ncomp"] == 3 and w["lmax"] == 8000 else ""), "peak_source": pk_kind,
 				"ms_per_launch": kms, "algorithmic_bytes": kbytes,
 				"note": "FP64-FMA bound kernel (intensity ~ lmax/12 flop/byte): see roofline_fp64"},
 			"roofline_fp64": {"bound": "fp64", "achieved": kflops/(kms*1e-3)/1e12, "peak": dpk.value/1e3, "unit": "TFLOP/s",

@@ -98,6 +98,100 @@ template<bool INV> __global__ void k_fft_axis(AxisArgs A)
 	}
 }
 
+// Specialised passes (P in {1, 2, 4, 8} known at compile time, loads of a thread issued together):
+//   MODE 0  complex lines (any loader / storer of the generic kernel)
+//   MODE 1  packed real-to-complex, forward: a real line of even length n is read as nc = n/2 complex numbers
+//           z_j = x_2j + i x_2j+1 (one 16-byte load each), transformed with length nc, and untangled on the way out:
+//           X_k = [(Z_k + conj Z_{nc-k}) - i w_n^k (Z_k - conj Z_{nc-k})]/2, k = 0..nc (needs P <= 2: both partners
+//           of a pair then live in the same CTA)
+//   MODE 2  packed complex-to-real, backward: Z_k = (X_k + conj X_{nc-k}) + i conj(w_n^k) (X_k - conj X_{nc-k}) is
+//           formed while loading, the inverse transform of length nc yields (x_2k, x_2k+1) pairs
+enum { FM_C2C, FM_R2C_PACKED, FM_C2R_PACKED };
+
+template<bool INV, int MODE, int P> __global__ void __launch_bounds__(512) k_fft_axis2(AxisArgs A)
+{
+	extern __shared__ __align__(16) double2 s[];
+	// the P CTAs of one tile are neighbours in the grid, so they run together and all but the first read the lines from L2
+	const int tid = threadIdx.x, T = blockDim.x, p = blockIdx.x % P;
+	const int64_t tile = blockIdx.x/P;
+	const int nb = A.nb, nl = A.nl, ls = A.lstride;
+	const int nc = nl*P;                                   // complex transform length (n, or n/2 for the packed modes)
+	const int64_t ntile = (A.n_in + nb - 1)/nb;
+	const int64_t outer = tile/ntile, i0 = (tile % ntile)*nb;
+	const int64_t o1 = outer/A.n_o2, o2 = outer % A.n_o2;
+	const int nbv = (int)min((int64_t)nb, A.n_in - i0);
+	const int64_t bin = o1*A.is_o1 + o2*A.is_o2 + i0*A.is_in, bout = o1*A.os_o1 + o2*A.os_o2 + i0*A.os_in;
+	const int tot = nb*nl;
+	const int twq = A.d.twmul/P;                            // table step of w_nc
+	const double2 *twsm = s + A.twoff;
+	fft_load_tw(s + A.twoff, A.d, tid, T);
+	double2 wq[P];
+	#pragma unroll
+	for (int q = 0; q < P; q++) wq[q] = cj(A.d.tw[(A.d.ntab/P)*((q*p) % P)], INV);
+	#pragma unroll 4
+	for (int idx = tid; idx < tot; idx += T) {
+		int line, j;
+		if (A.jfast) { line = idx/nl; j = idx - line*nl; } else { j = idx/nb; line = idx - j*nb; }
+		double2 v[P];
+		const int64_t b = bin + line*A.is_in;
+		#pragma unroll
+		for (int q = 0; q < P; q++) {
+			const int jj = j + q*nl;
+			if (line >= nbv) v[q] = make_double2(0, 0);
+			else if (MODE == FM_C2C) v[q] = ((const double2*)A.in)[b + jj*A.is_t];      // complex128 only (see run_pass)
+			else if (MODE == FM_R2C_PACKED) {
+				if (A.lk == LK_F64) v[q] = ((const double2*)((const double*)A.in + b))[jj];
+				else { float2 f = ((const float2*)((const float*)A.in + b))[jj]; v[q] = make_double2(f.x, f.y); }
+			} else {
+				const int jm = nc - jj;
+				double2 xa, xb;
+				if (A.lk == LK_C128) { xa = ((const double2*)A.in)[b + jj*A.is_t]; xb = ((const double2*)A.in)[b + jm*A.is_t]; }
+				else { float2 fa = ((const float2*)A.in)[b + jj*A.is_t], fb = ((const float2*)A.in)[b + jm*A.is_t]; xa = make_double2(fa.x, fa.y); xb = make_double2(fb.x, fb.y); }
+				double2 sm = make_double2(xa.x + xb.x, xa.y - xb.y), df = make_double2(xa.x - xb.x, xa.y + xb.y);
+				double2 w = A.d.tw[jj]; w.y = -w.y;                // e^{+2 pi i jj/n}
+				double2 u = cmul(df, w);
+				v[q] = make_double2(sm.x - u.y, sm.y + u.x);
+			}
+		}
+		double2 acc = v[0];
+		#pragma unroll
+		for (int q = 1; q < P; q++) acc = cadd(acc, p ? cmul(v[q], wq[q]) : v[q]);
+		if (P > 1 && p) acc = cmul(acc, cj(A.d.tw[twq*j*p], INV));
+		s[line*ls + fft_pad(A.d, j)] = acc;
+	}
+	__syncthreads();
+	fft_smem<INV>(s, A.d, tid, T, nb, twsm);
+	#pragma unroll 2
+	for (int idx = tid; idx < tot; idx += T) {
+		int line, kk;
+		if (A.jfast) { line = idx/nl; kk = idx - line*nl; } else { kk = idx/nb; line = idx - kk*nb; }
+		if (line >= nbv) continue;
+		const int k = p + P*kk;
+		const double2 x = s[line*ls + fft_pad(A.d, A.d.rev[kk])];
+		const int64_t bo = bout + line*A.os_in;
+		if (MODE == FM_C2C) ((double2*)A.out)[bo + k*A.os_t] = make_double2(x.x*A.scale, x.y*A.scale);
+		else if (MODE == FM_C2R_PACKED) {
+			if (A.sk == SK_F64) ((double2*)((double*)A.out + bo))[k] = make_double2(x.x*A.scale, x.y*A.scale);
+			else ((float2*)((float*)A.out + bo))[k] = make_float2((float)(x.x*A.scale), (float)(x.y*A.scale));
+		} else {
+			// partner nc - k has the same residue mod P (P <= 2)
+			const int kp = k ? nc - k : 0;
+			const double2 y = s[line*ls + fft_pad(A.d, A.d.rev[(kp - p)/P])];
+			double2 sm = make_double2(x.x + y.x, x.y - y.y), df = make_double2(x.x - y.x, x.y + y.y);
+			double2 u = cmul(df, A.d.tw[k]);                    // w_n^k (Z_k - conj Z_{nc-k})
+			double2 X = make_double2(0.5*(sm.x + u.y), 0.5*(sm.y - u.x));
+			const int savek = A.sk;      // complex storer without the k <= n/2 test
+			if (savek == SK_HC128 || savek == SK_C128) ((double2*)A.out)[bo + k*A.os_t] = make_double2(X.x*A.scale, X.y*A.scale);
+			else ((float2*)A.out)[bo + k*A.os_t] = make_float2((float)(X.x*A.scale), (float)(X.y*A.scale));
+			if (k == 0) {
+				double2 Xn = make_double2((x.x - x.y)*A.scale, 0.0);
+				if (savek == SK_HC128 || savek == SK_C128) ((double2*)A.out)[bo + nc*A.os_t] = Xn;
+				else ((float2*)A.out)[bo + nc*A.os_t] = make_float2((float)Xn.x, 0.f);
+			}
+		}
+	}
+}
+
 // ------------------------------------------------------------------------------------ plan
 
 struct ArrayDesc { int64_t stride[4]; int kind; };      // element strides; kind = LK_* (as input) / SK_* (as output)
@@ -114,16 +208,19 @@ struct b2_fft_plan {
 	int64_t istride[4] = {0, 0, 0, 0}, ostride[4] = {0, 0, 0, 0};
 	int64_t in_span = 0, out_span = 0;                              // elements touched in the caller's arrays
 	AxisPass pass[2];
+	AxisPass packed;       // real axis as a half-length complex transform (even length, line fits two CTAs); n = 0: unavailable
 	DevBuf<char> work, stage_in, stage_out;
 };
 
 static const size_t FFT_SMEM_MAX = 200*1024, FFT_TILE_ELEMS = 6144;
 
-static int setup_pass(AxisPass &ps, int axis, int n, bool can_batch)
+// strided: the axis is not the contiguous one, so a CTA should hold at least two neighbouring lines (full 32-byte sectors)
+static int setup_pass(AxisPass &ps, int axis, int n, bool can_batch, bool strided)
 {
 	ps.axis = axis; ps.n = n;
 	int P = 1;
-	while ((size_t)(FftTables::smem_len(n/P) + n/FFT_TWLO + FFT_TWLO + 1)*sizeof(double2) > FFT_SMEM_MAX) {
+	const int minb = (strided && can_batch) ? 2 : 1;
+	while ((size_t)(minb*FftTables::smem_len(n/P) + n/FFT_TWLO + FFT_TWLO + 1)*sizeof(double2) > FFT_SMEM_MAX) {
 		int np = P + 1;
 		while (np <= 64 && n % np) np++;
 		B2_REQUIRE(np <= 64, "fft: a transform of length %d does not fit in shared memory (no usable split)", n);
@@ -132,7 +229,25 @@ static int setup_pass(AxisPass &ps, int axis, int n, bool can_batch)
 	ps.P = P; ps.nl = n/P;
 	if (ps.tab.build(ps.nl, n)) return 1;
 	ps.nb = 1;
-	if (can_batch && FftTables::smooth(ps.nl)) ps.nb = (int)std::max<size_t>(1, FFT_TILE_ELEMS/FftTables::smem_len(ps.nl));
+	if (can_batch && FftTables::smooth(ps.nl)) ps.nb = (int)std::max<size_t>(minb, FFT_TILE_ELEMS/FftTables::smem_len(ps.nl));
+	return 0;
+}
+
+// the real axis of even length n as a complex transform of length n/2 over at most two CTAs
+static int setup_packed(AxisPass &ps, int axis, int n)
+{
+	ps.n = 0;
+	if (n % 2 || n < 4) return 0;
+	const int nc = n/2;
+	for (int P = 1; P <= 2; P++) {
+		if (nc % P) continue;
+		if ((size_t)(FftTables::smem_len(nc/P) + n/FFT_TWLO + FFT_TWLO + 1)*sizeof(double2) > FFT_SMEM_MAX) continue;
+		if (!FftTables::fast_ok(nc/P)) return 0;
+		ps.axis = axis; ps.n = n; ps.P = P; ps.nl = nc/P;
+		if (ps.tab.build(ps.nl, n)) return 1;
+		ps.nb = (int)std::max<size_t>(1, FFT_TILE_ELEMS/FftTables::smem_len(ps.nl));
+		return 0;
+	}
 	return 0;
 }
 
@@ -167,7 +282,8 @@ extern "C" int b2_fft_plan_create(b2_fft_plan **out, int ndim, const int64_t *sh
 	int order[2] = {p->axes[naxes - 1], p->axes[0]};
 	if (kind == B2_FFT_C2R && naxes == 2) std::swap(order[0], order[1]);
 	for (int i = 0; i < naxes; i++)
-		if (setup_pass(p->pass[i], order[i], (int)p->shape[order[i]], true)) return 1;
+		if (setup_pass(p->pass[i], order[i], (int)p->shape[order[i]], true, istride[order[i]] != 1 || ostride[order[i]] != 1)) return 1;
+	if (kind != B2_FFT_C2C && setup_packed(p->packed, last, (int)p->shape[last])) return 1;
 	*out = p.release();
 	return 0;
 }
@@ -177,8 +293,16 @@ extern "C" void b2_fft_plan_destroy(b2_fft_plan *plan) { delete plan; }
 // ------------------------------------------------------------------------------------ execution
 
 // run one pass over `axis` of an array with extents dims[], reading src (strides ss, loader lk) and writing dst
+template<bool INV, int MODE, int P> static int launch_axis2(const AxisArgs &A, dim3 grid, int threads, size_t smem, cudaStream_t st)
+{
+	if (smem > 48*1024) B2_CHECK(cudaFuncSetAttribute(k_fft_axis2<INV, MODE, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_fft_axis2<INV, MODE, P><<<grid, threads, smem, st>>>(A);
+	B2_LAUNCH_CHECK();
+	return 0;
+}
+
 static int run_pass(b2_fft_plan *p, AxisPass &ps, const int64_t *dims, const void *src, const int64_t *ss, int lk,
-	void *dst, const int64_t *ds, int sk, bool inverse, double scale, cudaStream_t st)
+	void *dst, const int64_t *ds, int sk, bool inverse, double scale, cudaStream_t st, int mode = FM_C2C)
 {
 	AxisArgs A;
 	A.d = ps.tab.d; A.n = ps.n; A.P = ps.P; A.nl = ps.nl; A.lk = lk; A.sk = sk; A.scale = scale;
@@ -198,6 +322,7 @@ static int run_pass(b2_fft_plan *p, AxisPass &ps, const int64_t *dims, const voi
 	A.os_t = ds[ps.axis]; A.os_in = sout[0]; A.os_o1 = sout[1]; A.os_o2 = sout[2];
 	A.jfast = (A.n_in == 1 || A.is_t <= A.is_in) ? 1 : 0;
 	A.nb = (int)std::min<int64_t>(ps.nb, A.n_in);
+	if (mode != FM_C2C) A.jfast = 1;
 	A.lstride = ps.tab.d.nsmem;
 	A.twoff = A.nb*ps.tab.d.nsmem;
 	size_t smem = sizeof(double2)*(size_t)(A.twoff + ps.tab.twsm_len());
@@ -206,6 +331,20 @@ static int run_pass(b2_fft_plan *p, AxisPass &ps, const int64_t *dims, const voi
 	int64_t nblk = ntile*A.n_o1*A.n_o2;
 	B2_REQUIRE(nblk < (1LL << 31), "fft: too many lines for one launch");
 	dim3 grid((unsigned)nblk, ps.P);
+	const bool plain128 = (mode != FM_C2C) || (lk == LK_C128 && sk == SK_C128);
+	if (ps.tab.d.fast && plain128 && (ps.P == 1 || ps.P == 2 || ps.P == 4 || ps.P == 8) && nblk*ps.P < (1LL << 31)) {
+		grid = dim3((unsigned)(nblk*ps.P), 1);
+		threads = (int)std::min<int64_t>(512, std::max<int64_t>(64, b2_round_up((int64_t)A.nb*ps.nl/8, 32)));
+		#define AX2(INV, MODE) (ps.P == 1 ? launch_axis2<INV, MODE, 1>(A, grid, threads, smem, st) : ps.P == 2 ? launch_axis2<INV, MODE, 2>(A, grid, threads, smem, st) : \
+			ps.P == 4 ? launch_axis2<INV, MODE, 4>(A, grid, threads, smem, st) : launch_axis2<INV, MODE, 8>(A, grid, threads, smem, st))
+		#define AX2P(INV, MODE) (ps.P == 1 ? launch_axis2<INV, MODE, 1>(A, grid, threads, smem, st) : launch_axis2<INV, MODE, 2>(A, grid, threads, smem, st))
+		if (mode == FM_R2C_PACKED) return AX2P(false, FM_R2C_PACKED);
+		if (mode == FM_C2R_PACKED) return AX2P(true, FM_C2R_PACKED);
+		return inverse ? AX2(true, FM_C2C) : AX2(false, FM_C2C);
+		#undef AX2
+		#undef AX2P
+	}
+	B2_REQUIRE(mode == FM_C2C, "fft: internal error (packed pass without a fast plan)");
 	if (inverse) {
 		if (smem > 48*1024) B2_CHECK(cudaFuncSetAttribute(k_fft_axis<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		k_fft_axis<true><<<grid, threads, smem, st>>>(A);
@@ -255,33 +394,52 @@ extern "C" int b2_fft_execute(b2_fft_plan *p, const void *in, void *out, int for
 		if (p->work.n < (size_t)n*16) return p->work.alloc((size_t)n*16);
 		return 0;
 	};
+	// the packed real passes need unit stride along the real axis and 16-byte (8 for float32) aligned line starts
+	const int last = p->axes[p->naxes - 1];
+	auto can_pack = [&](const void *ptr, const int64_t *str) -> bool {
+		if (p->packed.n == 0 || str[last] != 1) return false;
+		if (((uintptr_t)ptr) % (2*rsz)) return false;
+		for (int d = 0; d < p->ndim; d++) if (d != last && p->shape[d] > 1 && (str[d] % 2)) return false;
+		return true;
+	};
 	int rc = 0;
 	if (p->naxes == 1) {
 		AxisPass &a = p->pass[0];
 		const bool alias = (din == dout) && a.P > 1;
 		B2_REQUIRE(!alias, "fft: in-place transforms of lines longer than %d elements are not supported", (int)(FFT_SMEM_MAX/16));
 		if (p->kind == B2_FFT_C2C) rc = run_pass(p, a, p->shape, din, p->istride, c_lk, dout, p->ostride, c_sk, inverse, scale, st);
-		else if (p->kind == B2_FFT_R2C) rc = run_pass(p, a, p->shape, din, p->istride, r_lk, dout, p->ostride, h_sk, false, scale, st);
-		else rc = run_pass(p, a, p->shape, din, p->istride, h_lk, dout, p->ostride, r_sk, true, scale, st);
+		else if (p->kind == B2_FFT_R2C) {
+			if (can_pack(din, p->istride)) rc = run_pass(p, p->packed, p->shape, din, p->istride, r_lk, dout, p->ostride, h_sk, false, scale, st, FM_R2C_PACKED);
+			else rc = run_pass(p, a, p->shape, din, p->istride, r_lk, dout, p->ostride, h_sk, false, scale, st);
+		} else {
+			if (can_pack(dout, p->ostride)) rc = run_pass(p, p->packed, p->shape, din, p->istride, c_lk, dout, p->ostride, r_sk, true, scale, st, FM_C2R_PACKED);
+			else rc = run_pass(p, a, p->shape, din, p->istride, h_lk, dout, p->ostride, r_sk, true, scale, st);
+		}
 	} else {
 		AxisPass &a = p->pass[0], &b = p->pass[1];
 		if (p->kind == B2_FFT_C2R) {
 			// c2c along the first listed axis on the half spectrum (into the work array), then c2r along the last
 			if (need_work()) return 1;
 			rc = run_pass(p, a, p->cshape, din, p->istride, c_lk, p->work.p, wstride, SK_C128, true, 1.0, st);
-			if (!rc) rc = run_pass(p, b, p->shape, p->work.p, wstride, LK_H128, dout, p->ostride, r_sk, true, scale, st);
+			if (!rc) {
+				if (can_pack(dout, p->ostride)) rc = run_pass(p, p->packed, p->shape, p->work.p, wstride, LK_C128, dout, p->ostride, r_sk, true, scale, st, FM_C2R_PACKED);
+				else rc = run_pass(p, b, p->shape, p->work.p, wstride, LK_H128, dout, p->ostride, r_sk, true, scale, st);
+			}
 		} else {
 			// first pass along the last listed axis; the second runs in place on the output when its lines fit one CTA
 			const bool r2c = p->kind == B2_FFT_R2C;
 			const bool inplace2 = (b.P == 1) && !(a.P > 1 && din == dout);
 			const int64_t *dims1 = p->shape, *dims2 = r2c ? p->cshape : p->shape;
 			const int lk1 = r2c ? r_lk : c_lk;
+			const bool pack = r2c && can_pack(din, p->istride);
 			if (inplace2) {
-				rc = run_pass(p, a, dims1, din, p->istride, lk1, dout, p->ostride, r2c ? h_sk : c_sk, inverse, 1.0, st);
+				if (pack) rc = run_pass(p, p->packed, dims1, din, p->istride, lk1, dout, p->ostride, h_sk, false, 1.0, st, FM_R2C_PACKED);
+				else rc = run_pass(p, a, dims1, din, p->istride, lk1, dout, p->ostride, r2c ? h_sk : c_sk, inverse, 1.0, st);
 				if (!rc) rc = run_pass(p, b, dims2, dout, p->ostride, c_lk, dout, p->ostride, c_sk, inverse, scale, st);
 			} else {
 				if (need_work()) return 1;
-				rc = run_pass(p, a, dims1, din, p->istride, lk1, p->work.p, wstride, r2c ? SK_HC128 : SK_C128, inverse, 1.0, st);
+				if (pack) rc = run_pass(p, p->packed, dims1, din, p->istride, lk1, p->work.p, wstride, SK_HC128, false, 1.0, st, FM_R2C_PACKED);
+				else rc = run_pass(p, a, dims1, din, p->istride, lk1, p->work.p, wstride, r2c ? SK_HC128 : SK_C128, inverse, 1.0, st);
 				if (!rc) rc = run_pass(p, b, dims2, p->work.p, wstride, LK_C128, dout, p->ostride, c_sk, inverse, scale, st);
 			}
 		}

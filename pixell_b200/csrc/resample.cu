@@ -55,7 +55,7 @@ template<int STAGE, int P> __global__ void __launch_bounds__(512) k_resamp(Resam
 {
 	extern __shared__ __align__(16) double2 s[];
 	constexpr bool INV = (STAGE == 2 || STAGE == 5);
-	const int tid = threadIdx.x, T = blockDim.x, c = blockIdx.x, p = blockIdx.y;
+	const int tid = threadIdx.x, T = blockDim.x, c = blockIdx.y, p = blockIdx.x;      // the P CTAs of a column pair are neighbours in the grid (second reader hits L2)
 	const int N = R.N, Nl = N/P;
 	double2 *ca, *cb; double sigma;
 	pair_cols(R, R.col0 + c, ca, cb, sigma);
@@ -128,7 +128,7 @@ template<int STAGE, int P> __global__ void __launch_bounds__(512) k_resamp_adj(R
 {
 	extern __shared__ __align__(16) double2 s[];
 	constexpr bool INV = (STAGE == 2 || STAGE == 4 || STAGE == 5);
-	const int tid = threadIdx.x, T = blockDim.x, c = blockIdx.x, p = blockIdx.y;
+	const int tid = threadIdx.x, T = blockDim.x, c = blockIdx.y, p = blockIdx.x;      // the P CTAs of a column pair are neighbours in the grid (second reader hits L2)
 	const int N = R.N, Nl = N/P;
 	double2 *ca, *cb; double sigma;
 	pair_cols(R, R.col0 + c, ca, cb, sigma);
@@ -290,7 +290,7 @@ int ThetaResampler::build(const std::string &g, int ntheta, int64_t nphi_, int l
 template<int STAGE, int P> static int launch_stage_p(const ResampArgs &R, int ncols, int threads, size_t smem, cudaStream_t st)
 {
 	if (smem > 48*1024) B2_CHECK(cudaFuncSetAttribute(k_resamp<STAGE, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_resamp<STAGE, P><<<dim3(ncols, P), threads, smem, st>>>(R);
+	k_resamp<STAGE, P><<<dim3(P, ncols), threads, smem, st>>>(R);
 	B2_LAUNCH_CHECK();
 	return 0;
 }
@@ -307,7 +307,7 @@ template<int STAGE> static int launch_stage(const ResampArgs &R, int ncols, int 
 template<int STAGE, int P> static int launch_adj_p(const ResampArgs &R, int ncols, int threads, size_t smem, cudaStream_t st)
 {
 	if (smem > 48*1024) B2_CHECK(cudaFuncSetAttribute(k_resamp_adj<STAGE, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_resamp_adj<STAGE, P><<<dim3(ncols, P), threads, smem, st>>>(R);
+	k_resamp_adj<STAGE, P><<<dim3(P, ncols), threads, smem, st>>>(R);
 	B2_LAUNCH_CHECK();
 	return 0;
 }
