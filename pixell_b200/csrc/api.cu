@@ -3,6 +3,7 @@
 #include "plan.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 
 // ------------------------------------------------------------------------------------ errors
@@ -126,6 +127,7 @@ size_t b2_sht_plan::bytes() const
 {
 	size_t b = mstart.bytes() + geom.bytes() + fft.bytes() + leg.bytes() + w2d.bytes() + stage_alm.bytes() + stage_map.bytes();
 	for (auto &t : tables) b += t.second->bytes();
+	for (auto &t : starts) if (t.second) b += t.second->bytes();
 	if (resamp) b += resamp->bytes();
 	return b;
 }
@@ -138,6 +140,21 @@ LegTables *b2_sht_plan::get_tables(int spin)
 	if (t->build(lmax, mmax, spin)) return nullptr;
 	LegTables *p = t.get();
 	tables[spin] = std::move(t);
+	return p;
+}
+
+LegStart *b2_sht_plan::get_start(int spin)
+{
+	static const bool off = getenv("B2_NO_START_TABLE") && atoi(getenv("B2_NO_START_TABLE")) != 0;
+	if (off) return nullptr;
+	auto it = starts.find(spin);
+	if (it != starts.end()) return it->second.get();
+	LegTables *T = get_tables(spin);
+	if (!T) return nullptr;
+	std::unique_ptr<LegStart> s(new LegStart());
+	if (leg_build_start(*s, *T, geom)) { starts[spin] = nullptr; return nullptr; }      // e.g. out of memory: run without
+	LegStart *p = s.get();
+	starts[spin] = std::move(s);
 	return p;
 }
 
@@ -349,7 +366,7 @@ static int group_compute(Exec &E, GroupCtx &G)
 	}
 	B2_CHECK(cudaEventRecord(p->ev[1], E.st));
 	if (to_map) {
-		if (leg_alm2leg(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st)) return 1;
+		if (leg_alm2leg(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st, p->get_start(E.spin))) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[2], E.st));
 		if (E.op == OP_ADJ_ANALYSIS) {
 			if (p->resamp) { if (p->resamp->apply(p->leg.p, E.ncm, E.spin, E.st, true)) return 1; }
@@ -374,7 +391,7 @@ static int group_compute(Exec &E, GroupCtx &G)
 			}
 		}
 		B2_CHECK(cudaEventRecord(p->ev[3], E.st));
-		if (leg_leg2alm(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st)) return 1;
+		if (leg_leg2alm(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st, p->get_start(E.spin))) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[4], E.st));
 		if (!G.alm_direct && E.dtype == B2_F32) {
 			for (int c = 0; c < E.nca; c++) {
@@ -535,7 +552,7 @@ extern "C" int b2_alm2leg(b2_sht_plan *p, int spin, int mode, const void *alm_de
 	B2_REQUIRE(p && alm_dev && leg_dev, "alm2leg: null argument");
 	LegTables *T = p->get_tables(spin); if (!T) return 1;
 	AlmLayout L; L.lmax = p->lmax; L.mmax = p->mmax; L.mstart_d = p->mstart.p; L.lstride = p->lstride;
-	return leg_alm2leg(*T, p->geom, L, mode == B2_MODE_DERIV1, (const double2*)alm_dev, acs, (double2*)leg_dev, (cudaStream_t)stream);
+	return leg_alm2leg(*T, p->geom, L, mode == B2_MODE_DERIV1, (const double2*)alm_dev, acs, (double2*)leg_dev, (cudaStream_t)stream, p->get_start(spin));
 }
 
 extern "C" int b2_theta_weighting(b2_sht_plan *p, int spin, int ncomp, int adjoint, void *leg_dev, void *stream)
@@ -550,5 +567,5 @@ extern "C" int b2_leg2alm(b2_sht_plan *p, int spin, int mode, void *alm_dev, int
 	B2_REQUIRE(p && alm_dev && leg_dev, "leg2alm: null argument");
 	LegTables *T = p->get_tables(spin); if (!T) return 1;
 	AlmLayout L; L.lmax = p->lmax; L.mmax = p->mmax; L.mstart_d = p->mstart.p; L.lstride = p->lstride;
-	return leg_leg2alm(*T, p->geom, L, mode == B2_MODE_DERIV1, (double2*)alm_dev, acs, (const double2*)leg_dev, (cudaStream_t)stream);
+	return leg_leg2alm(*T, p->geom, L, mode == B2_MODE_DERIV1, (double2*)alm_dev, acs, (const double2*)leg_dev, (cudaStream_t)stream, p->get_start(spin));
 }

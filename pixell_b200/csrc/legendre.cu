@@ -141,6 +141,8 @@ struct LegArgs {
 	double2 *alm0, *alm1;
 	double2 *leg0, *leg1;
 	int64_t leg_mstride;
+	// start table (st_w == nullptr: none; kernels then start every ring at l = max(m, s))
+	const int *st_w; const double *st_p, *st_pp, *st_q, *st_qp; const signed char *st_sp, *st_sq; int ngroup;
 };
 
 // base^n = mant*2^ex with mant in [0.5,1) (or mant = 1, ex = 0 for n = 0; mant = 0 for base = 0)
@@ -291,6 +293,19 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template<int NW> __device__ __forceinline__ void cta_sync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
 template<int NW> __device__ __forceinline__ bool cta_or(bool v) { return NW == 1 ? __any_sync(0xffffffffu, v) : (__syncthreads_or(v) != 0); }
 
+// smallest of the warps' (warp-uniform) values; slot: one shared int per CTA
+template<int NW> __device__ __forceinline__ int cta_min(int v, int *slot)
+{
+	if (NW == 1) return v;
+	if (threadIdx.x == 0) *slot = LEG_NEVER;
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) atomicMin(slot, v);
+	__syncthreads();
+	int r = *slot;
+	__syncthreads();
+	return r;
+}
+
 // ------------------------------------------------------------------------------------ spin 0
 
 struct Tile0 { double ar, ai, a, pad; };            // alm*alpha (re, im), recurrence a_l
@@ -324,8 +339,10 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 	__shared__ __align__(16) Tile0 tiles[2][TL];
 	__shared__ __align__(16) double2 raw_alm[TL];       // cp.async staging: alm, (alpha, a)
 	__shared__ __align__(16) double raw_al[TL], raw_a[TL];
+	__shared__ int wslot;
 	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, l0 = m;
+	const bool tab = A.st_w != nullptr && R*32 == LEG_GROUP;
 	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
 	const double *ta = A.ta + A.toff[m], *tal = A.talpha + A.toff[m];
 	const double2 *alm = A.alm0 + A.mstart[m];
@@ -349,11 +366,21 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 			PairInfo pi; pi.rn = -1; pi.rs = -1; pi.x = 0; pi.sh = 0; pi.ch = 1;
 			if (chunk < nchunk) pi = A.pairs[(chunk*R + r)*32 + lane];
 			double dummy; int dsc;
-			use[r] = init_pair(pi, sc0, m, 0, lmax, x[r], dummy, dsc, g[r], sc[r]);
-			gp[r] = 0; rn[r] = pi.rn; rs[r] = pi.rs;
+			if (!tab) { use[r] = init_pair(pi, sc0, m, 0, lmax, x[r], dummy, dsc, g[r], sc[r]); gp[r] = 0; }
+			else {
+				x[r] = pi.x;
+				use[r] = pi.rn >= 0 && 2.0*pi.sh*pi.ch >= sc0.dead_sth;
+				g[r] = gp[r] = 0; sc[r] = 0;
+				if (chunk < nchunk) { int64_t k = (int64_t)m*A.npair_pad + (chunk*R + r)*32 + lane; g[r] = A.st_p[k]; gp[r] = A.st_pp[k]; sc[r] = A.st_sp[k]; }
+			}
+			rn[r] = pi.rn; rs[r] = pi.rs;
 			acc[r][0][0] = acc[r][0][1] = acc[r][1][0] = acc[r][1][1] = 0;
 			anyuse |= use[r];
 		}
+		// first window of 8 l in which this warp has work (start table), CTA-wide minimum for the shared tiles
+		int wc = 0;
+		if (tab) { wc = chunk < nchunk ? A.st_w[m*A.ngroup + chunk] : LEG_NEVER; if (wc == LEG_NEVER) anyuse = false; }
+		const int wc_cta = tab ? cta_min<NW>(wc, &wslot) : 0;
 		// a round in which no ring of the CTA can contribute only has to write zeros
 		const bool wuse = __any_sync(0xffffffffu, anyuse);
 		int phase = 0;
@@ -376,13 +403,15 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 					tiles[buf][tid] = t;
 				}
 			};
-			issue(0); finish(0, 0);
+			const int tile0 = min(wc_cta*8/TL, ntile - 1);
+			issue(tile0); finish(tile0, tile0 & 1);
 			cta_sync<NW>();
-			for (int tile = 0; tile < ntile; tile++) {
+			for (int tile = tile0; tile < ntile; tile++) {
 				const int buf = tile & 1;
 				if (tile + 1 < ntile) issue(tile + 1);
 				const int nwin = (min(TL, nl - tile*TL) + 7) >> 3;
 				for (int w = 0; wuse && w < nwin; w++) {
+					if (tile*(TL/8) + w < wc) continue;
 					if (phase < 2) {      // liveness only grows: once every lane is live no more votes are needed
 						bool mylive = true, anylive = false;
 						#pragma unroll
@@ -450,18 +479,36 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 	const double2 *leg = A.leg0 + (int64_t)m*A.leg_mstride;
 	bool first = true;
 	const int round0 = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R*NW);
+	// start table (single-warp CTAs): a chunk spans NG groups of LEG_GROUP pairs; each group's rings are injected
+	// with their recorded state at the group's first live window, the row is zeroed once and every round adds to it
+	constexpr int NG = (R*32)/LEG_GROUP;
+	const bool tab = A.st_w != nullptr && NW == 1 && NG >= 1 && NG*LEG_GROUP == R*32;
+	if (tab) {
+		for (int i = tid; i < nl; i += NW*32) *(double2*)&almr[2*(int64_t)(l0 + i)*A.lstride] = make_double2(0, 0);
+		__syncwarp();
+		first = false;
+	}
 
 	for (int round = round0; round*NW < nchunk; round++) {
 		const int chunk = round*NW + warp;
 		double x[R], g[R], gp[R], in[R][2][2]; int sc[R];
 		bool anyuse = false, use[R];
+		int wg[NG > 0 ? NG : 1], wc = 0;
+		if (tab) {
+			wc = LEG_NEVER;
+			#pragma unroll
+			for (int k = 0; k < NG; k++) { wg[k] = A.st_w[m*A.ngroup + chunk*NG + k]; wc = min(wc, wg[k]); }
+		}
 		#pragma unroll
 		for (int r = 0; r < R; r++) {
 			PairInfo pi; pi.rn = -1; pi.rs = -1; pi.x = 0; pi.sh = 0; pi.ch = 1;
 			if (chunk < nchunk) pi = A.pairs[(chunk*R + r)*32 + lane];
 			double dummy; int dsc;
-			use[r] = init_pair(pi, sc0, m, 0, lmax, x[r], dummy, dsc, g[r], sc[r]);
-			gp[r] = 0;
+			if (!tab) { use[r] = init_pair(pi, sc0, m, 0, lmax, x[r], dummy, dsc, g[r], sc[r]); gp[r] = 0; }
+			else {      // rings wait with zero state (contributing exact zeros) until their group is injected
+				x[r] = pi.x; g[r] = gp[r] = 0; sc[r] = 0;
+				use[r] = pi.rn >= 0 && 2.0*pi.sh*pi.ch >= sc0.dead_sth && wg[(r*32)/LEG_GROUP] != LEG_NEVER;
+			}
 			double2 gn = make_double2(0, 0), gs = make_double2(0, 0);
 			if (use[r]) { gn = leg[pi.rn]; if (pi.rs >= 0) gs = leg[pi.rs]; }
 			if (lane & 16) { gn = make_double2(gn.y, gn.x); gs = make_double2(gs.y, gs.x); }    // slot permutation of bfly_reduce
@@ -469,6 +516,7 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 			in[r][1][0] = gn.x - gs.x; in[r][1][1] = gn.y - gs.y;    // l - l0 odd
 			anyuse |= use[r];
 		}
+		if (tab && wc == LEG_NEVER) anyuse = false;
 		const bool wuse = __any_sync(0xffffffffu, anyuse);
 		int phase = 0;
 		if (!cta_or<NW>(anyuse)) continue;
@@ -481,9 +529,10 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 			}
 			cp_async_commit();
 		};
-		issue(0, 0); cp_async_wait_all();
+		const int tile0 = tab ? min(wc*8/TL, ntile - 1) : 0;
+		issue(tile0, tile0 & 1); cp_async_wait_all();
 		cta_sync<NW>();
-		for (int tile = 0; tile < ntile; tile++) {
+		for (int tile = tile0; tile < ntile; tile++) {
 			const int buf = tile & 1;
 			if (tile + 1 < ntile) issue(tile + 1, buf ^ 1);
 			const int nwin = (min(TL, nl - tile*TL) + W - 1)/W;
@@ -512,7 +561,18 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 			#pragma unroll 1
 			for (int w = 0; w < TL/W; w++) {
 				double tot = 0;
-				if (wuse && w < nwin) {
+				if (wuse && w < nwin && tile*TL + w*W >= wc*8) {
+					if (tab) {
+						#pragma unroll
+						for (int k = 0; k < NG; k++) if (tile*TL + w*W == wg[k]*8) {      // inject group k (warp-uniform)
+							#pragma unroll
+							for (int r = k*(LEG_GROUP/32); r < (k + 1)*(LEG_GROUP/32); r++) {
+								int64_t kk = (int64_t)m*A.npair_pad + (chunk*R + r)*32 + lane;
+								g[r] = A.st_p[kk]; gp[r] = A.st_pp[kk]; sc[r] = A.st_sp[kk];
+							}
+							phase = 0;
+						}
+					}
 					double v[NV];
 					#pragma unroll
 					for (int i = 0; i < NV; i++) v[i] = 0;
@@ -603,8 +663,10 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 	__shared__ __align__(16) Tile2 tiles[2][TL];
 	__shared__ __align__(16) double2 raw_e[TL], raw_b[TL];       // cp.async staging: E, B, (a, b, alpha)
 	__shared__ __align__(16) double raw_ta[TL], raw_tb[TL], raw_al[TL];
+	__shared__ int wslot;
 	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, s = A.spin, l0 = m > s ? m : s;
+	const bool tab = A.st_w != nullptr && R*32 == LEG_GROUP;
 	double2 *legq = A.leg0 + (int64_t)m*A.leg_mstride, *legu = A.leg1 + (int64_t)m*A.leg_mstride;
 	const int nchunk = A.npair_pad/(32*R);
 	if (l0 > lmax) {      // nothing to sum: zero this m column
@@ -635,12 +697,24 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 		for (int r = 0; r < R; r++) {
 			PairInfo pi; pi.rn = -1; pi.rs = -1; pi.x = 0; pi.sh = 0; pi.ch = 1;
 			if (chunk < nchunk) pi = A.pairs[(chunk*R + r)*32 + lane];
-			use[r] = init_pair(pi, sc0, m, s, lmax, x[r], p[r], sp[r], q[r], sq[r]);
-			pp[r] = qp[r] = 0; rn[r] = pi.rn; rs[r] = pi.rs;
+			if (!tab) { use[r] = init_pair(pi, sc0, m, s, lmax, x[r], p[r], sp[r], q[r], sq[r]); pp[r] = qp[r] = 0; }
+			else {
+				x[r] = pi.x;
+				use[r] = pi.rn >= 0 && 2.0*pi.sh*pi.ch >= sc0.dead_sth;
+				p[r] = pp[r] = q[r] = qp[r] = 0; sp[r] = sq[r] = 0;
+				if (chunk < nchunk) {
+					int64_t k = (int64_t)m*A.npair_pad + (chunk*R + r)*32 + lane;
+					p[r] = A.st_p[k]; pp[r] = A.st_pp[k]; q[r] = A.st_q[k]; qp[r] = A.st_qp[k]; sp[r] = A.st_sp[k]; sq[r] = A.st_sq[k];
+				}
+			}
+			rn[r] = pi.rn; rs[r] = pi.rs;
 			#pragma unroll
 			for (int k = 0; k < 8; k++) acc[r][k] = 0;
 			anyuse |= use[r];
 		}
+		int wc = 0;
+		if (tab) { wc = chunk < nchunk ? A.st_w[m*A.ngroup + chunk] : LEG_NEVER; if (wc == LEG_NEVER) anyuse = false; }
+		const int wc_cta = tab ? cta_min<NW>(wc, &wslot) : 0;
 		const bool wuse = __any_sync(0xffffffffu, anyuse);
 		int phase = 0;
 		if (cta_or<NW>(anyuse)) {
@@ -672,13 +746,15 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 					tiles[buf][tid] = t;
 				}
 			};
-			issue(0); finish(0, 0);
+			const int tile0 = min(wc_cta*8/TL, ntile - 1);
+			issue(tile0); finish(tile0, tile0 & 1);
 			cta_sync<NW>();
-			for (int tile = 0; tile < ntile; tile++) {
+			for (int tile = tile0; tile < ntile; tile++) {
 				const int buf = tile & 1;
 				if (tile + 1 < ntile) issue(tile + 1);
 				const int nwin = (min(TL, nl - tile*TL) + 7) >> 3;
 				for (int w = 0; wuse && w < nwin; w++) {
+					if (tile*(TL/8) + w < wc) continue;
 					if (phase < 2) {
 						bool mylive = true, anylive = false;
 						#pragma unroll
@@ -780,6 +856,17 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 	const int nchunk = A.npair_pad/(32*R);
 	bool first = true;
 	const int round0 = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R*NW);
+	// with a start table the rounds begin at different l: the row is zeroed once and every round adds to it
+	const bool tab = A.st_w != nullptr && R*32 == LEG_GROUP && NW == 1;
+	if (tab) {
+		for (int i = tid; i < nl; i += NW*32) {
+			int64_t idx = ms + (int64_t)(l0 + i)*A.lstride;
+			A.alm0[idx] = make_double2(0, 0);
+			if (!A.deriv1) A.alm1[idx] = make_double2(0, 0);
+		}
+		__syncwarp();
+		first = false;
+	}
 
 	for (int round = round0; round*NW < nchunk; round++) {
 		const int chunk = round*NW + warp;
@@ -789,8 +876,13 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 		for (int r = 0; r < R; r++) {
 			PairInfo pi; pi.rn = -1; pi.rs = -1; pi.x = 0; pi.sh = 0; pi.ch = 1;
 			if (chunk < nchunk) pi = A.pairs[(chunk*R + r)*32 + lane];
-			use[r] = init_pair(pi, sc0, m, s, lmax, x[r], p[r], sp[r], q[r], sq[r]);
-			pp[r] = qp[r] = 0;
+			if (!tab) { use[r] = init_pair(pi, sc0, m, s, lmax, x[r], p[r], sp[r], q[r], sq[r]); pp[r] = qp[r] = 0; }
+			else {
+				x[r] = pi.x;
+				use[r] = pi.rn >= 0 && 2.0*pi.sh*pi.ch >= sc0.dead_sth;
+				int64_t k = (int64_t)m*A.npair_pad + (chunk*R + r)*32 + lane;
+				p[r] = A.st_p[k]; pp[r] = A.st_pp[k]; q[r] = A.st_q[k]; qp[r] = A.st_qp[k]; sp[r] = A.st_sp[k]; sq[r] = A.st_sq[k];
+			}
 			double2 qn = make_double2(0, 0), un = qn, qs = qn, us = qn;
 			if (use[r]) { qn = legq[pi.rn]; un = legu[pi.rn]; if (pi.rs >= 0) { qs = legq[pi.rs]; us = legu[pi.rs]; } }
 			// Z+ = Q + iU = (Qr - Ui, Qi + Ur),  Z- = Q - iU = (Qr + Ui, Qi - Ur)
@@ -809,10 +901,13 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 					t = zin[r][k + 4]; zin[r][k + 4] = zin[r][k + 6]; zin[r][k + 6] = t;
 				}
 				double t = p[r]; p[r] = q[r]; q[r] = t;
+				t = pp[r]; pp[r] = qp[r]; qp[r] = t;
 				int ti = sp[r]; sp[r] = sq[r]; sq[r] = ti;
 			}
 			anyuse |= use[r];
 		}
+		int wc = 0;
+		if (tab) { wc = A.st_w[m*A.ngroup + chunk]; if (wc == LEG_NEVER) anyuse = false; }
 		const bool wuse = __any_sync(0xffffffffu, anyuse);
 		int phase = 0;
 		if (!cta_or<NW>(anyuse)) continue;
@@ -829,9 +924,10 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 			#pragma unroll
 			for (int t = tid; t < TL; t += NT) { TileAB &e = tiles[buf][t]; e.a2 = e.a; e.nb = -e.b; }
 		};
-		issue(0, 0); cp_async_wait_all(); finish(0);
+		const int tile0 = tab ? min(wc*8/TL, ntile - 1) : 0;
+		issue(tile0, tile0 & 1); cp_async_wait_all(); finish(tile0 & 1);
 		cta_sync<NW>();
-		for (int tile = 0; tile < ntile; tile++) {
+		for (int tile = tile0; tile < ntile; tile++) {
 			const int buf = tile & 1;
 			if (tile + 1 < ntile) issue(tile + 1, buf ^ 1);
 			const int nwin = (min(TL, nl - tile*TL) + W - 1)/W;
@@ -865,7 +961,7 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 			#pragma unroll 1
 			for (int w = 0; w < TL/W; w++) {
 				double tot = 0;
-				if (wuse && w < nwin) {
+				if (wuse && w < nwin && tile*TL + w*W >= wc*8) {
 					double v[NV];
 					#pragma unroll
 					for (int i = 0; i < NV; i++) v[i] = 0;
@@ -944,6 +1040,63 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 	}
 }
 
+// ------------------------------------------------------------------------------------ start table
+
+// One warp per (group of LEG_GROUP ring pairs, m): runs the recurrence exactly as the kernels' pre-phase does (same
+// window function, same rescaling cadence) until a ring of the group is live, and records window and state.
+template<int SPIN0> __global__ void __launch_bounds__(32) k_start_build(LegArgs A, int *w_out, double *o_p, double *o_pp,
+	double *o_q, double *o_qp, signed char *o_sp, signed char *o_sq)
+{
+	constexpr int R = LEG_GROUP/32;
+	__shared__ __align__(16) Tile2 t2[8];
+	__shared__ __align__(16) Tile0 t0[8];
+	const int grp = blockIdx.x, m = blockIdx.y, lane = threadIdx.x;
+	const int lmax = A.lmax, s = A.spin, l0 = m > s ? m : s;
+	int *wdst = &w_out[m*A.ngroup + grp];
+	const int64_t kbase = (int64_t)m*A.npair_pad + grp*LEG_GROUP + lane;
+	double x[R], p[R], pp[R], q[R], qp[R]; int sp[R], sq[R]; bool use[R], anyuse = false;
+	if (l0 <= lmax) {
+		const SeqConst sc0 = seq_const(m, s, lmax, A.pref);
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			PairInfo pi = A.pairs[grp*LEG_GROUP + r*32 + lane];
+			use[r] = init_pair(pi, sc0, m, s, lmax, x[r], p[r], sp[r], q[r], sq[r]);
+			pp[r] = qp[r] = 0;
+			anyuse |= use[r];
+		}
+	} else {
+		#pragma unroll
+		for (int r = 0; r < R; r++) { x[r] = p[r] = pp[r] = q[r] = qp[r] = 0; sp[r] = sq[r] = 0; use[r] = false; }
+	}
+	int wfound = LEG_NEVER;
+	if (__any_sync(0xffffffffu, anyuse)) {
+		const int nl = lmax - l0 + 1, nwin = (nl + 7) >> 3;
+		const double *ta = A.ta + A.toff[m], *tb = SPIN0 ? nullptr : A.tb + A.toff[m];
+		for (int w = 0; w < nwin; w++) {
+			bool anylive = false;
+			#pragma unroll
+			for (int r = 0; r < R; r++) anylive |= SPIN0 ? (use[r] && sq[r] == 0) : (use[r] & ((sp[r] == 0) | (sq[r] == 0)));
+			if (__any_sync(0xffffffffu, anylive)) { wfound = w; break; }
+			if (lane < 8) {
+				int i = w*8 + lane;
+				if (SPIN0) { Tile0 t; t.ar = t.ai = t.pad = 0; t.a = i < nl ? ta[i] : 0.0; t0[lane] = t; }
+				else { Tile2 t; t.apr = t.api = t.amr = t.ami = 0; t.a = i < nl ? ta[i] : 0.0; t.b = i < nl ? tb[i] : 0.0; t2[lane] = t; }
+			}
+			__syncwarp();
+			if (SPIN0) { double acc[R][2][2]; synth0_window<0, R>(t0, x, q, qp, sq, acc); }
+			else { double acc[R][8]; synth2_window<0, R>(t2, x, p, pp, q, qp, sp, sq, acc); }
+			__syncwarp();
+		}
+	}
+	if (lane == 0) *wdst = wfound;
+	#pragma unroll
+	for (int r = 0; r < R; r++) {
+		const int64_t k = kbase + r*32;
+		if (SPIN0) { o_p[k] = q[r]; o_pp[k] = qp[r]; o_sp[k] = (signed char)sq[r]; }      // spin 0 uses the q sequence (p = q)
+		else { o_p[k] = p[r]; o_pp[k] = pp[r]; o_q[k] = q[r]; o_qp[k] = qp[r]; o_sp[k] = (signed char)sp[r]; o_sq[k] = (signed char)sq[r]; }
+	}
+}
+
 // ------------------------------------------------------------------------------------ host entry points
 
 // Kernel variants: R ring pairs per lane, NW warps per CTA, MINB resident CTAs per SM the register
@@ -968,9 +1121,13 @@ int leg_set_variant(int which, int v)
 static int variant_of(int which) { variant_init(); return g_variant[which]; }
 
 static LegArgs make_args(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
-	double2 *alm, int64_t alm_cstride, double2 *leg)
+	double2 *alm, int64_t alm_cstride, double2 *leg, const LegStart *S = nullptr)
 {
 	LegArgs A;
+	A.st_w = nullptr; A.st_p = A.st_pp = A.st_q = A.st_qp = nullptr; A.st_sp = A.st_sq = nullptr; A.ngroup = G.npair_pad/LEG_GROUP;
+	if (S && S->spin == T.spin && S->w.n) {
+		A.st_w = S->w.p; A.st_p = S->p.p; A.st_pp = S->pp.p; A.st_q = S->q.p; A.st_qp = S->qp.p; A.st_sp = S->sp.p; A.st_sq = S->sq.p;
+	}
 	A.lmax = L.lmax; A.mmax = L.mmax; A.spin = T.spin; A.deriv1 = deriv1;
 	A.toff = T.toff.p; A.ta = T.a.p; A.tb = T.b.p; A.talpha = T.alpha.p; A.pref = T.pref.p;
 	A.pairs = G.pairs.p; A.npair_pad = G.npair_pad; A.npair = G.npair;
@@ -991,11 +1148,28 @@ static int check_args(const LegTables &T, const AlmLayout &L, int deriv1)
 #define LAUNCH(K, ...) K<__VA_ARGS__><<<L.mmax + 1, launch_threads<__VA_ARGS__>(), 0, st>>>(A)
 template<int R, int NW, int... REST> constexpr int launch_threads() { return NW*32; }
 
+int leg_build_start(LegStart &S, const LegTables &T, const LegGeom &G)
+{
+	// the table is built for mmax = T.mmax; mstart / alm are not touched by the build kernel
+	S.spin = T.spin; S.ngroup = G.npair_pad/LEG_GROUP;
+	const size_t nm = (size_t)T.mmax + 1, ne = nm*G.npair_pad;
+	if (S.w.alloc(nm*S.ngroup) || S.p.alloc(ne) || S.pp.alloc(ne) || S.sp.alloc(ne)) return 1;
+	if (T.spin > 0 && (S.q.alloc(ne) || S.qp.alloc(ne) || S.sq.alloc(ne))) return 1;
+	AlmLayout L; L.lmax = T.lmax; L.mmax = T.mmax; L.mstart_d = nullptr; L.lstride = 1;
+	LegArgs A = make_args(T, G, L, 0, nullptr, 0, nullptr);
+	dim3 grid(S.ngroup, (unsigned)nm);
+	if (T.spin == 0) k_start_build<1><<<grid, 32>>>(A, S.w.p, S.p.p, S.pp.p, nullptr, nullptr, S.sp.p, nullptr);
+	else k_start_build<0><<<grid, 32>>>(A, S.w.p, S.p.p, S.pp.p, S.q.p, S.qp.p, S.sp.p, S.sq.p);
+	B2_LAUNCH_CHECK();
+	B2_CHECK(cudaDeviceSynchronize());
+	return 0;
+}
+
 int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
-	const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st)
+	const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st, const LegStart *S)
 {
 	if (check_args(T, L, deriv1)) return 1;
-	LegArgs A = make_args(T, G, L, deriv1, (double2*)alm, alm_cstride, leg);
+	LegArgs A = make_args(T, G, L, deriv1, (double2*)alm, alm_cstride, leg, S);
 	// template arguments: R, NW, MINB, TL (variant 0 = fastest measured on B200 at lmax 8000, profiles/r1*_tune_*)
 	if (T.spin == 0) switch (variant_of(0)) {
 		case 0: LAUNCH(k_synth0, 4, 2, 8, 64); break;
@@ -1014,10 +1188,10 @@ int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 }
 
 int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
-	double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st)
+	double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st, const LegStart *S)
 {
 	if (check_args(T, L, deriv1)) return 1;
-	LegArgs A = make_args(T, G, L, deriv1, alm, alm_cstride, (double2*)leg);
+	LegArgs A = make_args(T, G, L, deriv1, alm, alm_cstride, (double2*)leg, S);
 	// template arguments: R, NW, MINB, TL, W
 	if (T.spin == 0) switch (variant_of(1)) {
 		case 0: LAUNCH(k_adj0, 8, 1, 8, 32, 8); break;

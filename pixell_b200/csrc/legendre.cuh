@@ -32,6 +32,20 @@ struct LegGeom {
 	size_t bytes() const { return pairs.bytes(); }
 };
 
+// Start table of one (plan geometry, spin): for every m and every group of 128 ring pairs (sorted order) the first
+// window of 8 l in which a ring of the group is live, and the recurrence state of all its rings at the start of that
+// window.  The Legendre kernels then begin there instead of running the scaled recurrence up from l = max(m, s):
+// same numbers, without the pre-phase (about 12 % of the synthesis time at lmax 8000).
+#define LEG_GROUP 128
+#define LEG_NEVER 0x7fffffff
+struct LegStart {
+	int spin = -1, ngroup = 0;
+	DevBuf<int> w;                    // [mmax+1][ngroup] first live window (LEG_NEVER: the group never contributes)
+	DevBuf<double> p, pp, q, qp;      // [mmax+1][npair_pad] state at that window (spin 0: p, pp only)
+	DevBuf<signed char> sp, sq;       // scale indices
+	size_t bytes() const { return w.bytes() + p.bytes() + pp.bytes() + q.bytes() + qp.bytes() + sp.bytes() + sq.bytes(); }
+};
+
 struct AlmLayout {
 	int lmax, mmax;
 	const int64_t *mstart_d;  // device [mmax+1]
@@ -39,9 +53,11 @@ struct AlmLayout {
 };
 
 // leg[ncomp_map][mmax+1][nring_pad] complex128; alm component c at alm + c*alm_cstride (complex elements)
+// S (nullable): start table built by leg_build_start for this (T, G)
 int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
-                const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st);
+                const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st, const LegStart *S = nullptr);
 int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
-                double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st);
+                double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st, const LegStart *S = nullptr);
+int leg_build_start(LegStart &S, const LegTables &T, const LegGeom &G);
 int dfma_peak_gflops(double *out);
 int leg_set_variant(int which, int v);

@@ -24,6 +24,7 @@ struct b2_sht_plan {
 	LegGeom geom;
 	RingFft fft;
 	std::map<int, std::unique_ptr<LegTables>> tables;   // by spin
+	std::map<int, std::unique_ptr<LegStart>> starts;    // by spin: where every ring group's recurrence becomes live (see LegStart)
 	DevBuf<double2> leg;               // [2][mmax+1][nring_pad]
 	// 2d plans
 	bool is2d = false;
@@ -39,6 +40,7 @@ struct b2_sht_plan {
 	cudaEvent_t gev[2*B2_MAX_GROUPS] = {};      // per group: operands on the device, results ready
 	double timing[4] = {0, 0, 0, 0};
 	LegTables *get_tables(int spin);
+	LegStart *get_start(int spin);      // nullptr when disabled (B2_NO_START_TABLE=1) or on allocation failure
 	size_t bytes() const;
 	~b2_sht_plan();
 };

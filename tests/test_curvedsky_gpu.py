@@ -213,3 +213,13 @@ def test_torch_tensors_through_curvedsky(cs, geom):
 	assert back.is_cuda and relerr(back.cpu().numpy(), alm) < 1e-12
 	cl = cs.alm2cl(talm[0], ainfo=ai)
 	assert cl.is_cuda and relerr(cl.cpu().numpy(), ao.alm2cl(ao.AlmInfo(lmax), alm[0])) < 1e-13
+
+def test_rand_alm_shapes(cs):
+	"""reference tests/test_pixell.py:320-337 (test_rand_alm): rand_alm and rand_alm_healpy agree on shapes; same seed, same alm"""
+	mypower = np.ones(50)
+	for lmax in [50, 100, 150, 300]:
+		palm = cs.rand_alm(mypower, lmax=lmax)
+		halm = cs.rand_alm_healpy(mypower, lmax=lmax)
+		assert palm.shape == halm.shape == ((lmax+1)*(lmax+2)//2,)
+	a = cs.rand_alm(mypower, lmax=60, seed=3); b = cs.rand_alm(mypower, lmax=60, seed=3)
+	assert np.array_equal(a, b) and np.all(a[:61].imag == 0)

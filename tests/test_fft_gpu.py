@@ -140,3 +140,76 @@ def test_enmap_fft_roundtrip():
 	ly, lx = enmap.laxes(shape, wcs)
 	want = np.fft.ifft2(np.fft.fft2(m)*np.exp(-0.5*sigma**2*(ly[:, None]**2+lx[None, :]**2))).real
 	assert rel(enmap.smooth_gauss(m, sigma), want) < 1e-12
+
+def test_fft_input_shape(F):
+	"""reference tests/test_pixell.py:380-432 (test_fft_input_shape), same five cases"""
+	signal = np.ones((1, 2, 5)); signal[0, 1, :] = 10.
+	out_exp = np.zeros((1, 2, 5), dtype=np.complex128); out_exp[0, 0, 0] = 5; out_exp[0, 1, 0] = 50
+	out = F.fft(signal)
+	np.testing.assert_allclose(out, out_exp, atol=1e-12); assert out.flags["C_CONTIGUOUS"]
+	signal = np.ones((1, 5, 2)); signal[0, :, 1] = 10.
+	out_exp = np.zeros((1, 5, 2), dtype=np.complex128); out_exp[0, 0, 0] = 5; out_exp[0, 0, 1] = 50
+	out = F.fft(signal, axes=[-2])
+	np.testing.assert_allclose(out, out_exp, atol=1e-12); assert out.flags["C_CONTIGUOUS"]
+	signal = np.ones((1, 2, 5, 10)); signal[0, 1, :] = 10.
+	out_exp = np.zeros((1, 2, 5, 10), dtype=np.complex128); out_exp[0, 0, 0, 0] = 50; out_exp[0, 1, 0, 0] = 500
+	out = F.fft(signal, axes=[-2, -1])
+	np.testing.assert_allclose(out, out_exp, atol=1e-12); assert out.flags["C_CONTIGUOUS"]
+	signal = np.ones((1, 2, 5, 10), dtype=np.complex128); signal[0, 1, :] = 10
+	ft = np.zeros((5, 10, 1, 2), dtype=np.complex128).transpose(2, 3, 0, 1)          # non-contiguous output
+	out = F.fft(signal, ft=ft, axes=[-2, -1])
+	np.testing.assert_allclose(out, out_exp, atol=1e-12)
+	assert np.shares_memory(ft, out) and not out.flags["C_CONTIGUOUS"]
+	signal = np.ones((1, 5, 10, 2)); signal[0, :, :, 1] = 10.
+	out_exp = np.zeros((1, 5, 10, 2), dtype=np.complex128); out_exp[0, 0, 0, 0] = 50; out_exp[0, 0, 0, 1] = 500
+	out = F.fft(signal, axes=[-3, -2])
+	np.testing.assert_allclose(out, out_exp, atol=1e-12); assert out.flags["C_CONTIGUOUS"]
+
+def test_ifft_input_shape(F):
+	"""reference tests/test_pixell.py:434-486 (test_ifft_input_shape)"""
+	fsignal = np.ones((1, 2, 5), dtype=np.complex128); fsignal[0, 1, :] = 10.
+	out_exp = np.zeros((1, 2, 5)); out_exp[0, 0, 0] = 5; out_exp[0, 1, 0] = 50
+	out = F.ifft(fsignal)
+	np.testing.assert_allclose(out, out_exp, atol=1e-12); assert out.flags["C_CONTIGUOUS"]
+	fsignal = np.ones((1, 5, 2), dtype=np.complex128); fsignal[0, :, 1] = 10.
+	out_exp = np.zeros((1, 5, 2)); out_exp[0, 0, 0] = 5; out_exp[0, 0, 1] = 50
+	out = F.ifft(fsignal, axes=[-2])
+	np.testing.assert_allclose(out, out_exp, atol=1e-12)
+	fsignal = np.ones((1, 2, 5, 10), dtype=np.complex128); fsignal[0, 1, :] = 10.
+	out_exp = np.zeros((1, 2, 5, 10)); out_exp[0, 0, 0, 0] = 50; out_exp[0, 1, 0, 0] = 500
+	out = F.ifft(fsignal, axes=[-2, -1])
+	np.testing.assert_allclose(out, out_exp, atol=1e-12)
+	tod = np.zeros((5, 10, 1, 2), dtype=np.complex128).transpose(2, 3, 0, 1)
+	out = F.ifft(fsignal, tod=tod, axes=[-2, -1])
+	assert np.shares_memory(tod, out) and not out.flags["C_CONTIGUOUS"]
+	np.testing.assert_allclose(out, out_exp, atol=1e-12)
+	fsignal = np.ones((1, 5, 10, 2), dtype=np.complex128); fsignal[0, :, :, 1] = 10.
+	out_exp = np.zeros((1, 5, 10, 2)); out_exp[0, 0, 0, 0] = 50; out_exp[0, 0, 0, 1] = 500
+	out = F.ifft(fsignal, axes=[-3, -2])
+	np.testing.assert_allclose(out, out_exp, atol=1e-12)
+
+def test_engine_behind_reference_fft_functions(F):
+	"""what pixell/fft.py:133-187 does with a registered engine (engines[name].FFTW(tod, ft, flags=, threads=, axes=,
+	direction=) then plan()): restated here because /root/reference does not travel to the GPU box"""
+	def ref_fft(tod, ft=None, axes=[-1]):
+		tod = np.asarray(tod, np.result_type(tod, 0.0))
+		if ft is None:
+			otype = np.result_type(tod.dtype, 0j); ft = F.engine.empty_aligned(tod.shape, otype, n=32); tod = tod.astype(otype, copy=False)
+		F.engine.FFTW(tod, ft, flags=["FFTW_ESTIMATE"], threads=8, axes=tuple(axes), direction="FFTW_FORWARD")()
+		return ft
+	def ref_ifft(ft, tod=None, axes=[-1], normalize=False):
+		if tod is None: tod = F.engine.empty_aligned(ft.shape, ft.dtype, n=32)
+		F.engine.FFTW(ft, tod, flags=["FFTW_ESTIMATE"], direction="FFTW_BACKWARD", threads=8, axes=tuple(axes))(normalise_idft=False)
+		if normalize: tod /= np.prod([tod.shape[i] for i in axes])
+		return tod
+	rng = np.random.default_rng(12)
+	a = rng.standard_normal((3, 40, 56))
+	f = ref_fft(a, axes=[-2, -1])
+	assert rel(f, np.fft.fft2(a)) < 1e-12
+	assert rel(ref_ifft(f, axes=[-2, -1], normalize=True).real, a) < 1e-12
+	hf = np.empty((3, 40, 29), complex)
+	ref_fft(a, hf, axes=[-2, -1])
+	assert rel(hf, np.fft.rfft2(a)) < 1e-12
+	back = np.empty_like(a)
+	ref_ifft(hf, back, axes=[-2, -1], normalize=True)
+	assert rel(back, a) < 1e-12

@@ -103,3 +103,27 @@ def test_sym_expand_and_multi_pow():
 	assert full.shape == (3, 3, 9) and np.array_equal(full[0, 1], ps[3]) and np.array_equal(full[1, 0], ps[3]) and np.array_equal(full[0, 2], ps[5])
 	cov = np.einsum("ikl,jkl->ijl", full, full)
 	assert np.allclose(cs.multi_pow_half(cov), ao.eigpow_half(cov))
+
+def test_prepare_alm_mmax():
+	"""reference tests/test_pixell.py:760-826 (test_prepare_alm_mmax), same six cases"""
+	from pixell_b200 import curvedsky
+	lmax, nalm = 3, 10
+	alm_in = np.arange(nalm, dtype=np.complex128)
+	ainfo_in = curvedsky.alm_info(lmax=3, mmax=3, nalm=nalm, stride=1, layout="triangular")
+	def same(a, b): return (a.lmax, a.mmax, a.nelem) == (b.lmax, b.mmax, b.nelem)
+	alm_out, ainfo_out = curvedsky.prepare_alm(alm=alm_in, ainfo=None)                      # 1: only alm
+	np.testing.assert_array_almost_equal(alm_out, alm_in); assert same(ainfo_out, ainfo_in)
+	alm_out, ainfo_out = curvedsky.prepare_alm(alm=None, ainfo=ainfo_in)                    # 2: only alm_info -> zeros
+	np.testing.assert_array_almost_equal(alm_out, alm_in*0); assert same(ainfo_out, ainfo_in)
+	alm_out, ainfo_out = curvedsky.prepare_alm(alm=alm_in, ainfo=ainfo_in)                  # 3: both
+	np.testing.assert_array_almost_equal(alm_out, alm_in); assert same(ainfo_out, ainfo_in)
+	with pytest.raises(AssertionError):                                                     # 4: lmax=3, mmax=1 alm alone
+		curvedsky.prepare_alm(alm=np.arange(7, dtype=np.complex128), ainfo=None, lmax=lmax)
+	ainfo1 = curvedsky.alm_info(lmax=3, mmax=1, nalm=7, stride=1, layout="triangular")
+	alm_out, ainfo_out = curvedsky.prepare_alm(alm=None, ainfo=ainfo1)                      # 5: only alm_info, mmax < lmax
+	np.testing.assert_array_almost_equal(alm_out, np.zeros(7, np.complex128)); assert same(ainfo_out, ainfo1)
+	alm7 = np.arange(7, dtype=np.complex128)
+	alm_out, ainfo_out = curvedsky.prepare_alm(alm=alm7, ainfo=ainfo1)                      # 6: both, mmax < lmax
+	np.testing.assert_array_almost_equal(alm_out, alm7); assert same(ainfo_out, ainfo1)
+	with pytest.raises(ValueError): curvedsky.prepare_alm()
+	with pytest.raises(ValueError): curvedsky.prepare_alm(alm=alm7.astype(np.complex64), ainfo=ainfo1)      # dtype contract (:1424)
