@@ -20,13 +20,18 @@ template<typename T> __global__ void k_alm2cl_partial(int lmax, int mmax, const 
 	int mb = blockIdx.y;
 	if (l > lmax) return;
 	double acc = 0;
-	int m0 = mb*MB, m1 = min(min(m0 + MB - 1, mmax), l);
-	for (int m = m0; m <= m1; m++) {
-		int64_t i = mstart[m] + l;
-		typename cplx_of<T>::type u = a1[i], v = a2[i];
-		// m = 0 uses the real parts only (cmisc_core.c:26, :58, :90)
-		if (m == 0) acc += (double)u.x*(double)v.x*0.5;
-		else acc += (double)u.x*(double)v.x + (double)u.y*(double)v.y;
+	const int m0 = mb*MB, m1 = min(min(m0 + MB - 1, mmax), l);
+	// fixed trip count: the loads of one thread are issued together
+	#pragma unroll 8
+	for (int k = 0; k < MB; k++) {
+		const int m = m0 + k;
+		if (m <= m1) {
+			int64_t i = mstart[m] + l;
+			typename cplx_of<T>::type u = a1[i], v = a2[i];
+			// m = 0 uses the real parts only (cmisc_core.c:26, :58, :90)
+			if (m == 0) acc += (double)u.x*(double)v.x*0.5;
+			else acc += (double)u.x*(double)v.x + (double)u.y*(double)v.y;
+		}
 	}
 	partial[(int64_t)mb*(lmax + 1) + l] = acc;
 }
@@ -131,6 +136,33 @@ struct Staged {       // host <-> device staging of one buffer
 	~Staged() { if (owned && dev) cudaFree(dev); }
 };
 
+// device copies of mstart arrays and the alm2cl scratch are kept between calls (a cudaMalloc / cudaFree pair per
+// call would cost more than the kernels); one small cache per process, guarded by a mutex
+#include <mutex>
+#include <list>
+struct MsEntry { int dev; std::vector<int64_t> key; DevBuf<int64_t> buf; };
+static std::mutex g_ms_mutex;
+static std::list<MsEntry> g_ms_cache;
+static DevBuf<double> g_partial;
+
+static int mstart_dev(const int64_t *mstart, int n, const int64_t **out)
+{
+	int dev = 0; B2_CHECK(cudaGetDevice(&dev));
+	std::lock_guard<std::mutex> lock(g_ms_mutex);
+	for (auto it = g_ms_cache.begin(); it != g_ms_cache.end(); ++it)
+		if (it->dev == dev && (int)it->key.size() == n && std::equal(mstart, mstart + n, it->key.begin())) {
+			g_ms_cache.splice(g_ms_cache.begin(), g_ms_cache, it);
+			*out = g_ms_cache.front().buf.p; return 0;
+		}
+	if (g_ms_cache.size() >= 16) g_ms_cache.pop_back();
+	g_ms_cache.emplace_front();
+	MsEntry &e = g_ms_cache.front();
+	e.dev = dev; e.key.assign(mstart, mstart + n);
+	if (e.buf.upload(e.key)) { g_ms_cache.pop_front(); return 1; }
+	*out = e.buf.p;
+	return 0;
+}
+
 static int64_t span_of(int lmax, int mmax, const int64_t *mstart, int64_t lstride)
 {
 	int64_t hi = 0;
@@ -154,22 +186,23 @@ extern "C" int b2_alm2cl(int lmax, int mmax, const int64_t *mstart, int dtype, c
 	if (!alm2) alm2 = alm1;
 	size_t esz = dtype == B2_F64 ? 16 : 8, csz = cl_dtype == B2_F64 ? 8 : 4;
 	int64_t span = span_of(lmax, mmax, mstart, 1);
-	DevBuf<int64_t> ms; if (ms.upload(std::vector<int64_t>(mstart, mstart + mmax + 1))) return 1;
+	const int64_t *msp; if (mstart_dev(mstart, mmax + 1, &msp)) return 1;
 	Staged a, b, c;
 	if (a.in(alm1, span*esz, mem, true, false, st)) return 1;
 	if (alm2 == alm1) b.dev = a.dev; else if (b.in(alm2, span*esz, mem, true, false, st)) return 1;
 	if (c.in(cl, (lmax + 1)*csz, mem, false, true, st)) return 1;
 	int nmb = mmax/MB + 1;
-	DevBuf<double> partial; if (partial.alloc((size_t)nmb*(lmax + 1))) return 1;
+	DevBuf<double> &partial = g_partial;      // persistent scratch (calls on one device are serialised by the caller's stream use)
+	if (partial.n < (size_t)nmb*(lmax + 1) && partial.alloc((size_t)nmb*(lmax + 1))) return 1;
 	dim3 grid((lmax + 256)/256, nmb);
-	if (dtype == B2_F64) k_alm2cl_partial<double><<<grid, 256, 0, st>>>(lmax, mmax, ms.p, (const double2*)a.dev, (const double2*)b.dev, partial.p);
-	else                 k_alm2cl_partial<float><<<grid, 256, 0, st>>>(lmax, mmax, ms.p, (const float2*)a.dev, (const float2*)b.dev, partial.p);
+	if (dtype == B2_F64) k_alm2cl_partial<double><<<grid, 256, 0, st>>>(lmax, mmax, msp, (const double2*)a.dev, (const double2*)b.dev, partial.p);
+	else                 k_alm2cl_partial<float><<<grid, 256, 0, st>>>(lmax, mmax, msp, (const float2*)a.dev, (const float2*)b.dev, partial.p);
 	B2_LAUNCH_CHECK();
 	if (cl_dtype == B2_F64) k_alm2cl_final<double><<<(lmax + 256)/256, 256, 0, st>>>(lmax, nmb, partial.p, (double*)c.dev);
 	else                    k_alm2cl_final<float><<<(lmax + 256)/256, 256, 0, st>>>(lmax, nmb, partial.p, (float*)c.dev);
 	B2_LAUNCH_CHECK();
 	if (c.finish(st)) return 1;
-	B2_CHECK(cudaStreamSynchronize(st));      // temporaries die here
+	if (mem == 0) B2_CHECK(cudaStreamSynchronize(st));      // staging buffers die here
 	return 0;
 }
 
@@ -181,16 +214,16 @@ extern "C" int b2_lmul(int lmax, int mmax, const int64_t *mstart, int dtype, voi
 	B2_REQUIRE(alm && lfun && lfmax >= 0, "lmul: bad arguments");
 	size_t esz = dtype == B2_F64 ? 16 : 8;
 	int64_t span = span_of(lmax, mmax, mstart, 1);
-	DevBuf<int64_t> ms; if (ms.upload(std::vector<int64_t>(mstart, mstart + mmax + 1))) return 1;
+	const int64_t *msp; if (mstart_dev(mstart, mmax + 1, &msp)) return 1;
 	Staged a, f;
 	if (a.in(alm, span*esz, mem, true, true, st)) return 1;
 	if (f.in(lfun, (size_t)(lfmax + 1)*esz/2, mem, true, false, st)) return 1;
 	dim3 grid((lmax + 256)/256, mmax + 1);
-	if (dtype == B2_F64) k_lmul<double><<<grid, 256, 0, st>>>(lmax, mmax, ms.p, (double2*)a.dev, lfmax, (const double*)f.dev);
-	else                 k_lmul<float><<<grid, 256, 0, st>>>(lmax, mmax, ms.p, (float2*)a.dev, lfmax, (const float*)f.dev);
+	if (dtype == B2_F64) k_lmul<double><<<grid, 256, 0, st>>>(lmax, mmax, msp, (double2*)a.dev, lfmax, (const double*)f.dev);
+	else                 k_lmul<float><<<grid, 256, 0, st>>>(lmax, mmax, msp, (float2*)a.dev, lfmax, (const float*)f.dev);
 	B2_LAUNCH_CHECK();
 	if (a.finish(st)) return 1;
-	B2_CHECK(cudaStreamSynchronize(st));
+	if (mem == 0) B2_CHECK(cudaStreamSynchronize(st));
 	return 0;
 }
 
@@ -203,7 +236,7 @@ extern "C" int b2_lmatmul(int N, int M, int lmax, int mmax, const int64_t *mstar
 	B2_REQUIRE(N >= 1 && M >= 1 && M <= LMAT_MAX && N <= LMAT_MAX, "lmatmul supports up to %d components", LMAT_MAX);
 	size_t esz = dtype == B2_F64 ? 16 : 8;
 	int64_t span = span_of(lmax, mmax, mstart, 1);
-	DevBuf<int64_t> ms; if (ms.upload(std::vector<int64_t>(mstart, mstart + mmax + 1))) return 1;
+	const int64_t *msp; if (mstart_dev(mstart, mmax + 1, &msp)) return 1;
 	Staged a, o, f;
 	bool inplace = (alm == oalm);
 	if (mem == 0) {
@@ -214,14 +247,14 @@ extern "C" int b2_lmatmul(int N, int M, int lmax, int mmax, const int64_t *mstar
 	} else { a.dev = (void*)alm; o.dev = oalm; }
 	if (f.in(lmat, (size_t)N*M*(lfmax + 1)*esz/2, mem, true, false, st)) return 1;
 	dim3 grid((lmax + 256)/256, mmax + 1);
-	if (dtype == B2_F64) k_lmatmul<double><<<grid, 256, 0, st>>>(N, M, lmax, mmax, ms.p, (const double2*)a.dev, acs, lfmax, (const double*)f.dev, (double2*)o.dev, ocs);
-	else                 k_lmatmul<float><<<grid, 256, 0, st>>>(N, M, lmax, mmax, ms.p, (const float2*)a.dev, acs, lfmax, (const float*)f.dev, (float2*)o.dev, ocs);
+	if (dtype == B2_F64) k_lmatmul<double><<<grid, 256, 0, st>>>(N, M, lmax, mmax, msp, (const double2*)a.dev, acs, lfmax, (const double*)f.dev, (double2*)o.dev, ocs);
+	else                 k_lmatmul<float><<<grid, 256, 0, st>>>(N, M, lmax, mmax, msp, (const float2*)a.dev, acs, lfmax, (const float*)f.dev, (float2*)o.dev, ocs);
 	B2_LAUNCH_CHECK();
 	if (mem == 0) {
 		if (inplace) B2_CHECK(cudaMemcpyAsync(oalm, a.dev, ((N - 1)*ocs + span)*esz, cudaMemcpyDeviceToHost, st));
 		else if (o.finish(st)) return 1;
 	}
-	B2_CHECK(cudaStreamSynchronize(st));
+	if (mem == 0) B2_CHECK(cudaStreamSynchronize(st));
 	return 0;
 }
 
@@ -233,16 +266,16 @@ extern "C" int b2_transpose_alm(int lmax, int mmax, const int64_t *mstart, int d
 	B2_REQUIRE(ialm && oalm && ialm != oalm, "transpose_alm: needs distinct input and output");
 	size_t esz = dtype == B2_F64 ? 16 : 8;
 	int64_t span = span_of(lmax, mmax, mstart, 1);
-	DevBuf<int64_t> ms; if (ms.upload(std::vector<int64_t>(mstart, mstart + mmax + 1))) return 1;
+	const int64_t *msp; if (mstart_dev(mstart, mmax + 1, &msp)) return 1;
 	Staged a, o;
 	if (a.in(ialm, span*esz, mem, true, false, st)) return 1;
 	if (o.in(oalm, span*esz, mem, true, true, st)) return 1;
 	dim3 grid((lmax + 256)/256, mmax + 1);
-	if (dtype == B2_F64) k_transpose_alm<double2><<<grid, 256, 0, st>>>(lmax, mmax, ms.p, (const double2*)a.dev, (double2*)o.dev);
-	else                 k_transpose_alm<float2><<<grid, 256, 0, st>>>(lmax, mmax, ms.p, (const float2*)a.dev, (float2*)o.dev);
+	if (dtype == B2_F64) k_transpose_alm<double2><<<grid, 256, 0, st>>>(lmax, mmax, msp, (const double2*)a.dev, (double2*)o.dev);
+	else                 k_transpose_alm<float2><<<grid, 256, 0, st>>>(lmax, mmax, msp, (const float2*)a.dev, (float2*)o.dev);
 	B2_LAUNCH_CHECK();
 	if (o.finish(st)) return 1;
-	B2_CHECK(cudaStreamSynchronize(st));
+	if (mem == 0) B2_CHECK(cudaStreamSynchronize(st));
 	return 0;
 }
 
@@ -254,16 +287,16 @@ extern "C" int b2_transfer_alm(int lmax1, int mmax1, const int64_t *mstart1, int
 	B2_REQUIRE(alm1 && alm2 && ls1 >= 1 && ls2 >= 1, "transfer_alm: bad arguments");
 	size_t esz = dtype == B2_F64 ? 16 : 8;
 	int lmax = std::min(lmax1, lmax2), mmax = std::min(mmax1, mmax2);
-	DevBuf<int64_t> m1, m2;
-	if (m1.upload(std::vector<int64_t>(mstart1, mstart1 + mmax1 + 1)) || m2.upload(std::vector<int64_t>(mstart2, mstart2 + mmax2 + 1))) return 1;
+	const int64_t *m1p, *m2p;
+	if (mstart_dev(mstart1, mmax1 + 1, &m1p) || mstart_dev(mstart2, mmax2 + 1, &m2p)) return 1;
 	Staged a, o;
 	if (a.in(alm1, span_of(lmax1, mmax1, mstart1, ls1)*esz, mem, true, false, st)) return 1;
 	if (o.in(alm2, span_of(lmax2, mmax2, mstart2, ls2)*esz, mem, true, true, st)) return 1;
 	dim3 grid((lmax + 256)/256, mmax + 1);
-	if (dtype == B2_F64) k_transfer_alm<double2><<<grid, 256, 0, st>>>(lmax, mmax, m1.p, ls1, (const double2*)a.dev, m2.p, ls2, (double2*)o.dev);
-	else                 k_transfer_alm<float2><<<grid, 256, 0, st>>>(lmax, mmax, m1.p, ls1, (const float2*)a.dev, m2.p, ls2, (float2*)o.dev);
+	if (dtype == B2_F64) k_transfer_alm<double2><<<grid, 256, 0, st>>>(lmax, mmax, m1p, ls1, (const double2*)a.dev, m2p, ls2, (double2*)o.dev);
+	else                 k_transfer_alm<float2><<<grid, 256, 0, st>>>(lmax, mmax, m1p, ls1, (const float2*)a.dev, m2p, ls2, (float2*)o.dev);
 	B2_LAUNCH_CHECK();
 	if (o.finish(st)) return 1;
-	B2_CHECK(cudaStreamSynchronize(st));
+	if (mem == 0) B2_CHECK(cudaStreamSynchronize(st));
 	return 0;
 }
