@@ -12,6 +12,7 @@
 #include "../../include/b200sht.h"
 #include "fft_smem.cuh"
 #include <algorithm>
+#include <stdlib.h>
 #include <memory>
 
 enum { LK_C128, LK_C64, LK_F64, LK_F32, LK_H128, LK_H64 };
@@ -94,7 +95,7 @@ template<bool INV> __global__ void k_fft_axis(AxisArgs A)
 	for (int idx = tid; idx < tot; idx += T) {
 		int line, kk;
 		if (A.jfast) { line = idx/nl; kk = idx - line*nl; } else { kk = idx/nb; line = idx - kk*nb; }
-		if (line < nbv) fft_st(A, bout + line*A.os_in, p + P*kk, s[line*ls + fft_pad(A.d, A.d.rev[kk])]);
+		if (line < nbv) fft_st(A, bout + line*A.os_in, p + P*kk, s[line*ls + fft_pad(A.d, __ldg(&A.d.rev[kk]))]);
 	}
 }
 
@@ -148,7 +149,7 @@ template<bool INV, int MODE, int P> __global__ void __launch_bounds__(512) k_fft
 				if (A.lk == LK_C128) { xa = ((const double2*)A.in)[b + jj*A.is_t]; xb = ((const double2*)A.in)[b + jm*A.is_t]; }
 				else { float2 fa = ((const float2*)A.in)[b + jj*A.is_t], fb = ((const float2*)A.in)[b + jm*A.is_t]; xa = make_double2(fa.x, fa.y); xb = make_double2(fb.x, fb.y); }
 				double2 sm = make_double2(xa.x + xb.x, xa.y - xb.y), df = make_double2(xa.x - xb.x, xa.y + xb.y);
-				double2 w = A.d.tw[jj]; w.y = -w.y;                // e^{+2 pi i jj/n}
+				double2 w = __ldg(&A.d.tw[jj]); w.y = -w.y;                // e^{+2 pi i jj/n}
 				double2 u = cmul(df, w);
 				v[q] = make_double2(sm.x - u.y, sm.y + u.x);
 			}
@@ -156,18 +157,18 @@ template<bool INV, int MODE, int P> __global__ void __launch_bounds__(512) k_fft
 		double2 acc = v[0];
 		#pragma unroll
 		for (int q = 1; q < P; q++) acc = cadd(acc, p ? cmul(v[q], wq[q]) : v[q]);
-		if (P > 1 && p) acc = cmul(acc, cj(A.d.tw[twq*j*p], INV));
+		if (P > 1 && p) acc = cmul(acc, cj(__ldg(&A.d.tw[twq*j*p]), INV));
 		s[line*ls + fft_pad(A.d, j)] = acc;
 	}
 	__syncthreads();
 	fft_smem<INV>(s, A.d, tid, T, nb, twsm);
-	#pragma unroll 2
+	#pragma unroll 4
 	for (int idx = tid; idx < tot; idx += T) {
 		int line, kk;
 		if (A.jfast) { line = idx/nl; kk = idx - line*nl; } else { kk = idx/nb; line = idx - kk*nb; }
 		if (line >= nbv) continue;
 		const int k = p + P*kk;
-		const double2 x = s[line*ls + fft_pad(A.d, A.d.rev[kk])];
+		const double2 x = s[line*ls + fft_pad(A.d, __ldg(&A.d.rev[kk]))];
 		const int64_t bo = bout + line*A.os_in;
 		if (MODE == FM_C2C) ((double2*)A.out)[bo + k*A.os_t] = make_double2(x.x*A.scale, x.y*A.scale);
 		else if (MODE == FM_C2R_PACKED) {
@@ -176,9 +177,9 @@ template<bool INV, int MODE, int P> __global__ void __launch_bounds__(512) k_fft
 		} else {
 			// partner nc - k has the same residue mod P (P <= 2)
 			const int kp = k ? nc - k : 0;
-			const double2 y = s[line*ls + fft_pad(A.d, A.d.rev[(kp - p)/P])];
+			const double2 y = s[line*ls + fft_pad(A.d, __ldg(&A.d.rev[(kp - p)/P]))];
 			double2 sm = make_double2(x.x + y.x, x.y - y.y), df = make_double2(x.x - y.x, x.y + y.y);
-			double2 u = cmul(df, A.d.tw[k]);                    // w_n^k (Z_k - conj Z_{nc-k})
+			double2 u = cmul(df, __ldg(&A.d.tw[k]));                    // w_n^k (Z_k - conj Z_{nc-k})
 			double2 X = make_double2(0.5*(sm.x + u.y), 0.5*(sm.y - u.x));
 			const int savek = A.sk;      // complex storer without the k <= n/2 test
 			if (savek == SK_HC128 || savek == SK_C128) ((double2*)A.out)[bo + k*A.os_t] = make_double2(X.x*A.scale, X.y*A.scale);
@@ -212,7 +213,10 @@ struct b2_fft_plan {
 	DevBuf<char> work, stage_in, stage_out;
 };
 
-static const size_t FFT_SMEM_MAX = 200*1024, FFT_TILE_ELEMS = 6144;
+static const size_t FFT_TILE_ELEMS = 6144;
+// shared memory one CTA may use (B2_FFT_SMEM_KB overrides, for tuning)
+static size_t fft_smem_max() { const char *e = getenv("B2_FFT_SMEM_KB"); return (size_t)(e ? atoi(e) : 200)*1024; }
+#define FFT_SMEM_MAX fft_smem_max()
 
 // strided: the axis is not the contiguous one, so a CTA should hold at least two neighbouring lines (full 32-byte sectors)
 static int setup_pass(AxisPass &ps, int axis, int n, bool can_batch, bool strided)
@@ -334,7 +338,7 @@ static int run_pass(b2_fft_plan *p, AxisPass &ps, const int64_t *dims, const voi
 	const bool plain128 = (mode != FM_C2C) || (lk == LK_C128 && sk == SK_C128);
 	if (ps.tab.d.fast && plain128 && (ps.P == 1 || ps.P == 2 || ps.P == 4 || ps.P == 8) && nblk*ps.P < (1LL << 31)) {
 		grid = dim3((unsigned)(nblk*ps.P), 1);
-		threads = (int)std::min<int64_t>(512, std::max<int64_t>(64, b2_round_up((int64_t)A.nb*ps.nl/8, 32)));
+		threads = (int)std::min<int64_t>(512, std::max<int64_t>(64, b2_round_up((int64_t)A.nb*ps.nl/16, 32)));
 		#define AX2(INV, MODE) (ps.P == 1 ? launch_axis2<INV, MODE, 1>(A, grid, threads, smem, st) : ps.P == 2 ? launch_axis2<INV, MODE, 2>(A, grid, threads, smem, st) : \
 			ps.P == 4 ? launch_axis2<INV, MODE, 4>(A, grid, threads, smem, st) : launch_axis2<INV, MODE, 8>(A, grid, threads, smem, st))
 		#define AX2P(INV, MODE) (ps.P == 1 ? launch_axis2<INV, MODE, 1>(A, grid, threads, smem, st) : launch_axis2<INV, MODE, 2>(A, grid, threads, smem, st))

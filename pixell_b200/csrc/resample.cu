@@ -15,6 +15,7 @@
 // (each CTA forms y_p[j] = w_N^{jp} sum_q x[j + qN/P] w_P^{qp} on load and owns outputs k = p mod P).
 #include "resample.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 struct ResampArgs {
 	FftDesc d;
@@ -73,36 +74,36 @@ template<int STAGE, int P> __global__ void __launch_bounds__(512) k_resamp(Resam
 		for (int q = 0; q < P; q++) {
 			const int idx = j + q*Nl;
 			if (STAGE == 1) v[q] = ext_load(R, ca, cb, idx, sigma);
-			else if (STAGE == 3) { int t = 2*idx + R.o2; v[q] = cscale(ext_load(R, ca, cb, idx, sigma), R.wfine[t >= 2*N ? t - 2*N : t]); }
+			else if (STAGE == 3) { int t = 2*idx + R.o2; v[q] = cscale(ext_load(R, ca, cb, idx, sigma), __ldg(&R.wfine[t >= 2*N ? t - 2*N : t])); }
 			else if (STAGE == 4) v[q] = B[idx];
 			else v[q] = A[idx];
 		}
 		double2 acc = v[0];
 		#pragma unroll
 		for (int q = 1; q < P; q++) acc = cadd(acc, p ? cmul(v[q], wq[q]) : v[q]);
-		if (P > 1 && p) acc = cmul(acc, cj(R.d.tw[2*j*p], INV));
+		if (P > 1 && p) acc = cmul(acc, cj(__ldg(&R.d.tw[2*j*p]), INV));
 		s[fft_pad(R.d, j)] = acc;
 	}
 	__syncthreads();
 	fft_smem<INV>(s, R.d, tid, T, 1, twsm);
 	const double inv = 1.0/N;
-	#pragma unroll 4
+	#pragma unroll 8
 	for (int kk = tid; kk < Nl; kk += T) {
 		const int k = p + P*kk;
-		double2 x = s[fft_pad(R.d, R.d.rev[kk])];
+		double2 x = s[fft_pad(R.d, __ldg(&R.d.rev[kk]))];
 		const int f = (2*k <= N) ? k : k - N;
 		const bool nyq = (2*k == N);
 		if (STAGE == 1) {
-			double2 w = R.d.tw[f >= 0 ? f : -f]; if (f >= 0) w.y = -w.y;     // e^{+i pi f/N}
+			double2 w = __ldg(&R.d.tw[f >= 0 ? f : -f]); if (f >= 0) w.y = -w.y;     // e^{+i pi f/N}
 			A[k] = nyq ? make_double2(0, 0) : cscale(cmul(x, w), inv);
 		} else if (STAGE == 2) {
 			int t = 2*k + R.o2 + 1;
-			B[k] = cscale(x, R.wfine[t >= 2*N ? t - 2*N : t]);
+			B[k] = cscale(x, __ldg(&R.wfine[t >= 2*N ? t - 2*N : t]));
 		} else if (STAGE == 3) {
 			A[k] = (abs(f) <= R.L && !nyq) ? cscale(x, inv) : make_double2(0, 0);
 		} else if (STAGE == 4) {
 			if (abs(f) <= R.L && !nyq) {
-				double2 w = R.d.tw[f >= 0 ? f : -f]; if (f < 0) w.y = -w.y;  // e^{-i pi f/N}
+				double2 w = __ldg(&R.d.tw[f >= 0 ? f : -f]); if (f < 0) w.y = -w.y;  // e^{-i pi f/N}
 				double2 b = cscale(cmul(x, w), inv), a = A[k];
 				A[k] = make_double2(0.5*(a.x + b.x), 0.5*(a.y + b.y));
 			}
@@ -156,7 +157,7 @@ template<int STAGE, int P> __global__ void __launch_bounds__(512) k_resamp_adj(R
 				else v[q] = cscale(sum, mu);
 			} else if (STAGE == 2) {
 				const int f = (2*idx <= N) ? idx : idx - N;
-				double2 w = R.d.tw[f >= 0 ? f : -f]; if (f >= 0) w.y = -w.y;     // e^{+i pi f/N}
+				double2 w = __ldg(&R.d.tw[f >= 0 ? f : -f]); if (f >= 0) w.y = -w.y;     // e^{+i pi f/N}
 				v[q] = cmul(A[idx], w);
 			} else if (STAGE == 3) v[q] = B[idx];
 			else if (STAGE == 4) v[q] = C[idx];
@@ -165,31 +166,31 @@ template<int STAGE, int P> __global__ void __launch_bounds__(512) k_resamp_adj(R
 		double2 acc = v[0];
 		#pragma unroll
 		for (int q = 1; q < P; q++) acc = cadd(acc, p ? cmul(v[q], wq[q]) : v[q]);
-		if (P > 1 && p) acc = cmul(acc, cj(R.d.tw[2*j*p], INV));
+		if (P > 1 && p) acc = cmul(acc, cj(__ldg(&R.d.tw[2*j*p]), INV));
 		s[fft_pad(R.d, j)] = acc;
 	}
 	__syncthreads();
 	fft_smem<INV>(s, R.d, tid, T, 1, twsm);
 	const double inv = 1.0/N;
-	#pragma unroll 4
+	#pragma unroll 8
 	for (int kk = tid; kk < Nl; kk += T) {
 		const int k = p + P*kk;
-		double2 x = s[fft_pad(R.d, R.d.rev[kk])];
+		double2 x = s[fft_pad(R.d, __ldg(&R.d.rev[kk]))];
 		const int f = (2*k <= N) ? k : k - N;
 		const bool nyq = (2*k == N);
 		if (STAGE == 1) {
 			A[k] = (abs(f) <= R.L && !nyq) ? cscale(x, 0.5) : make_double2(0, 0);
 		} else if (STAGE == 2) {
 			int t = 2*k + R.o2 + 1;
-			B[k] = cscale(x, inv*R.wfine[t >= 2*N ? t - 2*N : t]);
+			B[k] = cscale(x, inv*__ldg(&R.wfine[t >= 2*N ? t - 2*N : t]));
 		} else if (STAGE == 3) {
-			double2 w = R.d.tw[f >= 0 ? f : -f]; if (f < 0) w.y = -w.y;      // e^{-i pi f/N}
+			double2 w = __ldg(&R.d.tw[f >= 0 ? f : -f]); if (f < 0) w.y = -w.y;      // e^{-i pi f/N}
 			C[k] = nyq ? make_double2(0, 0) : cscale(cmul(x, w), inv);
 		} else if (STAGE == 4) {
 			B[k] = x;
 		} else {
 			int t = 2*k + R.o2;
-			C[k] = cscale(x, inv*R.wfine[t >= 2*N ? t - 2*N : t]);
+			C[k] = cscale(x, inv*__ldg(&R.wfine[t >= 2*N ? t - 2*N : t]));
 		}
 	}
 }
@@ -245,6 +246,14 @@ __global__ void k_wfine(double *w, int N, double scale)
 	if (t > 0 && t < N) w[2*N - t] = v;
 }
 
+// shared memory a CTA may use for one transform (measured: one CTA per SM with the transform split over two CTAs is as
+// fast as smaller pieces with several CTAs per SM; B2_RESAMP_SMEM_KB overrides, for tuning)
+static size_t resamp_smem_limit()
+{
+	const char *e = getenv("B2_RESAMP_SMEM_KB");
+	return (size_t)(e ? atoi(e) : 210)*1024;
+}
+
 bool ThetaResampler::needed(const std::string &g, int ntheta, int lmax)
 {
 	if (g == "DH" || g == "F2") return false;
@@ -269,7 +278,7 @@ int ThetaResampler::build(const std::string &g, int ntheta, int64_t nphi_, int l
 		if (mir[k] == pos[k]) mu[k] = 1.0; else sr[mir[k]] = k | 0x40000000;
 	}
 	P = 1;
-	while ((size_t)(FftTables::smem_len(N/P) + 2*N/FFT_TWLO + FFT_TWLO + 1)*sizeof(double2) > 210*1024) {
+	while ((size_t)(FftTables::smem_len(N/P) + 2*N/FFT_TWLO + FFT_TWLO + 1)*sizeof(double2) > resamp_smem_limit()) {
 		int np = P*2;
 		B2_REQUIRE(np <= 8 && N % np == 0, "theta transform of length %d does not fit in shared memory", N);
 		P = np;
@@ -277,7 +286,7 @@ int ThetaResampler::build(const std::string &g, int ntheta, int64_t nphi_, int l
 	if (tab.build(N/P, 2*N)) return 1;
 	twoff = (int)FftTables::smem_len(N/P);
 	smem = sizeof(double2)*(size_t)(twoff + tab.twsm_len());
-	threads = (int)std::min<int64_t>(512, std::max<int64_t>(64, b2_round_up(N/P/4, 32)));
+	threads = (int)std::min<int64_t>(512, std::max<int64_t>(64, b2_round_up(N/P/16, 32)));      // one radix-16 butterfly per thread and pass
 	if (src.upload(sr) || mult.upload(mu) || wfine.alloc(2*(size_t)N) || dpos.upload(pos) || dmir.upload(mir)) return 1;
 	k_wfine<<<(N + 128)/128, 128>>>(wfine.p, N, 4.0*M_PI/(2.0*N)/(double)nphi);
 	B2_LAUNCH_CHECK();
