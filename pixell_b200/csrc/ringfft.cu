@@ -230,26 +230,41 @@ template<typename MapT> __global__ void k_leg2map(RingArgs A)
 	const double2 *twsm = s + A.twoff;
 	fft_load_tw(s + A.twoff, A.d, tid, T);
 	if (A.half) {
-		// half spectrum X[0..nf] of the real ring, |m| aliased mod nphi
-		for (int k = tid; k <= nf; k += T) {
-			double2 acc = make_double2(0, 0);
-			if (k == 0 || k == nf) {
-				for (int m = k; m <= mmax; m += n) { double2 g = leg_phase(A, legc, m); acc.x += (m == 0 ? 1.0 : 2.0)*g.x; }
-			} else {
-				for (int m = k; m <= mmax; m += n) acc = cadd(acc, leg_phase(A, legc, m));
-				for (int m = n - k; m <= mmax; m += n) acc = cadd(acc, cconj(leg_phase(A, legc, m)));
+		if (mmax < nf) {
+			// no aliasing: X[k] = leg_k e^{i k phi0} for k <= mmax, 0 above; branch-free so that the loads of a thread overlap
+			const bool flip = A.xdir < 0;
+			#pragma unroll 4
+			for (int k = tid; k <= nf; k += T) {
+				const int kc = min(k, mmax);
+				double2 g = cmul(__ldg(&legc[(int64_t)kc*A.nring_pad]), __ldg(&A.phase[kc]));
+				if (flip) g.y = -g.y;
+				if (k == 0) g = make_double2(g.x, 0.0);
+				if (k > mmax) g = make_double2(0, 0);
+				s[SI(k)] = g;
 			}
-			s[SI(k)] = acc;
+		} else {
+			// half spectrum X[0..nf] of the real ring, |m| aliased mod nphi
+			for (int k = tid; k <= nf; k += T) {
+				double2 acc = make_double2(0, 0);
+				if (k == 0 || k == nf) {
+					for (int m = k; m <= mmax; m += n) { double2 g = leg_phase(A, legc, m); acc.x += (m == 0 ? 1.0 : 2.0)*g.x; }
+				} else {
+					for (int m = k; m <= mmax; m += n) acc = cadd(acc, leg_phase(A, legc, m));
+					for (int m = n - k; m <= mmax; m += n) acc = cadd(acc, cconj(leg_phase(A, legc, m)));
+				}
+				s[SI(k)] = acc;
+			}
 		}
 		__syncthreads();
 		// Z[k] = (X[k] + conj X[nf-k]) + i e^{+2 pi i k/n} (X[k] - conj X[nf-k]); z = IFFT(Z) packs (x_2j, x_2j+1)
+		#pragma unroll 4
 		for (int k = tid; 2*k <= nf; k += T) {
 			if (k == 0) { double x0 = s[0].x, xn = s[SI(nf)].x; s[0] = make_double2(x0 + xn, x0 - xn); }
 			else {
 				int kk = nf - k;
 				double2 a = s[SI(k)], b = s[SI(kk)];
 				double2 s1 = make_double2(a.x + b.x, a.y - b.y), d1 = make_double2(a.x - b.x, a.y + b.y);
-				double2 w = A.d.tw[k]; w.y = -w.y;
+				double2 w = __ldg(&A.d.tw[k]); w.y = -w.y;
 				double2 wd = cmul(w, d1);
 				s[SI(k)] = make_double2(s1.x - wd.y, s1.y + wd.x);
 				if (kk != k) s[SI(kk)] = make_double2(s1.x + wd.y, -s1.y + wd.x);
@@ -257,8 +272,9 @@ template<typename MapT> __global__ void k_leg2map(RingArgs A)
 		}
 		__syncthreads();
 		fft_smem<true>(s, A.d, tid, T, 1, twsm);
+		#pragma unroll 8
 		for (int64_t i = tid; i < A.npix; i += T) {
-			double2 z = s[SI(A.d.rev[i >> 1])];
+			double2 z = s[SI(__ldg(&A.d.rev[i >> 1]))];
 			row[i] = (MapT)((i & 1) ? z.y : z.x);
 		}
 	} else {
@@ -285,6 +301,7 @@ template<typename MapT> __global__ void k_map2leg(RingArgs A)
 	const double2 *twsm = s + A.twoff;
 	fft_load_tw(s + A.twoff, A.d, tid, T);
 	if (A.half) {
+		#pragma unroll 8
 		for (int j = tid; j < nf; j += T) {
 			int64_t i = 2*(int64_t)j;
 			double a = i < A.npix ? (double)row[i] : 0.0, b = i + 1 < A.npix ? (double)row[i + 1] : 0.0;
@@ -292,6 +309,21 @@ template<typename MapT> __global__ void k_map2leg(RingArgs A)
 		}
 		__syncthreads();
 		fft_smem<false>(s, A.d, tid, T, 1, twsm);
+		if (mmax < nf) {
+			// no aliasing (k = m): branch-free so that the table loads and the scattered stores of a thread overlap
+			const bool flip = A.xdir < 0;
+			#pragma unroll 4
+			for (int m = tid; m <= mmax; m += T) {
+				const int k2 = m == 0 ? 0 : nf - m;
+				double2 zk = s[SI(__ldg(&A.d.rev[m]))], zc = cconj(s[SI(__ldg(&A.d.rev[k2]))]);
+				double2 e = make_double2(0.5*(zk.x + zc.x), 0.5*(zk.y + zc.y));
+				double2 dd = make_double2(0.5*(zk.x - zc.x), 0.5*(zk.y - zc.y));
+				double2 o = make_double2(dd.y, -dd.x);
+				double2 x = cadd(e, cmul(__ldg(&A.d.tw[m]), o));
+				if (flip) x.y = -x.y;
+				legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, __ldg(&A.phase[m])), wgt);
+			}
+		} else
 		for (int m = tid; m <= mmax; m += T) {
 			int k = m % n; bool fold = k > nf; if (fold) k = n - k;
 			int k1 = k == nf ? 0 : k, k2 = k == 0 ? 0 : nf - k;
