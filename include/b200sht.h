@@ -154,6 +154,14 @@ int b2_fft_execute(b2_fft_plan *plan, const void *in, void *out, int forward, do
                    int mem, void *stream);
 void b2_fft_plan_destroy(b2_fft_plan *plan);
 
+/* QU <-> EB rotation of flat-sky Fourier maps: enmap.queb_rotmat + enmap.map_mul (pixell/enmap.py:1391-1400,
+ * 1418-1427) as used by map2harm / harm2map (:1358-1383).  Rotates, in place, nbatch pairs of complex [ny][nx]
+ * components (pair k: data + k*batch_stride and data + k*batch_stride + comp_stride, strides in complex elements)
+ * by the angle spin*atan2(sign*lx[x], ly[y]); ly[ny], lx[nx] are HOST arrays (enmap.laxes).  sign = +1: map2harm
+ * (HEALPix convention), -1: harm2map or iau=True (the product of the two flips, enmap.py:1394-1396). */
+int b2_queb_rotate(void *data, int64_t comp_stride, int64_t nbatch, int64_t batch_stride, int ny, int nx,
+                   const double *ly, const double *lx, int spin, int sign, int dtype, int mem, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

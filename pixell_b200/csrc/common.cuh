@@ -47,3 +47,20 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x-b.x, a.y-b.y); }
 __device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
 __device__ __forceinline__ double2 cscale(double2 a, double s) { return make_double2(a.x*s, a.y*s); }
+
+// cp.async (LDGSTS): global -> shared copies that hold no registers and do not stall the issuing thread;
+// .ca keeps the line in L1 (small tables that are re-read), .cg goes through L2 only (streamed map data)
+__device__ __forceinline__ void cp_async8(void *sm, const void *g)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(sm)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *sm, const void *g)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(sm)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(void *sm, const void *g)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(sm)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }

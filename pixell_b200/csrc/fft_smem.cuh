@@ -253,6 +253,35 @@ template<int R, bool INV> __device__ __forceinline__ void dft_small(double2 (&u)
 	else dft16<INV>(u);
 }
 
+// u[k] *= w1^k, k = 1..R-1; the powers are built by products of depth <= 4
+template<int R> __device__ __forceinline__ void mul_powers(double2 (&u)[R], double2 w1)
+{
+	u[1] = cmul(u[1], w1);
+	if constexpr (R > 2) {
+		double2 w2 = cmul(w1, w1);
+		u[2] = cmul(u[2], w2);
+		if constexpr (R > 3) {
+			double2 w3 = cmul(w2, w1);
+			u[3] = cmul(u[3], w3);
+			if constexpr (R > 4) {
+				double2 w4 = cmul(w2, w2);
+				u[4] = cmul(u[4], w4);
+				if constexpr (R > 5) {
+					double2 w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+					u[5] = cmul(u[5], w5); u[6] = cmul(u[6], w6); u[7] = cmul(u[7], w7);
+					if constexpr (R > 8) {
+						double2 w8 = cmul(w4, w4);
+						u[8] = cmul(u[8], w8);
+						u[9] = cmul(u[9], cmul(w8, w1)); u[10] = cmul(u[10], cmul(w8, w2)); u[11] = cmul(u[11], cmul(w8, w3));
+						u[12] = cmul(u[12], cmul(w8, w4)); u[13] = cmul(u[13], cmul(w8, w5)); u[14] = cmul(u[14], cmul(w8, w6));
+						u[15] = cmul(u[15], cmul(w8, w7));
+					}
+				}
+			}
+		}
+	}
+}
+
 // one decimation-in-frequency pass of radix R over blocks of length Ls (all threads; ends with __syncthreads())
 template<int R, bool INV> __device__ __forceinline__ void fft_pass_fast(double2 *s, const FftDesc &d, int Ls,
 	int tid, int nthreads, int nbatch, const double2 *twsm)
@@ -267,34 +296,7 @@ template<int R, bool INV> __device__ __forceinline__ void fft_pass_fast(double2 
 		#pragma unroll
 		for (int q = 0; q < R; q++) u[q] = S[fft_pad(d, base + q*m)];
 		dft_small<R, INV>(u);
-		if (j) {
-			// u[k] *= w^k, w = exp(-+ 2 pi i j / Ls); the powers are built by products of depth <= 4
-			double2 w1 = fft_tw<INV>(twsm, nhi, tws*j);
-			u[1] = cmul(u[1], w1);
-			if constexpr (R > 2) {
-				double2 w2 = cmul(w1, w1);
-				u[2] = cmul(u[2], w2);
-				if constexpr (R > 3) {
-					double2 w3 = cmul(w2, w1);
-					u[3] = cmul(u[3], w3);
-					if constexpr (R > 4) {
-						double2 w4 = cmul(w2, w2);
-						u[4] = cmul(u[4], w4);
-						if constexpr (R > 5) {
-							double2 w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
-							u[5] = cmul(u[5], w5); u[6] = cmul(u[6], w6); u[7] = cmul(u[7], w7);
-							if constexpr (R > 8) {
-								double2 w8 = cmul(w4, w4);
-								u[8] = cmul(u[8], w8);
-								u[9] = cmul(u[9], cmul(w8, w1)); u[10] = cmul(u[10], cmul(w8, w2)); u[11] = cmul(u[11], cmul(w8, w3));
-								u[12] = cmul(u[12], cmul(w8, w4)); u[13] = cmul(u[13], cmul(w8, w5)); u[14] = cmul(u[14], cmul(w8, w6));
-								u[15] = cmul(u[15], cmul(w8, w7));
-							}
-						}
-					}
-				}
-			}
-		}
+		if (j) mul_powers<R>(u, fft_tw<INV>(twsm, nhi, tws*j));      // u[k] *= w^k, w = exp(-+ 2 pi i j / Ls)
 		#pragma unroll
 		for (int q = 0; q < R; q++) S[fft_pad(d, base + q*m)] = u[q];
 	}

@@ -276,18 +276,8 @@ template<int NC, int W> __device__ __forceinline__ int bfly_element(int lane)
 	return NC*((lane & 15) >> S2) + ((lane >> 4) & 1);
 }
 
-// cp.async (LDGSTS): the next l tile travels global -> shared while the FP64 pipe works on the current
-// one, without holding registers and without a load-to-use stall in the instruction stream
-__device__ __forceinline__ void cp_async8(void *sm, const void *g)
-{
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(sm)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void *sm, const void *g)
-{
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(sm)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// cp_async8 / cp_async16 (common.cuh): the next l tile travels global -> shared while the FP64 pipe works on the
+// current one, without holding registers and without a load-to-use stall in the instruction stream
 
 // CTAs of one warp (NW = 1) are fully warp-synchronous: no block barriers at all
 template<int NW> __device__ __forceinline__ void cta_sync() { if (NW == 1) __syncwarp(); else __syncthreads(); }

@@ -1,7 +1,8 @@
 """pixell_b200.enmap -- the flat-sky harmonic functions of pixell.enmap that sit on the FFT engine
 (reference pixell/enmap.py): fft :1307-1322, ifft :1323-1337, laxes :1273-1294, lmap :1242-1250,
 modlmap :1252-1258, extent (cylindrical) :998-1014, area :1032-1036, pixsize :1097-1099,
-smooth_gauss :1429-1439.  Maps are geometry.ndmap (numpy + wcs) or torch CUDA tensors with wcs=.
+smooth_gauss :1429-1439, map2harm / harm2map and their adjoints :1358-1389, queb_rotmat :1391-1400,
+rotate_pol :1402-1416, map_mul :1418-1427, spin_helper :3378-3388.  Maps are geometry.ndmap (numpy + wcs) or torch CUDA tensors with wcs=.
 Only separable cylindrical (CAR) geometries are handled, as everywhere in this package.
 
 The normalisation factor of fft/ifft is folded into the last FFT pass (no extra sweep over the map).
@@ -104,3 +105,98 @@ def smooth_gauss(emap, sigma, wcs=None):
 	out = enfft.irfft(f, n=nx, axes=[-2, -1], normalize=True)
 	if not L.is_torch(out): out = geometry.ndmap(out, wcs)
 	return out
+
+# ------------------------------------------------------------------ T,Q,U <-> T,E,B (pixell/enmap.py:1358-1427)
+
+def spin_helper(spin, n):
+	"""(spin, first, last+1) component groups; the spin list is cycled (pixell/enmap.py:3378-3388)"""
+	spin = np.array(spin).reshape(-1)
+	i1 = 0; ci = 0
+	while i1 < n:
+		s = int(spin[ci % len(spin)])
+		i2 = i1 + (2 if s != 0 else 1)
+		if i2 > n: raise IndexError("Unpaired component in spin transform")
+		yield s, i1, i2
+		i1 = i2; ci += 1
+
+def queb_rotmat(lmap, inverse=False, iau=False, spin=2, wcs=None):
+	"""2x2 rotation [[c,-s],[s,c]], angle spin*atan2(+-lx, ly) (pixell/enmap.py:1391-1400).  lmap: [2,ny,nx] or the
+	broadcastable (ly[:,None], lx[None,:]) pair."""
+	sign = 1
+	if iau: sign = -sign
+	if inverse: sign = -sign
+	a = spin*np.arctan2(sign*lmap[1], lmap[0])
+	c, s = np.cos(a), np.sin(a)
+	return np.array([[c, -s], [s, c]])
+
+def map_mul(mat, vec):
+	"""element-wise matrix product along the last non-pixel axes (pixell/enmap.py:1418-1427)"""
+	mat = np.asanyarray(mat)
+	if mat.ndim <= 3: return mat*vec
+	return np.einsum("...abyx,...byx->...ayx", mat, vec)
+
+def rotate_pol(emap, angle, comps=[-2, -1], spin=2, axis=-3):
+	"""pixell/enmap.py:1402-1416"""
+	if spin == 0: return emap
+	axis %= emap.ndim
+	c, s = np.cos(spin*angle), np.sin(spin*angle)
+	res = emap.clone() if L.is_torch(emap) else emap.copy()
+	pre = (slice(None),)*axis
+	res[pre+(comps[0],)] = c*emap[pre+(comps[0],)] - s*emap[pre+(comps[1],)]
+	res[pre+(comps[1],)] = s*emap[pre+(comps[0],)] + c*emap[pre+(comps[1],)]
+	return res
+
+def _rotate_pairs(hmap, wcs, spin, sign):
+	"""in place QU<->EB rotation of a complex Fourier map [..., ncomp, ny, nx] on the device (b2_queb_rotate)"""
+	ny, nx = hmap.shape[-2:]
+	ncomp = hmap.shape[-3]
+	ly, lx = laxes(hmap.shape, wcs)
+	ly = np.ascontiguousarray(ly, dtype=np.float64); lx = np.ascontiguousarray(lx, dtype=np.float64)
+	ptr, mem, dt = L.buffer_info(hmap)
+	st = L.strides_elems(hmap)
+	if st[-1] != 1 or st[-2] != nx: raise ValueError("map2harm/harm2map: the pixel axes must be contiguous")
+	pre = hmap.shape[:-3]
+	prec = L.F64 if dt.itemsize == 16 else L.F32
+	stream = L.current_stream(hmap)
+	L.init()
+	for s, i1, i2 in spin_helper(spin, ncomp):
+		if s == 0: continue
+		for idx in (np.ndindex(*pre) if pre else [()]):
+			off = sum(i*k for i, k in zip(idx, st[:-3])) + i1*st[-3]
+			L.check(L.lib().b2_queb_rotate(ptr + off*dt.itemsize, int(st[-3]), 1, 0, int(ny), int(nx), L.p_dbl(ly), L.p_dbl(lx),
+				int(s), int(sign), prec, mem, stream))
+	return hmap
+
+def _on_device(emap):
+	"""(torch CUDA tensor, was_numpy): numpy maps visit the device once for the whole map2harm / harm2map"""
+	if L.is_torch(emap): return emap, False
+	import torch
+	L.init()
+	return torch.from_numpy(np.ascontiguousarray(emap)).cuda(), True
+
+def map2harm(emap, nthread=0, normalize=True, iau=False, spin=[0, 2], adjoint_harm2map=False, wcs=None):
+	"""2-D FFT of the pixels followed by the Q,U -> E,B rotation of every spin-s pair (pixell/enmap.py:1358-1372)."""
+	wcs = _wcs(emap, wcs)
+	dev, was_np = _on_device(emap)
+	hmap = fft(dev, normalize=normalize, adjoint_ifft=adjoint_harm2map, wcs=wcs)
+	if hmap.ndim > 2: _rotate_pairs(hmap, wcs, spin, -1 if iau else 1)
+	if was_np: hmap = geometry.ndmap(hmap.cpu().numpy(), wcs)
+	return hmap
+
+def harm2map(emap, nthread=0, normalize=True, iau=False, spin=[0, 2], keep_imag=False, adjoint_map2harm=False, wcs=None):
+	"""E,B -> Q,U rotation followed by the inverse 2-D FFT (pixell/enmap.py:1373-1383)."""
+	wcs = _wcs(emap, wcs)
+	dev, was_np = _on_device(emap)
+	if dev.ndim > 2:
+		if not was_np: dev = dev.clone()
+		_rotate_pairs(dev, wcs, spin, 1 if iau else -1)
+	res = ifft(dev, normalize=normalize, adjoint_fft=adjoint_map2harm, wcs=wcs)
+	if not keep_imag: res = res.real
+	if was_np: res = geometry.ndmap(res.cpu().numpy(), wcs)
+	return res
+
+def map2harm_adjoint(emap, nthread=0, normalize=True, iau=False, spin=[0, 2], keep_imag=False, wcs=None):
+	return harm2map(emap, nthread=nthread, normalize=normalize, iau=iau, spin=spin, keep_imag=keep_imag, adjoint_map2harm=True, wcs=wcs)
+
+def harm2map_adjoint(emap, nthread=0, normalize=True, iau=False, spin=[0, 2], wcs=None):
+	return map2harm(emap, nthread=nthread, normalize=normalize, iau=iau, spin=spin, adjoint_harm2map=True, wcs=wcs)

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pixell_b200 import _lib as L, sht
 
-W = {"c3": (8192, 16384, 8000), "c2": (4608, 9216, 4096), "c1": (512, 1024, 256)}
+W = {"c3": (8192, 16384, 8000), "c2": (4608, 9216, 4096), "c1": (512, 1024, 256), "c0": (100, 200, 95)}
 
 def main():
 	wl = sys.argv[1] if len(sys.argv) > 1 else "c3"

@@ -33,7 +33,8 @@ def test_c2c_strided_axis(F, shape):
 	back = F.ifft(got, axes=[0])
 	assert rel(back, a*shape[0]) < 1e-12
 
-@pytest.mark.parametrize("shape", [(3, 48, 80), (2, 33, 45), (1, 128, 4099), (2, 4, 6, 10)])
+# (2, 2048, 24), (1, 4096, 6000): both axes run as thread-block clusters (lines split over distributed shared memory)
+@pytest.mark.parametrize("shape", [(3, 48, 80), (2, 33, 45), (1, 128, 4099), (2, 4, 6, 10), (2, 2048, 24), (1, 4096, 6000), (1, 1280, 5000)])
 def test_c2c_2d(F, shape):
 	a = cdata(shape, 2)
 	got = F.fft(a, axes=[-2, -1])
@@ -67,7 +68,7 @@ def test_r2c_c2r_1d(F, shape):
 	back = F.irfft(ft, n=shape[-1], normalize=True)
 	assert rel(back, a) < 1e-12
 
-@pytest.mark.parametrize("shape", [(3, 50, 64), (2, 33, 45), (1, 64, 4100), (2, 1000, 18)])
+@pytest.mark.parametrize("shape", [(3, 50, 64), (2, 33, 45), (1, 64, 4100), (2, 1000, 18), (1, 2048, 10000), (2, 1536, 16384), (1, 6, 65536)])
 def test_r2c_c2r_2d(F, shape):
 	rng = np.random.default_rng(5)
 	a = rng.standard_normal(shape)
@@ -85,6 +86,41 @@ def test_float32(F):
 	ft = F.rfft(r, axes=[-2, -1])
 	assert ft.dtype == np.complex64 and rel(ft, np.fft.rfft2(r.astype(np.float64))) < 2e-6
 	assert rel(F.irfft(ft, n=50, axes=[-2, -1], normalize=True), r) < 2e-6
+
+def test_float32_long_lines(F):
+	"""float32 data on lines long enough for the split / cluster passes"""
+	rng = np.random.default_rng(16)
+	a = rng.standard_normal((2, 2048, 10000)).astype(np.float32)
+	ft = F.rfft(a, axes=[-2, -1])
+	assert ft.dtype == np.complex64
+	assert rel(ft, np.fft.rfft2(a.astype(np.float64))) < 5e-6
+	back = F.irfft(ft, n=a.shape[-1], axes=[-2, -1], normalize=True)
+	assert rel(back, a) < 5e-6
+	c = cdata((1, 2048, 6000), 17, np.complex64)
+	assert rel(F.fft(c, axes=[-2, -1]), np.fft.fft2(c.astype(np.complex128))) < 5e-6
+
+def test_cluster_split(F, monkeypatch):
+	"""B2_FFT_CLUSTER=1: long lines split over thread-block clusters (distributed shared memory) give the same results"""
+	monkeypatch.setenv("B2_FFT_CLUSTER", "1")
+	F.clear_plans()
+	try:
+		a = cdata((1, 4096, 6000), 20)
+		want = np.fft.fft2(a)
+		assert rel(F.fft(a, axes=[-2, -1]), want) < 1e-12
+		b = a.copy(); F.fft(b, b, axes=[-2, -1])
+		assert rel(b, want) < 1e-12
+		assert rel(F.ifft(want, axes=[-2, -1], normalize=True), a) < 1e-12
+		rng = np.random.default_rng(21)
+		for shape, dt, tol in [((2, 1536, 16384), np.float64, 1e-12), ((1, 6, 65536), np.float64, 1e-12), ((1, 2048, 10000), np.float32, 5e-6)]:
+			m = rng.standard_normal(shape).astype(dt)
+			ft = F.rfft(m, axes=[-2, -1])
+			assert rel(ft, np.fft.rfft2(m.astype(np.float64))) < tol
+			assert rel(F.irfft(ft, n=shape[-1], axes=[-2, -1], normalize=True), m) < tol
+		c = cdata((20000, 3), 22)
+		assert rel(F.fft(c, axes=[0]), np.fft.fft(c, axis=0)) < 1e-12
+	finally:
+		monkeypatch.delenv("B2_FFT_CLUSTER")
+		F.clear_plans()
 
 def test_engine_object(F):
 	"""the plug-in shape pixell.fft.engines expects (reference pixell/fft.py:8-60, 126-131)"""
@@ -213,3 +249,74 @@ def test_engine_behind_reference_fft_functions(F):
 	back = np.empty_like(a)
 	ref_ifft(hf, back, axes=[-2, -1], normalize=True)
 	assert rel(back, a) < 1e-12
+
+def _patch(shape, res=0.01):
+	"""small CAR patch centred on (0, 0) with `res` radians per pixel (enmap.geometry(pos=(0,0), shape=, res=))"""
+	from pixell_b200 import geometry
+	ny, nx = shape
+	d = np.rad2deg(res)
+	return geometry.CarWCS(crval=[0, 0], cdelt=[-d, d], crpix=[nx/2+0.5, ny/2+0.5])
+
+@pytest.mark.parametrize("ishape", [(10, 10), (10, 11), (11, 10), (11, 11)])
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_queb_rotmat_complex(ishape, dtype):
+	"""mirror of the reference tests/test_pixell.py:488-518: harm2map -> map2harm round trip of a map that is complex in real space"""
+	from pixell_b200 import enmap, geometry
+	wcs = _patch(ishape)
+	atol = 1e-10 if dtype == np.complex128 else 1e-5
+	for comp in (1, 2):
+		inp = geometry.ndmap(np.zeros((3,)+ishape, dtype), wcs)
+		inp[comp] += 1. + 1.j
+		out = enmap.map2harm(enmap.harm2map(inp, keep_imag=True))
+		assert out.dtype == dtype
+		assert np.allclose(out, inp, rtol=0, atol=atol), (ishape, dtype, comp)
+
+@pytest.mark.parametrize("ishape", [(10, 10), (10, 11), (11, 10), (11, 11)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_queb_rotmat_real(ishape, dtype):
+	"""mirror of the reference tests/test_pixell.py:520-541: map2harm(harm2map(h)) = h for the Fourier map of a real map"""
+	from pixell_b200 import enmap, geometry
+	wcs = _patch(ishape)
+	rng = np.random.default_rng(0)
+	m = geometry.ndmap(rng.standard_normal((3,)+ishape).astype(dtype), wcs)
+	h = enmap.map2harm(m)
+	atol = 1e-10 if dtype == np.float64 else 1e-5
+	assert np.allclose(enmap.map2harm(enmap.harm2map(h)), h, rtol=0, atol=atol)
+
+@pytest.mark.parametrize("iau", [False, True])
+@pytest.mark.parametrize("spin", [[0, 2], [0, 1], [2, 0]])
+def test_map2harm_against_numpy(iau, spin):
+	"""map2harm / harm2map against the reference formulas evaluated with numpy: fft2/sqrt(npix), then queb_rotmat and
+	map_mul per spin pair (pixell/enmap.py:1358-1400); torch CUDA input gives the same numbers as numpy input"""
+	import torch
+	from pixell_b200 import enmap, geometry
+	shape = (3, 36, 50)
+	wcs = _patch(shape[-2:], res=np.deg2rad(0.5))
+	rng = np.random.default_rng(7)
+	m = rng.standard_normal(shape)
+	want = np.fft.fft2(m)/np.sqrt(36*50)
+	lm = enmap.lmap(shape, wcs)
+	for s, i1, i2 in enmap.spin_helper(spin, 3):
+		if s == 0: continue
+		want[i1:i2] = enmap.map_mul(enmap.queb_rotmat(lm, iau=iau, spin=s), want[i1:i2])
+	got = enmap.map2harm(geometry.ndmap(m, wcs), iau=iau, spin=spin)
+	assert rel(np.asarray(got), want) < 1e-12
+	tgot = enmap.map2harm(torch.from_numpy(m).cuda(), iau=iau, spin=spin, wcs=wcs)
+	assert rel(tgot.cpu().numpy(), want) < 1e-12
+	back = enmap.harm2map(got, iau=iau, spin=spin)
+	assert back.dtype == np.float64 and rel(np.asarray(back), m) < 1e-12
+	# "phys" normalisation and the adjoint pair: <harm2map_adjoint(x), y> = <x, harm2map(y)>
+	h = enmap.map2harm(geometry.ndmap(m, wcs), normalize="phys", spin=spin)
+	assert rel(np.asarray(h), np.asarray(got if not iau else enmap.map2harm(geometry.ndmap(m, wcs), spin=spin))*enmap.pixsize(shape, wcs)**0.5) < 1e-12
+	y = geometry.ndmap(rng.standard_normal(shape) + 1j*rng.standard_normal(shape), wcs)
+	lhs = np.vdot(np.asarray(enmap.harm2map_adjoint(geometry.ndmap(m, wcs), spin=spin)), np.asarray(y))
+	rhs = np.vdot(m, np.asarray(enmap.harm2map(y, spin=spin, keep_imag=True)))
+	assert abs(lhs-rhs) < 1e-10*abs(lhs)
+
+def test_rotate_pol():
+	from pixell_b200 import enmap
+	rng = np.random.default_rng(8)
+	m = rng.standard_normal((3, 5, 6))
+	r = enmap.rotate_pol(m, 0.3)
+	c, s = np.cos(0.6), np.sin(0.6)
+	assert np.allclose(r[0], m[0]) and np.allclose(r[1], c*m[1]-s*m[2]) and np.allclose(r[2], s*m[1]+c*m[2])
