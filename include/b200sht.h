@@ -162,6 +162,22 @@ void b2_fft_plan_destroy(b2_fft_plan *plan);
 int b2_queb_rotate(void *data, int64_t comp_stride, int64_t nbatch, int64_t batch_stride, int ny, int nx,
                    const double *ly, const double *lx, int spin, int sign, int dtype, int mem, void *stream);
 
+/* ---- synthesis at arbitrary positions: the steps of ducc0.sht.experimental.synthesis_general (call site
+ * pixell/curvedsky.py:993-1016) around the Legendre stage (b2_alm2leg on a Clenshaw-Curtis plan) and the FFT
+ * engine (b2_fft_*).  All pointers are DEVICE pointers, complex128 / float64.
+ *   b2_general_extend   leg[ncomp][nm][nring_pad] on nt CC rings -> ext[ncomp][nm][N], N = 2 (nt - 1): the
+ *                       (-1)^(m+spin)-symmetric continuation to the full theta circle
+ *   b2_general_scatter  coef[ncomp][nm][N] (theta-FFT of ext, scaled 1/N) -> grid[ncomp][M][M/2+1]: modes |k| <= lmax,
+ *                       m < nm, each times corr[|k|] corr[m] (kernel deconvolution, corr on the device, lmax+1
+ *                       entries), zero elsewhere, m = 0 column Hermitian
+ *   b2_general_interp   fine[ncomp][M][M] (inverse FFT of grid) -> out[c*out_comp_stride + i], i < npos, at
+ *                       loc[i] = (theta, phi) radians: W x W "exponential of semicircle" interpolation */
+int b2_general_extend(const void *leg_dev, void *ext_dev, int ncomp, int nm, int nt, int64_t nring_pad, int spin, void *stream);
+int b2_general_scatter(const void *coef_dev, void *grid_dev, int ncomp, int lmax, int nm, int N, int M,
+                       const double *corr_dev, void *stream);
+int b2_general_interp(const void *fine_dev, int ncomp, int M, const double *loc_dev, int64_t npos, int W, double beta,
+                      void *out_dev, int64_t out_comp_stride, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

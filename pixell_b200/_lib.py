@@ -47,6 +47,9 @@ _PROTOS = {
 	"b2_fft_plan_create": ([ctypes.POINTER(c_vp), c_int, _i64p, _i64p, _i64p, c_int, _intp, c_int, c_int], c_int),
 	"b2_fft_execute": ([c_vp, c_vp, c_vp, c_int, c_dbl, c_int, c_vp], c_int),
 	"b2_fft_plan_destroy": ([c_vp], None),
+	"b2_general_extend": ([c_vp, c_vp, c_int, c_int, c_int, c_i64, c_int, c_vp], c_int),
+	"b2_general_scatter": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
+	"b2_general_interp": ([c_vp, c_int, c_int, c_vp, c_i64, c_int, c_dbl, c_vp, c_i64, c_vp], c_int),
 	"b2_queb_rotate": ([c_vp, c_i64, c_i64, c_i64, c_int, c_int, _dblp, _dblp, c_int, c_int, c_int, c_int, c_vp], c_int),
 }
 

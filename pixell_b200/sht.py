@@ -6,6 +6,7 @@ or torch CUDA tensors (zero-copy).  `nthreads` is accepted and ignored.
 
 Limits (outside the hot path of SURVEY.md section 8): rings must share nphi and phi0 (CAR maps;
 HEALPix ring sets are refused), and lstride/pixstride other than what pixell uses are refused.
+synthesis_general (arbitrary positions, call site curvedsky.py:993-1016) is provided; its adjoint is not.
 """
 import collections, ctypes
 import numpy as np
@@ -226,3 +227,76 @@ def maxlmax(geometry, ny):
 	elif geometry == "DH": return (ny-2)//2
 	elif geometry == "F2": return (ny-1)//2
 	else:                  return ny-1
+
+# ------------------------------------------------------------------ arbitrary positions (ducc0 synthesis_general)
+
+GENERAL_W, GENERAL_BETA = 13, 2.30*13        # interpolation kernel exp(beta (sqrt(1 - z^2) - 1)), |z| <= 1, over W grid points
+
+def _fast_len(n):
+	"""smallest even length >= n with prime factors 2, 3, 5 only (the FFT engine's register-butterfly path)"""
+	n = int(n) + (int(n) & 1)
+	while True:
+		k = n
+		for p in (2, 3, 5):
+			while k % p == 0: k //= p
+		if k == 1: return n
+		n += 2
+
+def _kernel_corr(lmax, M, W=GENERAL_W, beta=GENERAL_BETA):
+	"""1/P_k, k = 0..lmax: P_k = (W/2) int_{-1}^{1} exp(beta (sqrt(1-z^2) - 1)) cos(k W pi z / M) dz is what the
+	periodic sum of the interpolation kernel multiplies mode k with (Gauss-Legendre quadrature, 240 nodes)"""
+	z, w = np.polynomial.legendre.leggauss(240)
+	phi = np.exp(beta*(np.sqrt(1-z*z)-1))
+	k = np.arange(lmax+1)[:, None]
+	P = 0.5*W*np.sum(w*phi*np.cos(k*(W*np.pi/M)*z), 1)
+	return 1.0/P
+
+def synthesis_general(*, alm, loc, spin, lmax, mmax=None, mstart=None, lstride=1, epsilon=1e-10, map=None, mode="STANDARD",
+		nthreads=0, **kw):
+	"""ducc0.sht.experimental.synthesis_general: alm[nca, nalm] -> map[ncm, npos] at loc[npos, 2] = (theta, phi) radians.
+	alm / loc / map: numpy arrays or torch CUDA tensors (complex128 / float64).  The kernel width is fixed (W = 13,
+	about 1e-12), so any epsilon >= 1e-12 is honoured."""
+	import torch
+	from . import fft as enfft
+	if epsilon < 1e-12: raise ValueError("synthesis_general: epsilon below 1e-12 is not supported")
+	md = _MODES[mode]
+	lmax, mmax, mstart, lstride = _layout(lmax, mmax, mstart, lstride)
+	ncm = 1 if spin == 0 else 2
+	nca = 1 if (spin == 0 or md == L.MODE_DERIV1) else 2
+	if alm.ndim != 2 or alm.shape[0] != nca: raise ValueError("alm must have shape [%d, nalm] for spin %d" % (nca, spin))
+	if L.buffer_info(alm)[2] != np.complex128: raise ValueError("synthesis_general: alm must be complex128")
+	dev = torch.device("cuda", L.init())
+	host = not L.is_torch(alm)
+	talm = torch.from_numpy(np.ascontiguousarray(alm)).to(dev) if host else alm.contiguous()
+	tloc = (torch.from_numpy(np.ascontiguousarray(loc, dtype=np.float64)) if not L.is_torch(loc) else loc).to(dev).contiguous()
+	if tloc.ndim != 2 or tloc.shape[1] != 2 or tloc.dtype != torch.float64: raise ValueError("loc must be float64 [npos, 2] = (theta, phi)")
+	npos = tloc.shape[0]
+	# Legendre stage on a Clenshaw-Curtis ring set whose doubled circle has a fast FFT length
+	N = _fast_len(2*lmax+2); nt = N//2+1
+	M = _fast_len(2*(2*lmax+2))
+	plan = plan_2d("CC", nt, N, 0.0, lmax, mmax, mstart, lstride)
+	nring_pad = (nt+31)//32*32
+	nm = mmax+1
+	lib = L.lib(); st = torch.cuda.current_stream(dev).cuda_stream
+	leg = torch.empty((ncm, nm, nring_pad), dtype=torch.complex128, device=dev)
+	L.check(lib.b2_alm2leg(plan.handle, int(spin), md, talm.data_ptr(), int(talm.stride(0)) if nca > 1 else 0, leg.data_ptr(), st))
+	ext = torch.empty((ncm, nm, N), dtype=torch.complex128, device=dev)
+	L.check(lib.b2_general_extend(leg.data_ptr(), ext.data_ptr(), ncm, nm, nt, nring_pad, int(spin), st))
+	del leg
+	enfft.transform(ext, ext, (-1,), True, 1.0/N)                  # theta Fourier coefficients c[c][m][k]
+	corr = torch.from_numpy(_kernel_corr(lmax, M)).to(dev)
+	grid = torch.empty((ncm, M, M//2+1), dtype=torch.complex128, device=dev)
+	L.check(lib.b2_general_scatter(ext.data_ptr(), grid.data_ptr(), ncm, lmax, nm, N, M, corr.data_ptr(), st))
+	del ext
+	fine = torch.empty((ncm, M, M), dtype=torch.float64, device=dev)
+	enfft.transform(grid, fine, (-2, -1), False, 1.0)            # unnormalised inverse: the Fourier series on the M x M grid
+	del grid
+	tout = torch.empty((ncm, npos), dtype=torch.float64, device=dev) if (host or map is None or not L.is_torch(map)) else map
+	if tout.shape != (ncm, npos) or tout.stride(-1) != 1: raise ValueError("map must have shape [%d, npos] with a contiguous last axis" % ncm)
+	L.check(lib.b2_general_interp(fine.data_ptr(), ncm, M, tloc.data_ptr(), npos, GENERAL_W, GENERAL_BETA, tout.data_ptr(), int(tout.stride(0)), st))
+	if map is None: return tout.cpu().numpy() if host else tout
+	if not L.is_torch(map): map[...] = tout.cpu().numpy().astype(map.dtype, copy=False)
+	return map
+
+def adjoint_synthesis_general(**kw):
+	raise NotImplementedError("pixell_b200: adjoint_synthesis_general (spreading) is not provided")
