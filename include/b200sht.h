@@ -177,6 +177,17 @@ int b2_general_scatter(const void *coef_dev, void *grid_dev, int ncomp, int lmax
                        const double *corr_dev, void *stream);
 int b2_general_interp(const void *fine_dev, int ncomp, int M, const double *loc_dev, int64_t npos, int W, double beta,
                       void *out_dev, int64_t out_comp_stride, void *stream);
+/* the transposed steps (ducc0.sht.experimental.adjoint_synthesis_general, same call site with adjoint=True):
+ *   b2_general_spread  val[c*val_comp_stride + i] -> fine[ncomp][M][M] (zeroed first; atomic adds)
+ *   b2_general_gather  grid[ncomp][M][M/2+1] (forward r2c FFT of fine) -> coef[ncomp][nm][N], modes |k| <= lmax
+ *                      times corr[|k|] corr[m], zero elsewhere
+ *   b2_general_fold    ext[ncomp][nm][N] (unnormalised inverse theta-FFT of coef, scaled 1/N) -> leg[ncomp][nm][nring_pad]
+ *                      for b2_leg2alm on the same Clenshaw-Curtis plan */
+int b2_general_spread(void *fine_dev, int ncomp, int M, const double *loc_dev, int64_t npos, int W, double beta,
+                      const void *val_dev, int64_t val_comp_stride, void *stream);
+int b2_general_gather(void *coef_dev, const void *grid_dev, int ncomp, int lmax, int nm, int N, int M,
+                      const double *corr_dev, void *stream);
+int b2_general_fold(void *leg_dev, const void *ext_dev, int ncomp, int nm, int nt, int64_t nring_pad, int spin, void *stream);
 
 #ifdef __cplusplus
 }

@@ -303,10 +303,11 @@ def alm2map(alm, map, spin=[0,2], deriv=False, adjoint=False, copy=False, method
 	return alm if adjoint else map
 
 def alm2map_raw_general(alm, map, loc, ainfo=None, spin=[0,2], deriv=False, copy=False, verbose=False, adjoint=False, nthread=None, epsilon=None):
-	"""alm[..., ncomp, nelem] -> map[..., ncomp, npos] (deriv: alm[..., nelem] -> map[..., 2, npos]) at loc[npos, 2] =
-	(codec, ra) by the non-uniform-FFT synthesis (reference curvedsky.py:993-1016)."""
-	if adjoint: raise NotImplementedError("alm2map_raw_general: adjoint=True (adjoint_synthesis_general) is not provided by pixell_b200")
-	if copy: map = map.clone() if L.is_torch(map) else map.copy()
+	"""alm[..., ncomp, nelem] <-> map[..., ncomp, npos] (deriv: alm[..., nelem], map[..., 2, npos]) at loc[npos, 2] =
+	(codec, ra) by the non-uniform-FFT synthesis or, with adjoint=True, its transpose (reference curvedsky.py:993-1016)."""
+	if copy:
+		if adjoint: alm = alm.clone() if L.is_torch(alm) else alm.copy()
+		else: map = map.clone() if L.is_torch(map) else map.copy()
 	if ainfo is None: ainfo = alm_info(nalm=alm.shape[-1])
 	if epsilon is None: epsilon = 1e-10 if _rdtype(map) == np.float64 else 1e-6
 	epsilon = max(epsilon, 1e-12)
@@ -316,22 +317,28 @@ def alm2map_raw_general(alm, map, loc, ainfo=None, spin=[0,2], deriv=False, copy
 	ctype = np.complex128
 	for I in np.ndindex(*map_full.shape[:-2]):
 		if deriv:
-			a = _astype(alm_full[I][None], ctype)
-			out = sht.synthesis_general(alm=a, spin=1, mode="DERIV1", **kw)
-			out[0] *= -1                          # theta derivative -> dec derivative (reference :1010-1011)
-			_assign(map_full[I], out)
+			if adjoint:
+				m = _astype(map_full[I], np.float64)
+				m = m.clone() if L.is_torch(m) else m.copy()
+				m[0] *= -1
+				_assign(alm_full[I], sht.adjoint_synthesis_general(map=m, spin=1, mode="DERIV1", **kw)[0])
+			else:
+				out = sht.synthesis_general(alm=_astype(alm_full[I][None], ctype), spin=1, mode="DERIV1", **kw)
+				out[0] *= -1                          # theta derivative -> dec derivative (reference :1010-1011)
+				_assign(map_full[I], out)
 		else:
 			for s, j1, j2 in spin_helper(spin, alm_full.shape[-2]):
 				Ij = I+(slice(j1, j2),)
-				out = sht.synthesis_general(alm=_astype(alm_full[Ij], ctype), spin=s, **kw)
-				_assign(map_full[Ij], out)
-	return map
+				if adjoint: _assign(alm_full[Ij], sht.adjoint_synthesis_general(map=_astype(map_full[Ij], np.float64), spin=s, **kw))
+				else: _assign(map_full[Ij], sht.synthesis_general(alm=_astype(alm_full[Ij], ctype), spin=s, **kw))
+	return alm if adjoint else map
 
 def alm2map_pos(alm, pos=None, loc=None, ainfo=None, map=None, spin=[0,2], deriv=False, copy=False, verbose=False, adjoint=False, nthread=None, epsilon=None):
 	"""Like alm2map, but evaluated at arbitrary positions (reference curvedsky.py:174-207):
-	pos: [{dec,ra},...] radians, or loc: [...,{codec,ra}] radians."""
-	if adjoint: raise NotImplementedError("alm2map_pos: adjoint=True is not provided by pixell_b200")
-	if copy and map is not None: map = map.copy()
+	pos: [{dec,ra},...] radians, or loc: [...,{codec,ra}] radians.  adjoint=True: map -> alm (alm must be given)."""
+	if adjoint:
+		if copy and alm is not None: alm = alm.copy()
+	elif copy and map is not None: map = map.copy()
 	if loc is None:
 		loc = np.moveaxis(np.asarray(pos, dtype=np.float64), 0, -1).copy(order="C")
 		loc[..., 0] *= -1
@@ -343,11 +350,12 @@ def alm2map_pos(alm, pos=None, loc=None, ainfo=None, map=None, spin=[0,2], deriv
 	else:     oshape = alm.shape[:-1]+(len(loc),)
 	if map is None: map = np.zeros(oshape, np.zeros(1, _rdtype(alm)).real.dtype)
 	map = map.reshape(oshape)
-	if map.ndim < 2: alm2map_raw_general(alm[None], map[None], loc, ainfo=ainfo, spin=spin, deriv=deriv, epsilon=epsilon)
+	if map.ndim < 2: alm2map_raw_general(alm[None], map[None], loc, ainfo=ainfo, spin=spin, deriv=deriv, epsilon=epsilon, adjoint=adjoint)
 	else:
 		for I in np.ndindex(*map.shape[:-2]):
-			alm2map_raw_general(alm[I], map[I], loc, ainfo=ainfo, spin=spin, deriv=deriv, epsilon=epsilon)
-	return map.reshape(map.shape[:-1]+lpre)
+			alm2map_raw_general(alm[I], map[I], loc, ainfo=ainfo, spin=spin, deriv=deriv, epsilon=epsilon, adjoint=adjoint)
+	map = map.reshape(map.shape[:-1]+lpre)
+	return alm if adjoint else map
 
 def _same(a, b):
 	return L.buffer_info(a)[0] == L.buffer_info(b)[0]

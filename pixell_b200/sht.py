@@ -6,7 +6,7 @@ or torch CUDA tensors (zero-copy).  `nthreads` is accepted and ignored.
 
 Limits (outside the hot path of SURVEY.md section 8): rings must share nphi and phi0 (CAR maps;
 HEALPix ring sets are refused), and lstride/pixstride other than what pixell uses are refused.
-synthesis_general (arbitrary positions, call site curvedsky.py:993-1016) is provided; its adjoint is not.
+synthesis_general / adjoint_synthesis_general (arbitrary positions, call site curvedsky.py:993-1016) are provided.
 """
 import collections, ctypes
 import numpy as np
@@ -298,5 +298,47 @@ def synthesis_general(*, alm, loc, spin, lmax, mmax=None, mstart=None, lstride=1
 	if not L.is_torch(map): map[...] = tout.cpu().numpy().astype(map.dtype, copy=False)
 	return map
 
-def adjoint_synthesis_general(**kw):
-	raise NotImplementedError("pixell_b200: adjoint_synthesis_general (spreading) is not provided")
+def adjoint_synthesis_general(*, map, loc, spin, lmax, mmax=None, mstart=None, lstride=1, epsilon=1e-10, alm=None, mode="STANDARD",
+		nthreads=0, **kw):
+	"""ducc0.sht.experimental.adjoint_synthesis_general: map[ncm, npos] at loc[npos, 2] -> alm[nca, nalm] = Y^T map, the
+	exact transpose of synthesis_general step by step (spread, forward FFT, gather, inverse theta-FFT, fold, K2)."""
+	import torch
+	from . import fft as enfft
+	if epsilon < 1e-12: raise ValueError("adjoint_synthesis_general: epsilon below 1e-12 is not supported")
+	md = _MODES[mode]
+	lmax, mmax, mstart, lstride = _layout(lmax, mmax, mstart, lstride)
+	ncm = 1 if spin == 0 else 2
+	nca = 1 if (spin == 0 or md == L.MODE_DERIV1) else 2
+	if map.ndim != 2 or map.shape[0] != ncm: raise ValueError("map must have shape [%d, npos] for spin %d" % (ncm, spin))
+	dev = torch.device("cuda", L.init())
+	host = not L.is_torch(map)
+	tmap = (torch.from_numpy(np.ascontiguousarray(map, dtype=np.float64)).to(dev) if host else map.to(torch.float64)).contiguous()
+	tloc = (torch.from_numpy(np.ascontiguousarray(loc, dtype=np.float64)) if not L.is_torch(loc) else loc).to(dev).contiguous()
+	if tloc.ndim != 2 or tloc.shape[1] != 2 or tloc.shape[0] != tmap.shape[1]: raise ValueError("loc must be float64 [npos, 2] = (theta, phi)")
+	npos = tloc.shape[0]
+	N = _fast_len(2*lmax+2); nt = N//2+1
+	M = _fast_len(2*(2*lmax+2))
+	plan = plan_2d("CC", nt, N, 0.0, lmax, mmax, mstart, lstride)
+	nring_pad = (nt+31)//32*32
+	nm = mmax+1
+	lib = L.lib(); st = torch.cuda.current_stream(dev).cuda_stream
+	fine = torch.empty((ncm, M, M), dtype=torch.float64, device=dev)
+	L.check(lib.b2_general_spread(fine.data_ptr(), ncm, M, tloc.data_ptr(), npos, GENERAL_W, GENERAL_BETA, tmap.data_ptr(), int(tmap.stride(0)), st))
+	grid = torch.empty((ncm, M, M//2+1), dtype=torch.complex128, device=dev)
+	enfft.transform(fine, grid, (-2, -1), True, 1.0)
+	del fine
+	corr = torch.from_numpy(_kernel_corr(lmax, M)).to(dev)
+	ext = torch.empty((ncm, nm, N), dtype=torch.complex128, device=dev)
+	L.check(lib.b2_general_gather(ext.data_ptr(), grid.data_ptr(), ncm, lmax, nm, N, M, corr.data_ptr(), st))
+	del grid
+	enfft.transform(ext, ext, (-1,), False, 1.0/N)
+	leg = torch.empty((ncm, nm, nring_pad), dtype=torch.complex128, device=dev)
+	L.check(lib.b2_general_fold(leg.data_ptr(), ext.data_ptr(), ncm, nm, nt, nring_pad, int(spin), st))
+	del ext
+	nalm = _alm_len(mstart, lmax, lstride)
+	talm = torch.zeros((nca, nalm), dtype=torch.complex128, device=dev)
+	L.check(lib.b2_leg2alm(plan.handle, int(spin), md, talm.data_ptr(), nalm if nca > 1 else 0, leg.data_ptr(), st))
+	if alm is None: return talm.cpu().numpy() if host else talm
+	if L.is_torch(alm): alm.copy_(talm)
+	else: alm[...] = talm.cpu().numpy().astype(alm.dtype, copy=False)
+	return alm

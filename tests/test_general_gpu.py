@@ -73,7 +73,6 @@ def test_alm2map_pos_interface():
 	assert d.shape == (2, 7, 9)
 	dw = direct(alm[:1], loc, 1, lmax, mode="DERIV1").reshape(2, 7, 9); dw[0] *= -1
 	assert rel(d, dw) < 1e-10
-	with pytest.raises(NotImplementedError): cs.alm2map_pos(alm, pos, adjoint=True)
 
 def test_alm2map_pos_agrees_with_ring_synthesis_at_scale():
 	"""lmax 1500 on the pixel centres of a CAR patch: the non-uniform path against the ring path (K1 + K3)"""
@@ -93,3 +92,39 @@ def test_alm2map_pos_agrees_with_ring_synthesis_at_scale():
 	got = cs.alm2map_pos(alm, np.stack([dec, ra]))
 	want = np.asarray(m)[:, ys][:, :, xs]
 	assert rel(got, want) < 1e-10
+
+def direct_adjoint(map, loc, spin, lmax, mode="STANDARD"):
+	from oracle import sht_oracle as so
+	n = len(loc)
+	return so.adjoint_synthesis(map=map, theta=loc[:, 0], nphi=np.ones(n, int), phi0=loc[:, 1], ringstart=np.arange(n), spin=spin, lmax=lmax, mode=mode)
+
+@pytest.mark.parametrize("spin,lmax,mode", [(0, 47, "STANDARD"), (2, 64, "STANDARD"), (1, 30, "STANDARD"), (1, 36, "DERIV1")])
+def test_adjoint_synthesis_general_matches_direct_sum(spin, lmax, mode):
+	from pixell_b200 import sht
+	ncm = 1 if spin == 0 else 2
+	loc = positions(300, 20+spin)
+	if mode == "DERIV1": loc = loc[8:]
+	rng = np.random.default_rng(30+spin)
+	m = rng.standard_normal((ncm, len(loc)))
+	want = direct_adjoint(m, loc, spin, lmax, mode)
+	got = sht.adjoint_synthesis_general(map=m, loc=loc, spin=spin, lmax=lmax, mode=mode)
+	assert got.shape == want.shape
+	assert rel(got, want) < 1e-10
+
+def test_alm2map_pos_adjointness():
+	"""<alm2map_pos(a), v> = <a, alm2map_pos(v, adjoint)> in the zipped real alm basis of the reference's adjointness
+	test (tests/test_pixell.py:218-230, 1051-1085): m = 0 real parts, sqrt(2) (re, im) of the m > 0 coefficients"""
+	from pixell_b200 import curvedsky as cs
+	lmax = 40
+	ai = cs.alm_info(lmax)
+	alm = rand_alm(3, lmax, 40)
+	alm[1:, [ai.lm2ind(0, 0), ai.lm2ind(1, 0), ai.lm2ind(1, 1)]] = 0
+	rng = np.random.default_rng(41)
+	pos = np.stack([rng.uniform(-np.pi/2, np.pi/2, 250), rng.uniform(-np.pi, np.pi, 250)])
+	v = rng.standard_normal((3, 250))
+	fwd = cs.alm2map_pos(alm, pos)
+	back = cs.alm2map_pos(np.zeros_like(alm), pos, map=v.copy(), adjoint=True)
+	lhs = np.sum(fwd*v)
+	w = np.full(ai.nelem, 2.0); w[:lmax+1] = 1.0
+	rhs = np.sum(w*alm.real*back.real) + np.sum((w*alm.imag*back.imag)[:, lmax+1:])
+	assert abs(lhs-rhs) < 1e-10*abs(lhs)
