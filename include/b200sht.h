@@ -58,6 +58,13 @@ int         b2_dfma_peak_gflops(double *out);
 int b2_sht_plan_rings(b2_sht_plan **out, int nring, const double *theta, int64_t nphi, double phi0,
                       int xdir, int64_t npix_ring, const int64_t *ringstart, const double *weight,
                       int lmax, int mmax, const int64_t *mstart, int64_t lstride);
+/* Ring sets whose rings differ in nphi / phi0 (HEALPix: pixell/curvedsky.py:1192-1222 get_ring_info_healpix, used by
+ * alm2map_healpix :312-353 and map2alm_healpix :355-405; single-pixel rings: get_ring_info_radial :1224-1234).
+ * nphi[nring], phi0[nring], ringstart[nring]; pixel j of ring r is element ringstart[r] + j.  Rings are grouped by
+ * nphi internally (one FFT table per distinct length, any length: mixed radix or Bluestein). */
+int b2_sht_plan_rings_general(b2_sht_plan **out, int nring, const double *theta, const int64_t *nphi, const double *phi0,
+                              const int64_t *ringstart, const double *weight /* nullable */,
+                              int lmax, int mmax, const int64_t *mstart, int64_t lstride);
 
 /* b2_sht_plan_2d replaces the geometry arguments of ducc0.sht.experimental.synthesis_2d /
  * adjoint_synthesis_2d / analysis_2d / adjoint_analysis_2d (curvedsky.py:907-924, 1032-1046):

@@ -25,6 +25,7 @@ _PROTOS = {
 	"b2_launch_count": ([], c_i64),
 	"b2_dfma_peak_gflops": ([_dblp], c_int),
 	"b2_sht_plan_rings": ([ctypes.POINTER(c_vp), c_int, _dblp, c_i64, c_dbl, c_int, c_i64, _i64p, _dblp, c_int, c_int, _i64p, c_i64], c_int),
+	"b2_sht_plan_rings_general": ([ctypes.POINTER(c_vp), c_int, _dblp, _i64p, _dblp, _i64p, _dblp, c_int, c_int, _i64p, c_i64], c_int),
 	"b2_sht_plan_2d": ([ctypes.POINTER(c_vp), c_cp, c_int, c_i64, c_dbl, c_int, c_int, c_int, c_int, _i64p, c_i64], c_int),
 	"b2_sht_plan_destroy": ([c_vp], None),
 	"b2_sht_plan_bytes": ([c_vp], c_i64),

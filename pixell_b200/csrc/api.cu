@@ -126,6 +126,7 @@ b2_sht_plan::~b2_sht_plan()
 size_t b2_sht_plan::bytes() const
 {
 	size_t b = mstart.bytes() + geom.bytes() + fft.bytes() + leg.bytes() + w2d.bytes() + stage_alm.bytes() + stage_map.bytes();
+	for (auto &g : groups) b += g->bytes();
 	for (auto &t : tables) b += t.second->bytes();
 	for (auto &t : starts) if (t.second) b += t.second->bytes();
 	if (resamp) b += resamp->bytes();
@@ -193,7 +194,7 @@ static int plan_common(b2_sht_plan *p, int nring, const double *theta, int64_t n
 		if (ok) p->row_pitch = d;
 	} else p->row_pitch = npix;
 	if (p->geom.build(nring, theta)) return 1;
-	if (p->fft.build(nphi, phi0, xdir, npix, nring, ringstart, weight, mmax)) return 1;
+	if (nphi > 0 && p->fft.build(nphi, phi0, xdir, npix, nring, ringstart, weight, mmax)) return 1;      // nphi <= 0: ring groups follow
 	if (p->leg.alloc((size_t)2*(mmax + 1)*p->geom.nring_pad)) return 1;
 	B2_CHECK(cudaMemset(p->leg.p, 0, p->leg.bytes()));
 	for (auto &e : p->ev) B2_CHECK(cudaEventCreate(&e));
@@ -207,6 +208,35 @@ extern "C" int b2_sht_plan_rings(b2_sht_plan **out, int nring, const double *the
 	B2_REQUIRE(out, "plan: null output pointer");
 	std::unique_ptr<b2_sht_plan> p(new b2_sht_plan());
 	if (plan_common(p.get(), nring, theta, nphi, phi0, xdir, npix_ring, ringstart, weight, lmax, mmax, mstart, lstride)) return 1;
+	*out = p.release();
+	return 0;
+}
+
+extern "C" int b2_sht_plan_rings_general(b2_sht_plan **out, int nring, const double *theta, const int64_t *nphi, const double *phi0,
+	const int64_t *ringstart, const double *weight, int lmax, int mmax, const int64_t *mstart, int64_t lstride)
+{
+	B2_REQUIRE(out && nphi && phi0, "plan: null argument");
+	std::unique_ptr<b2_sht_plan> p(new b2_sht_plan());
+	if (plan_common(p.get(), nring, theta, 0, 0.0, 1, 0, ringstart, weight, lmax, mmax, mstart, lstride)) return 1;
+	std::map<int64_t, std::vector<int>> by_nphi;
+	int64_t total = 0;
+	p->npix_h.assign(nphi, nphi + nring);
+	p->map_hi = 0;
+	for (int r = 0; r < nring; r++) {
+		B2_REQUIRE(nphi[r] >= 1, "plan: ring %d has nphi=%lld", r, (long long)nphi[r]);
+		by_nphi[nphi[r]].push_back(r);
+		total += nphi[r];
+		p->map_hi = std::max(p->map_hi, ringstart[r] + nphi[r]);
+	}
+	p->dense_rings = (total == p->map_hi - p->map_lo);
+	p->row_pitch = 0; p->nphi = 0; p->npix = 0;
+	for (auto &g : by_nphi) {
+		std::vector<double> ph(g.second.size());
+		for (size_t i = 0; i < ph.size(); i++) ph[i] = phi0[g.second[i]];
+		std::unique_ptr<RingFft> f(new RingFft());
+		if (f->build_group(g.first, (int)g.second.size(), g.second.data(), ph.data(), nring, ringstart, weight, mmax)) return 1;
+		p->groups.push_back(std::move(f));
+	}
 	*out = p.release();
 	return 0;
 }
@@ -296,15 +326,16 @@ static int copy_map(Exec &E, void *host, void *dev, bool to_dev, cudaStream_t st
 	// host component pointer `host` addresses element 0; the rings occupy [map_lo, map_hi)
 	char *h = (char*)host + p->map_lo*E.msz; char *d = (char*)dev;
 	cudaMemcpyKind kind = to_dev ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-	if (p->row_pitch == p->npix || p->row_pitch == -p->npix || p->nring == 1) {
+	if (p->groups.empty() ? (p->row_pitch == p->npix || p->row_pitch == -p->npix || p->nring == 1) : p->dense_rings) {
 		if (to_dev) B2_CHECK(cudaMemcpyAsync(d, h, (p->map_hi - p->map_lo)*E.msz, kind, st));
 		else        B2_CHECK(cudaMemcpyAsync(h, d, (p->map_hi - p->map_lo)*E.msz, kind, st));
 	} else {
 		// only the ring pixels move (rows with gaps between them)
 		for (int r = 0; r < p->nring; r++) {
 			size_t off = (p->ringstart_h[r] - p->map_lo)*E.msz;
-			if (to_dev) B2_CHECK(cudaMemcpyAsync(d + off, h + off, p->npix*E.msz, kind, st));
-			else        B2_CHECK(cudaMemcpyAsync(h + off, d + off, p->npix*E.msz, kind, st));
+			const int64_t np = p->groups.empty() ? p->npix : p->npix_h[r];
+			if (to_dev) B2_CHECK(cudaMemcpyAsync(d + off, h + off, np*E.msz, kind, st));
+			else        B2_CHECK(cudaMemcpyAsync(h + off, d + off, np*E.msz, kind, st));
 		}
 	}
 	return 0;
@@ -377,10 +408,12 @@ static int group_compute(Exec &E, GroupCtx &G)
 			}
 		}
 		B2_CHECK(cudaEventRecord(p->ev[3], E.st));
-		if (ring_leg2map(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.st)) return 1;
+		if (p->groups.empty()) { if (ring_leg2map(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.st)) return 1; }
+		else for (auto &g : p->groups) if (ring_leg2map(*g, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.st)) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[4], E.st));
 	} else {
-		if (ring_map2leg(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, E.st)) return 1;
+		if (p->groups.empty()) { if (ring_map2leg(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, E.st)) return 1; }
+		else for (auto &g : p->groups) if (ring_map2leg(*g, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, E.st)) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[2], E.st));
 		if (E.op == OP_ANALYSIS) {
 			if (p->resamp) { if (p->resamp->apply(p->leg.p, E.ncm, E.spin, E.st)) return 1; }

@@ -4,6 +4,7 @@
 #include "ringfft.cuh"
 #include "resample.cuh"
 #include <map>
+#include <vector>
 #include <memory>
 #include <string>
 
@@ -23,6 +24,10 @@ struct b2_sht_plan {
 	int64_t row_pitch = 0;             // constant ring pitch (0: irregular)
 	LegGeom geom;
 	RingFft fft;
+	// ring sets with per-ring nphi / phi0 (b2_sht_plan_rings_general): one RingFft per distinct nphi instead of `fft`
+	std::vector<std::unique_ptr<RingFft>> groups;
+	std::vector<int64_t> npix_h;        // pixels of every ring (general plans)
+	bool dense_rings = true;           // the rings tile [map_lo, map_hi) without gaps
 	std::map<int, std::unique_ptr<LegTables>> tables;   // by spin
 	std::map<int, std::unique_ptr<LegStart>> starts;    // by spin: where every ring group's recurrence becomes live (see LegStart)
 	DevBuf<double2> leg;               // [2][mmax+1][nring_pad]

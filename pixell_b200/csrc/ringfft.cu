@@ -202,6 +202,18 @@ int RingFft::build(int64_t nphi_, double phi0, int xdir_, int64_t npix_, int nri
 	return 0;
 }
 
+int RingFft::build_group(int64_t nphi_, int nids, const int *ids, const double *phi0_of_id, int nring_total, const int64_t *rs,
+	const double *w, int mmax_)
+{
+	B2_REQUIRE(nids >= 1 && ids && phi0_of_id, "bad ring group");
+	if (build(nphi_, 0.0, 1, nphi_, nring_total, rs, w, mmax_)) return 1;
+	nring = nids;                          // blocks per launch; ringstart / weight stay indexed by the plan's ring number
+	std::vector<int> iv(ids, ids + nids);
+	std::vector<double> pv(phi0_of_id, phi0_of_id + nids);
+	if (ring_ids.upload(iv) || phi0s.upload(pv)) return 1;
+	return 0;
+}
+
 // ------------------------------------------------------------------------------------ kernels
 
 struct RingArgs {
@@ -209,12 +221,21 @@ struct RingArgs {
 	int half, nfft, mmax, xdir, nring, twoff;
 	int64_t nphi, npix, nring_pad;
 	const double2 *phase; const int64_t *ringstart; const double *weight;
+	const int *ring_ids; const double *phi0s;      // ring groups (null: block b = ring b, phases from the table)
 	double2 *leg; void *map; int64_t map_cstride;
 };
 
+// e^{i m phi0} of this block's ring
+__device__ __forceinline__ double2 ring_phase(const RingArgs &A, int m)
+{
+	if (!A.phi0s) return __ldg(&A.phase[m]);
+	double sn, c; sincos((double)m*A.phi0s[blockIdx.x], &sn, &c);
+	return make_double2(c, sn);
+}
+
 __device__ __forceinline__ double2 leg_phase(const RingArgs &A, const double2 *legc, int m)
 {
-	double2 g = cmul(legc[(int64_t)m*A.nring_pad], A.phase[m]);
+	double2 g = cmul(legc[(int64_t)m*A.nring_pad], ring_phase(A, m));
 	if (A.xdir < 0) g.y = -g.y;
 	return g;
 }
@@ -222,7 +243,7 @@ __device__ __forceinline__ double2 leg_phase(const RingArgs &A, const double2 *l
 template<typename MapT> __global__ void k_leg2map(RingArgs A)
 {
 	extern __shared__ __align__(16) double2 s[];
-	const int ring = blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+	const int ring = A.ring_ids ? A.ring_ids[blockIdx.x] : blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
 	const double2 *legc = A.leg + ((int64_t)comp*(A.mmax + 1))*A.nring_pad + ring;
 	MapT *row = (MapT*)A.map + (int64_t)comp*A.map_cstride + A.ringstart[ring];
 	const int n = (int)A.nphi, nf = A.nfft, mmax = A.mmax;
@@ -236,7 +257,7 @@ template<typename MapT> __global__ void k_leg2map(RingArgs A)
 			#pragma unroll 4
 			for (int k = tid; k <= nf; k += T) {
 				const int kc = min(k, mmax);
-				double2 g = cmul(__ldg(&legc[(int64_t)kc*A.nring_pad]), __ldg(&A.phase[kc]));
+				double2 g = cmul(__ldg(&legc[(int64_t)kc*A.nring_pad]), ring_phase(A, kc));
 				if (flip) g.y = -g.y;
 				if (k == 0) g = make_double2(g.x, 0.0);
 				if (k > mmax) g = make_double2(0, 0);
@@ -293,7 +314,7 @@ template<typename MapT> __global__ void k_leg2map(RingArgs A)
 template<typename MapT> __global__ void k_map2leg(RingArgs A)
 {
 	extern __shared__ __align__(16) double2 s[];
-	const int ring = blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+	const int ring = A.ring_ids ? A.ring_ids[blockIdx.x] : blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
 	double2 *legc = A.leg + ((int64_t)comp*(A.mmax + 1))*A.nring_pad + ring;
 	const MapT *row = (const MapT*)A.map + (int64_t)comp*A.map_cstride + A.ringstart[ring];
 	const int n = (int)A.nphi, nf = A.nfft, mmax = A.mmax;
@@ -321,7 +342,7 @@ template<typename MapT> __global__ void k_map2leg(RingArgs A)
 				double2 o = make_double2(dd.y, -dd.x);
 				double2 x = cadd(e, cmul(__ldg(&A.d.tw[m]), o));
 				if (flip) x.y = -x.y;
-				legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, __ldg(&A.phase[m])), wgt);
+				legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, ring_phase(A, m)), wgt);
 			}
 		} else
 		for (int m = tid; m <= mmax; m += T) {
@@ -334,7 +355,7 @@ template<typename MapT> __global__ void k_map2leg(RingArgs A)
 			double2 x = cadd(e, cmul(A.d.tw[k], o));
 			if (fold) x.y = -x.y;
 			if (A.xdir < 0) x.y = -x.y;
-			legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, A.phase[m]), wgt);
+			legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, ring_phase(A, m)), wgt);
 		}
 	} else {
 		for (int j = tid; j < n; j += T) s[SI(j)] = make_double2(j < A.npix ? (double)row[j] : 0.0, 0.0);
@@ -343,7 +364,7 @@ template<typename MapT> __global__ void k_map2leg(RingArgs A)
 		for (int m = tid; m <= mmax; m += T) {
 			double2 x = s[SI(A.d.rev[m % n])];
 			if (A.xdir < 0) x.y = -x.y;
-			legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, A.phase[m]), wgt);
+			legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, ring_phase(A, m)), wgt);
 		}
 	}
 }
@@ -356,6 +377,7 @@ static RingArgs ring_args(const RingFft &F, const double2 *leg, int64_t nring_pa
 	A.d = F.tab.d; A.twoff = F.twoff; A.half = F.half; A.nfft = F.nfft; A.mmax = F.mmax; A.xdir = F.xdir; A.nring = F.nring;
 	A.nphi = F.nphi; A.npix = F.npix; A.nring_pad = nring_pad;
 	A.phase = F.phase.p; A.ringstart = F.ringstart.p; A.weight = (use_weight && F.weight.n) ? F.weight.p : nullptr;
+	A.ring_ids = F.ring_ids.n ? F.ring_ids.p : nullptr; A.phi0s = F.phi0s.n ? F.phi0s.p : nullptr;
 	A.leg = (double2*)leg; A.map = (void*)map; A.map_cstride = map_cstride;
 	return A;
 }

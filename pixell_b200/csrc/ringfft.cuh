@@ -14,12 +14,20 @@ struct RingFft {
 	DevBuf<double2> phase;  // exp(i m phi0), m = 0..mmax
 	DevBuf<int64_t> ringstart;
 	DevBuf<double> weight;  // empty: no weights
+	// ring sets whose rings differ in nphi / phi0 (HEALPix, pixell/curvedsky.py:1192-1222) are served by one RingFft
+	// per distinct nphi: block b of a launch works on ring ring_ids[b] (leg column, ringstart, weight are indexed by
+	// the plan's ring number) with its own phi0s[b]; both empty for cylindrical maps
+	DevBuf<int> ring_ids;
+	DevBuf<double> phi0s;
 	int threads = 256;
 	size_t smem = 0;
 	int twoff = 0;          // offset (elements) of the twiddle tables inside the dynamic shared memory
 	int build(int64_t nphi, double phi0, int xdir, int64_t npix, int nring, const int64_t *ringstart,
 	          const double *weight, int mmax);
-	size_t bytes() const { return tab.bytes() + phase.bytes() + ringstart.bytes() + weight.bytes(); }
+	// group form: `ids` lists the plan rings with this nphi, phi0_of_id their phi0 (all rings' ringstart / weight arrays are passed whole)
+	int build_group(int64_t nphi, int nids, const int *ids, const double *phi0_of_id, int nring_total, const int64_t *ringstart,
+	                const double *weight, int mmax);
+	size_t bytes() const { return tab.bytes() + phase.bytes() + ringstart.bytes() + weight.bytes() + ring_ids.bytes() + phi0s.bytes(); }
 };
 
 // leg: [ncomp][mmax+1][nring_pad] complex128 (device); map component c at map + c*map_cstride (elements of MapT)

@@ -302,6 +302,158 @@ def alm2map(alm, map, spin=[0,2], deriv=False, adjoint=False, copy=False, method
 				if not adjoint and mcopied: map_full[I][j1:j2] = m
 	return alm if adjoint else map
 
+# ------------------------------------------------------------------ HEALPix and radial ring sets
+
+def npix2nside(npix): return int(round((npix/12)**0.5))
+
+def prepare_healmap(healmap, nside=None, pre=(), dtype=np.float64):
+	if healmap is not None: return healmap
+	return np.zeros(tuple(pre)+(12*nside**2,), dtype)
+
+def get_ring_info_healpix(nside, rings=None):
+	"""theta, nphi, phi0 and pixel offset of every HEALPix ring (reference curvedsky.py:1192-1222)"""
+	nside = int(nside)
+	rings = np.arange(4*nside-1) if rings is None else np.asarray(rings)
+	nring, npix = len(rings), 12*nside**2
+	theta, phi0, nphi = np.zeros(nring), np.zeros(nring), np.zeros(nring, np.uint64)
+	rings = rings+1                              # one-based
+	north = np.where(rings > 2*nside, 4*nside-rings, rings)
+	cap = np.where(north < nside)[0]
+	theta[cap] = 2*np.arcsin(north[cap]/(6**0.5*nside))
+	nphi[cap] = 4*north[cap]
+	phi0[cap] = np.pi/(4*north[cap])
+	rest = np.where(north >= nside)[0]
+	theta[rest] = np.arccos((2*nside-north[rest])*(8*nside/npix))
+	nphi[rest] = 4*nside
+	phi0[rest] = np.pi/(4*nside)*(((north[rest]-nside) & 1) == 0)
+	south = np.where(north != rings)[0]
+	theta[south] = np.pi-theta[south]
+	offsets = np.concatenate([[0], np.cumsum(nphi)[:-1]]).astype(np.uint64)
+	return _Bunch(theta=theta, nphi=nphi, phi0=phi0, offsets=offsets, stride=np.ones(nring, np.int32), npix=npix, nrow=nring)
+
+def get_ring_info_radial(r):
+	"""one single-pixel ring per colatitude r (reference curvedsky.py:1224-1234): radially symmetric (mmax = 0) transforms"""
+	theta = np.asarray(r, dtype=np.float64)
+	assert theta.ndim == 1, "r must be one-dimensional!"
+	n = len(theta)
+	return _Bunch(theta=theta, nphi=np.ones(n, np.uint64), phi0=np.zeros(n), offsets=np.arange(n, dtype=np.uint64),
+		stride=np.ones(n, np.int32), npix=n, nrow=n)
+
+def apply_minfo_theta_lim(minfo, theta_min=None, theta_max=None):
+	if theta_min is None and theta_max is None: return minfo
+	mask = np.full(minfo.nrow, True, bool)
+	if theta_min is not None: mask &= minfo.theta >= theta_min
+	if theta_max is not None: mask &= minfo.theta <= theta_max
+	res = _Bunch(minfo)
+	for key in ["theta", "nphi", "phi0", "offsets"]: res[key] = res[key][mask]
+	return res
+
+def _ring_kwargs(rinfo, ainfo):
+	return dict(theta=rinfo.theta, nphi=rinfo.nphi, phi0=rinfo.phi0, ringstart=rinfo.offsets, lmax=ainfo.lmax, mmax=ainfo.mmax,
+		mstart=ainfo.mstart, lstride=ainfo.stride)
+
+def alm2map_healpix(alm, healmap=None, spin=[0,2], deriv=False, adjoint=False, copy=False, ainfo=None, nside=None,
+		theta_min=None, theta_max=None, nthread=None):
+	"""alm[..., ncomp, nalm] -> HEALPix map[..., ncomp, npix] (RING order), or its transpose (reference curvedsky.py:312-353)."""
+	rdt = np.zeros(1, _rdtype(alm)).real.dtype
+	if ainfo is None: ainfo = alm_info(nalm=alm.shape[-1])
+	healmap = prepare_healmap(healmap, nside, alm.shape[:-1] if not deriv else alm.shape[:-1]+(2,), rdt)
+	if copy:
+		if adjoint: alm = alm.copy()
+		else: healmap = healmap.copy()
+	alm_full = _atleast(alm, 2 if deriv else 3)
+	map_full = _atleast(healmap, 3)
+	if deriv and (alm_full.shape[:-1] != map_full.shape[:-2] or map_full.shape[-2] != 2):
+		raise ValueError("When deriv is True, alm must have shape [...,nelem] and map shape [...,2,npix]")
+	if not deriv and (alm_full.shape[:-1] != map_full.shape[:-1]):
+		raise ValueError("alm must have shape [...,[ncomp,]nelem] and map shape [...,[ncomp,]npix]")
+	func = sht.adjoint_synthesis if adjoint else sht.synthesis
+	rinfo = apply_minfo_theta_lim(get_ring_info_healpix(npix2nside(map_full.shape[-1])), theta_min, theta_max)
+	if (theta_min is not None or theta_max is not None) and not adjoint: map_full[:] = 0
+	kw = _ring_kwargs(rinfo, ainfo)
+	ctype = np.result_type(rdt, 0j)
+	for I in np.ndindex(*map_full.shape[:-2]):
+		if deriv:
+			a = np.ascontiguousarray(alm_full[I][None]).astype(ctype, copy=False); m = np.ascontiguousarray(map_full[I])
+			if adjoint:
+				m = m.copy(); m[0] *= -1
+				func(alm=a, map=m, mode="DERIV1", spin=1, **kw); alm_full[I] = a[0]
+			else:
+				func(alm=a, map=m, mode="DERIV1", spin=1, **kw)
+				m[0] *= -1; map_full[I] = m
+		else:
+			for s, j1, j2 in spin_helper(spin, alm_full[I].shape[-2]):
+				Ij = I+(slice(j1, j2),)
+				a = np.ascontiguousarray(alm_full[Ij]).astype(ctype, copy=False); m = np.ascontiguousarray(map_full[Ij])
+				func(alm=a, map=m, spin=s, **kw)
+				if adjoint: alm_full[Ij] = a
+				else: map_full[Ij] = m
+	return alm if adjoint else healmap
+
+def map2alm_healpix(healmap, alm=None, ainfo=None, lmax=None, spin=[0,2], weights=None, deriv=False, copy=False, verbose=False,
+		adjoint=False, niter=0, theta_min=None, theta_max=None, nthread=None):
+	"""HEALPix map -> alm with pixel-area weights and niter Jacobi iterations, like healpy's map2alm
+	(reference curvedsky.py:355-405)."""
+	if deriv: raise NotImplementedError("map2alm_healpix with deriv=True is broken")
+	if copy:
+		if adjoint: healmap = healmap.copy()
+		elif alm is not None: alm = alm.copy()
+	pre = healmap.shape[:-1]
+	alm, ainfo = prepare_alm(alm=alm, ainfo=ainfo, lmax=lmax, pre=pre, dtype=_rdtype(healmap), convert=adjoint, like=healmap)
+	alm_full = _atleast(alm, 3)
+	map_full = _atleast(healmap, 3)
+	rinfo = apply_minfo_theta_lim(get_ring_info_healpix(npix2nside(map_full.shape[-1])), theta_min, theta_max)
+	kw = _ring_kwargs(rinfo, ainfo)
+	if weights is None: weights = 4*np.pi/rinfo.npix
+	for I in np.ndindex(*map_full.shape[:-2]):
+		for s, j1, j2 in spin_helper(spin, alm_full.shape[-2]):
+			Ij = I+(slice(j1, j2),)
+			def Y(a): return sht.synthesis(map=np.zeros_like(np.ascontiguousarray(map_full[Ij])), alm=np.ascontiguousarray(a), spin=s, **kw)
+			def YT(m): return sht.adjoint_synthesis(map=np.ascontiguousarray(m), spin=s, **kw)
+			def YTW(m): return YT(m*weights)
+			def WY(a): return Y(a)*weights
+			if adjoint:
+				a = np.ascontiguousarray(alm_full[Ij]); x = WY(a)
+				for it in range(niter): x -= WY(YT(x)-a)
+				map_full[Ij] = x
+			else:
+				y = np.ascontiguousarray(map_full[Ij]); x = YTW(y)
+				for it in range(niter): x -= YTW(Y(x)-y)
+				alm_full[Ij] = x
+	return healmap if adjoint else alm
+
+def profile2harm(br, r, lmax=None, oversample=1, left=None, right=None):
+	"""Radial profile br[..., nr] at ascending radii r -> bl[..., nl]: an mmax = 0 transform on single-pixel
+	Clenshaw-Curtis rings (reference curvedsky.py:1544-1577)."""
+	br, r = np.asarray(br), np.asarray(r)
+	dr = (r[-1]-r[0])/(len(r)-1)
+	nfull = int(round(np.pi/dr))+1
+	dr = np.pi/(nfull-1)
+	ncut = int(np.ceil(r[-1]/dr))
+	if lmax is None: lmax = int(nfull//2-1)
+	l = np.arange(lmax+1)
+	rinfo = get_ring_info_radial(np.arange(ncut)*dr)
+	weights = sht.get_gridweights("CC", nfull)[:ncut]
+	harm = np.zeros(br.shape[:-1]+(lmax+1,), br.dtype)
+	for I in np.ndindex(*br.shape[:-1]):
+		map = np.interp(rinfo.theta, r, br[I], left=left, right=right).reshape(1, -1)
+		alm = sht.adjoint_synthesis(map=np.ascontiguousarray(map*weights, dtype=np.float64), theta=rinfo.theta, nphi=rinfo.nphi,
+			phi0=rinfo.phi0, ringstart=rinfo.offsets, spin=0, lmax=lmax, mmax=0)[0]
+		harm[I] = alm.real*(4*np.pi/(2*l+1))**0.5
+	return harm
+
+def harm2profile(bl, r):
+	"""bl[..., nl] -> br[..., nr] = sum_l bl (2l+1)/(4 pi) P_l(cos r) (reference curvedsky.py:1579-1593)"""
+	bl, r = np.asarray(bl), np.asarray(r)
+	l = np.arange(bl.shape[-1])
+	rinfo = get_ring_info_radial(r.reshape(-1))
+	alm = (bl*((2*l+1)/(4*np.pi))**0.5).astype(np.complex128)
+	br = np.zeros(bl.shape[:-1]+(r.size,), np.float64)
+	for I in np.ndindex(*bl.shape[:-1]):
+		br[I] = sht.synthesis(alm=np.ascontiguousarray(alm[I][None]), theta=rinfo.theta, nphi=rinfo.nphi, phi0=rinfo.phi0,
+			ringstart=rinfo.offsets, spin=0, lmax=bl.shape[-1]-1, mmax=0)[0]
+	return br.astype(bl.dtype, copy=False) if bl.dtype.kind == "f" else br
+
 def alm2map_raw_general(alm, map, loc, ainfo=None, spin=[0,2], deriv=False, copy=False, verbose=False, adjoint=False, nthread=None, epsilon=None):
 	"""alm[..., ncomp, nelem] <-> map[..., ncomp, npos] (deriv: alm[..., nelem], map[..., 2, npos]) at loc[npos, 2] =
 	(codec, ra) by the non-uniform-FFT synthesis or, with adjoint=True, its transpose (reference curvedsky.py:993-1016)."""

@@ -4,8 +4,8 @@
 in-place-and-return behaviour.  Inputs may be numpy arrays (host memory: staged through the GPU)
 or torch CUDA tensors (zero-copy).  `nthreads` is accepted and ignored.
 
-Limits (outside the hot path of SURVEY.md section 8): rings must share nphi and phi0 (CAR maps;
-HEALPix ring sets are refused), and lstride/pixstride other than what pixell uses are refused.
+Rings may share nphi and phi0 (CAR maps: the fast path) or carry their own (HEALPix, single-pixel rings).
+Limits: lstride/pixstride other than what pixell uses are refused.
 synthesis_general / adjoint_synthesis_general (arbitrary positions, call site curvedsky.py:993-1016) are provided.
 """
 import collections, ctypes
@@ -59,7 +59,20 @@ def plan_rings(theta, nphi, phi0, ringstart, lmax, mmax=None, mstart=None, lstri
 	theta = np.ascontiguousarray(theta, dtype=np.float64)
 	nphi_a = np.atleast_1d(np.asarray(nphi)).astype(np.int64); phi0_a = np.atleast_1d(np.asarray(phi0, dtype=np.float64))
 	if np.any(nphi_a != nphi_a[0]) or np.any(phi0_a != phi0_a[0]):
-		raise NotImplementedError("pixell_b200: rings must share nphi and phi0 (cylindrical maps only)")
+		# HEALPix-like ring sets: per-ring nphi / phi0 (one FFT group per distinct nphi inside the engine)
+		if xdir != 1 or npix is not None: raise NotImplementedError("pixell_b200: rings with individual nphi/phi0 cannot be flipped or cut")
+		nphi_a = np.ascontiguousarray(np.broadcast_to(nphi_a, theta.shape)); phi0_a = np.ascontiguousarray(np.broadcast_to(phi0_a, theta.shape))
+		ringstart = L.as_i64(ringstart)
+		lmax, mmax, mstart, lstride = _layout(lmax, mmax, mstart, lstride)
+		w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+		key = ("general", theta.tobytes(), nphi_a.tobytes(), phi0_a.tobytes(), ringstart.tobytes(),
+			None if w is None else w.tobytes(), lmax, mmax, mstart.tobytes(), lstride)
+		def make():
+			h = ctypes.c_void_p()
+			L.check(L.lib().b2_sht_plan_rings_general(ctypes.byref(h), len(theta), L.p_dbl(theta), L.p_i64(nphi_a), L.p_dbl(phi0_a),
+				L.p_i64(ringstart), None if w is None else L.p_dbl(w), lmax, mmax, L.p_i64(mstart), lstride), ValueError)
+			return Plan(h)
+		return _cached(key, make)
 	nphi0, phi00 = int(nphi_a[0]), float(phi0_a[0])
 	ringstart = L.as_i64(ringstart)
 	lmax, mmax, mstart, lstride = _layout(lmax, mmax, mstart, lstride)
@@ -150,7 +163,7 @@ def synthesis(*, alm, theta, nphi, phi0, ringstart, spin, lmax, mmax=None, mstar
 	md = _MODES[mode]
 	if map is None:
 		ncm = 1 if spin == 0 else 2
-		n = int(np.max(np.asarray(ringstart)) + (np.atleast_1d(nphi)[0] if npix is None else npix))
+		n = int(np.max(np.asarray(ringstart).astype(np.int64) + (np.broadcast_to(np.asarray(nphi).astype(np.int64), np.shape(ringstart)) if npix is None else npix)))
 		map = _empty_like(alm, (ncm, n), np.float64 if L.buffer_info(alm)[2] == np.complex128 else np.float32)
 	_run(L.lib().b2_synthesis, plan, spin, md, alm, map, 1)
 	return map
