@@ -118,6 +118,9 @@ b2_sht_plan::~b2_sht_plan()
 {
 	for (auto &e : ev) if (e) cudaEventDestroy(e);
 	for (auto &e : gev) if (e) cudaEventDestroy(e);
+	for (auto &g : gstreams) if (g) cudaStreamDestroy(g);
+	for (auto &e : gjoin) if (e) cudaEventDestroy(e);
+	if (gfork) cudaEventDestroy(gfork);
 	if (s_in) cudaStreamDestroy(s_in);
 	if (s_out) cudaStreamDestroy(s_out);
 	if (s_comp) cudaStreamDestroy(s_comp);
@@ -237,7 +240,28 @@ extern "C" int b2_sht_plan_rings_general(b2_sht_plan **out, int nring, const dou
 		if (f->build_group(g.first, (int)g.second.size(), g.second.data(), ph.data(), nring, ringstart, weight, mmax)) return 1;
 		p->groups.push_back(std::move(f));
 	}
+	const int ns = (int)std::min<size_t>(16, p->groups.size());
+	p->gstreams.assign(ns, nullptr); p->gjoin.assign(ns, nullptr);
+	for (int i = 0; i < ns; i++) {
+		B2_CHECK(cudaStreamCreateWithFlags(&p->gstreams[i], cudaStreamNonBlocking));
+		B2_CHECK(cudaEventCreateWithFlags(&p->gjoin[i], cudaEventDisableTiming));
+	}
+	B2_CHECK(cudaEventCreateWithFlags(&p->gfork, cudaEventDisableTiming));
 	*out = p.release();
+	return 0;
+}
+
+// ring FFTs of a general plan: fork the groups over the side streams, join back into st
+template<typename F> static int run_groups(b2_sht_plan *p, cudaStream_t st, F launch)
+{
+	const int ns = (int)p->gstreams.size();
+	B2_CHECK(cudaEventRecord(p->gfork, st));
+	for (int i = 0; i < ns; i++) B2_CHECK(cudaStreamWaitEvent(p->gstreams[i], p->gfork, 0));
+	for (size_t g = 0; g < p->groups.size(); g++) if (launch(*p->groups[g], p->gstreams[g % ns])) return 1;
+	for (int i = 0; i < ns; i++) {
+		B2_CHECK(cudaEventRecord(p->gjoin[i], p->gstreams[i]));
+		B2_CHECK(cudaStreamWaitEvent(st, p->gjoin[i], 0));
+	}
 	return 0;
 }
 
@@ -409,11 +433,11 @@ static int group_compute(Exec &E, GroupCtx &G)
 		}
 		B2_CHECK(cudaEventRecord(p->ev[3], E.st));
 		if (p->groups.empty()) { if (ring_leg2map(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.st)) return 1; }
-		else for (auto &g : p->groups) if (ring_leg2map(*g, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.st)) return 1;
+		else if (run_groups(p, E.st, [&](const RingFft &g, cudaStream_t s) { return ring_leg2map(g, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, s); })) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[4], E.st));
 	} else {
 		if (p->groups.empty()) { if (ring_map2leg(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, E.st)) return 1; }
-		else for (auto &g : p->groups) if (ring_map2leg(*g, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, E.st)) return 1;
+		else if (run_groups(p, E.st, [&](const RingFft &g, cudaStream_t s) { return ring_map2leg(g, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, s); })) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[2], E.st));
 		if (E.op == OP_ANALYSIS) {
 			if (p->resamp) { if (p->resamp->apply(p->leg.p, E.ncm, E.spin, E.st)) return 1; }

@@ -27,6 +27,10 @@ struct b2_sht_plan {
 	// ring sets with per-ring nphi / phi0 (b2_sht_plan_rings_general): one RingFft per distinct nphi instead of `fft`
 	std::vector<std::unique_ptr<RingFft>> groups;
 	std::vector<int64_t> npix_h;        // pixels of every ring (general plans)
+	// the groups' launches are small (a cap ring pair each): they are spread over side streams so that they overlap
+	std::vector<cudaStream_t> gstreams;
+	std::vector<cudaEvent_t> gjoin;
+	cudaEvent_t gfork = nullptr;
 	bool dense_rings = true;           // the rings tile [map_lo, map_hi) without gaps
 	std::map<int, std::unique_ptr<LegTables>> tables;   // by spin
 	std::map<int, std::unique_ptr<LegStart>> starts;    // by spin: where every ring group's recurrence becomes live (see LegStart)

@@ -7,6 +7,7 @@
 // One CTA per (ring, component); the ring lives in shared memory as a packed half-length complex
 // sequence (even nphi) or a full complex one (odd nphi); fft_smem.cuh does the passes.
 #include "ringfft.cuh"
+#include <map>
 #include <algorithm>
 #include <complex>
 
@@ -382,9 +383,18 @@ static RingArgs ring_args(const RingFft &F, const double2 *leg, int64_t nring_pa
 	return A;
 }
 
+// raise the kernel's dynamic shared-memory limit when a launch needs more than any before it (the limit is per
+// kernel and device; plans with many ring groups would otherwise pay the driver call on every launch)
 template<typename K> static int set_smem(K kern, size_t smem)
 {
-	if (smem > 48*1024) B2_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	static thread_local std::map<std::pair<int, const void*>, size_t> granted;
+	if (smem <= 48*1024) return 0;
+	int dev; B2_CHECK(cudaGetDevice(&dev));
+	size_t &g = granted[std::make_pair(dev, (const void*)kern)];
+	if (smem > g) {
+		B2_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		g = smem;
+	}
 	return 0;
 }
 
