@@ -10,9 +10,14 @@ def main():
 	out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 	allrows = list(csv.reader(out.splitlines()))
 	heads = [i for i, r in enumerate(allrows) if r and r[0] == "Address"]
-	for n, hi in enumerate(heads):       # one section per captured launch
+	seen = set()
+	for n, hi in enumerate(heads):       # one section per captured launch (ncu repeats a launch's table per source view)
 		end = heads[n+1]-1 if n+1 < len(heads) else len(allrows)
-		if hi > 0 and allrows[hi-1] and allrows[hi-1][0] == "Kernel Name": print("==== %s" % allrows[hi-1][1])
+		name = allrows[hi-1][1] if hi > 0 and allrows[hi-1] and allrows[hi-1][0] == "Kernel Name" else ""
+		key = (name, end-hi, tuple(allrows[hi+1][:1]) if hi+1 < end else ())
+		if key in seen: continue
+		seen.add(key)
+		if name: print("==== %s" % name)
 		section(allrows[hi], allrows[hi+1:end], ntop)
 
 def section(H, data, ntop):
