@@ -454,6 +454,42 @@ def harm2profile(bl, r):
 			ringstart=rinfo.offsets, spin=0, lmax=bl.shape[-1]-1, mmax=0)[0]
 	return br.astype(bl.dtype, copy=False) if bl.dtype.kind == "f" else br
 
+# zyz Euler angles between coordinate systems (pixell/curvedsky.py:714-716)
+euler_angs = {}
+euler_angs[("gal", "equ")] = np.array([57.06793215, 62.87115487, -167.14056929])*DEG
+euler_angs[("equ", "gal")] = -euler_angs[("gal", "equ")][::-1]
+
+def rotate_alm(alm, psi, theta, phi, lmax=None, method="auto", nthread=None, inplace=False):
+	"""Rotate alm[..., :] by the zyz Euler angles psi, theta, phi (reference curvedsky.py:717-742, ducc0.sht.rotate_alm):
+	the field is rotated actively by R = Rz(phi) Ry(theta) Rz(psi), f'(x) = f(R^-1 x), every component as a scalar.
+	Instead of Wigner matrices the engine evaluates f at the back-rotated nodes of a Clenshaw-Curtis grid that carries
+	lmax exactly (K8, 1e-12) and analyses the result (exact quadrature), which is the same operator for band-limited f."""
+	import torch
+	if lmax is None: lmax = nalm2lmax(alm.shape[-1])
+	ainfo = alm_info(lmax)
+	if ainfo.nelem != alm.shape[-1]: raise ValueError("rotate_alm needs the triangular layout with mmax = lmax")
+	tor = L.is_torch(alm)
+	out = alm if inplace else (alm.clone() if tor else alm.copy())
+	dev = torch.device("cuda", L.init())
+	nt, nphi = lmax+2, sht._fast_len(2*lmax+2)
+	th = torch.arange(nt, device=dev, dtype=torch.float64)*(np.pi/(nt-1))
+	ph = torch.arange(nphi, device=dev, dtype=torch.float64)*(2*np.pi/nphi) - phi       # Rz(-phi)
+	st, ct = torch.sin(th)[:, None], torch.cos(th)[:, None]
+	x, y, z = st*torch.cos(ph)[None, :], st*torch.sin(ph)[None, :], ct.expand(nt, nphi)
+	c, sn = np.cos(theta), np.sin(theta)                                                 # Ry(-theta)
+	x2, z2 = x*c - z*sn, x*sn + z*c
+	loc = torch.stack([torch.atan2(torch.sqrt(x2*x2 + y*y), z2), torch.atan2(y, x2) - psi], -1).reshape(-1, 2).contiguous()
+	del x, y, z, x2, z2
+	flat = out.reshape(-1, out.shape[-1])
+	for i in range(flat.shape[0]):
+		a = flat[i]
+		a = (a if tor else torch.from_numpy(np.ascontiguousarray(a))).to(dev).to(torch.complex128).reshape(1, -1)
+		m = sht.synthesis_general(alm=a, loc=loc, spin=0, lmax=lmax).reshape(1, nt, nphi)
+		b = sht.analysis_2d(map=m, spin=0, lmax=lmax, geometry="CC")
+		if tor: flat[i] = b[0].to(flat.dtype)
+		else: flat[i] = b[0].cpu().numpy().astype(flat.dtype, copy=False)
+	return out
+
 def alm2map_raw_general(alm, map, loc, ainfo=None, spin=[0,2], deriv=False, copy=False, verbose=False, adjoint=False, nthread=None, epsilon=None):
 	"""alm[..., ncomp, nelem] <-> map[..., ncomp, npos] (deriv: alm[..., nelem], map[..., 2, npos]) at loc[npos, 2] =
 	(codec, ra) by the non-uniform-FFT synthesis or, with adjoint=True, its transpose (reference curvedsky.py:993-1016)."""

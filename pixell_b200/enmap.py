@@ -2,7 +2,7 @@
 (reference pixell/enmap.py): fft :1307-1322, ifft :1323-1337, laxes :1273-1294, lmap :1242-1250,
 modlmap :1252-1258, extent (cylindrical) :998-1014, area :1032-1036, pixsize :1097-1099,
 smooth_gauss :1429-1439, map2harm / harm2map and their adjoints :1358-1389, queb_rotmat :1391-1400,
-rotate_pol :1402-1416, map_mul :1418-1427, spin_helper :3378-3388.  Maps are geometry.ndmap (numpy + wcs) or torch CUDA tensors with wcs=.
+rotate_pol :1402-1416, map_mul :1418-1427, calc_window / apply_window :1470-1500, spin_helper :3378-3388.  Maps are geometry.ndmap (numpy + wcs) or torch CUDA tensors with wcs=.
 Only separable cylindrical (CAR) geometries are handled, as everywhere in this package.
 
 The normalisation factor of fft/ifft is folded into the last FFT pass (no extra sweep over the map).
@@ -105,6 +105,44 @@ def smooth_gauss(emap, sigma, wcs=None):
 	out = enfft.irfft(f, n=nx, axes=[-2, -1], normalize=True)
 	if not L.is_torch(out): out = geometry.ndmap(out, wcs)
 	return out
+
+def pixwin_1d(f, order=0):
+	"""1-D pixel window at dimensionless frequency f (pixell/utils.py:856-868)"""
+	if order is None or order == "none": return f*0+1
+	if order == 0 or order == "nn": return np.sinc(f)
+	if order == 1 or order == "lin": return np.sinc(f)**2/(1/3*(2+np.cos(2*np.pi*f)))
+	raise ValueError("Unsupported pixwin order %s" % str(order))
+
+def calc_window(shape, order=0, scale=1):
+	"""separable Fourier-space pixel window wy, wx (pixell/enmap.py:1470-1482)"""
+	return pixwin_1d(np.fft.fftfreq(shape[-2], scale), order=order), pixwin_1d(np.fft.fftfreq(shape[-1], scale), order=order)
+
+def apply_window(emap, pow=1.0, order=0, scale=1, nofft=False, wcs=None):
+	"""Multiply by the pixel window to the given power in Fourier space (pixell/enmap.py:1484-1496); real maps go
+	through the real transforms (half the spectrum), nofft=True takes and returns a Fourier map."""
+	wy, wx = calc_window(emap.shape, order=order, scale=scale)
+	wy, wx = wy**pow, wx**pow
+	def mul(f, wy, wx):
+		if L.is_torch(f):
+			import torch
+			f *= torch.as_tensor(wy, device=f.device).to(f.real.dtype)[:, None]
+			f *= torch.as_tensor(wx, device=f.device).to(f.real.dtype)[None, :]
+		else:
+			f *= wy.astype(f.real.dtype)[:, None]; f *= wx.astype(f.real.dtype)[None, :]
+		return f
+	if nofft: return mul(emap.clone() if L.is_torch(emap) else emap.copy(), wy, wx)
+	nx = emap.shape[-1]
+	if L.buffer_info(emap)[2].kind == "c":
+		out = ifft(mul(fft(emap, wcs=wcs), wy, wx), wcs=wcs)
+		return out
+	f = mul(enfft.rfft(emap, axes=[-2, -1]), wy, wx[:nx//2+1])
+	out = enfft.irfft(f, n=nx, axes=[-2, -1], normalize=True)
+	w = getattr(emap, "wcs", wcs)
+	if not L.is_torch(out) and w is not None: out = geometry.ndmap(out, w)
+	return out
+
+def unapply_window(emap, pow=1.0, order=0, scale=1, nofft=False, wcs=None):
+	return apply_window(emap, pow=-pow, order=order, scale=scale, nofft=nofft, wcs=wcs)
 
 # ------------------------------------------------------------------ T,Q,U <-> T,E,B (pixell/enmap.py:1358-1427)
 

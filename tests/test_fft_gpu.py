@@ -320,3 +320,18 @@ def test_rotate_pol():
 	r = enmap.rotate_pol(m, 0.3)
 	c, s = np.cos(0.6), np.sin(0.6)
 	assert np.allclose(r[0], m[0]) and np.allclose(r[1], c*m[1]-s*m[2]) and np.allclose(r[2], s*m[1]+c*m[2])
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_apply_window(order):
+	"""pixel window in Fourier space (reference enmap.py:1470-1500) against numpy; unapply undoes it"""
+	from pixell_b200 import enmap, geometry
+	wcs = _patch((40, 54))
+	rng = np.random.default_rng(11)
+	m = geometry.ndmap(rng.standard_normal((2, 40, 54)), wcs)
+	wy, wx = enmap.calc_window(m.shape, order=order)
+	want = np.fft.ifft2(np.fft.fft2(m)*wy[:, None]*wx[None, :]).real
+	got = enmap.apply_window(m, order=order)
+	assert rel(np.asarray(got), want) < 1e-12
+	assert rel(np.asarray(enmap.unapply_window(got, order=order)), np.asarray(m)) < 1e-10
+	f = enmap.fft(m)
+	assert rel(np.asarray(enmap.apply_window(f, order=order, nofft=True)), np.asarray(f)*wy[:, None]*wx[None, :]) < 1e-13

@@ -128,3 +128,28 @@ def test_alm2map_pos_adjointness():
 	w = np.full(ai.nelem, 2.0); w[:lmax+1] = 1.0
 	rhs = np.sum(w*alm.real*back.real) + np.sum((w*alm.imag*back.imag)[:, lmax+1:])
 	assert abs(lhs-rhs) < 1e-10*abs(lhs)
+
+def test_rotate_alm():
+	"""zyz Euler rotation of alm (reference curvedsky.py:714-742): z rotations are phases, the inverse angles undo a
+	rotation, and the reference's own gal -> equ angles carry the galactic pole to RA 192.86, Dec 27.13 (J2000)"""
+	from pixell_b200 import curvedsky as cs
+	lmax = 48
+	ai = cs.alm_info(lmax)
+	alm = rand_alm(2, lmax, 50)
+	mval = np.zeros(ai.nelem, int)
+	for m in range(lmax+1): mval[ai.lm2ind(np.arange(m, lmax+1), m)] = m
+	r = cs.rotate_alm(alm, 0.3, 0, 0.4)
+	assert rel(r, alm*np.exp(-1j*mval*0.7)) < 1e-10
+	ang = np.array([0.5, 1.1, -2.0])
+	fwd = cs.rotate_alm(alm, *ang)
+	assert rel(fwd, alm) > 0.1
+	assert rel(cs.rotate_alm(fwd, *(-ang[::-1])), alm) < 1e-10
+	# a narrow beam at the north pole of the "gal" frame, moved to "equ"
+	l = np.arange(lmax+1)
+	bl = np.exp(-0.5*l*(l+1)*0.08**2)*np.sqrt((2*l+1)/(4*np.pi))
+	pole = np.zeros(ai.nelem, complex); pole[:lmax+1] = bl
+	eq = cs.rotate_alm(pole, *cs.euler_angs[("gal", "equ")])
+	dec, ra = np.deg2rad(27.12825), np.deg2rad(192.85948)
+	peak = cs.alm2map_pos(eq[None], np.array([[dec, dec+0.05, dec-0.05, -dec], [ra, ra, ra+0.05, ra]]))[0]
+	top = np.sum(bl*np.sqrt((2*l+1)/(4*np.pi)))
+	assert abs(peak[0]-top) < 1e-6*top and peak[1] < peak[0] and peak[2] < peak[0] and peak[3] < 0.01*top
