@@ -296,11 +296,13 @@ def synthesis_general(*, alm, loc, spin, lmax, mmax=None, mstart=None, lstride=1
 	ext = torch.empty((ncm, nm, N), dtype=torch.complex128, device=dev)
 	L.check(lib.b2_general_extend(leg.data_ptr(), ext.data_ptr(), ncm, nm, nt, nring_pad, int(spin), st))
 	del leg
-	enfft.transform(ext, ext, (-1,), True, 1.0/N)                  # theta Fourier coefficients c[c][m][k]
+	coef = torch.empty_like(ext)                                   # (lines too long for one CTA are not transformed in place)
+	enfft.transform(ext, coef, (-1,), True, 1.0/N)                 # theta Fourier coefficients c[c][m][k]
+	del ext
 	corr = torch.from_numpy(_kernel_corr(lmax, M)).to(dev)
 	grid = torch.empty((ncm, M, M//2+1), dtype=torch.complex128, device=dev)
-	L.check(lib.b2_general_scatter(ext.data_ptr(), grid.data_ptr(), ncm, lmax, nm, N, M, corr.data_ptr(), st))
-	del ext
+	L.check(lib.b2_general_scatter(coef.data_ptr(), grid.data_ptr(), ncm, lmax, nm, N, M, corr.data_ptr(), st))
+	del coef
 	fine = torch.empty((ncm, M, M), dtype=torch.float64, device=dev)
 	enfft.transform(grid, fine, (-2, -1), False, 1.0)            # unnormalised inverse: the Fourier series on the M x M grid
 	del grid
@@ -341,10 +343,12 @@ def adjoint_synthesis_general(*, map, loc, spin, lmax, mmax=None, mstart=None, l
 	enfft.transform(fine, grid, (-2, -1), True, 1.0)
 	del fine
 	corr = torch.from_numpy(_kernel_corr(lmax, M)).to(dev)
-	ext = torch.empty((ncm, nm, N), dtype=torch.complex128, device=dev)
-	L.check(lib.b2_general_gather(ext.data_ptr(), grid.data_ptr(), ncm, lmax, nm, N, M, corr.data_ptr(), st))
+	coef = torch.empty((ncm, nm, N), dtype=torch.complex128, device=dev)
+	L.check(lib.b2_general_gather(coef.data_ptr(), grid.data_ptr(), ncm, lmax, nm, N, M, corr.data_ptr(), st))
 	del grid
-	enfft.transform(ext, ext, (-1,), False, 1.0/N)
+	ext = torch.empty_like(coef)
+	enfft.transform(coef, ext, (-1,), False, 1.0/N)
+	del coef
 	leg = torch.empty((ncm, nm, nring_pad), dtype=torch.complex128, device=dev)
 	L.check(lib.b2_general_fold(leg.data_ptr(), ext.data_ptr(), ncm, nm, nt, nring_pad, int(spin), st))
 	del ext

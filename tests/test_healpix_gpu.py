@@ -82,3 +82,23 @@ def test_profile_transforms():
 	rr = np.linspace(0, np.pi, 2001)
 	back = cs.profile2harm(cs.harm2profile(bl, rr), rr, lmax=lmax)
 	assert rel(back, bl) < 1e-6
+
+def test_reproject_between_car_and_healpix():
+	"""reproject.map2healpix / healpix2map, method "harm" (reference reproject.py:118-361): CAR -> HEALPix is exact for a
+	band-limited sky (exact analysis, then synthesis on the HEALPix rings); with a rotation it equals rotate_alm in between"""
+	from pixell_b200 import reproject, curvedsky as cs, geometry
+	lmax, nside = 40, 32
+	alm = rand_alm(3, lmax, 12); alm[1:, [0, 1, lmax+1]] = 0
+	shape, wcs = geometry.fullsky_geometry(res=np.deg2rad(2.0))
+	m = cs.alm2map(alm, geometry.zeros((3,)+shape, wcs), spin=[0, 2])
+	heal = reproject.map2healpix(m, nside=nside, lmax=lmax)
+	assert heal.shape == (3, 12*nside**2)
+	assert rel(heal, cs.alm2map_healpix(alm, nside=nside, spin=[0, 2])) < 1e-10
+	hrot = reproject.map2healpix(m, nside=nside, lmax=lmax, rot="cel,gal")
+	ang = reproject.rot2euler("cel,gal")
+	assert rel(hrot, cs.alm2map_healpix(cs.rotate_alm(alm, *ang), nside=nside, spin=[0, 2])) < 1e-9
+	# and back: the HEALPix analysis is approximate (pixel weights + Jacobi iterations)
+	back = reproject.healpix2map(heal, shape, wcs, lmax=lmax, niter=3)
+	assert rel(np.asarray(back), np.asarray(m)) < 2e-3
+	with pytest.raises(NotImplementedError): reproject.map2healpix(m, nside=nside, method="spline")
+	assert reproject.restrict_nside(100, "pow2") == 128 and reproject.restrict_nside(100, "mul32") == 128 and reproject.restrict_nside(100.2, "any") == 101
