@@ -127,3 +127,80 @@ def test_prepare_alm_mmax():
 	np.testing.assert_array_almost_equal(alm_out, alm7); assert same(ainfo_out, ainfo1)
 	with pytest.raises(ValueError): curvedsky.prepare_alm()
 	with pytest.raises(ValueError): curvedsky.prepare_alm(alm=alm7.astype(np.complex64), ainfo=ainfo1)      # dtype contract (:1424)
+
+def test_healpix_ring_info():
+	"""get_ring_info_healpix (reference curvedsky.py:1192-1222): ring counts, pixel offsets, HEALPix ring formulas"""
+	from pixell_b200 import curvedsky as cs
+	for nside in (1, 2, 8, 64):
+		ri = cs.get_ring_info_healpix(nside)
+		assert ri.nrow == 4*nside-1 and ri.npix == 12*nside**2
+		assert int(ri.offsets[-1]+ri.nphi[-1]) == 12*nside**2 and np.all(np.diff(ri.offsets.astype(np.int64)) == ri.nphi[:-1].astype(np.int64))
+		assert np.all(np.diff(ri.theta) > 0) and np.allclose(ri.theta + ri.theta[::-1], np.pi)
+		assert np.all(ri.nphi == ri.nphi[::-1]) and ri.nphi.max() == 4*nside and ri.nphi[0] == 4
+	ri = cs.get_ring_info_healpix(4)
+	# z = 1 - i^2/(3 nside^2) in the caps, z = 4/3 - 2i/(3 nside) in the belt; first pixel at pi/(4i) or 0 / pi/(4 nside)
+	assert np.allclose(np.cos(ri.theta[:3]), 1-np.arange(1, 4)**2/48.0)
+	assert np.allclose(np.cos(ri.theta[3:8]), 4/3.0-2*np.arange(4, 9)/12.0)
+	assert np.allclose(ri.phi0[:3], np.pi/(4*np.arange(1, 4))) and np.allclose(ri.phi0[3:7], [np.pi/16, 0, np.pi/16, 0])
+	sub = cs.apply_minfo_theta_lim(ri, 1.0, 2.0)
+	assert np.all((sub.theta >= 1.0) & (sub.theta <= 2.0)) and len(sub.theta) < ri.nrow
+	rr = cs.get_ring_info_radial([0.1, 0.2, 0.5])
+	assert np.all(rr.nphi == 1) and list(rr.offsets) == [0, 1, 2]
+
+def test_general_synthesis_host_helpers():
+	"""grid sizes and kernel deconvolution factors of the arbitrary-position synthesis (sht.synthesis_general)"""
+	from pixell_b200 import sht
+	for n in (2, 17, 100, 4098, 16002, 32004):
+		f = sht._fast_len(n)
+		assert f >= n and f % 2 == 0
+		k = f
+		for p in (2, 3, 5):
+			while k % p == 0: k //= p
+		assert k == 1
+	lmax, M = 64, sht._fast_len(2*(2*64+2))
+	corr = sht._kernel_corr(lmax, M)
+	assert corr.shape == (lmax+1,) and np.all(corr > 0) and np.all(np.diff(corr) > 0)      # the kernel transform decays with k
+	# P_0 is the integral of the kernel over its support: check against a plain Riemann sum
+	z = np.linspace(-1, 1, 200001)
+	P0 = 0.5*sht.GENERAL_W*np.trapezoid(np.exp(sht.GENERAL_BETA*(np.sqrt(1-z*z)-1)), z)
+	assert abs(1/corr[0]-P0) < 1e-8*P0
+
+def test_flat_sky_host_helpers():
+	"""enmap mirrors that need no device: spin_helper, queb_rotmat / map_mul, calc_window, reproject helpers"""
+	from pixell_b200 import enmap, reproject, geometry
+	assert list(enmap.spin_helper([0, 2], 3)) == [(0, 0, 1), (2, 1, 3)]
+	assert list(enmap.spin_helper([0, 2], 6)) == [(0, 0, 1), (2, 1, 3), (0, 3, 4), (2, 4, 6)]
+	with pytest.raises(IndexError): list(enmap.spin_helper([0, 2], 2))
+	ny, nx = 6, 8
+	wcs = geometry.CarWCS(crval=[0, 0], cdelt=[-0.5, 0.5], crpix=[nx/2+0.5, ny/2+0.5])
+	lm = enmap.lmap((ny, nx), wcs)
+	rot = enmap.queb_rotmat(lm)
+	inv = enmap.queb_rotmat(lm, inverse=True)
+	assert rot.shape == (2, 2, ny, nx)
+	v = np.random.default_rng(0).standard_normal((2, ny, nx))
+	assert np.allclose(enmap.map_mul(inv, enmap.map_mul(rot, v)), v)
+	assert np.allclose(enmap.queb_rotmat(lm, iau=True), inv)
+	wy, wx = enmap.calc_window((ny, nx))
+	assert wy[0] == 1 and wx[0] == 1 and np.allclose(wy, np.sinc(np.fft.fftfreq(ny)))
+	e = reproject.rot2euler("gal,cel")
+	assert np.allclose(e, np.deg2rad([57.06793215, 62.87115487, -167.14056929]))
+	from scipy.spatial.transform import Rotation
+	R = Rotation.from_euler("zyz", reproject.rot2euler("cel,gal"))*Rotation.from_euler("zyz", e)
+	assert np.allclose(R.as_matrix(), np.eye(3), atol=1e-12)
+	assert np.allclose(reproject.rot2euler([0.1, 0.2, 0.3]), [0.1, 0.2, 0.3])
+	with pytest.raises(ValueError): reproject.rot2euler("gal")
+
+def test_uht_flat_host_side():
+	from pixell_b200 import uharm, geometry, enmap
+	ny, nx = 32, 48
+	d = 2/60
+	wcs = geometry.CarWCS(crval=[0, 0], cdelt=[-d, d], crpix=[nx/2+0.5, ny/2+0.5])
+	uht = uharm.UHT((3, ny, nx), wcs)
+	assert uht.mode == "flat" and uht.shape == (ny, nx) and uht.npix == ny*nx
+	bl = np.linspace(1, 0, 30000)
+	hp = uht.lprof2hprof(bl)
+	assert np.allclose(np.asarray(hp), np.interp(np.asarray(enmap.modlmap((ny, nx), wcs)), np.arange(30000), bl))
+	assert np.isclose(uht.sum_hprof(np.ones((ny, nx))), uht.ntot)
+	shape, fw = geometry.fullsky_geometry(res=np.deg2rad(2.0))
+	assert uharm.UHT(shape, fw).mode == "curved"
+	assert uharm.res2lmax(np.deg2rad(1.0)) == 180
