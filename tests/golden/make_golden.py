@@ -8,6 +8,10 @@ known-answer tests for this path):
   unlensed_071123.npz    every 2nd row (incl. both pole rows) of MM_unlensed_071123.fits =
                          alm2map(rand_alm(ps,lmax=400,seed=1)[1:], spin=[0,2]) on the CC 181x360 grid,
                          plus the WCS numbers from the FITS header
+  lensed_071123.npz      every 2nd row of MM_lensed_071123.fits = lensing.rand_map(seed=1, lmax=400, geodesic=True) on the
+                         same grid (tests/test_pixell.py:351-356): alm2map(deriv) -> offset_by_grad -> alm2map_pos
+  offset_071123.npz      every 10th row of MM_offset_{obs_pos,grad,raw_pos}_071123.fits (tests/test_pixell.py:200-206, 333-349):
+                         raw_pos = lensing.offset_by_grad(obs_pos, grad, pol=True, geodesic=True)
   pixels_041121.npz      the 36 reference pixels + mean square of MM_041121.pkl['fullsky_10arc_car']
                          for both spectra (rand_map(seed=10,lmax=1500), tests/test_pixell.py:568-580)
 """
@@ -55,6 +59,11 @@ def main():
 	np.savez(os.path.join(here, "unlensed_071123.npz"), rows=rows, map=m[:,rows],
 		shape=np.array(m.shape), crpix=[float(hdr["CRPIX1"]), float(hdr["CRPIX2"])],
 		cdelt=[float(hdr["CDELT1"]), float(hdr["CDELT2"])], crval=[float(hdr["CRVAL1"]), float(hdr["CRVAL2"])])
+	ml, _ = read_fits_primary(os.path.join(D, "MM_lensed_071123.fits"))
+	np.savez(os.path.join(here, "lensed_071123.npz"), rows=rows, map=ml[:, rows])
+	r10 = np.arange(0, m.shape[1], 10)
+	off = {k: read_fits_primary(os.path.join(D, "MM_offset_%s_071123.fits" % k))[0][:, r10] for k in ("obs_pos", "grad", "raw_pos")}
+	np.savez(os.path.join(here, "offset_071123.npz"), rows=r10, **off)
 	pk = pickle.load(open(os.path.join(D, "MM_041121.pkl"), "rb"))["fullsky_10arc_car"]
 	np.savez(os.path.join(here, "pixels_041121.npz"),
 		white_10=pk["white_10"]["refpixels"], white_10_ms=pk["white_10"]["meansquare"],

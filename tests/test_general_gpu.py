@@ -153,3 +153,35 @@ def test_rotate_alm():
 	peak = cs.alm2map_pos(eq[None], np.array([[dec, dec+0.05, dec-0.05, -dec], [ra, ra, ra+0.05, ra]]))[0]
 	top = np.sum(bl*np.sqrt((2*l+1)/(4*np.pi)))
 	assert abs(peak[0]-top) < 1e-6*top and peak[1] < peak[0] and peak[2] < peak[0] and peak[3] < 0.01*top
+
+def test_golden_lensed_map():
+	"""The reference's lensing golden MM_lensed_071123.fits (reference tests/test_pixell.py:351-356 through
+	lensing.rand_map -> lens_map_curved, lensing.py:468-492): rand_alm(seed=1) -> phi gradient with alm2map(deriv=True)
+	-> offset_by_grad (host geometry, tests/lens_helper.py) -> alm2map_pos at the displaced positions -> rotate_pol.
+	Pins the arbitrary-position synthesis (K8) and the DERIV1 path to the reference's own output (which ducc produced
+	with its NUFFT at epsilon = 1e-10)."""
+	import os
+	import lens_helper
+	from conftest import GOLDEN
+	from pixell_b200 import curvedsky as cs, geometry, enmap
+	g = np.load(os.path.join(GOLDEN, "lensed_071123.npz")); u = np.load(os.path.join(GOLDEN, "unlensed_071123.npz"))
+	ps = np.load(os.path.join(GOLDEN, "lens_ps_400.npy"))
+	alm = cs.rand_alm(ps, lmax=400, seed=1)
+	phi_alm, cmb_alm = alm[0], alm[1:]
+	wcs = geometry.CarWCS(u["crval"], u["cdelt"], u["crpix"])
+	shape = tuple(int(v) for v in u["shape"][1:])
+	grad = cs.alm2map(phi_alm, geometry.zeros((2,)+shape, wcs), deriv=True)
+	dec = geometry.dec_of(wcs, np.arange(shape[0]))[:, None] + np.zeros(shape)
+	ra = geometry.ra_of(wcs, np.arange(shape[1]))[None, :] + np.zeros(shape)
+	raw = lens_helper.offset_by_grad(np.array([dec, ra]), np.asarray(grad))
+	lensed = cs.alm2map_pos(cmb_alm, raw[:2], spin=[0, 2])
+	lensed = enmap.rotate_pol(lensed, raw[2])
+	got, want = lensed[:, g["rows"]], g["map"]
+	# the reference's own criterion
+	assert np.all(np.isclose(got, want))
+	# and tighter, away from the pole rows (where the reference's positions are degenerate): T to 2e-9 of its range
+	inner = slice(1, -1)
+	assert np.abs(got[0, inner]-want[0, inner]).max() < 2e-9*np.abs(want[0]).max()
+	assert np.abs(got[1:, inner]-want[1:, inner]).max() < 2e-9*np.abs(want[1:]).max()
+	# lensing moves the map: the same comparison against the unlensed golden must fail by a wide margin
+	assert np.abs(got[0, inner]-u["map"][0, inner]).max() > 1e-2*np.abs(want[0]).max()

@@ -47,3 +47,14 @@ def test_pixels_pkl_rand_map_scalar():
 		cut = m[0][510:570][:, (2130+np.arange(60)) % 2160]   # the cut_span_180_2 extract
 		# upstream's "meansquare" is literally np.mean(arr*2.) (tests/test_pixell.py:94-95)
 		assert np.isclose(np.mean(cut*2.), g[name+"_ms"], rtol=1e-9, atol=1e-12), name
+
+def test_offset_by_grad_golden():
+	"""the numpy restatement of lensing.offset_by_grad (tests/lens_helper.py) against the reference's own offset
+	goldens MM_offset_{obs_pos,grad,raw_pos}_071123.fits (reference tests/test_pixell.py:333-349)"""
+	import lens_helper
+	g = np.load(os.path.join(os.path.dirname(__file__), "golden", "offset_071123.npz"))
+	got = lens_helper.offset_by_grad(g["obs_pos"], g["grad"])
+	want = g["raw_pos"]
+	assert np.all(np.isclose(got[:2], want[:2], rtol=1e-12, atol=1e-13))
+	ok = np.isfinite(want[2])
+	assert np.all(np.isclose(got[2][ok], want[2][ok], rtol=1e-9, atol=1e-11))
