@@ -204,3 +204,29 @@ def test_uht_flat_host_side():
 	shape, fw = geometry.fullsky_geometry(res=np.deg2rad(2.0))
 	assert uharm.UHT(shape, fw).mode == "curved"
 	assert uharm.res2lmax(np.deg2rad(1.0)) == 180
+
+def test_wavelet_bases_and_scale_geometries():
+	"""host side of pixell_b200.wavelets (reference wavelets.py:48-75, 131-161, 402-417, 472-495)"""
+	from pixell_b200 import wavelets, geometry
+	l = np.arange(400.0)
+	cn = wavelets.CosineNeedlet([10, 30, 90, 270])
+	assert cn.n == 4 and list(cn.lmaxs) == [30, 90, 270, 270] and list(cn.lmins) == [10, 10, 30, 90]
+	tot = sum(cn(i, l)**2 for i in range(cn.n))
+	assert np.allclose(tot[10:270], 1) and np.all(tot[:10] == 0) and np.all(tot[271:] == 0)
+	assert cn(1, l)[30] == 1 and abs(cn(1, l)[10]) < 1e-15 and cn(1, l)[90] == 0
+	bt = wavelets.ButterTrim(lmin=10, lmax=320)
+	assert bt.n == 4 and bt.lmaxs[-1] == 320 and np.all(np.diff(bt.lmaxs) > 0)
+	assert np.allclose(sum(bt(i, l)**2 for i in range(bt.n)), 1)
+	for i in range(bt.n-1): assert np.all(bt(i, l)[l > bt.lmaxs[i]] == 0)        # harmonically compact
+	assert np.all(wavelets.trim_kernel(np.array([0.0, 0.005, 0.5, 1.0]), 1e-2) == np.clip(np.array([0.0, 0.005, 0.5, 1.0])*1.02-0.01, 0, 1))
+	# scale grids: full sky at the scale's resolution (never coarser than 2 degrees), cropped to the map's rows
+	shape, wcs = geometry.fullsky_geometry(res=np.deg2rad(0.5))
+	gs, gw = wavelets.make_wavelet_geometry_curved(shape, wcs, np.pi/100)
+	assert gs == (100, 200)
+	assert wavelets.make_wavelet_geometry_curved(shape, wcs, np.deg2rad(10))[0] == (90, 180)
+	bs, bw = geometry.band_geometry(np.deg2rad([-30, 10]), res=np.deg2rad(0.5))
+	cs_, cw = wavelets.make_wavelet_geometry_curved(bs, bw, np.pi/60)
+	dec = np.rad2deg(geometry.dec_of(cw, np.array([-0.5, cs_[-2]-0.5])))
+	assert cs_[-1] == 180 and dec.min() <= -30+1e-9 and dec.max() >= 10 and cs_[-2] <= 22      # 2 degree grid (minres), 21 rows
+	cut, cutw = geometry.slice_geometry(shape, wcs, 0, shape[0], 0, shape[1]//2)
+	with pytest.raises(NotImplementedError): wavelets.make_wavelet_geometry_curved(cut, cutw, np.pi/60)
