@@ -6,7 +6,8 @@ Same names, argument meaning and error behaviour as the reference (pixell/curved
   almxfl :630-651   filter :653-669   alm2cl :672-712   transfer_alm :744-750
   analyse_geometry :1252-1306   get_method :478-488   quad_weights :492-505
 for methods "2d" and "cyl" (cylindrical CAR maps, spin 0 and spin s, deriv, adjoints).
-The "general" method (NUFFT), HEALPix rings and rotate_alm are outside this build.
+The "general" method (non-uniform FFT at the pixel centres), HEALPix rings and rotate_alm follow further down
+(SURVEY.md 8f).
 
 Differences that are deliberate:
   * maps may be numpy arrays / ndmaps (host) or torch CUDA tensors (pass wcs=); nothing is
@@ -250,7 +251,7 @@ def _grouped(pk, op, groups, alm2, map3):
 	return True
 
 def _check_method(method, minfo, shape):
-	if method == "general": raise NotImplementedError("pixell_b200 implements the '2d' and 'cyl' methods only (cylindrical maps)")
+	if method == "general": return          # any map whose pixel centres geometry.py can locate (handled by *_general)
 	if method not in ("2d", "cyl"): raise ValueError("Unrecognized alm2map method '%s'" % str(method))
 	if minfo.case == "general": raise NotImplementedError("non-cylindrical geometry: only the reference's 'general' method applies")
 	if method == "2d" and minfo.case != "2d":
@@ -266,6 +267,9 @@ def alm2map(alm, map, spin=[0,2], deriv=False, adjoint=False, copy=False, method
 	if method == "auto": method = get_method(map.shape, wcs, minfo=minfo)
 	_check_method(method, minfo, map.shape)
 	if verbose: print("method: %s" % method)
+	if method == "general":
+		return alm2map_general(alm, map, ainfo=ainfo, spin=spin, deriv=deriv, copy=copy, adjoint=adjoint, locinfo=locinfo,
+			epsilon=None if epsilon == 1e-6 else epsilon, wcs=wcs)
 	if copy:
 		if adjoint and alm is not None: alm = alm.clone() if L.is_torch(alm) else alm.copy()
 		else: map = map.clone() if L.is_torch(map) else map.copy()
@@ -521,6 +525,79 @@ def alm2map_raw_general(alm, map, loc, ainfo=None, spin=[0,2], deriv=False, copy
 				else: _assign(map_full[Ij], sht.synthesis_general(alm=_astype(alm_full[Ij], ctype), spin=s, **kw))
 	return alm if adjoint else map
 
+def calc_locinfo(shape, wcs, bsize=1000):
+	"""(codec, ra) of every pixel centre, [npix, 2] (reference curvedsky.py:1355-1382; separable CAR maps: no invalid pixels)"""
+	dec = geometry.dec_of(wcs, np.arange(shape[-2])); ra = geometry.ra_of(wcs, np.arange(shape[-1]))
+	loc = np.empty((shape[-2], shape[-1], 2))
+	loc[..., 0] = (np.pi/2-dec)[:, None]
+	loc[..., 1] = np.mod(ra, 2*np.pi)[None, :]
+	return _Bunch(loc=loc.reshape(-1, 2), mask=np.ones(tuple(shape[-2:]), bool), masked=False)
+
+def alm2map_general(alm, map, ainfo=None, spin=[0,2], deriv=False, copy=False, verbose=False, adjoint=False, nthread=None,
+		locinfo=None, epsilon=None, wcs=None):
+	"""alm2map through the arbitrary-position synthesis at the pixel centres (reference curvedsky.py:796-820): works on any
+	pixelisation whose pixel centres are known, at a few times the cost of the ring methods."""
+	wcs = geometry.wcs_of(map, wcs)
+	if L.is_torch(map): raise NotImplementedError("alm2map_general: pass numpy maps (use sht.synthesis_general directly for device tensors)")
+	if copy:
+		if adjoint and alm is not None: alm = alm.copy()
+		else: map = map.copy()
+	if adjoint: alm, ainfo = prepare_alm(alm=alm, ainfo=ainfo, pre=map.shape[:-2] if not deriv else map.shape[:-3], dtype=_rdtype(map), convert=False, like=map)
+	if locinfo is None: locinfo = calc_locinfo(map.shape, wcs)
+	mview = np.asarray(map)
+	for I in np.ndindex(*mview.shape[:-3]):
+		tmap = np.ascontiguousarray(mview[I].reshape(mview[I].shape[:-2]+(-1,)))
+		alm2map_raw_general(alm[I], tmap, locinfo.loc, ainfo=ainfo, spin=spin, deriv=deriv, epsilon=epsilon, adjoint=adjoint)
+		if not adjoint: mview[I] = tmap.reshape(mview[I].shape)
+	return alm if adjoint else map
+
+def map2alm_raw_general(map, loc, alm=None, ainfo=None, lmax=None, spin=[0,2], weights=None, deriv=False, copy=False, verbose=False,
+		adjoint=False, nthread=None, niter=0, epsilon=None):
+	"""map[..., ncomp, npix] at loc -> alm = Y^T (W map), refined by niter Jacobi iterations, or the adjoint of that
+	(reference curvedsky.py:1088-1120)."""
+	if deriv: raise NotImplementedError("map2alm_raw_general: deriv=True is not provided")
+	if epsilon is None: epsilon = 1e-10 if _rdtype(map) == np.float64 else 1e-6
+	epsilon = max(epsilon, 1e-12)
+	if ainfo is None: ainfo = alm_info(lmax=lmax) if alm is None else alm_info(nalm=alm.shape[-1])
+	if weights is None: weights = np.ones(1)
+	alm_full, map_full = _atleast(alm, 3), _atleast(map, 3)
+	kw = dict(loc=loc, lmax=ainfo.lmax, mmax=ainfo.mmax, mstart=ainfo.mstart, lstride=ainfo.stride, epsilon=epsilon)
+	for I in np.ndindex(*map_full.shape[:-2]):
+		for s, j1, j2 in spin_helper(spin, alm_full.shape[-2]):
+			Ij = I+(slice(j1, j2),)
+			def Y(a): return sht.synthesis_general(alm=np.ascontiguousarray(a, dtype=np.complex128), spin=s, **kw)
+			def YT(m): return sht.adjoint_synthesis_general(map=np.ascontiguousarray(m, dtype=np.float64), spin=s, **kw)
+			def YTW(m): return YT(m*weights)
+			def WY(a): return Y(a)*weights
+			if adjoint:
+				a = alm_full[Ij]; x = WY(a)
+				for it in range(niter): x -= WY(YT(x)-a)
+				map_full[Ij] = x
+			else:
+				y = map_full[Ij]; x = YTW(y)
+				for it in range(niter): x -= YTW(Y(x)-y)
+				alm_full[Ij] = x
+	return map if adjoint else alm
+
+def map2alm_general(map, alm=None, ainfo=None, minfo=None, lmax=None, spin=[0,2], weights=None, deriv=False, copy=False,
+		verbose=False, adjoint=False, nthread=None, locinfo=None, epsilon=None, niter=0, wcs=None):
+	"""map2alm with pixel-area weights at arbitrary pixel centres (reference curvedsky.py:875-898)"""
+	wcs = geometry.wcs_of(map, wcs)
+	if L.is_torch(map): raise NotImplementedError("map2alm_general: pass numpy maps")
+	if adjoint:
+		if copy and map is not None: map = map.copy()
+	elif copy and alm is not None: alm = alm.copy()
+	alm, ainfo = prepare_alm(alm=alm, ainfo=ainfo, lmax=lmax, pre=map.shape[:-2], dtype=_rdtype(map), convert=adjoint, like=map)
+	if locinfo is None: locinfo = calc_locinfo(map.shape, wcs)
+	if weights is None: weights = np.repeat(geometry.pixsize_rows(map.shape, wcs), map.shape[-1]).astype(_rdtype(map), copy=False)
+	mview = np.asarray(map)
+	for I in np.ndindex(*mview.shape[:-3]):
+		tmap = np.ascontiguousarray(mview[I].reshape(mview[I].shape[:-2]+(-1,)))
+		map2alm_raw_general(tmap, locinfo.loc, alm[I], ainfo=ainfo, lmax=lmax, spin=spin, deriv=deriv, weights=weights,
+			adjoint=adjoint, niter=niter, epsilon=epsilon)
+		if adjoint: mview[I] = tmap.reshape(mview[I].shape)
+	return map if adjoint else alm
+
 def alm2map_pos(alm, pos=None, loc=None, ainfo=None, map=None, spin=[0,2], deriv=False, copy=False, verbose=False, adjoint=False, nthread=None, epsilon=None):
 	"""Like alm2map, but evaluated at arbitrary positions (reference curvedsky.py:174-207):
 	pos: [{dec,ra},...] radians, or loc: [...,{codec,ra}] radians.  adjoint=True: map -> alm (alm must be given)."""
@@ -565,6 +642,9 @@ def map2alm(map, alm=None, lmax=None, spin=[0,2], deriv=False, adjoint=False, co
 	if method == "auto": method = get_method(map.shape, wcs, minfo=minfo)
 	_check_method(method, minfo, map.shape)
 	if verbose: print("method: %s" % method)
+	if method == "general":
+		return map2alm_general(map, alm=alm, ainfo=ainfo, lmax=lmax, spin=spin, weights=weights, deriv=deriv, copy=copy,
+			adjoint=adjoint, locinfo=locinfo, epsilon=epsilon, niter=niter, wcs=wcs)
 	if adjoint:
 		if copy and map is not None: map = map.clone() if L.is_torch(map) else map.copy()
 	elif copy and alm is not None: alm = alm.clone() if L.is_torch(alm) else alm.copy()

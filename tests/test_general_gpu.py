@@ -185,3 +185,32 @@ def test_golden_lensed_map():
 	assert np.abs(got[1:, inner]-want[1:, inner]).max() < 2e-9*np.abs(want[1:]).max()
 	# lensing moves the map: the same comparison against the unlensed golden must fail by a wide margin
 	assert np.abs(got[0, inner]-u["map"][0, inner]).max() > 1e-2*np.abs(want[0]).max()
+
+def test_method_general_matches_ring_methods():
+	"""alm2map / map2alm with method="general" (reference curvedsky.py:796-820, 875-898, 1088-1120): the non-uniform path at the
+	pixel centres gives what the ring methods give, on a full-sky grid and on a cut-sky patch, with adjoints and Jacobi steps"""
+	from pixell_b200 import curvedsky as cs, geometry
+	lmax = 36
+	ai = cs.alm_info(lmax)
+	alm = rand_alm(3, lmax, 60); alm[1:, [ai.lm2ind(0, 0), ai.lm2ind(1, 0), ai.lm2ind(1, 1)]] = 0
+	fshape, fwcs = geometry.fullsky_geometry(res=np.deg2rad(4.0))
+	pshape, pwcs = geometry.slice_geometry(fshape, fwcs, 8, 31, 10, 60)
+	rng = np.random.default_rng(61)
+	for shape, wcs in ((fshape, fwcs), (pshape, pwcs)):
+		want = cs.alm2map(alm, geometry.zeros((3,)+shape, wcs), spin=[0, 2])
+		got = cs.alm2map(alm, geometry.zeros((3,)+shape, wcs), spin=[0, 2], method="general")
+		assert rel(np.asarray(got), np.asarray(want)) < 1e-10
+		d = cs.alm2map(alm[0], geometry.zeros((2,)+shape, wcs), deriv=True, method="general")
+		assert rel(np.asarray(d), np.asarray(cs.alm2map(alm[0], geometry.zeros((2,)+shape, wcs), deriv=True))) < 1e-10
+		m = geometry.ndmap(rng.standard_normal((3,)+shape), wcs)
+		a1 = cs.alm2map_adjoint(m, spin=[0, 2], ainfo=ai, method="general")
+		a0 = cs.alm2map_adjoint(m, spin=[0, 2], ainfo=ai)
+		assert rel(a1, a0) < 1e-10
+		# same weights on both sides: per-pixel areas for "general", the same numbers per ring (north first) for "cyl";
+		# Jacobi steps only on the full sky (on a patch "cyl" iterates on zero-padded full rings, "general" on the patch)
+		wring = geometry.pixsize_rows(shape, wcs)[::-1]
+		for niter in ((0, 2) if shape == fshape else (0,)):
+			b1 = cs.map2alm(want, lmax=lmax, spin=[0, 2], method="general", niter=niter)
+			b0 = cs.map2alm(want, lmax=lmax, spin=[0, 2], method="cyl", niter=niter, weights=wring)
+			assert rel(b1, b0) < 1e-9
+	assert cs.calc_locinfo(pshape, pwcs).loc.shape == (pshape[0]*pshape[1], 2)
