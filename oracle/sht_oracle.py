@@ -385,3 +385,21 @@ def adjoint_analysis_2d(*, alm, spin, lmax, geometry, ntheta=None, nphi=None, mm
 	if map is None: return res
 	map[...] = res
 	return map
+
+# ------------------------------------------------------------------ arbitrary positions
+
+def synthesis_general(*, alm, loc, spin, lmax, mmax=None, mstart=None, mode="STANDARD", **kw):
+	"""ducc0.sht.experimental.synthesis_general restatement (call site pixell/curvedsky.py:993-1016): the series evaluated
+	directly at loc[npos, 2] = (theta, phi), as a ring synthesis with one single-pixel ring per position (no NUFFT, so
+	this is exact to rounding; cost O(npos lmax^2))."""
+	loc = np.asarray(loc, np.float64)
+	n = len(loc)
+	return synthesis(alm=alm, theta=loc[:, 0], nphi=np.ones(n, np.int64), phi0=loc[:, 1], ringstart=np.arange(n),
+		spin=spin, lmax=lmax, mmax=mmax, mstart=mstart, mode=mode)
+
+def adjoint_synthesis_general(*, map, loc, spin, lmax, mmax=None, mstart=None, mode="STANDARD", **kw):
+	"""transpose of synthesis_general (ducc0.sht.experimental.adjoint_synthesis_general, same call site with adjoint=True)"""
+	loc = np.asarray(loc, np.float64)
+	n = len(loc)
+	return adjoint_synthesis(map=map, theta=loc[:, 0], nphi=np.ones(n, np.int64), phi0=loc[:, 1], ringstart=np.arange(n),
+		spin=spin, lmax=lmax, mmax=mmax, mstart=mstart, mode=mode)

@@ -58,3 +58,30 @@ def test_offset_by_grad_golden():
 	assert np.all(np.isclose(got[:2], want[:2], rtol=1e-12, atol=1e-13))
 	ok = np.isfinite(want[2])
 	assert np.all(np.isclose(got[2][ok], want[2][ok], rtol=1e-9, atol=1e-11))
+
+def test_lensed_golden_through_the_oracle():
+	"""MM_lensed_071123.fits (reference tests/test_pixell.py:351-356; lensing.py:468-492) replayed on the CPU: the oracle's
+	DERIV1 synthesis for the gradient of phi, the pinned offset_by_grad helper, and the oracle's direct evaluation at the
+	displaced positions.  Every 8th row of the grid keeps this to a few seconds."""
+	import lens_helper
+	g = np.load(os.path.join(GOLDEN, "lensed_071123.npz")); u = np.load(os.path.join(GOLDEN, "unlensed_071123.npz"))
+	ps = np.load(os.path.join(GOLDEN, "lens_ps_400.npy"))
+	alm = ao.rand_alm(ps, 400, 1)
+	ny, nx = (int(v) for v in u["shape"][1:])
+	sel = np.arange(2, len(g["rows"])-1, 4)                    # rows of the fixture (which holds every 2nd map row), poles excluded
+	rows = g["rows"][sel]
+	dec = np.deg2rad(u["crval"][1] + (rows+1-u["crpix"][1])*u["cdelt"][1])
+	ra = np.deg2rad(u["crval"][0] + (np.arange(nx)+1-u["crpix"][0])*u["cdelt"][0])
+	pos = np.array([dec[:, None]+0*ra[None, :], ra[None, :]+0*dec[:, None]])
+	loc = np.stack([np.pi/2-pos[0].reshape(-1), pos[1].reshape(-1)], 1)
+	grad = so.synthesis_general(alm=alm[:1], loc=loc, spin=1, lmax=400, mode="DERIV1").reshape(2, len(rows), nx)
+	grad[0] *= -1                                              # theta derivative -> dec derivative (curvedsky.py:918-920)
+	raw = lens_helper.offset_by_grad(pos, grad)
+	rloc = np.stack([np.pi/2-raw[0].reshape(-1), raw[1].reshape(-1)], 1)
+	t = so.synthesis_general(alm=alm[1:2], loc=rloc, spin=0, lmax=400)
+	qu = so.synthesis_general(alm=alm[2:4], loc=rloc, spin=2, lmax=400)
+	c, s2 = np.cos(2*raw[2].reshape(-1)), np.sin(2*raw[2].reshape(-1))
+	got = np.array([t[0], c*qu[0]-s2*qu[1], s2*qu[0]+c*qu[1]]).reshape(3, len(rows), nx)
+	want = g["map"][:, sel]
+	assert np.all(np.isclose(got, want))
+	assert np.abs(got-want).max() < 2e-9*np.abs(want[0]).max()
