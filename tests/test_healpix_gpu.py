@@ -102,3 +102,45 @@ def test_reproject_between_car_and_healpix():
 	assert rel(np.asarray(back), np.asarray(m)) < 2e-3
 	with pytest.raises(NotImplementedError): reproject.map2healpix(m, nside=nside, method="spline")
 	assert reproject.restrict_nside(100, "pow2") == 128 and reproject.restrict_nside(100, "mul32") == 128 and reproject.restrict_nside(100.2, "any") == 101
+
+def test_alm2map_healpix_roundtrip():
+	"""mirror of the reference tests/test_pixell.py:967-1026: nside 2, lmax 4, one coefficient set, spin 0 and spin 1,
+	1-, 2- and 3-dimensional alm, float64 and float32, with and without a preallocated output, niter = 7"""
+	from pixell_b200 import curvedsky
+	nside = 2
+	lmax = nside*2
+	nside = lmax//2
+	ainfo = curvedsky.alm_info(lmax)
+	npix = 12*nside**2
+	niter = 7
+	for use_oalm in [False, True]:
+		for dtype in [np.float64, np.float32]:
+			ctype = np.result_type(dtype, 0j)
+			spin = 0
+			alm = np.zeros((ainfo.nelem), dtype=ctype)
+			i = ainfo.lm2ind(lmax, lmax)
+			alm[i] = 1. + 1.j
+			omap = np.zeros(npix, dtype)
+			curvedsky.alm2map_healpix(alm, omap, spin=spin)
+			assert np.any(omap != 0)
+			alm_out = np.zeros_like(alm) if use_oalm else None
+			alm_out = curvedsky.map2alm_healpix(omap, alm=alm_out, spin=spin, ainfo=ainfo, niter=niter)
+			np.testing.assert_array_almost_equal(alm_out, alm)
+			spin = 1
+			alm = np.zeros((2, ainfo.nelem), dtype=ctype)
+			alm[0, i] = 1. + 1.j
+			alm[1, i] = 2. - 2.j
+			omap = np.zeros((2, npix), dtype)
+			curvedsky.alm2map_healpix(alm, omap, spin=spin)
+			alm_out = np.zeros_like(alm) if use_oalm else None
+			alm_out = curvedsky.map2alm_healpix(omap, alm=alm_out, spin=spin, ainfo=ainfo, niter=niter)
+			np.testing.assert_array_almost_equal(alm_out, alm)
+			alm = np.zeros((3, 2, ainfo.nelem), dtype=ctype)
+			for k in range(3):
+				alm[k, 0, i] = (2*k+1)*(1. + 1.j)
+				alm[k, 1, i] = (2*k+2)*(1. - 1.j)
+			omap = np.zeros((3, 2, npix), dtype)
+			curvedsky.alm2map_healpix(alm, omap, spin=spin)
+			alm_out = np.zeros_like(alm) if use_oalm else None
+			alm_out = curvedsky.map2alm_healpix(omap, alm=alm_out, spin=spin, ainfo=ainfo, niter=niter)
+			np.testing.assert_array_almost_equal(alm_out, alm)
