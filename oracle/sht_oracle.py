@@ -46,6 +46,71 @@ def _load():
 def nthreads():
 	return _load().orc_num_threads()
 
+# ------------------------------------------------------------------ tuned CPU Legendre stage (bench.py's CPU arm)
+
+_fast = None
+def build_fast(force=False):
+	"""Compile sht_fast.c -> oracle/_build/libshtfast.so for the cores of THIS machine (-march=native, 512-bit vectors
+	where the CPU has them).  bench.py's CPU arm builds it on the box it runs on."""
+	out = os.path.join(_here, "_build", "libshtfast.so")
+	src = os.path.join(_here, "sht_fast.c")
+	tag = out + ".cpu"
+	cpu = ""
+	try:
+		with open("/proc/cpuinfo") as f:
+			for line in f:
+				if line.startswith("model name"): cpu = line.split(":", 1)[1].strip(); break
+	except OSError: pass
+	stale = not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src)
+	if not stale:
+		try: stale = open(tag).read() != cpu
+		except OSError: stale = True
+	if force or stale:
+		os.makedirs(os.path.dirname(out), exist_ok=True)
+		subprocess.check_call(["gcc", "-O3", "-march=native", "-mprefer-vector-width=512", "-fopenmp", "-shared", "-fPIC",
+			"-o", out, src, "-lm"])
+		with open(tag, "w") as f: f.write(cpu)
+	return out
+
+def _load_fast():
+	global _fast
+	if _fast is None:
+		_fast = ctypes.CDLL(build_fast())
+		i64p = ctypes.POINTER(ctypes.c_int64); dp = ctypes.POINTER(ctypes.c_double); ip = ctypes.POINTER(ctypes.c_int)
+		_fast.fast_alm2leg.argtypes = [ctypes.c_int]*3 + [i64p, ctypes.c_int, ip, ctypes.c_int, dp, dp, ctypes.c_int64, dp]
+		_fast.fast_leg2alm.argtypes = [ctypes.c_int]*3 + [i64p, ctypes.c_int, ip, ctypes.c_int, dp, dp, dp, ctypes.c_int64]
+	return _fast
+
+def fast_nthreads(): return _load_fast().fast_num_threads()
+
+def fast_alm2leg(alm, theta, spin, lmax, mmax, mstart, mlist=None):
+	"""alm[nca, nalm] c128 -> leg[ncm, len(mlist), nring] c128 (ring fastest), only for the m in mlist (default all)"""
+	lib = _load_fast()
+	alm = np.ascontiguousarray(alm, dtype=np.complex128); theta = np.ascontiguousarray(theta, dtype=np.float64)
+	mstart = np.ascontiguousarray(mstart).astype(np.int64)
+	mlist = np.arange(mmax+1, dtype=np.int32) if mlist is None else np.ascontiguousarray(mlist, dtype=np.int32)
+	ncm = 1 if spin == 0 else 2
+	assert alm.shape[0] == ncm
+	leg = np.empty((ncm, len(mlist), len(theta)), np.complex128)
+	err = lib.fast_alm2leg(spin, lmax, mmax, _ip(mstart), len(mlist), mlist.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+		len(theta), _dp(theta), _dp(alm.view(np.float64)), alm.shape[1], _dp(leg.view(np.float64)))
+	if err: raise ValueError("fast_alm2leg failed")
+	return leg
+
+def fast_leg2alm(leg, theta, spin, lmax, mmax, mstart, nalm, mlist=None, alm=None):
+	"""leg[ncm, len(mlist), nring] -> alm[nca, nalm] (entries of the listed m only; others untouched / zero)"""
+	lib = _load_fast()
+	leg = np.ascontiguousarray(leg, dtype=np.complex128); theta = np.ascontiguousarray(theta, dtype=np.float64)
+	mstart = np.ascontiguousarray(mstart).astype(np.int64)
+	mlist = np.arange(mmax+1, dtype=np.int32) if mlist is None else np.ascontiguousarray(mlist, dtype=np.int32)
+	ncm = 1 if spin == 0 else 2
+	assert leg.shape == (ncm, len(mlist), len(theta))
+	if alm is None: alm = np.zeros((ncm, nalm), np.complex128)
+	err = lib.fast_leg2alm(spin, lmax, mmax, _ip(mstart), len(mlist), mlist.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+		len(theta), _dp(theta), _dp(leg.view(np.float64)), _dp(alm.view(np.float64)), alm.shape[1])
+	if err: raise ValueError("fast_leg2alm failed")
+	return alm
+
 def set_mstride(s):
 	"""bench.py only: restrict the Legendre stage to every s-th m (bounded CPU-baseline sample)"""
 	_load().orc_set_mstride(int(s))

@@ -5,7 +5,7 @@ import os, subprocess, sys, concurrent.futures
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200sht.so")
-SOURCES = ["api.cu", "legendre.cu", "ringfft.cu", "resample.cu", "almops.cu", "fft2d.cu", "general.cu"]
+SOURCES = ["api.cu", "legendre.cu", "ringfft.cu", "resample.cu", "almops.cu", "fft2d.cu", "tfft.cu", "general.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
 	"-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -11,6 +11,7 @@
 // Normalisation (and any caller-supplied factor) is a multiplication in the store of the last pass.
 #include "../../include/b200sht.h"
 #include "fft_smem.cuh"
+#include "tfft.cuh"
 #include <algorithm>
 #include <stdlib.h>
 #include <memory>
@@ -425,6 +426,8 @@ struct b2_fft_plan {
 	AxisPass pass[2];
 	AxisPass packed;       // real axis as a half-length complex transform (even length, line fits two CTAs); n = 0: unavailable
 	DevBuf<char> work, stage_in, stage_out;
+	TfPlan *tf = nullptr;  // TMA-pipelined path (tfft.cu) for float64 transforms over the last two axes; null: not applicable
+	~b2_fft_plan() { if (tf) tfft_plan_destroy(tf); }
 };
 
 static const size_t FFT_TILE_ELEMS = 6144;
@@ -548,6 +551,8 @@ extern "C" int b2_fft_plan_create(b2_fft_plan **out, int ndim, const int64_t *sh
 	for (int i = 0; i < naxes; i++)
 		if (setup_pass(p->pass[i], order[i], (int)p->shape[order[i]], true, istride[order[i]] != 1 || ostride[order[i]] != 1)) return 1;
 	if (kind != B2_FFT_C2C && setup_packed(p->packed, last, (int)p->shape[last])) return 1;
+	if (tfft_eligible(kind, dtype, ndim, p->shape, p->istride, p->ostride, naxes, p->axes) &&
+		tfft_plan_create(&p->tf, kind, ndim, p->shape, p->istride, p->ostride)) p->tf = nullptr;      // fall back to the axis passes
 	*out = p.release();
 	return 0;
 }
@@ -695,7 +700,8 @@ extern "C" int b2_fft_execute(b2_fft_plan *p, const void *in, void *out, int for
 		return true;
 	};
 	int rc = 0;
-	if (p->naxes == 1) {
+	if (p->tf && ((uintptr_t)din % 16 == 0) && ((uintptr_t)dout % 16 == 0)) rc = tfft_execute(p->tf, din, dout, forward, scale, st);
+	else if (p->naxes == 1) {
 		AxisPass &a = p->pass[0];
 		const bool alias = (din == dout) && a.P > 1 && !(a.cluster && p->dtype == B2_F64 && p->kind == B2_FFT_C2C);
 		B2_REQUIRE(!alias, "fft: in-place transforms of lines longer than %d elements are not supported", (int)(FFT_SMEM_MAX/16));

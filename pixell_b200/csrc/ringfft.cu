@@ -241,7 +241,7 @@ __device__ __forceinline__ double2 leg_phase(const RingArgs &A, const double2 *l
 	return g;
 }
 
-template<typename MapT> __global__ void k_leg2map(RingArgs A)
+template<typename MapT> __global__ void __launch_bounds__(512) k_leg2map(RingArgs A)
 {
 	extern __shared__ __align__(16) double2 s[];
 	const int ring = A.ring_ids ? A.ring_ids[blockIdx.x] : blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
@@ -312,7 +312,7 @@ template<typename MapT> __global__ void k_leg2map(RingArgs A)
 	}
 }
 
-template<typename MapT> __global__ void k_map2leg(RingArgs A)
+template<typename MapT> __global__ void __launch_bounds__(512) k_map2leg(RingArgs A)
 {
 	extern __shared__ __align__(16) double2 s[];
 	const int ring = A.ring_ids ? A.ring_ids[blockIdx.x] : blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;

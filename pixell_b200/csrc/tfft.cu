@@ -1,0 +1,561 @@
+// tfft.cu -- K7t: the TMA-pipelined 2-D FFT (float64) behind the pixell.fft plug-in / enmap.fft
+// (reference pixell/fft.py:8-113 engine objects, :133-209 fft/ifft/rfft/irfft; pixell/enmap.py:1307-1337).
+//
+// Every 1-D transform of length N = N1 N2 along an axis of a [batch][ny][nx] array runs as two "tile-DFT" launches:
+//   sub-pass 1   tiles [N1 strided elements][W contiguous columns]: DFT over j1, times w_N^(k1 j2), stored so that
+//                sub-pass 2 finds its lines (row axis: transposed inside the tile; column axis: rows permuted)
+//   sub-pass 2   tiles [N2][W]: DFT over j2; output k = k1 + N1 k2 lands in natural order
+// In both, the transformed dimension is the tile's slow dimension and the lanes of a warp run across the W contiguous
+// columns, so every shared-memory access of the butterflies is a contiguous, conflict-free row segment and every
+// global access is a TMA box with W*16-byte contiguous rows.  The intermediate array is blocked in slabs small
+// enough to stay in the 126 MB L2 between the two launches, so HBM sees one read and one write per axis.
+//
+// One kernel (k_tfft) serves all sub-passes: persistent CTAs, one producer warp issuing cp.async.bulk.tensor loads
+// into a 3-stage mbarrier ring, 8 consumer warps doing register butterflies in shared memory, TMA (tensor or 1-D
+// bulk) stores from two alternating output tiles, so the load of tile i+2 and the store of tile i-1 overlap the
+// butterflies of tile i.  Real transforms use the packed half-length complex transform along x; the untangling
+// X_k = f(Z_k, conj Z_{Nc-k}) (r2c) / its inverse (c2r) is fused into the neighbouring column sub-pass, whose tiles
+// then carry the mirrored column blocks [a, a+W) and [Nc-a-W+1, Nc-a] (plus the self-mirrored column Nc/2 once).
+#include "../../include/b200sht.h"
+#include "fft_smem.cuh"
+#include "tma.cuh"
+#include "tfft.cuh"
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <stdlib.h>
+
+#define TF_MAXFAC 6
+#define TF_STAGES 3
+#define TF_NCONS 256
+#define TF_THREADS (TF_NCONS + 32)
+
+struct TfMaps { CUtensorMap ld[3], st[3]; };      // regions A, B (mirror), M (self-mirrored column)
+
+struct TfArgs {
+	int n, nfac, fac[TF_MAXFAC];
+	int W, wshift, nreg, LW;
+	int midcol;                  // mirrored tiles: the self-mirrored column (carried by the last column block), else -1
+	int ncb;                     // column blocks in the whole array
+	int cb0, ncb_l;              // column blocks of this launch
+	int G2, g2_0, G3, g3_0;      // tile coordinates 2 and 3: count and offset in this launch
+	int mirror;                  // Nc: region B starts at column Nc - a - W + 1
+	int tw_mode, inv, op, tstore;
+	double scale;
+	double2 *tbase; long long t_g2stride; int ncols_valid;      // transposed bulk stores (row axis, sub-pass 1)
+	const double2 *twn; const int *natk; const double2 *twN_hi, *twN_lo, *twR_hi, *twR_lo; int nhiN, nhiR;
+	int tile_bytes, out_bytes, off_out, off_tab;
+	long long ntiles;
+};
+
+__device__ __forceinline__ double2 tw2(const double2 *hi, const double2 *lo, int e)
+{
+	const double2 a = hi[e >> 7], b = lo[e & 127];
+	return make_double2(fma(a.x, b.x, -a.y*b.y), fma(a.x, b.y, a.y*b.x));
+}
+
+// one radix-R decimation-in-frequency pass over the tile (rows = transform index, lanes across columns)
+template<int R, bool INV, bool LAST> __device__ __forceinline__ void tf_pass(double2 *__restrict__ S, double2 *__restrict__ O, const TfArgs &A,
+	const double2 *__restrict__ twn, const int *__restrict__ natk, const double2 *__restrict__ hiN, const double2 *__restrict__ loN,
+	int Ls, int Wcur, int tid, int col0, int g2)
+{
+	const int n = A.n, m = Ls/R, nb = n/R, W = A.W, LW = A.LW, nrw = A.nreg*W;
+	const int tx = tid & (LW - 1), ty = tid/LW, NTY = TF_NCONS/LW;
+	const int tws = n/Ls;
+	for (int b = ty; b < nb; b += NTY) {
+		const int blk = b/m, jj = b - blk*m, base = blk*Ls + jj;
+		for (int cc = tx; cc < Wcur; cc += LW) {
+			int off, pitch;
+			if (cc < nrw) { const int r = cc >> A.wshift; off = r*n*W + (cc & (W - 1)); pitch = W; }
+			else { off = nrw*n; pitch = 1; }
+			double2 u[R];
+			#pragma unroll
+			for (int q = 0; q < R; q++) u[q] = S[off + (base + q*m)*pitch];
+			dft_small<R, INV>(u);
+			if (!LAST) {
+				if (jj) {
+					#pragma unroll
+					for (int k = 1; k < R; k++) { double2 w = twn[tws*jj*k]; if (INV) w.y = -w.y; u[k] = cmul(u[k], w); }
+				}
+				#pragma unroll
+				for (int q = 0; q < R; q++) S[off + (base + q*m)*pitch] = u[q];
+			} else {
+				const int t = A.tw_mode == 1 ? col0 + cc : g2;
+				#pragma unroll
+				for (int k = 0; k < R; k++) {
+					const int row = natk[base + k];
+					double2 v = u[k];
+					if (A.tw_mode) {
+						const int e = row*t;
+						if (e) { double2 w = tw2(hiN, loN, e); if (INV) w.y = -w.y; v = cmul(v, w); }
+					}
+					v.x *= A.scale; v.y *= A.scale;
+					if (A.tstore) O[cc*(n + 1) + row] = v;
+					else O[off + row*pitch] = v;
+				}
+			}
+		}
+	}
+}
+
+template<bool INV, bool LAST> __device__ __forceinline__ void tf_pass_r(int R, double2 *S, double2 *O, const TfArgs &A,
+	const double2 *twn, const int *natk, const double2 *hiN, const double2 *loN, int Ls, int Wcur, int tid, int col0, int g2)
+{
+	switch (R) {
+		case 2:  tf_pass<2, INV, LAST>(S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
+		case 3:  tf_pass<3, INV, LAST>(S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
+		case 4:  tf_pass<4, INV, LAST>(S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
+		case 5:  tf_pass<5, INV, LAST>(S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
+		case 8:  tf_pass<8, INV, LAST>(S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
+		default: tf_pass<16, INV, LAST>(S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
+	}
+}
+
+template<bool INV> __global__ void __launch_bounds__(TF_THREADS, 1) k_tfft(const __grid_constant__ TfMaps M, const TfArgs A)
+{
+	extern __shared__ __align__(1024) unsigned char smem[];
+	__shared__ __align__(8) uint64_t bars[2*TF_STAGES];
+	uint64_t *full = bars, *empty = bars + TF_STAGES;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int n = A.n, W = A.W;
+	double2 *twn = (double2*)(smem + A.off_tab);
+	double2 *hiN = twn + n, *loN = hiN + A.nhiN, *hiR = loN + 128, *loR = hiR + A.nhiR;
+	int *natk = (int*)(loR + 128);
+	if (tid == 0) {
+		for (int s = 0; s < TF_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+		mbar_fence_init();
+	}
+	for (int i = tid; i < n; i += TF_THREADS) { twn[i] = A.twn[i]; natk[i] = A.natk[i]; }
+	for (int i = tid; i < 128; i += TF_THREADS) { loN[i] = A.tw_mode ? A.twN_lo[i] : make_double2(1, 0); loR[i] = A.op ? A.twR_lo[i] : make_double2(1, 0); }
+	for (int i = tid; i < A.nhiN; i += TF_THREADS) hiN[i] = A.twN_hi[i];
+	for (int i = tid; i < A.nhiR; i += TF_THREADS) hiR[i] = A.twR_hi[i];
+	__syncthreads();
+	const long long tiles_per_g = (long long)A.ncb_l*A.G2;
+	const int region_bytes = n*W*16;
+
+	if (warp == TF_NCONS/32) {
+		// ---------------- producer: one lane keeps the ring of stages full
+		if (lane == 0) {
+			tma_prefetch_desc(&M.ld[0]); tma_prefetch_desc(&M.st[0]);
+			int it = 0;
+			for (long long t = blockIdx.x; t < A.ntiles; t += gridDim.x, it++) {
+				const int s = it % TF_STAGES, round = it/TF_STAGES;
+				if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+				const int g3 = A.g3_0 + (int)(t/tiles_per_g); const long long r = t % tiles_per_g;
+				const int g2 = A.g2_0 + (int)(r/A.ncb_l), cb = A.cb0 + (int)(r % A.ncb_l);
+				const bool mid = A.midcol >= 0 && cb == A.ncb - 1;
+				unsigned char *dst = smem + (size_t)s*A.tile_bytes;
+				mbar_expect_tx(&full[s], (uint32_t)(A.nreg*region_bytes + (mid ? n*16 : 0)));
+				const int a = cb*W;
+				tma_load_4d(dst, &M.ld[0], &full[s], 2*a, 0, g2, g3);
+				if (A.nreg == 2) tma_load_4d(dst + region_bytes, &M.ld[1], &full[s], 2*(A.mirror - a - W + 1), 0, g2, g3);
+				if (mid) tma_load_4d(dst + 2*region_bytes, &M.ld[2], &full[s], 2*A.midcol, 0, g2, g3);
+			}
+		}
+		return;
+	}
+
+	// ---------------- consumers
+	int it = 0;
+	for (long long t = blockIdx.x; t < A.ntiles; t += gridDim.x, it++) {
+		const int s = it % TF_STAGES, round = it/TF_STAGES;
+		const int g3 = A.g3_0 + (int)(t/tiles_per_g); const long long r = t % tiles_per_g;
+		const int g2 = A.g2_0 + (int)(r/A.ncb_l), cb = A.cb0 + (int)(r % A.ncb_l);
+		const bool mid = A.midcol >= 0 && cb == A.ncb - 1;
+		const int a = cb*W, Wcur = A.nreg*W + (mid ? 1 : 0);
+		double2 *S = (double2*)(smem + (size_t)s*A.tile_bytes);
+		double2 *O = (double2*)(smem + A.off_out + (size_t)(it & 1)*A.out_bytes);
+		mbar_wait(&full[s], round & 1);
+		if (A.op == 1) {
+			// r2c: packed spectrum Z -> X on the mirrored column blocks (same row), in place in the stage
+			double2 *SA = S, *SB = S + n*W;
+			for (int idx = tid; idx < n*W; idx += TF_NCONS) {
+				const int j = idx >> A.wshift, i = idx & (W - 1), k = a + i;
+				const double2 zk = SA[j*W + i];
+				double2 zp = SB[j*W + (W - 1 - i)];
+				if (k == 0) zp = zk;                                     // Z_Nc = Z_0 (the box column beyond the array was zero-filled)
+				const double2 sm = make_double2(zk.x + zp.x, zk.y - zp.y), df = make_double2(zk.x - zp.x, zk.y + zp.y);
+				const double2 u = cmul(df, tw2(hiR, loR, k));            // w_nx^k (Z_k - conj Z_{Nc-k})
+				SA[j*W + i] = make_double2(0.5*(sm.x + u.y), 0.5*(sm.y - u.x));
+				SB[j*W + (W - 1 - i)] = make_double2(0.5*(sm.x - u.y), -0.5*(sm.y + u.x));
+			}
+			if (mid) for (int j = tid; j < n; j += TF_NCONS) { double2 *p = S + 2*n*W + j; p->y = -p->y; }
+			bar_sync(1, TF_NCONS);
+		}
+		int Ls = n;
+		for (int f = 0; f < A.nfac - 1; f++) {
+			tf_pass_r<INV, false>(A.fac[f], S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, a, g2);
+			Ls /= A.fac[f];
+			if (f == A.nfac - 2 && it >= 2) {
+				// the output tile about to be overwritten was handed to TMA two tiles ago: its reads must be done
+				if (A.tstore ? (warp == 0 && lane < W) : tid == 0) bulk_wait_read<1>();
+			}
+			bar_sync(1, TF_NCONS);
+		}
+		if (A.nfac == 1) {
+			if (it >= 2 && (A.tstore ? (warp == 0 && lane < W) : tid == 0)) bulk_wait_read<1>();
+			if (it >= 2) bar_sync(1, TF_NCONS);
+		}
+		tf_pass_r<INV, true>(A.fac[A.nfac - 1], S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, a, g2);
+		if (A.op == 2) {
+			// c2r: X -> packed spectrum Z on the mirrored column blocks of the output tile
+			bar_sync(1, TF_NCONS);
+			double2 *OA = O, *OB = O + n*W;
+			for (int idx = tid; idx < n*W; idx += TF_NCONS) {
+				const int j = idx >> A.wshift, i = idx & (W - 1), k = a + i;
+				const double2 xa = OA[j*W + i], xb = OB[j*W + (W - 1 - i)];
+				const double2 sm = make_double2(xa.x + xb.x, xa.y - xb.y), df = make_double2(xa.x - xb.x, xa.y + xb.y);
+				double2 w = tw2(hiR, loR, k); w.y = -w.y;                // conj(w_nx^k)
+				const double2 u = cmul(df, w);
+				OA[j*W + i] = make_double2(sm.x - u.y, sm.y + u.x);
+				OB[j*W + (W - 1 - i)] = make_double2(sm.x + u.y, u.x - sm.y);
+			}
+			if (mid) for (int j = tid; j < n; j += TF_NCONS) { double2 *p = O + 2*n*W + j; *p = make_double2(2*p->x, -2*p->y); }
+		}
+		fence_proxy_async();
+		bar_sync(1, TF_NCONS);
+		if (A.tstore) {
+			if (warp == 0) {
+				if (lane == 0) mbar_arrive(&empty[s]);
+				if (lane < W) {
+					const int col = a + lane;
+					if (col < A.ncols_valid) bulk_store_1d(A.tbase + (long long)g2*A.t_g2stride + (long long)g3*0 + (long long)col*n, O + lane*(n + 1), (uint32_t)n*16);
+					bulk_commit();
+				}
+			}
+		} else if (tid == 0) {
+			mbar_arrive(&empty[s]);
+			tma_store_4d(&M.st[0], O, 2*a, 0, g2, g3);
+			if (A.nreg == 2) tma_store_4d(&M.st[1], O + n*W, 2*(A.mirror - a - W + 1), 0, g2, g3);
+			if (mid) tma_store_4d(&M.st[2], O + 2*n*W, 2*A.midcol, 0, g2, g3);
+			bulk_commit();
+		}
+	}
+	if (A.tstore ? (warp == 0 && lane < W) : tid == 0) bulk_wait_read<0>();
+}
+
+// ------------------------------------------------------------------------------------ host: tables
+
+typedef long double ld_t;
+static const ld_t TF_TAU = 6.283185307179586476925286766559005768L;
+
+static bool tf_factor(int n, int *fac, int &nfac)
+{
+	// 5s and 3s first, then a leftover 2 / 4, then 8s and 16s (the last radix has unit stride)
+	nfac = 0;
+	int rem = n, a = 0;
+	while (rem % 5 == 0) { if (nfac >= TF_MAXFAC) return false; fac[nfac++] = 5; rem /= 5; }
+	while (rem % 3 == 0) { if (nfac >= TF_MAXFAC) return false; fac[nfac++] = 3; rem /= 3; }
+	while (rem % 2 == 0) { a++; rem /= 2; }
+	if (rem != 1) return false;
+	int f2[8], n2 = 0;
+	if (a == 1) f2[n2++] = 2;
+	else if (a == 2) f2[n2++] = 4;
+	else if (a == 3) f2[n2++] = 8;
+	else if (a == 4) f2[n2++] = 16;
+	else if (a == 5) { f2[n2++] = 4; f2[n2++] = 8; }
+	else if (a == 6) { f2[n2++] = 8; f2[n2++] = 8; }
+	else if (a == 7) { f2[n2++] = 16; f2[n2++] = 8; }
+	else if (a == 8) { f2[n2++] = 16; f2[n2++] = 16; }
+	else if (a > 8) return false;
+	for (int i = 0; i < n2; i++) { if (nfac >= TF_MAXFAC) return false; fac[nfac++] = f2[i]; }
+	return nfac >= 1;
+}
+
+struct TfLen {      // tables of one in-tile transform length
+	int n = 0, nfac = 0, fac[TF_MAXFAC];
+	DevBuf<double2> twn; DevBuf<int> natk;
+	int build(int n_) {
+		n = n_;
+		if (!tf_factor(n, fac, nfac)) { b2_set_error("tfft: length %d has no radix plan", n); return 1; }
+		std::vector<double2> tw(n); std::vector<int> nk(n);
+		for (int k = 0; k < n; k++) { ld_t a = TF_TAU*(ld_t)k/(ld_t)n; tw[k] = make_double2((double)cosl(a), (double)-sinl(a)); }
+		for (int k = 0; k < n; k++) {
+			int kk = k, pos = 0, len = n;
+			for (int f = 0; f < nfac; f++) { int r = fac[f]; len /= r; pos += (kk % r)*len; kk /= r; }
+			nk[pos] = k;
+		}
+		return twn.upload(tw) || natk.upload(nk);
+	}
+};
+
+struct TfTw2 {      // two-level table of exp(-2 pi i e / mod), e < count
+	int nhi = 0; DevBuf<double2> hi, lo;
+	int build(long long mod, long long count) {
+		nhi = (int)((count + 127)/128) + 1;
+		std::vector<double2> h(nhi), l(128);
+		for (int i = 0; i < nhi; i++) { ld_t a = TF_TAU*(ld_t)((128LL*i) % mod)/(ld_t)mod; h[i] = make_double2((double)cosl(a), (double)-sinl(a)); }
+		for (int i = 0; i < 128; i++) { ld_t a = TF_TAU*(ld_t)(i % mod)/(ld_t)mod; l[i] = make_double2((double)cosl(a), (double)-sinl(a)); }
+		return hi.upload(h) || lo.upload(l);
+	}
+};
+
+struct TfAxis {     // a transform length N = N1 N2 along one axis
+	int N = 0, N1 = 0, N2 = 0;
+	TfLen L1, L2; TfTw2 tw;
+	int build(int N_) {
+		N = N_;
+		// balanced split into two tile-sized factors with radix plans
+		int best = 0;
+		for (int a = 1; a <= 256 && a <= N; a++) {
+			if (N % a) continue;
+			int b = N/a;
+			if (a > 256 || b > 256 || a < 4 || b < 4) continue;
+			int fa[TF_MAXFAC], fb[TF_MAXFAC], na, nb;
+			if (!tf_factor(a, fa, na) || !tf_factor(b, fb, nb)) continue;
+			if (!best || std::max(a, b) < std::max(best, N/best) || (std::max(a, b) == std::max(best, N/best) && a > best)) best = a;
+		}
+		if (!best) { b2_set_error("tfft: no split of %d", N); return 1; }
+		N1 = best; N2 = N/best;
+		return L1.build(N1) || L2.build(N2) || tw.build(N, (long long)N1*N2);
+	}
+	static bool ok(int N) {
+		for (int a = 4; a <= 256 && a <= N; a++) {
+			if (N % a) continue;
+			int b = N/a, fa[TF_MAXFAC], fb[TF_MAXFAC], na, nb;
+			if (b > 256 || b < 4) continue;
+			if (tf_factor(a, fa, na) && tf_factor(b, fb, nb)) return true;
+		}
+		return false;
+	}
+};
+
+struct TfPlan {
+	int kind = 0;
+	int64_t nb = 1, ny = 0, nx = 0;      // nx: real length for r2c / c2r
+	int Nc = 0;                           // complex length along x
+	int64_t in_pitch = 0, out_pitch = 0, in_bstride = 0, out_bstride = 0;      // elements of the respective type
+	TfAxis ax, ay; TfTw2 twR;
+	DevBuf<char> work, work2;
+	int nsm = 148;
+};
+
+static int pow2_floor(int v) { int p = 1; while (2*p <= v) p *= 2; return p; }
+static size_t tf_slab_bytes() { const char *e = getenv("B2_TFFT_SLAB_MB"); return (size_t)(e ? atoi(e) : 24) << 20; }
+static int tf_tile_elems() { const char *e = getenv("B2_TFFT_TILE"); return e ? atoi(e) : 2048; }
+
+// columns per tile for a transform length n with `cols` columns available
+static int tf_width(int n, int64_t cols)
+{
+	int w = pow2_floor(std::max(8, tf_tile_elems()/n));
+	w = std::min(w, 128);
+	while (w > 8 && w > cols) w /= 2;
+	return w;
+}
+
+bool tfft_eligible(int kind, int dtype, int ndim, const int64_t *shape, const int64_t *istride, const int64_t *ostride, int naxes, const int *axes)
+{
+	static const bool off = getenv("B2_FFT_NO_TMA") && atoi(getenv("B2_FFT_NO_TMA"));
+	if (off || dtype != B2_F64 || naxes != 2 || ndim < 2 || ndim > 3) return false;
+	if (axes[0] != ndim - 2 || axes[1] != ndim - 1) return false;
+	if (!b2_get_encode_tiled()) return false;
+	const int64_t ny = shape[ndim - 2], nx = shape[ndim - 1];
+	if (istride[ndim - 1] != 1 || ostride[ndim - 1] != 1) return false;
+	const int64_t Nc = kind == B2_FFT_C2C ? nx : nx/2;
+	if (kind != B2_FFT_C2C && (nx % 2 || (Nc/2) % 8 || Nc % 2)) return false;
+	if (ny < 64 || Nc < 64 || ny > 65536 || Nc > 65536) return false;
+	if (!TfAxis::ok((int)ny) || !TfAxis::ok((int)Nc)) return false;
+	// real rows must start on 16-byte boundaries
+	if (kind == B2_FFT_R2C && (istride[ndim - 2] % 2 || (ndim == 3 && istride[0] % 2))) return false;
+	if (kind == B2_FFT_C2R && (ostride[ndim - 2] % 2 || (ndim == 3 && ostride[0] % 2))) return false;
+	const int64_t in_cols = kind == B2_FFT_C2R ? Nc + 1 : nx, out_cols = kind == B2_FFT_R2C ? Nc + 1 : nx;
+	if (istride[ndim - 2] < in_cols || ostride[ndim - 2] < out_cols) return false;
+	return true;
+}
+
+int tfft_plan_create(TfPlan **out, int kind, int ndim, const int64_t *shape, const int64_t *istride, const int64_t *ostride)
+{
+	std::unique_ptr<TfPlan> p(new TfPlan());
+	p->kind = kind; p->ny = shape[ndim - 2]; p->nx = shape[ndim - 1];
+	p->nb = ndim == 3 ? shape[0] : 1;
+	p->Nc = (int)(kind == B2_FFT_C2C ? p->nx : p->nx/2);
+	p->in_pitch = istride[ndim - 2]; p->out_pitch = ostride[ndim - 2];
+	p->in_bstride = ndim == 3 ? istride[0] : 0; p->out_bstride = ndim == 3 ? ostride[0] : 0;
+	if (p->ax.build(p->Nc) || p->ay.build((int)p->ny)) return 1;
+	if (kind != B2_FFT_C2C && p->twR.build(p->nx, p->Nc + 1)) return 1;
+	int dev; B2_CHECK(cudaGetDevice(&dev));
+	B2_CHECK(cudaDeviceGetAttribute(&p->nsm, cudaDevAttrMultiProcessorCount, dev));
+	*out = p.release();
+	return 0;
+}
+void tfft_plan_destroy(TfPlan *p) { delete p; }
+
+// ------------------------------------------------------------------------------------ host: launches
+
+static int tf_launch(TfMaps &M, TfArgs &A, const TfLen &L, const TfTw2 *twN, const TfTw2 *twR, int nsm, cudaStream_t st)
+{
+	A.n = L.n; A.nfac = L.nfac; for (int i = 0; i < L.nfac; i++) A.fac[i] = L.fac[i];
+	A.twn = L.twn.p; A.natk = L.natk.p;
+	A.twN_hi = twN ? twN->hi.p : nullptr; A.twN_lo = twN ? twN->lo.p : nullptr; A.nhiN = twN ? twN->nhi : 1;
+	A.twR_hi = twR ? twR->hi.p : nullptr; A.twR_lo = twR ? twR->lo.p : nullptr; A.nhiR = twR ? twR->nhi : 1;
+	if (!twN) A.nhiN = 0;
+	if (!twR) A.nhiR = 0;
+	A.wshift = 0; while ((1 << A.wshift) < A.W) A.wshift++;
+	const int Wtot = A.nreg*A.W + (A.midcol >= 0 ? 1 : 0);
+	A.LW = std::min(32, A.W);
+	A.tile_bytes = (int)b2_round_up((int64_t)Wtot*A.n*16, 128);
+	A.out_bytes = (int)b2_round_up(A.tstore ? (int64_t)A.W*(A.n + 1)*16 : (int64_t)Wtot*A.n*16, 128);
+	A.off_out = TF_STAGES*A.tile_bytes;
+	A.off_tab = A.off_out + 2*A.out_bytes;
+	const size_t smem = (size_t)A.off_tab + ((size_t)A.n + A.nhiN + 128 + A.nhiR + 128)*16 + (size_t)A.n*4 + 16;
+	B2_REQUIRE(smem <= 227*1024, "tfft: tile of %d x %d needs %zu bytes of shared memory", A.n, Wtot, smem);
+	A.ntiles = (long long)A.ncb_l*A.G2*A.G3;
+	if (A.ntiles <= 0) return 0;
+	const unsigned grid = (unsigned)std::min<long long>(A.ntiles, nsm);
+	static thread_local std::map<std::pair<int, int>, size_t> granted;
+	int dev; B2_CHECK(cudaGetDevice(&dev));
+	size_t &g = granted[std::make_pair(dev, A.inv)];
+	if (smem > g) {
+		if (A.inv) B2_CHECK(cudaFuncSetAttribute(k_tfft<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		else B2_CHECK(cudaFuncSetAttribute(k_tfft<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		g = smem;
+	}
+	if (A.inv) k_tfft<true><<<grid, TF_THREADS, smem, st>>>(M, A);
+	else k_tfft<false><<<grid, TF_THREADS, smem, st>>>(M, A);
+	B2_LAUNCH_CHECK();
+	return 0;
+}
+
+static void tf_args_init(TfArgs &A, int inv)
+{
+	A = TfArgs();
+	A.nreg = 1; A.midcol = -1; A.G2 = A.G3 = 1; A.g2_0 = A.g3_0 = 0; A.cb0 = 0; A.mirror = 0;
+	A.tw_mode = 0; A.inv = inv; A.op = 0; A.tstore = 0; A.scale = 1.0; A.tbase = nullptr; A.t_g2stride = 0; A.ncols_valid = 0;
+}
+
+#define TF_MAP(m, base, d0, d1, d2, d3, s1, s2, s3, b0, b1) do { \
+	uint64_t dims_[4] = {(uint64_t)(d0), (uint64_t)(d1), (uint64_t)(d2), (uint64_t)(d3)}; \
+	uint64_t str_[3] = {(uint64_t)(s1), (uint64_t)(s2), (uint64_t)(s3)}; \
+	uint32_t box_[4] = {(uint32_t)(b0), (uint32_t)(b1), 1, 1}; \
+	int rc_ = b2_make_map_f64(&(m), (base), dims_, str_, box_); \
+	B2_REQUIRE(rc_ == 0, "tfft: cuTensorMapEncodeTiled failed (%d) dims %llu %llu %llu %llu strides %llu %llu %llu box %u %u", rc_, \
+		(unsigned long long)dims_[0], (unsigned long long)dims_[1], (unsigned long long)dims_[2], (unsigned long long)dims_[3], \
+		(unsigned long long)str_[0], (unsigned long long)str_[1], (unsigned long long)str_[2], box_[0], box_[1]); } while (0)
+
+// transform along x (the contiguous axis) of `nlines` lines of Nc complex elements: src line pitch ps / dst pitch pd (bytes)
+static int tf_rows(TfPlan *p, const char *src, int64_t ps, char *dst, int64_t pd, int64_t nlines, int inv, double scale, cudaStream_t st)
+{
+	const TfAxis &X = p->ax;
+	const int N1 = X.N1, N2 = X.N2, N = X.N;
+	const int w1 = tf_width(N1, N2), w2 = tf_width(N2, N1);
+	double2 *work = (double2*)p->work.p;
+	const int64_t slab = std::max<int64_t>(1, (int64_t)(tf_slab_bytes()/((size_t)N*16)));
+	for (int64_t l0 = 0; l0 < nlines; l0 += slab) {
+		const int64_t nl = std::min(slab, nlines - l0);
+		TfMaps M; TfArgs A;
+		// sub-pass 1: tiles [j1: N1, stride N2][j2: w1] -> work[line][j2][k1]
+		tf_args_init(A, inv);
+		A.W = w1; A.ncb = (N2 + w1 - 1)/w1; A.ncb_l = A.ncb; A.G2 = (int)nl; A.g2_0 = (int)l0;
+		A.tw_mode = 1; A.tstore = 1; A.tbase = work; A.t_g2stride = N; A.ncols_valid = N2;
+		TF_MAP(M.ld[0], src, 2*N2, N1, nlines, 1, (int64_t)N2*16, ps, ps*nlines, 2*w1, N1);
+		M.st[0] = M.ld[0];
+		if (tf_launch(M, A, X.L1, &X.tw, nullptr, p->nsm, st)) return 1;
+		// sub-pass 2: tiles [j2: N2, stride N1][k1: w2] of work -> dst[line][k1 + N1 k2]
+		tf_args_init(A, inv);
+		A.W = w2; A.ncb = (N1 + w2 - 1)/w2; A.ncb_l = A.ncb; A.G2 = (int)nl; A.g2_0 = (int)l0; A.scale = scale;
+		TF_MAP(M.ld[0], work, 2*N1, N2, nlines, 1, (int64_t)N1*16, (int64_t)N*16, (int64_t)N*16*nlines, 2*w2, N2);
+		TF_MAP(M.st[0], dst, 2*N1, N2, nlines, 1, (int64_t)N1*16, pd, pd*nlines, 2*w2, N2);
+		if (tf_launch(M, A, X.L2, nullptr, nullptr, p->nsm, st)) return 1;
+	}
+	return 0;
+}
+
+// columns per region of a mirrored tile (two regions per tile) over a half range of `half` columns
+static int tf_width_m(int n, int half)
+{
+	int w = pow2_floor(std::max(8, tf_tile_elems()/(2*n)));
+	w = std::min(w, 64);
+	while (w > 8 && half % w) w /= 2;
+	return w;
+}
+
+// transform along y of [nb][ny][ncols] complex arrays (pitches in bytes).  mode 0: plain; 1: r2c untangle fused into the
+// load of sub-pass 1 (src holds Nc columns, work and dst Nc + 1); 2: c2r tangle fused into the store of sub-pass 2 (src and
+// work hold Nc + 1 columns, dst Nc).  In modes 1 and 2 both sub-passes walk the mirrored column blocks, so that a slab
+// is the same set of columns in both.
+static int tf_cols(TfPlan *p, const char *src, int64_t ps, int64_t bs_s, char *dst, int64_t pd, int64_t bs_d, char *work, int64_t pw,
+	int ncols_src, int ncols_mid, int ncols_dst, int mode, int inv, double scale, cudaStream_t st)
+{
+	const TfAxis &Y = p->ay;
+	const int N1 = Y.N1, N2 = Y.N2, ny = Y.N, Nc = p->Nc;
+	const int64_t bs_w = (int64_t)ny*pw;
+	const bool mir = mode != 0;
+	const int ext = mir ? Nc/2 : std::max(ncols_src, ncols_dst);      // the range the column-block index runs over
+	const int w1 = mir ? tf_width_m(N1, ext) : tf_width(N1, ext), w2 = mir ? tf_width_m(N2, ext) : tf_width(N2, ext);
+	const int ncb1 = (ext + w1 - 1)/w1, ncb2 = (ext + w2 - 1)/w2, wmax = std::max(w1, w2);
+	int64_t slab_cols = std::max<int64_t>(wmax, (int64_t)(tf_slab_bytes()/((size_t)ny*16*(mir ? 2 : 1))));
+	slab_cols = slab_cols/wmax*wmax;
+	for (int64_t b = 0; b < p->nb; b++) {
+		for (int64_t c0 = 0; c0 < ext; c0 += slab_cols) {
+			const int64_t c1 = std::min<int64_t>(ext, c0 + slab_cols);
+			TfMaps M; TfArgs A;
+			// ---- sub-pass 1: rows j1 (stride N2 rows) of a column block, fixed j2 -> work rows j2 N1 + k1, times w^(k1 j2)
+			tf_args_init(A, inv);
+			A.W = w1; A.ncb = ncb1; A.G2 = N2; A.G3 = 1; A.g3_0 = (int)b; A.tw_mode = 2;
+			A.cb0 = (int)(c0/w1); A.ncb_l = (int)((c1 + w1 - 1)/w1) - A.cb0;
+			if (mir) { A.nreg = 2; A.mirror = Nc; A.midcol = Nc/2; A.op = mode == 1 ? 1 : 0; }
+			TF_MAP(M.ld[0], src, 2*(int64_t)ncols_src, N1, N2, p->nb, (int64_t)N2*ps, ps, bs_s, 2*w1, N1);
+			TF_MAP(M.st[0], work, 2*(int64_t)ncols_mid, N1, N2, p->nb, pw, (int64_t)N1*pw, bs_w, 2*w1, N1);
+			M.ld[1] = M.ld[0]; M.st[1] = M.st[0]; M.ld[2] = M.ld[0]; M.st[2] = M.st[0];
+			if (mir) {
+				TF_MAP(M.ld[2], src, 2*(int64_t)ncols_src, N1, N2, p->nb, (int64_t)N2*ps, ps, bs_s, 2, N1);
+				TF_MAP(M.st[2], work, 2*(int64_t)ncols_mid, N1, N2, p->nb, pw, (int64_t)N1*pw, bs_w, 2, N1);
+			}
+			if (tf_launch(M, A, Y.L1, &Y.tw, mode == 1 ? &p->twR : nullptr, p->nsm, st)) return 1;
+			// ---- sub-pass 2: work rows j2 (stride N1 rows), fixed k1 -> dst rows k1 + N1 k2
+			tf_args_init(A, inv);
+			A.W = w2; A.ncb = ncb2; A.G2 = N1; A.G3 = 1; A.g3_0 = (int)b; A.scale = scale;
+			A.cb0 = (int)(c0/w2); A.ncb_l = (int)((c1 + w2 - 1)/w2) - A.cb0;
+			if (mir) { A.nreg = 2; A.mirror = Nc; A.midcol = Nc/2; A.op = mode == 2 ? 2 : 0; }
+			TF_MAP(M.ld[0], work, 2*(int64_t)ncols_mid, N2, N1, p->nb, (int64_t)N1*pw, pw, bs_w, 2*w2, N2);
+			TF_MAP(M.st[0], dst, 2*(int64_t)ncols_dst, N2, N1, p->nb, (int64_t)N1*pd, pd, bs_d, 2*w2, N2);
+			M.ld[1] = M.ld[0]; M.st[1] = M.st[0]; M.ld[2] = M.ld[0]; M.st[2] = M.st[0];
+			if (mir) {
+				TF_MAP(M.ld[2], work, 2*(int64_t)ncols_mid, N2, N1, p->nb, (int64_t)N1*pw, pw, bs_w, 2, N2);
+				TF_MAP(M.st[2], dst, 2*(int64_t)ncols_dst, N2, N1, p->nb, (int64_t)N1*pd, pd, bs_d, 2, N2);
+			}
+			if (tf_launch(M, A, Y.L2, nullptr, mode == 2 ? &p->twR : nullptr, p->nsm, st)) return 1;
+		}
+	}
+	return 0;
+}
+
+int tfft_execute(TfPlan *p, const void *in, void *out, int forward, double scale, cudaStream_t st)
+{
+	B2_REQUIRE(((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0), "tfft: arrays must be 16-byte aligned");
+	const int inv = forward ? 0 : 1;
+	const int64_t ny = p->ny, nb = p->nb; const int Nc = p->Nc;
+	const int64_t nlines = nb*ny;
+	const size_t wbytes = (size_t)nlines*(Nc + 1)*16;
+	if (p->work.n < wbytes && p->work.alloc(wbytes)) return 1;
+	const int64_t pw = (int64_t)(Nc + 1)*16;
+	if (p->kind == B2_FFT_C2C) {
+		const int64_t ps = p->in_pitch*16, pd = p->out_pitch*16;
+		const bool lines_in = nb == 1 || p->in_bstride == ny*p->in_pitch, lines_out = nb == 1 || p->out_bstride == ny*p->out_pitch;
+		if (lines_in && lines_out) { if (tf_rows(p, (const char*)in, ps, (char*)out, pd, nlines, inv, 1.0, st)) return 1; }
+		else for (int64_t b = 0; b < nb; b++)
+			if (tf_rows(p, (const char*)in + b*p->in_bstride*16, ps, (char*)out + b*p->out_bstride*16, pd, ny, inv, 1.0, st)) return 1;
+		return tf_cols(p, (const char*)out, pd, p->out_bstride*16, (char*)out, pd, p->out_bstride*16, p->work.p, (int64_t)Nc*16,
+			Nc, Nc, Nc, 0, inv, scale, st);
+	}
+	if (p->kind == B2_FFT_R2C) {
+		const int64_t ps = p->in_pitch*8, pd = p->out_pitch*16;
+		const bool lines_in = nb == 1 || p->in_bstride == ny*p->in_pitch, lines_out = nb == 1 || p->out_bstride == ny*p->out_pitch;
+		if (lines_in && lines_out) { if (tf_rows(p, (const char*)in, ps, (char*)out, pd, nlines, 0, 1.0, st)) return 1; }
+		else for (int64_t b = 0; b < nb; b++)
+			if (tf_rows(p, (const char*)in + b*p->in_bstride*8, ps, (char*)out + b*p->out_bstride*16, pd, ny, 0, 1.0, st)) return 1;
+		return tf_cols(p, (const char*)out, pd, p->out_bstride*16, (char*)out, pd, p->out_bstride*16, p->work.p, pw,
+			Nc, Nc + 1, Nc + 1, 1, 0, scale, st);
+	}
+	// c2r: columns first (on the half spectrum), tangle into the packed spectrum, then the rows
+	const size_t w2bytes = (size_t)nlines*Nc*16;
+	if (p->work2.n < w2bytes && p->work2.alloc(w2bytes)) return 1;
+	if (tf_cols(p, (const char*)in, p->in_pitch*16, p->in_bstride*16, p->work2.p, (int64_t)Nc*16, (int64_t)ny*Nc*16, p->work.p, pw,
+		Nc + 1, Nc + 1, Nc, 2, 1, 1.0, st)) return 1;
+	const int64_t pd = p->out_pitch*8;
+	const bool lines_out = nb == 1 || p->out_bstride == ny*p->out_pitch;
+	if (lines_out) return tf_rows(p, p->work2.p, (int64_t)Nc*16, (char*)out, pd, nlines, 1, scale, st);
+	for (int64_t b = 0; b < nb; b++)
+		if (tf_rows(p, p->work2.p + b*ny*Nc*16, (int64_t)Nc*16, (char*)out + b*p->out_bstride*8, pd, ny, 1, scale, st)) return 1;
+	return 0;
+}
