@@ -26,7 +26,7 @@
 #include <stdlib.h>
 
 #define TF_MAXFAC 6
-#define TF_STAGES 3
+#define TF_MAXSTAGES 6
 #define TF_NCONS 256
 #define TF_THREADS (TF_NCONS + 32)
 
@@ -44,7 +44,7 @@ struct TfArgs {
 	double scale;
 	double2 *tbase; long long t_g2stride; int ncols_valid;      // transposed bulk stores (row axis, sub-pass 1)
 	const double2 *twn; const int *natk; const double2 *twN_hi, *twN_lo, *twR_hi, *twR_lo; int nhiN, nhiR;
-	int tile_bytes, out_bytes, off_out, off_tab;
+	int tile_bytes, out_bytes, off_work, off_out, off_tab, nstage;
 	long long ntiles;
 };
 
@@ -54,8 +54,10 @@ __device__ __forceinline__ double2 tw2(const double2 *hi, const double2 *lo, int
 	return make_double2(fma(a.x, b.x, -a.y*b.y), fma(a.x, b.y, a.y*b.x));
 }
 
-// one radix-R decimation-in-frequency pass over the tile (rows = transform index, lanes across columns)
-template<int R, bool INV, bool LAST> __device__ __forceinline__ void tf_pass(double2 *__restrict__ S, double2 *__restrict__ O, const TfArgs &A,
+// one radix-R decimation-in-frequency pass over the tile (rows = transform index, lanes across columns): reads S, writes D
+// (D == S: in place).  LAST: the rows go to their natural positions in D, times the twiddle between the two sub-passes
+// and the scale.
+template<int R, bool INV, bool LAST> __device__ __forceinline__ void tf_pass(const double2 *__restrict__ S, double2 *__restrict__ D, const TfArgs &A,
 	const double2 *__restrict__ twn, const int *__restrict__ natk, const double2 *__restrict__ hiN, const double2 *__restrict__ loN,
 	int Ls, int Wcur, int tid, int col0, int g2)
 {
@@ -69,16 +71,20 @@ template<int R, bool INV, bool LAST> __device__ __forceinline__ void tf_pass(dou
 			if (cc < nrw) { const int r = cc >> A.wshift; off = r*n*W + (cc & (W - 1)); pitch = W; }
 			else { off = nrw*n; pitch = 1; }
 			double2 u[R];
+			const double2 *sp = S + off + base*pitch;
+			const int mp = m*pitch;
 			#pragma unroll
-			for (int q = 0; q < R; q++) u[q] = S[off + (base + q*m)*pitch];
+			for (int q = 0; q < R; q++) u[q] = sp[q*mp];
 			dft_small<R, INV>(u);
 			if (!LAST) {
 				if (jj) {
+					const double2 *tp = twn + tws*jj;
 					#pragma unroll
-					for (int k = 1; k < R; k++) { double2 w = twn[tws*jj*k]; if (INV) w.y = -w.y; u[k] = cmul(u[k], w); }
+					for (int k = 1; k < R; k++) { double2 w = tp[(k - 1)*tws*jj]; if (INV) w.y = -w.y; u[k] = cmul(u[k], w); }
 				}
+				double2 *dp = D + off + base*pitch;
 				#pragma unroll
-				for (int q = 0; q < R; q++) S[off + (base + q*m)*pitch] = u[q];
+				for (int q = 0; q < R; q++) dp[q*mp] = u[q];
 			} else {
 				const int t = A.tw_mode == 1 ? col0 + cc : g2;
 				#pragma unroll
@@ -86,45 +92,50 @@ template<int R, bool INV, bool LAST> __device__ __forceinline__ void tf_pass(dou
 					const int row = natk[base + k];
 					double2 v = u[k];
 					if (A.tw_mode) {
-						const int e = row*t;
-						if (e) { double2 w = tw2(hiN, loN, e); if (INV) w.y = -w.y; v = cmul(v, w); }
+						double2 w = tw2(hiN, loN, row*t); if (INV) w.y = -w.y;
+						v = cmul(v, w);
 					}
 					v.x *= A.scale; v.y *= A.scale;
-					if (A.tstore) O[cc*(n + 1) + row] = v;
-					else O[off + row*pitch] = v;
+					if (A.tstore) D[cc*(n + 1) + row] = v;
+					else D[off + row*pitch] = v;
 				}
 			}
 		}
 	}
 }
 
-template<bool INV, bool LAST> __device__ __forceinline__ void tf_pass_r(int R, double2 *S, double2 *O, const TfArgs &A,
+template<bool INV, bool LAST> __device__ __forceinline__ void tf_pass_r(int R, const double2 *S, double2 *D, const TfArgs &A,
 	const double2 *twn, const int *natk, const double2 *hiN, const double2 *loN, int Ls, int Wcur, int tid, int col0, int g2)
 {
 	switch (R) {
-		case 2:  tf_pass<2, INV, LAST>(S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
-		case 3:  tf_pass<3, INV, LAST>(S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
-		case 4:  tf_pass<4, INV, LAST>(S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
-		case 5:  tf_pass<5, INV, LAST>(S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
-		case 8:  tf_pass<8, INV, LAST>(S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
-		default: tf_pass<16, INV, LAST>(S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
+		case 2:  tf_pass<2, INV, LAST>(S, D, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
+		case 3:  tf_pass<3, INV, LAST>(S, D, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
+		case 4:  tf_pass<4, INV, LAST>(S, D, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
+		case 5:  tf_pass<5, INV, LAST>(S, D, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
+		case 8:  tf_pass<8, INV, LAST>(S, D, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
+		default: tf_pass<16, INV, LAST>(S, D, A, twn, natk, hiN, loN, Ls, Wcur, tid, col0, g2); break;
 	}
 }
 
+// shared memory: [nstage landing tiles][work tile][output tile][tables]; the landing tile is released to the producer as
+// soon as the first pass has moved its contents into the work tile
 template<bool INV> __global__ void __launch_bounds__(TF_THREADS, 1) k_tfft(const __grid_constant__ TfMaps M, const TfArgs A)
 {
 	extern __shared__ __align__(1024) unsigned char smem[];
-	__shared__ __align__(8) uint64_t bars[2*TF_STAGES];
-	uint64_t *full = bars, *empty = bars + TF_STAGES;
+	__shared__ __align__(8) uint64_t bars[2*TF_MAXSTAGES];
+	__shared__ int sfac[TF_MAXFAC];
+	const int NS = A.nstage;
+	uint64_t *full = bars, *empty = bars + TF_MAXSTAGES;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int n = A.n, W = A.W;
 	double2 *twn = (double2*)(smem + A.off_tab);
 	double2 *hiN = twn + n, *loN = hiN + A.nhiN, *hiR = loN + 128, *loR = hiR + A.nhiR;
 	int *natk = (int*)(loR + 128);
 	if (tid == 0) {
-		for (int s = 0; s < TF_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+		for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
 		mbar_fence_init();
 	}
+	if (tid < TF_MAXFAC) sfac[tid] = A.fac[tid];
 	for (int i = tid; i < n; i += TF_THREADS) { twn[i] = A.twn[i]; natk[i] = A.natk[i]; }
 	for (int i = tid; i < 128; i += TF_THREADS) { loN[i] = A.tw_mode ? A.twN_lo[i] : make_double2(1, 0); loR[i] = A.op ? A.twR_lo[i] : make_double2(1, 0); }
 	for (int i = tid; i < A.nhiN; i += TF_THREADS) hiN[i] = A.twN_hi[i];
@@ -134,12 +145,11 @@ template<bool INV> __global__ void __launch_bounds__(TF_THREADS, 1) k_tfft(const
 	const int region_bytes = n*W*16;
 
 	if (warp == TF_NCONS/32) {
-		// ---------------- producer: one lane keeps the ring of stages full
+		// ---------------- producer: one lane keeps the ring of landing tiles full
 		if (lane == 0) {
 			tma_prefetch_desc(&M.ld[0]); tma_prefetch_desc(&M.st[0]);
-			int it = 0;
-			for (long long t = blockIdx.x; t < A.ntiles; t += gridDim.x, it++) {
-				const int s = it % TF_STAGES, round = it/TF_STAGES;
+			int s = 0, round = 0;
+			for (long long t = blockIdx.x; t < A.ntiles; t += gridDim.x) {
 				if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
 				const int g3 = A.g3_0 + (int)(t/tiles_per_g); const long long r = t % tiles_per_g;
 				const int g2 = A.g2_0 + (int)(r/A.ncb_l), cb = A.cb0 + (int)(r % A.ncb_l);
@@ -150,24 +160,26 @@ template<bool INV> __global__ void __launch_bounds__(TF_THREADS, 1) k_tfft(const
 				tma_load_4d(dst, &M.ld[0], &full[s], 2*a, 0, g2, g3);
 				if (A.nreg == 2) tma_load_4d(dst + region_bytes, &M.ld[1], &full[s], 2*(A.mirror - a - W + 1), 0, g2, g3);
 				if (mid) tma_load_4d(dst + 2*region_bytes, &M.ld[2], &full[s], 2*A.midcol, 0, g2, g3);
+				if (++s == NS) { s = 0; round++; }
 			}
 		}
 		return;
 	}
 
 	// ---------------- consumers
-	int it = 0;
-	for (long long t = blockIdx.x; t < A.ntiles; t += gridDim.x, it++) {
-		const int s = it % TF_STAGES, round = it/TF_STAGES;
+	double2 *Wk = (double2*)(smem + A.off_work), *O = (double2*)(smem + A.off_out);
+	const bool storer = A.tstore ? warp == 0 : tid == 0;
+	const int nfac = A.nfac;
+	int s = 0, round = 0;
+	for (long long t = blockIdx.x; t < A.ntiles; t += gridDim.x) {
 		const int g3 = A.g3_0 + (int)(t/tiles_per_g); const long long r = t % tiles_per_g;
 		const int g2 = A.g2_0 + (int)(r/A.ncb_l), cb = A.cb0 + (int)(r % A.ncb_l);
 		const bool mid = A.midcol >= 0 && cb == A.ncb - 1;
 		const int a = cb*W, Wcur = A.nreg*W + (mid ? 1 : 0);
 		double2 *S = (double2*)(smem + (size_t)s*A.tile_bytes);
-		double2 *O = (double2*)(smem + A.off_out + (size_t)(it & 1)*A.out_bytes);
 		mbar_wait(&full[s], round & 1);
 		if (A.op == 1) {
-			// r2c: packed spectrum Z -> X on the mirrored column blocks (same row), in place in the stage
+			// r2c: packed spectrum Z -> X on the mirrored column blocks (same row), in place in the landing tile
 			double2 *SA = S, *SB = S + n*W;
 			for (int idx = tid; idx < n*W; idx += TF_NCONS) {
 				const int j = idx >> A.wshift, i = idx & (W - 1), k = a + i;
@@ -180,23 +192,28 @@ template<bool INV> __global__ void __launch_bounds__(TF_THREADS, 1) k_tfft(const
 				SB[j*W + (W - 1 - i)] = make_double2(0.5*(sm.x - u.y), -0.5*(sm.y + u.x));
 			}
 			if (mid) for (int j = tid; j < n; j += TF_NCONS) { double2 *p = S + 2*n*W + j; p->y = -p->y; }
+			fence_proxy_async();                                         // the landing tile was written by the generic proxy
 			bar_sync(1, TF_NCONS);
 		}
 		int Ls = n;
-		for (int f = 0; f < A.nfac - 1; f++) {
-			tf_pass_r<INV, false>(A.fac[f], S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, a, g2);
-			Ls /= A.fac[f];
-			if (f == A.nfac - 2 && it >= 2) {
-				// the output tile about to be overwritten was handed to TMA two tiles ago: its reads must be done
-				if (A.tstore ? (warp == 0 && lane < W) : tid == 0) bulk_wait_read<1>();
+		if (nfac > 1) {
+			tf_pass_r<INV, false>(sfac[0], S, Wk, A, twn, natk, hiN, loN, Ls, Wcur, tid, a, g2);
+			Ls /= sfac[0];
+			for (int f = 1; f < nfac - 1; f++) {
+				bar_sync(1, TF_NCONS);
+				if (f == 1 && tid == 0) mbar_arrive(&empty[s]);          // every consumer is past the first pass: landing tile free
+				tf_pass_r<INV, false>(sfac[f], Wk, Wk, A, twn, natk, hiN, loN, Ls, Wcur, tid, a, g2);
+				Ls /= sfac[f];
 			}
+			if (storer) bulk_wait_read<0>();                             // the output tile's previous contents have left
 			bar_sync(1, TF_NCONS);
+			if (nfac == 2 && tid == 0) mbar_arrive(&empty[s]);
+			tf_pass_r<INV, true>(sfac[nfac - 1], Wk, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, a, g2);
+		} else {
+			if (storer) bulk_wait_read<0>();
+			bar_sync(1, TF_NCONS);
+			tf_pass_r<INV, true>(sfac[0], S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, a, g2);
 		}
-		if (A.nfac == 1) {
-			if (it >= 2 && (A.tstore ? (warp == 0 && lane < W) : tid == 0)) bulk_wait_read<1>();
-			if (it >= 2) bar_sync(1, TF_NCONS);
-		}
-		tf_pass_r<INV, true>(A.fac[A.nfac - 1], S, O, A, twn, natk, hiN, loN, Ls, Wcur, tid, a, g2);
 		if (A.op == 2) {
 			// c2r: X -> packed spectrum Z on the mirrored column blocks of the output tile
 			bar_sync(1, TF_NCONS);
@@ -214,24 +231,216 @@ template<bool INV> __global__ void __launch_bounds__(TF_THREADS, 1) k_tfft(const
 		}
 		fence_proxy_async();
 		bar_sync(1, TF_NCONS);
+		if (nfac == 1 && tid == 0) mbar_arrive(&empty[s]);
 		if (A.tstore) {
 			if (warp == 0) {
-				if (lane == 0) mbar_arrive(&empty[s]);
-				if (lane < W) {
-					const int col = a + lane;
-					if (col < A.ncols_valid) bulk_store_1d(A.tbase + (long long)g2*A.t_g2stride + (long long)g3*0 + (long long)col*n, O + lane*(n + 1), (uint32_t)n*16);
-					bulk_commit();
-				}
+				for (int c = lane; c < W; c += 32)
+					if (a + c < A.ncols_valid) bulk_store_1d(A.tbase + (long long)g2*A.t_g2stride + (long long)(a + c)*n, O + c*(n + 1), (uint32_t)n*16);
+				bulk_commit();
 			}
 		} else if (tid == 0) {
-			mbar_arrive(&empty[s]);
 			tma_store_4d(&M.st[0], O, 2*a, 0, g2, g3);
 			if (A.nreg == 2) tma_store_4d(&M.st[1], O + n*W, 2*(A.mirror - a - W + 1), 0, g2, g3);
 			if (mid) tma_store_4d(&M.st[2], O + 2*n*W, 2*A.midcol, 0, g2, g3);
 			bulk_commit();
 		}
+		if (++s == NS) { s = 0; round++; }
 	}
-	if (A.tstore ? (warp == 0 && lane < W) : tid == 0) bulk_wait_read<0>();
+	if (storer) bulk_wait_read<0>();
+}
+
+// ------------------------------------------------------------------------------------ specialised kernel
+// Power-of-two tile lengths N = R0 R1 with compile-time strides.  Two teams of four warps work on alternate tiles (each
+// with its own output tile), so one team's barrier and mbarrier waits are covered by the other team's butterflies.
+// Pass 0 reads the landing tile and writes the output tile in transposed digit order (row jj R0 + k0), which frees the
+// landing tile at once; pass 1 then runs in place on rows {q R0 + k0} and leaves row k0 + R0 k1 in natural order.
+#define TF_TEAM 128
+
+template<int N, int W, int NREG, bool TS> __device__ __forceinline__ int tf2_addr(int c, int row)
+{
+	if (TS) return c*(N + 1) + row;
+	if (NREG == 1) return row*W + c;
+	return (c/W)*N*W + row*W + (c % W);
+}
+
+template<bool INV, int N, int R0, int R1, int W, int NREG, bool TS>
+__device__ __forceinline__ void tf2_tile(const double2 *__restrict__ S, double2 *__restrict__ O, const TfArgs &A, const double2 *__restrict__ twn,
+	const double2 *__restrict__ hiN, const double2 *__restrict__ loN, int ttid, int team, int a, int g2, bool mid, uint64_t *empty_bar, bool storer)
+{
+	constexpr int WT = NREG*W;
+	// ---- pass 0: radix R0 over rows jj + q R1, twiddle w_N^(jj k), to rows jj R0 + k of the output tile
+	#pragma unroll 1
+	for (int item = ttid; item < R1*WT; item += TF_TEAM) {
+		const int c = item % WT, jj = item / WT;
+		double2 u[R0];
+		const double2 *sp = S + (NREG == 1 ? c : (c/W)*N*W + (c % W)) + jj*W;
+		#pragma unroll
+		for (int q = 0; q < R0; q++) u[q] = sp[q*R1*W];
+		dft_small<R0, INV>(u);
+		if (jj) { double2 w1 = twn[jj]; if (INV) w1.y = -w1.y; mul_powers<R0>(u, w1); }
+		double2 *dp = O + tf2_addr<N, W, NREG, TS>(c, jj*R0);
+		#pragma unroll
+		for (int k = 0; k < R0; k++) dp[TS ? k : k*W] = u[k];
+	}
+	if (mid) {
+		// the self-mirrored column (pitch 1, after the two regions)
+		for (int jj = ttid; jj < R1; jj += TF_TEAM) {
+			double2 u[R0];
+			const double2 *sp = S + 2*N*W + jj;
+			#pragma unroll
+			for (int q = 0; q < R0; q++) u[q] = sp[q*R1];
+			dft_small<R0, INV>(u);
+			if (jj) { double2 w1 = twn[jj]; if (INV) w1.y = -w1.y; mul_powers<R0>(u, w1); }
+			double2 *dp = O + 2*N*W + jj*R0;
+			#pragma unroll
+			for (int k = 0; k < R0; k++) dp[k] = u[k];
+		}
+	}
+	bar_sync(1 + team, TF_TEAM);
+	if (ttid == 0) mbar_arrive(empty_bar);                       // the landing tile is free
+	// ---- pass 1: radix R1 in place over rows q R0 + k0; twiddle between the sub-passes; scale
+	#pragma unroll 1
+	for (int item = ttid; item < R0*WT; item += TF_TEAM) {
+		const int c = item % WT, k0 = item / WT;
+		double2 u[R1];
+		double2 *dp = O + tf2_addr<N, W, NREG, TS>(c, k0);
+		#pragma unroll
+		for (int q = 0; q < R1; q++) u[q] = dp[(TS ? 1 : W)*q*R0];
+		dft_small<R1, INV>(u);
+		if (A.tw_mode) {
+			const int t = A.tw_mode == 1 ? a + c : g2;
+			double2 w = tw2(hiN, loN, k0*t), ws = tw2(hiN, loN, R0*t);
+			if (INV) { w.y = -w.y; ws.y = -ws.y; }
+			#pragma unroll
+			for (int k = 0; k < R1; k++) { u[k] = cmul(u[k], w); if (k + 1 < R1) w = cmul(w, ws); }
+		}
+		const double sc = A.scale;
+		#pragma unroll
+		for (int k = 0; k < R1; k++) dp[(TS ? 1 : W)*k*R0] = make_double2(u[k].x*sc, u[k].y*sc);
+	}
+	if (mid) {
+		for (int k0 = ttid; k0 < R0; k0 += TF_TEAM) {
+			double2 u[R1];
+			double2 *dp = O + 2*N*W + k0;
+			#pragma unroll
+			for (int q = 0; q < R1; q++) u[q] = dp[q*R0];
+			dft_small<R1, INV>(u);
+			if (A.tw_mode) {
+				double2 w = tw2(hiN, loN, k0*g2), ws = tw2(hiN, loN, R0*g2);
+				if (INV) { w.y = -w.y; ws.y = -ws.y; }
+				#pragma unroll
+				for (int k = 0; k < R1; k++) { u[k] = cmul(u[k], w); if (k + 1 < R1) w = cmul(w, ws); }
+			}
+			#pragma unroll
+			for (int k = 0; k < R1; k++) dp[k*R0] = make_double2(u[k].x*A.scale, u[k].y*A.scale);
+		}
+	}
+}
+
+template<bool INV, int N, int R0, int R1, int W, int NREG, bool TS>
+__global__ void __launch_bounds__(TF_THREADS, 1) k_tfft2(const __grid_constant__ TfMaps M, const TfArgs A)
+{
+	extern __shared__ __align__(1024) unsigned char smem[];
+	__shared__ __align__(8) uint64_t bars[2*TF_MAXSTAGES];
+	const int NS = A.nstage;
+	uint64_t *full = bars, *empty = bars + TF_MAXSTAGES;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	double2 *twn = (double2*)(smem + A.off_tab);
+	double2 *hiN = twn + N, *loN = hiN + A.nhiN, *hiR = loN + 128, *loR = hiR + A.nhiR;
+	if (tid == 0) {
+		for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+		mbar_fence_init();
+	}
+	for (int i = tid; i < N; i += TF_THREADS) twn[i] = A.twn[i];
+	for (int i = tid; i < 128; i += TF_THREADS) { loN[i] = A.tw_mode ? A.twN_lo[i] : make_double2(1, 0); loR[i] = A.op ? A.twR_lo[i] : make_double2(1, 0); }
+	for (int i = tid; i < A.nhiN; i += TF_THREADS) hiN[i] = A.twN_hi[i];
+	for (int i = tid; i < A.nhiR; i += TF_THREADS) hiR[i] = A.twR_hi[i];
+	__syncthreads();
+	const long long tiles_per_g = (long long)A.ncb_l*A.G2;
+	constexpr int region_bytes = N*W*16;
+
+	if (warp == TF_NCONS/32) {
+		if (lane == 0) {
+			tma_prefetch_desc(&M.ld[0]); tma_prefetch_desc(&M.st[0]);
+			int s = 0, round = 0;
+			for (long long t = blockIdx.x; t < A.ntiles; t += gridDim.x) {
+				if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+				const int g3 = A.g3_0 + (int)(t/tiles_per_g); const long long r = t % tiles_per_g;
+				const int g2 = A.g2_0 + (int)(r/A.ncb_l), cb = A.cb0 + (int)(r % A.ncb_l);
+				const bool mid = NREG == 2 && A.midcol >= 0 && cb == A.ncb - 1;
+				unsigned char *dst = smem + (size_t)s*A.tile_bytes;
+				mbar_expect_tx(&full[s], (uint32_t)(NREG*region_bytes + (mid ? N*16 : 0)));
+				const int a = cb*W;
+				tma_load_4d(dst, &M.ld[0], &full[s], 2*a, 0, g2, g3);
+				if (NREG == 2) tma_load_4d(dst + region_bytes, &M.ld[1], &full[s], 2*(A.mirror - a - W + 1), 0, g2, g3);
+				if (mid) tma_load_4d(dst + 2*region_bytes, &M.ld[2], &full[s], 2*A.midcol, 0, g2, g3);
+				if (++s == NS) { s = 0; round++; }
+			}
+		}
+		return;
+	}
+
+	const int team = warp >> 2, ttid = tid & (TF_TEAM - 1), twarp = warp & 3;
+	double2 *O = (double2*)(smem + A.off_out + (size_t)team*A.out_bytes);
+	const bool storer = TS ? twarp == 0 : ttid == 0;
+	int it = 0;
+	for (long long t = blockIdx.x; t < A.ntiles; t += gridDim.x, it++) {
+		if ((it & 1) != team) continue;
+		const int s = it % NS, round = it/NS;
+		const int g3 = A.g3_0 + (int)(t/tiles_per_g); const long long r = t % tiles_per_g;
+		const int g2 = A.g2_0 + (int)(r/A.ncb_l), cb = A.cb0 + (int)(r % A.ncb_l);
+		const bool mid = NREG == 2 && A.midcol >= 0 && cb == A.ncb - 1;
+		const int a = cb*W;
+		double2 *S = (double2*)(smem + (size_t)s*A.tile_bytes);
+		if (storer) bulk_wait_read<0>();                         // this team's output tile has left
+		mbar_wait(&full[s], round & 1);
+		if (NREG == 2 && A.op == 1) {
+			double2 *SA = S, *SB = S + N*W;
+			for (int idx = ttid; idx < N*W; idx += TF_TEAM) {
+				const int j = idx / W, i = idx % W, k = a + i;
+				const double2 zk = SA[j*W + i];
+				double2 zp = SB[j*W + (W - 1 - i)];
+				if (k == 0) zp = zk;
+				const double2 sm = make_double2(zk.x + zp.x, zk.y - zp.y), df = make_double2(zk.x - zp.x, zk.y + zp.y);
+				const double2 u = cmul(df, tw2(hiR, loR, k));
+				SA[j*W + i] = make_double2(0.5*(sm.x + u.y), 0.5*(sm.y - u.x));
+				SB[j*W + (W - 1 - i)] = make_double2(0.5*(sm.x - u.y), -0.5*(sm.y + u.x));
+			}
+			if (mid) for (int j = ttid; j < N; j += TF_TEAM) { double2 *p = S + 2*N*W + j; p->y = -p->y; }
+			fence_proxy_async();
+		}
+		bar_sync(1 + team, TF_TEAM);
+		tf2_tile<INV, N, R0, R1, W, NREG, TS>(S, O, A, twn, hiN, loN, ttid, team, a, g2, mid, &empty[s], storer);
+		if (NREG == 2 && A.op == 2) {
+			bar_sync(1 + team, TF_TEAM);
+			double2 *OA = O, *OB = O + N*W;
+			for (int idx = ttid; idx < N*W; idx += TF_TEAM) {
+				const int j = idx / W, i = idx % W, k = a + i;
+				const double2 xa = OA[j*W + i], xb = OB[j*W + (W - 1 - i)];
+				const double2 sm = make_double2(xa.x + xb.x, xa.y - xb.y), df = make_double2(xa.x - xb.x, xa.y + xb.y);
+				double2 w = tw2(hiR, loR, k); w.y = -w.y;
+				const double2 u = cmul(df, w);
+				OA[j*W + i] = make_double2(sm.x - u.y, sm.y + u.x);
+				OB[j*W + (W - 1 - i)] = make_double2(sm.x + u.y, u.x - sm.y);
+			}
+			if (mid) for (int j = ttid; j < N; j += TF_TEAM) { double2 *p = O + 2*N*W + j; *p = make_double2(2*p->x, -2*p->y); }
+		}
+		fence_proxy_async();
+		bar_sync(1 + team, TF_TEAM);
+		if (TS) {
+			if (twarp == 0) {
+				for (int c = lane; c < W; c += 32)
+					if (a + c < A.ncols_valid) bulk_store_1d(A.tbase + (long long)g2*A.t_g2stride + (long long)(a + c)*N, O + c*(N + 1), (uint32_t)N*16);
+				bulk_commit();
+			}
+		} else if (ttid == 0) {
+			tma_store_4d(&M.st[0], O, 2*a, 0, g2, g3);
+			if (NREG == 2) tma_store_4d(&M.st[1], O + N*W, 2*(A.mirror - a - W + 1), 0, g2, g3);
+			if (mid) tma_store_4d(&M.st[2], O + 2*N*W, 2*A.midcol, 0, g2, g3);
+			bulk_commit();
+		}
+	}
+	if (storer) bulk_wait_read<0>();
 }
 
 // ------------------------------------------------------------------------------------ host: tables
@@ -382,6 +591,44 @@ void tfft_plan_destroy(TfPlan *p) { delete p; }
 
 // ------------------------------------------------------------------------------------ host: launches
 
+template<bool INV, int N, int R0, int R1, int W, int NREG, bool TS> static int tf_launch2_k(const TfMaps &M, const TfArgs &A, unsigned grid, size_t smem, cudaStream_t st)
+{
+	static thread_local std::map<int, size_t> granted;
+	int dev; B2_CHECK(cudaGetDevice(&dev));
+	size_t &g = granted[dev];
+	if (smem > g) { B2_CHECK(cudaFuncSetAttribute(k_tfft2<INV, N, R0, R1, W, NREG, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g = smem; }
+	k_tfft2<INV, N, R0, R1, W, NREG, TS><<<grid, TF_THREADS, smem, st>>>(M, A);
+	B2_LAUNCH_CHECK();
+	return 0;
+}
+
+// the specialised two-team kernel for power-of-two tiles; returns -1 when there is no instance for this shape
+static int tf_launch2(const TfMaps &M, TfArgs &A, int nsm, size_t tabs, cudaStream_t st)
+{
+	static const bool off = getenv("B2_TFFT_GENERIC") && atoi(getenv("B2_TFFT_GENERIC"));
+	if (off || A.nfac != 2) return -1;
+	const int Wtot = A.nreg*A.W + (A.midcol >= 0 ? 1 : 0);
+	A.tile_bytes = (int)b2_round_up((int64_t)Wtot*A.n*16, 128);
+	A.out_bytes = (int)b2_round_up(A.tstore ? (int64_t)A.W*(A.n + 1)*16 : (int64_t)Wtot*A.n*16, 128);
+	const size_t fixed = 2*(size_t)A.out_bytes + tabs;
+	if (226*1024 < fixed + 2*(size_t)A.tile_bytes) return -1;
+	static const int max_stage = getenv("B2_TFFT_STAGES") ? atoi(getenv("B2_TFFT_STAGES")) : TF_MAXSTAGES;
+	A.nstage = (int)std::min<size_t>(std::min(max_stage, TF_MAXSTAGES), (226*1024 - fixed)/A.tile_bytes);
+	A.off_work = 0; A.off_out = A.nstage*A.tile_bytes; A.off_tab = A.off_out + 2*A.out_bytes;
+	const size_t smem = (size_t)A.off_tab + tabs;
+	const unsigned grid = (unsigned)std::min<long long>(A.ntiles, nsm);
+	#define TF2_PLAIN(N_, R0_, R1_, W_) if (A.n == N_ && A.W == W_ && A.nreg == 1 && A.fac[0] == R0_ && A.fac[1] == R1_) { \
+		if (A.tstore) return A.inv ? tf_launch2_k<true, N_, R0_, R1_, W_, 1, true>(M, A, grid, smem, st) : tf_launch2_k<false, N_, R0_, R1_, W_, 1, true>(M, A, grid, smem, st); \
+		return A.inv ? tf_launch2_k<true, N_, R0_, R1_, W_, 1, false>(M, A, grid, smem, st) : tf_launch2_k<false, N_, R0_, R1_, W_, 1, false>(M, A, grid, smem, st); }
+	#define TF2_MIRR(N_, R0_, R1_, W_) if (A.n == N_ && A.W == W_ && A.nreg == 2 && !A.tstore && A.fac[0] == R0_ && A.fac[1] == R1_) \
+		return A.inv ? tf_launch2_k<true, N_, R0_, R1_, W_, 2, false>(M, A, grid, smem, st) : tf_launch2_k<false, N_, R0_, R1_, W_, 2, false>(M, A, grid, smem, st);
+	TF2_PLAIN(32, 4, 8, 64) TF2_PLAIN(32, 4, 8, 32) TF2_PLAIN(64, 8, 8, 32) TF2_PLAIN(64, 8, 8, 16) TF2_PLAIN(128, 16, 8, 16) TF2_PLAIN(256, 16, 16, 8)
+	TF2_MIRR(32, 4, 8, 32) TF2_MIRR(32, 4, 8, 16) TF2_MIRR(64, 8, 8, 16) TF2_MIRR(64, 8, 8, 8) TF2_MIRR(128, 16, 8, 8)
+	#undef TF2_PLAIN
+	#undef TF2_MIRR
+	return -1;
+}
+
 static int tf_launch(TfMaps &M, TfArgs &A, const TfLen &L, const TfTw2 *twN, const TfTw2 *twR, int nsm, cudaStream_t st)
 {
 	A.n = L.n; A.nfac = L.nfac; for (int i = 0; i < L.nfac; i++) A.fac[i] = L.fac[i];
@@ -395,10 +642,18 @@ static int tf_launch(TfMaps &M, TfArgs &A, const TfLen &L, const TfTw2 *twN, con
 	A.LW = std::min(32, A.W);
 	A.tile_bytes = (int)b2_round_up((int64_t)Wtot*A.n*16, 128);
 	A.out_bytes = (int)b2_round_up(A.tstore ? (int64_t)A.W*(A.n + 1)*16 : (int64_t)Wtot*A.n*16, 128);
-	A.off_out = TF_STAGES*A.tile_bytes;
-	A.off_tab = A.off_out + 2*A.out_bytes;
-	const size_t smem = (size_t)A.off_tab + ((size_t)A.n + A.nhiN + 128 + A.nhiR + 128)*16 + (size_t)A.n*4 + 16;
-	B2_REQUIRE(smem <= 227*1024, "tfft: tile of %d x %d needs %zu bytes of shared memory", A.n, Wtot, smem);
+	const size_t tabs = ((size_t)A.n + A.nhiN + 128 + A.nhiR + 128)*16 + (size_t)A.n*4 + 16;
+	A.ntiles = (long long)A.ncb_l*A.G2*A.G3;
+	if (A.ntiles <= 0) return 0;
+	{ int rc = tf_launch2(M, A, nsm, tabs, st); if (rc >= 0) return rc; }
+	const size_t fixed = (A.nfac > 1 ? A.tile_bytes : 0) + A.out_bytes + tabs;
+	static const int max_stage = getenv("B2_TFFT_STAGES") ? atoi(getenv("B2_TFFT_STAGES")) : TF_MAXSTAGES;
+	A.nstage = (int)std::min<size_t>(std::min(max_stage, TF_MAXSTAGES), (226*1024 - fixed)/A.tile_bytes);
+	B2_REQUIRE(A.nstage >= 2, "tfft: tile of %d x %d does not leave room for two landing tiles", A.n, Wtot);
+	A.off_work = A.nstage*A.tile_bytes;
+	A.off_out = A.off_work + (A.nfac > 1 ? A.tile_bytes : 0);
+	A.off_tab = A.off_out + A.out_bytes;
+	const size_t smem = (size_t)A.off_tab + tabs;
 	A.ntiles = (long long)A.ncb_l*A.G2*A.G3;
 	if (A.ntiles <= 0) return 0;
 	const unsigned grid = (unsigned)std::min<long long>(A.ntiles, nsm);
