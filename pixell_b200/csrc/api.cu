@@ -46,6 +46,7 @@ int grid_theta_host(const char *g, int n, std::vector<double> &theta)
 		else if (s == "DH")     theta[k] = k*M_PI/n;
 		else if (s == "F2")     theta[k] = (k + 1)*M_PI/(n + 1);
 		else { b2_set_error("unknown geometry '%s'", g); return 1; }
+		if (theta[k] > M_PI) theta[k] = M_PI;      // k pi/(n-1) can round one ulp above pi for the last Clenshaw-Curtis ring
 	}
 	return 0;
 }

@@ -188,10 +188,10 @@ template<bool INV> __global__ void __launch_bounds__(TF_THREADS, 1) k_tfft(const
 				if (k == 0) zp = zk;                                     // Z_Nc = Z_0 (the box column beyond the array was zero-filled)
 				const double2 sm = make_double2(zk.x + zp.x, zk.y - zp.y), df = make_double2(zk.x - zp.x, zk.y + zp.y);
 				const double2 u = cmul(df, tw2(hiR, loR, k));            // w_nx^k (Z_k - conj Z_{Nc-k})
-				SA[j*W + i] = make_double2(0.5*(sm.x + u.y), 0.5*(sm.y - u.x));
-				SB[j*W + (W - 1 - i)] = make_double2(0.5*(sm.x - u.y), -0.5*(sm.y + u.x));
+				SA[j*W + i] = make_double2(sm.x + u.y, sm.y - u.x);      // 2 X_k: the factor 1/2 rides on the row pass
+				SB[j*W + (W - 1 - i)] = make_double2(sm.x - u.y, -(sm.y + u.x));
 			}
-			if (mid) for (int j = tid; j < n; j += TF_NCONS) { double2 *p = S + 2*n*W + j; p->y = -p->y; }
+			if (mid) for (int j = tid; j < n; j += TF_NCONS) { double2 *p = S + 2*n*W + j; *p = make_double2(2*p->x, -2*p->y); }
 			fence_proxy_async();                                         // the landing tile was written by the generic proxy
 			bar_sync(1, TF_NCONS);
 		}
@@ -254,7 +254,6 @@ template<bool INV> __global__ void __launch_bounds__(TF_THREADS, 1) k_tfft(const
 // with its own output tile), so one team's barrier and mbarrier waits are covered by the other team's butterflies.
 // Pass 0 reads the landing tile and writes the output tile in transposed digit order (row jj R0 + k0), which frees the
 // landing tile at once; pass 1 then runs in place on rows {q R0 + k0} and leaves row k0 + R0 k1 in natural order.
-#define TF_TEAM 128
 
 template<int N, int W, int NREG, bool TS> __device__ __forceinline__ int tf2_addr(int c, int row)
 {
@@ -263,11 +262,15 @@ template<int N, int W, int NREG, bool TS> __device__ __forceinline__ int tf2_add
 	return (c/W)*N*W + row*W + (c % W);
 }
 
-template<bool INV, int N, int R0, int R1, int W, int NREG, bool TS>
+// Twiddles come from shared-memory tables, not from products: the FP64 pipe (64 lanes per SM and clock) is the scarce
+// unit of these kernels.  twn: w_N^j.  TT (row sub-pass 1, TS): scale w_Ntot^(row (a + c)) for the whole tile, the same
+// for every tile of a CTA (all its tiles share the column block).  V (column sub-pass 1): scale w_Ntot^(row g2), one
+// vector per tile.
+template<bool INV, int N, int R0, int R1, int W, int NREG, bool TS, int NT>
 __device__ __forceinline__ void tf2_tile(const double2 *__restrict__ S, double2 *__restrict__ O, const TfArgs &A, const double2 *__restrict__ twn,
-	const double2 *__restrict__ hiN, const double2 *__restrict__ loN, int ttid, int team, int a, int g2, bool mid, uint64_t *empty_bar, bool storer)
+	const double2 *__restrict__ TT, const double2 *__restrict__ V, int ttid, int team, bool mid, uint64_t *empty_bar)
 {
-	constexpr int WT = NREG*W;
+	constexpr int WT = NREG*W, TF_TEAM = TF_NCONS/NT;
 	// ---- pass 0: radix R0 over rows jj + q R1, twiddle w_N^(jj k), to rows jj R0 + k of the output tile
 	#pragma unroll 1
 	for (int item = ttid; item < R1*WT; item += TF_TEAM) {
@@ -277,7 +280,10 @@ __device__ __forceinline__ void tf2_tile(const double2 *__restrict__ S, double2 
 		#pragma unroll
 		for (int q = 0; q < R0; q++) u[q] = sp[q*R1*W];
 		dft_small<R0, INV>(u);
-		if (jj) { double2 w1 = twn[jj]; if (INV) w1.y = -w1.y; mul_powers<R0>(u, w1); }
+		if (jj) {
+			#pragma unroll
+			for (int k = 1; k < R0; k++) { double2 w = twn[jj*k]; if (INV) w.y = -w.y; u[k] = cmul(u[k], w); }
+		}
 		double2 *dp = O + tf2_addr<N, W, NREG, TS>(c, jj*R0);
 		#pragma unroll
 		for (int k = 0; k < R0; k++) dp[TS ? k : k*W] = u[k];
@@ -290,7 +296,10 @@ __device__ __forceinline__ void tf2_tile(const double2 *__restrict__ S, double2 
 			#pragma unroll
 			for (int q = 0; q < R0; q++) u[q] = sp[q*R1];
 			dft_small<R0, INV>(u);
-			if (jj) { double2 w1 = twn[jj]; if (INV) w1.y = -w1.y; mul_powers<R0>(u, w1); }
+			if (jj) {
+				#pragma unroll
+				for (int k = 1; k < R0; k++) { double2 w = twn[jj*k]; if (INV) w.y = -w.y; u[k] = cmul(u[k], w); }
+			}
 			double2 *dp = O + 2*N*W + jj*R0;
 			#pragma unroll
 			for (int k = 0; k < R0; k++) dp[k] = u[k];
@@ -298,25 +307,30 @@ __device__ __forceinline__ void tf2_tile(const double2 *__restrict__ S, double2 
 	}
 	bar_sync(1 + team, TF_TEAM);
 	if (ttid == 0) mbar_arrive(empty_bar);                       // the landing tile is free
-	// ---- pass 1: radix R1 in place over rows q R0 + k0; twiddle between the sub-passes; scale
+	// ---- pass 1: radix R1 in place over rows q R0 + k0; twiddle between the sub-passes and scale from the tables
+	const double sc = A.scale;
 	#pragma unroll 1
 	for (int item = ttid; item < R0*WT; item += TF_TEAM) {
 		const int c = item % WT, k0 = item / WT;
 		double2 u[R1];
-		double2 *dp = O + tf2_addr<N, W, NREG, TS>(c, k0);
+		const int ad = tf2_addr<N, W, NREG, TS>(c, k0);
+		double2 *dp = O + ad;
 		#pragma unroll
 		for (int q = 0; q < R1; q++) u[q] = dp[(TS ? 1 : W)*q*R0];
 		dft_small<R1, INV>(u);
-		if (A.tw_mode) {
-			const int t = A.tw_mode == 1 ? a + c : g2;
-			double2 w = tw2(hiN, loN, k0*t), ws = tw2(hiN, loN, R0*t);
-			if (INV) { w.y = -w.y; ws.y = -ws.y; }
+		if (TS) {
 			#pragma unroll
-			for (int k = 0; k < R1; k++) { u[k] = cmul(u[k], w); if (k + 1 < R1) w = cmul(w, ws); }
+			for (int k = 0; k < R1; k++) dp[k*R0] = cmul(u[k], TT[ad + k*R0]);
+		} else if (A.tw_mode == 2) {
+			#pragma unroll
+			for (int k = 0; k < R1; k++) dp[W*k*R0] = cmul(u[k], V[k0 + k*R0]);
+		} else if (sc != 1.0) {
+			#pragma unroll
+			for (int k = 0; k < R1; k++) dp[W*k*R0] = make_double2(u[k].x*sc, u[k].y*sc);
+		} else {
+			#pragma unroll
+			for (int k = 0; k < R1; k++) dp[W*k*R0] = u[k];
 		}
-		const double sc = A.scale;
-		#pragma unroll
-		for (int k = 0; k < R1; k++) dp[(TS ? 1 : W)*k*R0] = make_double2(u[k].x*sc, u[k].y*sc);
 	}
 	if (mid) {
 		for (int k0 = ttid; k0 < R0; k0 += TF_TEAM) {
@@ -325,19 +339,16 @@ __device__ __forceinline__ void tf2_tile(const double2 *__restrict__ S, double2 
 			#pragma unroll
 			for (int q = 0; q < R1; q++) u[q] = dp[q*R0];
 			dft_small<R1, INV>(u);
-			if (A.tw_mode) {
-				double2 w = tw2(hiN, loN, k0*g2), ws = tw2(hiN, loN, R0*g2);
-				if (INV) { w.y = -w.y; ws.y = -ws.y; }
-				#pragma unroll
-				for (int k = 0; k < R1; k++) { u[k] = cmul(u[k], w); if (k + 1 < R1) w = cmul(w, ws); }
-			}
 			#pragma unroll
-			for (int k = 0; k < R1; k++) dp[k*R0] = make_double2(u[k].x*A.scale, u[k].y*A.scale);
+			for (int k = 0; k < R1; k++) dp[k*R0] = A.tw_mode == 2 ? cmul(u[k], V[k0 + k*R0]) : make_double2(u[k].x*sc, u[k].y*sc);
 		}
 	}
 }
 
-template<bool INV, int N, int R0, int R1, int W, int NREG, bool TS>
+// Tile order.  TS kernels (row sub-pass 1): CTA b owns column block cb0 + b % ncb_l and walks the lines b / ncb_l,
+// + gridDim.x / ncb_l, ... (the grid is a multiple of ncb_l), so its twiddle tile never changes.  Others: tile
+// t = blockIdx.x + i gridDim.x with the column block fastest.
+template<bool INV, int N, int R0, int R1, int W, int NREG, bool TS, int NT>
 __global__ void __launch_bounds__(TF_THREADS, 1) k_tfft2(const __grid_constant__ TfMaps M, const TfArgs A)
 {
 	extern __shared__ __align__(1024) unsigned char smem[];
@@ -347,6 +358,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tfft2(const __grid_constant__
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	double2 *twn = (double2*)(smem + A.off_tab);
 	double2 *hiN = twn + N, *loN = hiN + A.nhiN, *hiR = loN + 128, *loR = hiR + A.nhiR;
+	double2 *Vbase = loR + 128;                                  // two vectors of N (one per team)
+	double2 *TT = (double2*)(smem + A.off_work);                 // TS: the twiddle tile
 	if (tid == 0) {
 		for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
 		mbar_fence_init();
@@ -358,15 +371,38 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tfft2(const __grid_constant__
 	__syncthreads();
 	const long long tiles_per_g = (long long)A.ncb_l*A.G2;
 	constexpr int region_bytes = N*W*16;
+	// tile walk of this CTA
+	long long t_first, t_step, t_count;
+	int cb_fixed = 0;
+	if (TS) {
+		const int per = gridDim.x/A.ncb_l;                       // CTAs per column block
+		cb_fixed = A.cb0 + (int)(blockIdx.x % A.ncb_l);
+		t_first = blockIdx.x/A.ncb_l; t_step = per;
+		const long long nl = (long long)A.G2*A.G3;
+		t_count = t_first < nl ? (nl - t_first + per - 1)/per : 0;
+		// the twiddle tile of this column block: scale w^(row (a + c)), in the layout of the output tile
+		const int a = cb_fixed*W;
+		for (int idx = tid; idx < N*W; idx += TF_THREADS) {
+			const int c = idx / N, row = idx % N;
+			double2 w = tw2(hiN, loN, row*(a + c)); if (INV) w.y = -w.y;
+			TT[c*(N + 1) + row] = make_double2(w.x*A.scale, w.y*A.scale);
+		}
+		__syncthreads();
+	} else {
+		t_first = blockIdx.x; t_step = gridDim.x;
+		t_count = t_first < A.ntiles ? (A.ntiles - t_first + t_step - 1)/t_step : 0;
+	}
 
 	if (warp == TF_NCONS/32) {
 		if (lane == 0) {
 			tma_prefetch_desc(&M.ld[0]); tma_prefetch_desc(&M.st[0]);
 			int s = 0, round = 0;
-			for (long long t = blockIdx.x; t < A.ntiles; t += gridDim.x) {
+			for (long long i = 0; i < t_count; i++) {
+				const long long t = t_first + i*t_step;
 				if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
-				const int g3 = A.g3_0 + (int)(t/tiles_per_g); const long long r = t % tiles_per_g;
-				const int g2 = A.g2_0 + (int)(r/A.ncb_l), cb = A.cb0 + (int)(r % A.ncb_l);
+				int g2, g3, cb;
+				if (TS) { g3 = A.g3_0 + (int)(t/A.G2); g2 = A.g2_0 + (int)(t % A.G2); cb = cb_fixed; }
+				else { g3 = A.g3_0 + (int)(t/tiles_per_g); const long long r = t % tiles_per_g; g2 = A.g2_0 + (int)(r/A.ncb_l); cb = A.cb0 + (int)(r % A.ncb_l); }
 				const bool mid = NREG == 2 && A.midcol >= 0 && cb == A.ncb - 1;
 				unsigned char *dst = smem + (size_t)s*A.tile_bytes;
 				mbar_expect_tx(&full[s], (uint32_t)(NREG*region_bytes + (mid ? N*16 : 0)));
@@ -380,48 +416,57 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_tfft2(const __grid_constant__
 		return;
 	}
 
-	const int team = warp >> 2, ttid = tid & (TF_TEAM - 1), twarp = warp & 3;
+	constexpr int TF_TEAM = TF_NCONS/NT;
+	const int team = NT == 2 ? warp >> 2 : 0, ttid = tid & (TF_TEAM - 1), twarp = NT == 2 ? warp & 3 : warp;
 	double2 *O = (double2*)(smem + A.off_out + (size_t)team*A.out_bytes);
+	double2 *V = Vbase + team*N;
 	const bool storer = TS ? twarp == 0 : ttid == 0;
-	int it = 0;
-	for (long long t = blockIdx.x; t < A.ntiles; t += gridDim.x, it++) {
-		if ((it & 1) != team) continue;
-		const int s = it % NS, round = it/NS;
-		const int g3 = A.g3_0 + (int)(t/tiles_per_g); const long long r = t % tiles_per_g;
-		const int g2 = A.g2_0 + (int)(r/A.ncb_l), cb = A.cb0 + (int)(r % A.ncb_l);
+	for (long long i = team; i < t_count; i += NT) {
+		const long long t = t_first + i*t_step;
+		const int s = (int)(i % NS), round = (int)(i/NS);
+		int g2, g3, cb;
+		if (TS) { g3 = A.g3_0 + (int)(t/A.G2); g2 = A.g2_0 + (int)(t % A.G2); cb = cb_fixed; }
+		else { g3 = A.g3_0 + (int)(t/tiles_per_g); const long long r = t % tiles_per_g; g2 = A.g2_0 + (int)(r/A.ncb_l); cb = A.cb0 + (int)(r % A.ncb_l); }
 		const bool mid = NREG == 2 && A.midcol >= 0 && cb == A.ncb - 1;
 		const int a = cb*W;
 		double2 *S = (double2*)(smem + (size_t)s*A.tile_bytes);
 		if (storer) bulk_wait_read<0>();                         // this team's output tile has left
+		if (!TS && A.tw_mode == 2) {
+			for (int row = ttid; row < N; row += TF_TEAM) {
+				double2 w = tw2(hiN, loN, row*g2); if (INV) w.y = -w.y;
+				V[row] = make_double2(w.x*A.scale, w.y*A.scale);
+			}
+		}
 		mbar_wait(&full[s], round & 1);
 		if (NREG == 2 && A.op == 1) {
+			// r2c: packed spectrum Z -> 2 X on the mirrored column blocks (the factor 1/2 is folded into the scale of the row pass)
 			double2 *SA = S, *SB = S + N*W;
 			for (int idx = ttid; idx < N*W; idx += TF_TEAM) {
-				const int j = idx / W, i = idx % W, k = a + i;
-				const double2 zk = SA[j*W + i];
-				double2 zp = SB[j*W + (W - 1 - i)];
+				const int j = idx / W, i2 = idx % W, k = a + i2;
+				const double2 zk = SA[j*W + i2];
+				double2 zp = SB[j*W + (W - 1 - i2)];
 				if (k == 0) zp = zk;
 				const double2 sm = make_double2(zk.x + zp.x, zk.y - zp.y), df = make_double2(zk.x - zp.x, zk.y + zp.y);
 				const double2 u = cmul(df, tw2(hiR, loR, k));
-				SA[j*W + i] = make_double2(0.5*(sm.x + u.y), 0.5*(sm.y - u.x));
-				SB[j*W + (W - 1 - i)] = make_double2(0.5*(sm.x - u.y), -0.5*(sm.y + u.x));
+				SA[j*W + i2] = make_double2(sm.x + u.y, sm.y - u.x);
+				SB[j*W + (W - 1 - i2)] = make_double2(sm.x - u.y, -(sm.y + u.x));
 			}
-			if (mid) for (int j = ttid; j < N; j += TF_TEAM) { double2 *p = S + 2*N*W + j; p->y = -p->y; }
+			if (mid) for (int j = ttid; j < N; j += TF_TEAM) { double2 *p = S + 2*N*W + j; *p = make_double2(2*p->x, -2*p->y); }
 			fence_proxy_async();
 		}
 		bar_sync(1 + team, TF_TEAM);
-		tf2_tile<INV, N, R0, R1, W, NREG, TS>(S, O, A, twn, hiN, loN, ttid, team, a, g2, mid, &empty[s], storer);
+		tf2_tile<INV, N, R0, R1, W, NREG, TS, NT>(S, O, A, twn, TT, V, ttid, team, mid, &empty[s]);
 		if (NREG == 2 && A.op == 2) {
 			bar_sync(1 + team, TF_TEAM);
 			double2 *OA = O, *OB = O + N*W;
 			for (int idx = ttid; idx < N*W; idx += TF_TEAM) {
-				const int j = idx / W, i = idx % W, k = a + i;
-				const double2 xa = OA[j*W + i], xb = OB[j*W + (W - 1 - i)];
+				const int j = idx / W, i2 = idx % W, k = a + i2;
+				const double2 xa = OA[j*W + i2], xb = OB[j*W + (W - 1 - i2)];
 				const double2 sm = make_double2(xa.x + xb.x, xa.y - xb.y), df = make_double2(xa.x - xb.x, xa.y + xb.y);
 				double2 w = tw2(hiR, loR, k); w.y = -w.y;
 				const double2 u = cmul(df, w);
-				OA[j*W + i] = make_double2(sm.x - u.y, sm.y + u.x);
-				OB[j*W + (W - 1 - i)] = make_double2(sm.x + u.y, u.x - sm.y);
+				OA[j*W + i2] = make_double2(sm.x - u.y, sm.y + u.x);
+				OB[j*W + (W - 1 - i2)] = make_double2(sm.x + u.y, u.x - sm.y);
 			}
 			if (mid) for (int j = ttid; j < N; j += TF_TEAM) { double2 *p = O + 2*N*W + j; *p = make_double2(2*p->x, -2*p->y); }
 		}
@@ -540,7 +585,10 @@ struct TfPlan {
 };
 
 static int pow2_floor(int v) { int p = 1; while (2*p <= v) p *= 2; return p; }
-static size_t tf_slab_bytes() { const char *e = getenv("B2_TFFT_SLAB_MB"); return (size_t)(e ? atoi(e) : 24) << 20; }
+// Slabs: run the two sub-passes of an axis on blocks of lines small enough for the intermediate to stay in L2.  Measured
+// on B200 (profiles/r2*_tfft_*): the launches this takes cost more than the HBM traffic they save, so the default is one
+// slab (every sub-pass streams the whole array); B2_TFFT_SLAB_MB sets a slab size for experiments.
+static size_t tf_slab_bytes() { const char *e = getenv("B2_TFFT_SLAB_MB"); return e ? (size_t)atoi(e) << 20 : (size_t)1 << 60; }
 static int tf_tile_elems() { const char *e = getenv("B2_TFFT_TILE"); return e ? atoi(e) : 2048; }
 
 // columns per tile for a transform length n with `cols` columns available
@@ -591,14 +639,20 @@ void tfft_plan_destroy(TfPlan *p) { delete p; }
 
 // ------------------------------------------------------------------------------------ host: launches
 
-template<bool INV, int N, int R0, int R1, int W, int NREG, bool TS> static int tf_launch2_k(const TfMaps &M, const TfArgs &A, unsigned grid, size_t smem, cudaStream_t st)
+template<bool INV, int N, int R0, int R1, int W, int NREG, bool TS, int NT> static int tf_launch2_k(const TfMaps &M, const TfArgs &A, unsigned grid, size_t smem, cudaStream_t st)
 {
 	static thread_local std::map<int, size_t> granted;
 	int dev; B2_CHECK(cudaGetDevice(&dev));
 	size_t &g = granted[dev];
-	if (smem > g) { B2_CHECK(cudaFuncSetAttribute(k_tfft2<INV, N, R0, R1, W, NREG, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g = smem; }
-	k_tfft2<INV, N, R0, R1, W, NREG, TS><<<grid, TF_THREADS, smem, st>>>(M, A);
+	if (smem > g) { B2_CHECK(cudaFuncSetAttribute(k_tfft2<INV, N, R0, R1, W, NREG, TS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); g = smem; }
+	k_tfft2<INV, N, R0, R1, W, NREG, TS, NT><<<grid, TF_THREADS, smem, st>>>(M, A);
 	B2_LAUNCH_CHECK();
+	static const bool dbg = getenv("B2_TFFT_SYNC") && atoi(getenv("B2_TFFT_SYNC"));
+	if (dbg) {
+		cudaError_t e = cudaStreamSynchronize(st);
+		B2_REQUIRE(e == cudaSuccess, "k_tfft2<%d,%d,%d,%d,%d,%d,%d> grid %u smem %zu ntiles %lld ncb_l %d G2 %d G3 %d nstage %d tw_mode %d op %d: %s",
+			(int)INV, N, R0, R1, W, NREG, (int)TS, grid, smem, A.ntiles, A.ncb_l, A.G2, A.G3, A.nstage, A.tw_mode, A.op, cudaGetErrorString(e));
+	}
 	return 0;
 }
 
@@ -610,20 +664,33 @@ static int tf_launch2(const TfMaps &M, TfArgs &A, int nsm, size_t tabs, cudaStre
 	const int Wtot = A.nreg*A.W + (A.midcol >= 0 ? 1 : 0);
 	A.tile_bytes = (int)b2_round_up((int64_t)Wtot*A.n*16, 128);
 	A.out_bytes = (int)b2_round_up(A.tstore ? (int64_t)A.W*(A.n + 1)*16 : (int64_t)Wtot*A.n*16, 128);
-	const size_t fixed = 2*(size_t)A.out_bytes + tabs;
+	tabs += 2*(size_t)A.n*16;                                    // the teams' twiddle vectors
+	// two teams of four warps on alternate tiles, or (tiles of 64 KB) one team of eight warps with a single output tile
+	const int nteam = A.tile_bytes > 40*1024 ? 1 : 2;
+	const size_t fixed = (nteam + (A.tstore ? 1 : 0))*(size_t)A.out_bytes + tabs;      // TS: + the twiddle tile
 	if (226*1024 < fixed + 2*(size_t)A.tile_bytes) return -1;
 	static const int max_stage = getenv("B2_TFFT_STAGES") ? atoi(getenv("B2_TFFT_STAGES")) : TF_MAXSTAGES;
 	A.nstage = (int)std::min<size_t>(std::min(max_stage, TF_MAXSTAGES), (226*1024 - fixed)/A.tile_bytes);
-	A.off_work = 0; A.off_out = A.nstage*A.tile_bytes; A.off_tab = A.off_out + 2*A.out_bytes;
+	// the two teams take alternate tiles: with an even ring every landing tile belongs to one team, whose waits on its
+	// mbarrier are then consecutive phases (an odd ring lets a team test a phase parity that an older fill satisfies)
+	if (nteam == 2) A.nstage &= ~1;
+	A.off_out = A.nstage*A.tile_bytes; A.off_work = A.off_out + nteam*A.out_bytes; A.off_tab = A.off_work + (A.tstore ? A.out_bytes : 0);
 	const size_t smem = (size_t)A.off_tab + tabs;
-	const unsigned grid = (unsigned)std::min<long long>(A.ntiles, nsm);
-	#define TF2_PLAIN(N_, R0_, R1_, W_) if (A.n == N_ && A.W == W_ && A.nreg == 1 && A.fac[0] == R0_ && A.fac[1] == R1_) { \
-		if (A.tstore) return A.inv ? tf_launch2_k<true, N_, R0_, R1_, W_, 1, true>(M, A, grid, smem, st) : tf_launch2_k<false, N_, R0_, R1_, W_, 1, true>(M, A, grid, smem, st); \
-		return A.inv ? tf_launch2_k<true, N_, R0_, R1_, W_, 1, false>(M, A, grid, smem, st) : tf_launch2_k<false, N_, R0_, R1_, W_, 1, false>(M, A, grid, smem, st); }
-	#define TF2_MIRR(N_, R0_, R1_, W_) if (A.n == N_ && A.W == W_ && A.nreg == 2 && !A.tstore && A.fac[0] == R0_ && A.fac[1] == R1_) \
-		return A.inv ? tf_launch2_k<true, N_, R0_, R1_, W_, 2, false>(M, A, grid, smem, st) : tf_launch2_k<false, N_, R0_, R1_, W_, 2, false>(M, A, grid, smem, st);
+	unsigned grid = (unsigned)std::min<long long>(A.ntiles, nsm);
+	if (A.tstore) {
+		// every CTA owns one column block: the grid is a multiple of the number of column blocks
+		if (A.ncb_l > nsm) return -1;
+		const long long per = std::max<long long>(1, std::min<long long>(nsm/A.ncb_l, (long long)A.G2*A.G3));
+		grid = (unsigned)(per*A.ncb_l);
+	}
+	#define TF2_PLAIN(N_, R0_, R1_, W_) if (A.n == N_ && A.W == W_ && A.nreg == 1 && nteam == 2 && A.fac[0] == R0_ && A.fac[1] == R1_) { \
+		if (A.tstore) return A.inv ? tf_launch2_k<true, N_, R0_, R1_, W_, 1, true, 2>(M, A, grid, smem, st) : tf_launch2_k<false, N_, R0_, R1_, W_, 1, true, 2>(M, A, grid, smem, st); \
+		return A.inv ? tf_launch2_k<true, N_, R0_, R1_, W_, 1, false, 2>(M, A, grid, smem, st) : tf_launch2_k<false, N_, R0_, R1_, W_, 1, false, 2>(M, A, grid, smem, st); }
+	#define TF2_MIRR(N_, R0_, R1_, W_, NT_) if (A.n == N_ && A.W == W_ && A.nreg == 2 && nteam == NT_ && !A.tstore && A.fac[0] == R0_ && A.fac[1] == R1_) \
+		return A.inv ? tf_launch2_k<true, N_, R0_, R1_, W_, 2, false, NT_>(M, A, grid, smem, st) : tf_launch2_k<false, N_, R0_, R1_, W_, 2, false, NT_>(M, A, grid, smem, st);
 	TF2_PLAIN(32, 4, 8, 64) TF2_PLAIN(32, 4, 8, 32) TF2_PLAIN(64, 8, 8, 32) TF2_PLAIN(64, 8, 8, 16) TF2_PLAIN(128, 16, 8, 16) TF2_PLAIN(256, 16, 16, 8)
-	TF2_MIRR(32, 4, 8, 32) TF2_MIRR(32, 4, 8, 16) TF2_MIRR(64, 8, 8, 16) TF2_MIRR(64, 8, 8, 8) TF2_MIRR(128, 16, 8, 8)
+	TF2_MIRR(32, 4, 8, 32, 2) TF2_MIRR(32, 4, 8, 16, 2) TF2_MIRR(64, 8, 8, 16, 2) TF2_MIRR(64, 8, 8, 8, 2) TF2_MIRR(128, 16, 8, 8, 2)
+	TF2_MIRR(64, 8, 8, 32, 1) TF2_MIRR(128, 16, 8, 16, 1) TF2_MIRR(32, 4, 8, 64, 1)
 	#undef TF2_PLAIN
 	#undef TF2_MIRR
 	return -1;
@@ -718,7 +785,9 @@ static int tf_rows(TfPlan *p, const char *src, int64_t ps, char *dst, int64_t pd
 // columns per region of a mirrored tile (two regions per tile) over a half range of `half` columns
 static int tf_width_m(int n, int half)
 {
-	int w = pow2_floor(std::max(8, tf_tile_elems()/(2*n)));
+	static const int big = getenv("B2_TFFT_MTILE") ? atoi(getenv("B2_TFFT_MTILE")) : 4096;      // elements of a mirrored tile
+	const bool spec = n == 32 || n == 64 || n == 128;            // lengths with a single-team instance of the specialised kernel
+	int w = pow2_floor(std::max(8, (spec ? big : tf_tile_elems())/(2*n)));
 	w = std::min(w, 64);
 	while (w > 8 && half % w) w /= 2;
 	return w;
@@ -726,50 +795,58 @@ static int tf_width_m(int n, int half)
 
 // transform along y of [nb][ny][ncols] complex arrays (pitches in bytes).  mode 0: plain; 1: r2c untangle fused into the
 // load of sub-pass 1 (src holds Nc columns, work and dst Nc + 1); 2: c2r tangle fused into the store of sub-pass 2 (src and
-// work hold Nc + 1 columns, dst Nc).  In modes 1 and 2 both sub-passes walk the mirrored column blocks, so that a slab
-// is the same set of columns in both.
+// work hold Nc + 1 columns, dst Nc).  The fused step needs tiles of mirrored column blocks; with slabs (the intermediate
+// array kept in L2 between the two sub-passes) both sub-passes walk the mirrored blocks so that a slab is the same set
+// of columns in both, without slabs the other sub-pass uses plain tiles of twice the width.
 static int tf_cols(TfPlan *p, const char *src, int64_t ps, int64_t bs_s, char *dst, int64_t pd, int64_t bs_d, char *work, int64_t pw,
 	int ncols_src, int ncols_mid, int ncols_dst, int mode, int inv, double scale, cudaStream_t st)
 {
 	const TfAxis &Y = p->ay;
 	const int N1 = Y.N1, N2 = Y.N2, ny = Y.N, Nc = p->Nc;
 	const int64_t bs_w = (int64_t)ny*pw;
-	const bool mir = mode != 0;
-	const int ext = mir ? Nc/2 : std::max(ncols_src, ncols_dst);      // the range the column-block index runs over
-	const int w1 = mir ? tf_width_m(N1, ext) : tf_width(N1, ext), w2 = mir ? tf_width_m(N2, ext) : tf_width(N2, ext);
-	const int ncb1 = (ext + w1 - 1)/w1, ncb2 = (ext + w2 - 1)/w2, wmax = std::max(w1, w2);
-	int64_t slab_cols = std::max<int64_t>(wmax, (int64_t)(tf_slab_bytes()/((size_t)ny*16*(mir ? 2 : 1))));
-	slab_cols = slab_cols/wmax*wmax;
-	for (int64_t b = 0; b < p->nb; b++) {
-		for (int64_t c0 = 0; c0 < ext; c0 += slab_cols) {
-			const int64_t c1 = std::min<int64_t>(ext, c0 + slab_cols);
+	const int next = std::max(ncols_src, ncols_dst);
+	const bool slabbed = tf_slab_bytes() < (size_t)ny*16*next;
+	const bool mir1 = mode == 1 || (slabbed && mode != 0), mir2 = mode == 2 || (slabbed && mode != 0);
+	const int ext1 = mir1 ? Nc/2 : next, ext2 = mir2 ? Nc/2 : next;      // the range the column-block index runs over
+	const int w1 = mir1 ? tf_width_m(N1, ext1) : tf_width(N1, ext1), w2 = mir2 ? tf_width_m(N2, ext2) : tf_width(N2, ext2);
+	const int ncb1 = (ext1 + w1 - 1)/w1, ncb2 = (ext2 + w2 - 1)/w2, wmax = std::max(w1, w2);
+	int64_t slab_cols = std::max(ext1, ext2);
+	if (slabbed) {
+		slab_cols = std::max<int64_t>(wmax, (int64_t)(tf_slab_bytes()/((size_t)ny*16*(mode != 0 ? 2 : 1))));
+		slab_cols = slab_cols/wmax*wmax;
+	}
+	// without slabs one launch per sub-pass covers every batch member
+	const int64_t bstep = slabbed ? 1 : p->nb;
+	for (int64_t b = 0; b < p->nb; b += bstep) {
+		for (int64_t c0 = 0; c0 < std::max(ext1, ext2); c0 += slab_cols) {
+			const int64_t c1 = c0 + slab_cols;
 			TfMaps M; TfArgs A;
 			// ---- sub-pass 1: rows j1 (stride N2 rows) of a column block, fixed j2 -> work rows j2 N1 + k1, times w^(k1 j2)
 			tf_args_init(A, inv);
-			A.W = w1; A.ncb = ncb1; A.G2 = N2; A.G3 = 1; A.g3_0 = (int)b; A.tw_mode = 2;
-			A.cb0 = (int)(c0/w1); A.ncb_l = (int)((c1 + w1 - 1)/w1) - A.cb0;
-			if (mir) { A.nreg = 2; A.mirror = Nc; A.midcol = Nc/2; A.op = mode == 1 ? 1 : 0; }
+			A.W = w1; A.ncb = ncb1; A.G2 = N2; A.G3 = (int)bstep; A.g3_0 = (int)b; A.tw_mode = 2;
+			A.cb0 = (int)(c0/w1); A.ncb_l = (int)((std::min<int64_t>(c1, ext1) + w1 - 1)/w1) - A.cb0;
+			if (mir1) { A.nreg = 2; A.mirror = Nc; A.midcol = Nc/2; A.op = mode == 1 ? 1 : 0; }
 			TF_MAP(M.ld[0], src, 2*(int64_t)ncols_src, N1, N2, p->nb, (int64_t)N2*ps, ps, bs_s, 2*w1, N1);
 			TF_MAP(M.st[0], work, 2*(int64_t)ncols_mid, N1, N2, p->nb, pw, (int64_t)N1*pw, bs_w, 2*w1, N1);
 			M.ld[1] = M.ld[0]; M.st[1] = M.st[0]; M.ld[2] = M.ld[0]; M.st[2] = M.st[0];
-			if (mir) {
+			if (mir1) {
 				TF_MAP(M.ld[2], src, 2*(int64_t)ncols_src, N1, N2, p->nb, (int64_t)N2*ps, ps, bs_s, 2, N1);
 				TF_MAP(M.st[2], work, 2*(int64_t)ncols_mid, N1, N2, p->nb, pw, (int64_t)N1*pw, bs_w, 2, N1);
 			}
-			if (tf_launch(M, A, Y.L1, &Y.tw, mode == 1 ? &p->twR : nullptr, p->nsm, st)) return 1;
+			if (A.ncb_l > 0 && tf_launch(M, A, Y.L1, &Y.tw, mode == 1 ? &p->twR : nullptr, p->nsm, st)) return 1;
 			// ---- sub-pass 2: work rows j2 (stride N1 rows), fixed k1 -> dst rows k1 + N1 k2
 			tf_args_init(A, inv);
-			A.W = w2; A.ncb = ncb2; A.G2 = N1; A.G3 = 1; A.g3_0 = (int)b; A.scale = scale;
-			A.cb0 = (int)(c0/w2); A.ncb_l = (int)((c1 + w2 - 1)/w2) - A.cb0;
-			if (mir) { A.nreg = 2; A.mirror = Nc; A.midcol = Nc/2; A.op = mode == 2 ? 2 : 0; }
+			A.W = w2; A.ncb = ncb2; A.G2 = N1; A.G3 = (int)bstep; A.g3_0 = (int)b; A.scale = scale;
+			A.cb0 = (int)(c0/w2); A.ncb_l = (int)((std::min<int64_t>(c1, ext2) + w2 - 1)/w2) - A.cb0;
+			if (mir2) { A.nreg = 2; A.mirror = Nc; A.midcol = Nc/2; A.op = mode == 2 ? 2 : 0; }
 			TF_MAP(M.ld[0], work, 2*(int64_t)ncols_mid, N2, N1, p->nb, (int64_t)N1*pw, pw, bs_w, 2*w2, N2);
 			TF_MAP(M.st[0], dst, 2*(int64_t)ncols_dst, N2, N1, p->nb, (int64_t)N1*pd, pd, bs_d, 2*w2, N2);
 			M.ld[1] = M.ld[0]; M.st[1] = M.st[0]; M.ld[2] = M.ld[0]; M.st[2] = M.st[0];
-			if (mir) {
+			if (mir2) {
 				TF_MAP(M.ld[2], work, 2*(int64_t)ncols_mid, N2, N1, p->nb, (int64_t)N1*pw, pw, bs_w, 2, N2);
 				TF_MAP(M.st[2], dst, 2*(int64_t)ncols_dst, N2, N1, p->nb, (int64_t)N1*pd, pd, bs_d, 2, N2);
 			}
-			if (tf_launch(M, A, Y.L2, nullptr, mode == 2 ? &p->twR : nullptr, p->nsm, st)) return 1;
+			if (A.ncb_l > 0 && tf_launch(M, A, Y.L2, nullptr, mode == 2 ? &p->twR : nullptr, p->nsm, st)) return 1;
 		}
 	}
 	return 0;
@@ -781,36 +858,38 @@ int tfft_execute(TfPlan *p, const void *in, void *out, int forward, double scale
 	const int inv = forward ? 0 : 1;
 	const int64_t ny = p->ny, nb = p->nb; const int Nc = p->Nc;
 	const int64_t nlines = nb*ny;
-	const size_t wbytes = (size_t)nlines*(Nc + 1)*16;
+	// intermediate arrays are ours: their rows start on 128-byte boundaries whatever the caller's pitches are
+	const int64_t pwe = b2_round_up(Nc + 1, 8), pw = pwe*16;
+	const size_t wbytes = (size_t)nlines*pwe*16;
 	if (p->work.n < wbytes && p->work.alloc(wbytes)) return 1;
-	const int64_t pw = (int64_t)(Nc + 1)*16;
 	if (p->kind == B2_FFT_C2C) {
 		const int64_t ps = p->in_pitch*16, pd = p->out_pitch*16;
 		const bool lines_in = nb == 1 || p->in_bstride == ny*p->in_pitch, lines_out = nb == 1 || p->out_bstride == ny*p->out_pitch;
 		if (lines_in && lines_out) { if (tf_rows(p, (const char*)in, ps, (char*)out, pd, nlines, inv, 1.0, st)) return 1; }
 		else for (int64_t b = 0; b < nb; b++)
 			if (tf_rows(p, (const char*)in + b*p->in_bstride*16, ps, (char*)out + b*p->out_bstride*16, pd, ny, inv, 1.0, st)) return 1;
-		return tf_cols(p, (const char*)out, pd, p->out_bstride*16, (char*)out, pd, p->out_bstride*16, p->work.p, (int64_t)Nc*16,
+		return tf_cols(p, (const char*)out, pd, p->out_bstride*16, (char*)out, pd, p->out_bstride*16, p->work.p, pw,
 			Nc, Nc, Nc, 0, inv, scale, st);
 	}
+	if (p->work2.n < wbytes && p->work2.alloc(wbytes)) return 1;
 	if (p->kind == B2_FFT_R2C) {
-		const int64_t ps = p->in_pitch*8, pd = p->out_pitch*16;
-		const bool lines_in = nb == 1 || p->in_bstride == ny*p->in_pitch, lines_out = nb == 1 || p->out_bstride == ny*p->out_pitch;
-		if (lines_in && lines_out) { if (tf_rows(p, (const char*)in, ps, (char*)out, pd, nlines, 0, 1.0, st)) return 1; }
+		// rows: in -> (work) -> work2 [line][Nc of pwe]; columns with the untangling: work2 -> work -> out
+		const int64_t ps = p->in_pitch*8;
+		const bool lines_in = nb == 1 || p->in_bstride == ny*p->in_pitch;
+		// the untangling step of the column pass produces 2 X: the factor 1/2 rides on the row pass
+		if (lines_in) { if (tf_rows(p, (const char*)in, ps, p->work2.p, pw, nlines, 0, 0.5, st)) return 1; }
 		else for (int64_t b = 0; b < nb; b++)
-			if (tf_rows(p, (const char*)in + b*p->in_bstride*8, ps, (char*)out + b*p->out_bstride*16, pd, ny, 0, 1.0, st)) return 1;
-		return tf_cols(p, (const char*)out, pd, p->out_bstride*16, (char*)out, pd, p->out_bstride*16, p->work.p, pw,
+			if (tf_rows(p, (const char*)in + b*p->in_bstride*8, ps, p->work2.p + b*ny*pw, pw, ny, 0, 0.5, st)) return 1;
+		return tf_cols(p, p->work2.p, pw, ny*pw, (char*)out, p->out_pitch*16, p->out_bstride*16, p->work.p, pw,
 			Nc, Nc + 1, Nc + 1, 1, 0, scale, st);
 	}
-	// c2r: columns first (on the half spectrum), tangle into the packed spectrum, then the rows
-	const size_t w2bytes = (size_t)nlines*Nc*16;
-	if (p->work2.n < w2bytes && p->work2.alloc(w2bytes)) return 1;
-	if (tf_cols(p, (const char*)in, p->in_pitch*16, p->in_bstride*16, p->work2.p, (int64_t)Nc*16, (int64_t)ny*Nc*16, p->work.p, pw,
+	// c2r: columns first (on the half spectrum), tangle into the packed spectrum work2 [line][Nc of pwe], then the rows
+	if (tf_cols(p, (const char*)in, p->in_pitch*16, p->in_bstride*16, p->work2.p, pw, ny*pw, p->work.p, pw,
 		Nc + 1, Nc + 1, Nc, 2, 1, 1.0, st)) return 1;
 	const int64_t pd = p->out_pitch*8;
 	const bool lines_out = nb == 1 || p->out_bstride == ny*p->out_pitch;
-	if (lines_out) return tf_rows(p, p->work2.p, (int64_t)Nc*16, (char*)out, pd, nlines, 1, scale, st);
+	if (lines_out) return tf_rows(p, p->work2.p, pw, (char*)out, pd, nlines, 1, scale, st);
 	for (int64_t b = 0; b < nb; b++)
-		if (tf_rows(p, p->work2.p + b*ny*Nc*16, (int64_t)Nc*16, (char*)out + b*p->out_bstride*8, pd, ny, 1, scale, st)) return 1;
+		if (tf_rows(p, p->work2.p + b*ny*pw, pw, (char*)out + b*p->out_bstride*8, pd, ny, 1, scale, st)) return 1;
 	return 0;
 }
