@@ -145,6 +145,15 @@ int b2_transfer_alm(int lmax1, int mmax1, const int64_t *mstart1, int64_t lstrid
                     int lmax2, int mmax2, const int64_t *mstart2, int64_t lstride2, void *alm2,
                     int dtype, int mem, void *stream);
 
+/* b2_rand_alm: curvedsky.rand_alm (pixell/curvedsky.py:61-77) on the device: white unit normals in the reference's fill
+ * order (rand_alm_white / fill_gauss, :602-628: memory order of the l-major array, component after component) from a
+ * counter-based Philox4x32-10 stream keyed by `seed`, coloured with ps12[r][c][l]/sqrt(2) (ps12 = multi_pow(ps, 0.5),
+ * [ncomp][ncomp][lmax+1]; NULL: white alm as rand_alm_white returns them), m = 0 made real with the sqrt(2) restored.
+ * Component r of the result starts at alm + r*alm_cstride (complex elements).  The numbers differ from numpy's MT19937
+ * stream (which pixell_b200.curvedsky.rand_alm reproduces on the host); the statistics and the fill order are the same. */
+int b2_rand_alm(int lmax, int mmax, const int64_t *mstart, int ncomp, uint64_t seed, const double *ps12,
+                int dtype, void *alm, int64_t alm_cstride, int mem, void *stream);
+
 /* ---- FFT engine: replaces the engines[...] .FFTW plan objects of pixell/fft.py:8-113 -------------
  * Batched multi-dimensional DFT over up to 2 axes of a strided array (what enmap.fft / fft.rfft /
  * fft.irfft need, pixell/fft.py:133-209, enmap.py:1307-1337).

@@ -146,3 +146,46 @@ def ref_cmisc():
 		if not os.path.exists(path): return None
 		_ref = ctypes.CDLL(path)
 	return _ref
+
+# ------------------------------------------------------------------ device random stream (b2_rand_alm), restated in numpy
+
+def philox4x32_10(counter, seed):
+	"""Philox4x32-10 (Salmon et al. 2011): counter = (lo32, hi32, 0, 0) of the uint64 array `counter`, key = the two halves
+	of `seed`; returns the four output words as uint32 arrays"""
+	c = np.asarray(counter, dtype=np.uint64)
+	M32 = np.uint64(0xffffffff)
+	c0 = c & M32; c1 = c >> np.uint64(32); c2 = np.zeros_like(c0); c3 = np.zeros_like(c0)
+	k0 = np.uint64(int(seed) & 0xffffffff); k1 = np.uint64((int(seed) >> 32) & 0xffffffff)
+	for r in range(10):
+		p0 = np.uint64(0xD2511F53)*c0; p1 = np.uint64(0xCD9E8D57)*c2
+		hi0, lo0 = p0 >> np.uint64(32), p0 & M32
+		hi1, lo1 = p1 >> np.uint64(32), p1 & M32
+		c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+		k0 = (k0 + np.uint64(0x9E3779B9)) & M32; k1 = (k1 + np.uint64(0xBB67AE85)) & M32
+	return c0, c1, c2, c3
+
+def philox_normal_pairs(counter, seed):
+	"""Box-Muller on two 53-bit uniforms per counter: complex array re + i im of unit normals"""
+	x0, x1, x2, x3 = philox4x32_10(counter, seed)
+	a = (x1 << np.uint64(32)) | x0; b = (x3 << np.uint64(32)) | x2
+	u1 = ((a >> np.uint64(11)).astype(np.float64) + 0.5)*2.0**-53
+	u2 = ((b >> np.uint64(11)).astype(np.float64) + 0.5)*2.0**-53
+	r = np.sqrt(-2.0*np.log(u1))
+	return r*np.cos(2*np.pi*u2) + 1j*r*np.sin(2*np.pi*u2)
+
+def rand_alm_philox(ainfo, ncomp, seed, ps12=None):
+	"""What b2_rand_alm computes: white pairs in the reference's fill order (pixell/curvedsky.py:602-628: memory order of the
+	l-major array, component after component), coloured with ps12/sqrt(2), m = 0 real with the sqrt(2) restored (:61-77)"""
+	lmax, mmax = ainfo.lmax, ainfo.mmax
+	nlm = sum(lmax-m+1 for m in range(mmax+1))
+	alm = np.zeros((ncomp, ainfo.nelem), np.complex128)
+	for m in range(mmax+1):
+		l = np.arange(m, lmax+1, dtype=np.int64)
+		j = np.where(l <= mmax, l*(l+1)//2+m, (mmax+1)*(mmax+2)//2 + (l-mmax-1)*(mmax+1) + m)
+		w = np.array([philox_normal_pairs((c*nlm+j).astype(np.uint64), seed) for c in range(ncomp)])
+		if ps12 is not None:
+			v = np.einsum("rcl,cl->rl", np.asarray(ps12)[:, :, l]/2**0.5, w)
+			if m == 0: v = v.real*2**0.5 + 0j
+		else: v = w
+		alm[:, ainfo.mstart[m]+l*ainfo.stride] = v
+	return alm

@@ -181,6 +181,32 @@ def map2leg(map, nm, phi0, workers=-1):
 		F = sfft.fft(map, axis=-1, workers=workers)[..., m % nphi]
 	return F*np.exp(-1j*m[None,:]*phi0[:,None])[None]
 
+def _nworkers():
+	return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+def map2leg_t(map, nm, phi0):
+	"""map2leg with the result in the Legendre stage's layout [ncomp, nm, nring], blocks of rings spread over a thread
+	pool (the FFT, the phase factors and the transposition all run in parallel) -- bench.py's CPU arm"""
+	import concurrent.futures
+	ncomp, nring, nphi = map.shape
+	out = np.empty((ncomp, nm, nring), np.complex128)
+	w = _nworkers(); step = max(1, min(128, (nring+w-1)//w))
+	def work(r0):
+		out[:, :, r0:r0+step] = map2leg(map[:, r0:r0+step], nm, phi0, workers=1).transpose(0, 2, 1)
+	with concurrent.futures.ThreadPoolExecutor(max_workers=w) as ex: list(ex.map(work, range(0, nring, step)))
+	return out
+
+def leg2map_t(leg, nphi, phi0):
+	"""leg2map from the layout [ncomp, nm, nring], blocks of rings spread over a thread pool"""
+	import concurrent.futures
+	ncomp, nm, nring = leg.shape
+	out = np.empty((ncomp, nring, nphi), np.float64)
+	w = _nworkers(); step = max(1, min(128, (nring+w-1)//w))
+	def work(r0):
+		out[:, r0:r0+step] = leg2map(np.ascontiguousarray(leg[:, :, r0:r0+step].transpose(0, 2, 1)), nphi, phi0, workers=1)
+	with concurrent.futures.ThreadPoolExecutor(max_workers=w) as ex: list(ex.map(work, range(0, nring, step)))
+	return out
+
 # ------------------------------------------------------------------ grids and weights
 
 def grid_theta(name, n):
@@ -296,6 +322,48 @@ def resample_to_cc(leg, name, nt, spin, workers=-1):
 		Cp[:, ki % Np] = C
 	out = sfft.ifft(Cp, axis=1, workers=workers)*Np
 	return out[:, :nt]
+
+def _resample_chunk_t(leg, name, nt, sig, N, o, pos, mir):
+	ncomp, nm, n = leg.shape
+	ext = np.zeros((ncomp, nm, N), np.complex128)
+	ext[:, :, pos[0]:pos[0]+n] = leg
+	ok = mir >= 0
+	ext[:, :, mir[ok]] = leg[:, :, ok]*sig[None, :, None]
+	C = sfft.fft(ext, axis=-1, overwrite_x=True)
+	k = sfft.fftfreq(N, 1.0/N)
+	C *= (np.exp(-1j*k*o*2*np.pi/N)/N)[None, None, :]
+	Np = 2*(nt-1)
+	Cp = np.zeros((ncomp, nm, Np), np.complex128)
+	if N % 2 == 0:
+		h = N//2
+		Cp[:, :, :h] = C[:, :, :h]; Cp[:, :, Np-h+1:] = C[:, :, h+1:]
+		nyq = C[:, :, h]
+		if Np > N: Cp[:, :, h] += 0.5*nyq; Cp[:, :, Np-h] += 0.5*nyq
+		else:      Cp[:, :, h] += nyq
+	else:
+		h = (N+1)//2
+		Cp[:, :, :h] = C[:, :, :h]; Cp[:, :, Np-(N-h):] = C[:, :, h:]
+	out = sfft.ifft(Cp, axis=-1, overwrite_x=True)
+	out *= Np
+	return out[:, :, :nt]
+
+def resample_to_cc_t(leg, name, nt, spin, workers=None):
+	"""resample_to_cc on the transposed layout leg[ncomp, nm, n] -> [ncomp, nm, nt] (theta contiguous: what the Legendre
+	stage of sht_fast.c reads and writes; no strided FFTs, no transposes), blocks of m columns spread over a thread pool
+	(numpy and scipy.fft release the GIL) -- the CPU arm of bench.py uses this form"""
+	import concurrent.futures
+	ncomp, nm, n = leg.shape
+	N, o, pos, mir = _ext_index(name, n)
+	assert name in ("CC", "F1", "MW", "MWflip") and 2*(nt-1) >= N
+	sig = (-1.0)**(np.arange(nm)+spin)
+	if workers is None: workers = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+	out = np.empty((ncomp, nm, nt), np.complex128)
+	step = max(1, min(64, (nm+workers-1)//workers))
+	def work(m0):
+		out[:, m0:m0+step] = _resample_chunk_t(leg[:, m0:m0+step], name, nt, sig[m0:m0+step], N, o, pos, mir)
+	with concurrent.futures.ThreadPoolExecutor(max_workers=workers) as ex:
+		list(ex.map(work, range(0, nm, step)))
+	return out
 
 def resample_to_cc_adjoint(legcc, name, n, spin, workers=-1):
 	"""Hermitian transpose of resample_to_cc: leg on CC(nt) -> leg on `name`(n)."""

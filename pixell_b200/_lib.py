@@ -45,6 +45,7 @@ _PROTOS = {
 	"b2_lmatmul": ([c_int, c_int, c_int, c_int, _i64p, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_int, c_vp], c_int),
 	"b2_transpose_alm": ([c_int, c_int, _i64p, c_int, c_vp, c_vp, c_int, c_vp], c_int),
 	"b2_transfer_alm": ([c_int, c_int, _i64p, c_i64, c_vp, c_int, c_int, _i64p, c_i64, c_vp, c_int, c_int, c_vp], c_int),
+	"b2_rand_alm": ([c_int, c_int, _i64p, c_int, ctypes.c_uint64, c_vp, c_int, c_vp, c_i64, c_int, c_vp], c_int),
 	"b2_fft_plan_create": ([ctypes.POINTER(c_vp), c_int, _i64p, _i64p, _i64p, c_int, _intp, c_int, c_int], c_int),
 	"b2_fft_execute": ([c_vp, c_vp, c_vp, c_int, c_dbl, c_int, c_vp], c_int),
 	"b2_fft_plan_destroy": ([c_vp], None),

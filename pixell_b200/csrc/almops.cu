@@ -143,7 +143,6 @@ struct Staged {       // host <-> device staging of one buffer
 struct MsEntry { int dev; std::vector<int64_t> key; DevBuf<int64_t> buf; };
 static std::mutex g_ms_mutex;
 static std::list<MsEntry> g_ms_cache;
-static DevBuf<double> g_partial;
 
 static int mstart_dev(const int64_t *mstart, int n, const int64_t **out)
 {
@@ -192,8 +191,9 @@ extern "C" int b2_alm2cl(int lmax, int mmax, const int64_t *mstart, int dtype, c
 	if (alm2 == alm1) b.dev = a.dev; else if (b.in(alm2, span*esz, mem, true, false, st)) return 1;
 	if (c.in(cl, (lmax + 1)*csz, mem, false, true, st)) return 1;
 	int nmb = mmax/MB + 1;
-	DevBuf<double> &partial = g_partial;      // persistent scratch (calls on one device are serialised by the caller's stream use)
-	if (partial.n < (size_t)nmb*(lmax + 1) && partial.alloc((size_t)nmb*(lmax + 1))) return 1;
+	// scratch from the stream-ordered pool: per call, per device, safe with concurrent streams / threads
+	struct { double *p; } partial = {nullptr};
+	B2_CHECK(cudaMallocAsync((void**)&partial.p, sizeof(double)*(size_t)nmb*(lmax + 1), st));
 	dim3 grid((lmax + 256)/256, nmb);
 	if (dtype == B2_F64) k_alm2cl_partial<double><<<grid, 256, 0, st>>>(lmax, mmax, msp, (const double2*)a.dev, (const double2*)b.dev, partial.p);
 	else                 k_alm2cl_partial<float><<<grid, 256, 0, st>>>(lmax, mmax, msp, (const float2*)a.dev, (const float2*)b.dev, partial.p);
@@ -201,6 +201,7 @@ extern "C" int b2_alm2cl(int lmax, int mmax, const int64_t *mstart, int dtype, c
 	if (cl_dtype == B2_F64) k_alm2cl_final<double><<<(lmax + 256)/256, 256, 0, st>>>(lmax, nmb, partial.p, (double*)c.dev);
 	else                    k_alm2cl_final<float><<<(lmax + 256)/256, 256, 0, st>>>(lmax, nmb, partial.p, (float*)c.dev);
 	B2_LAUNCH_CHECK();
+	B2_CHECK(cudaFreeAsync(partial.p, st));
 	if (c.finish(st)) return 1;
 	if (mem == 0) B2_CHECK(cudaStreamSynchronize(st));      // staging buffers die here
 	return 0;
@@ -297,6 +298,87 @@ extern "C" int b2_transfer_alm(int lmax1, int mmax1, const int64_t *mstart1, int
 	else                 k_transfer_alm<float2><<<grid, 256, 0, st>>>(lmax, mmax, m1p, ls1, (const float2*)a.dev, m2p, ls2, (float2*)o.dev);
 	B2_LAUNCH_CHECK();
 	if (o.finish(st)) return 1;
+	if (mem == 0) B2_CHECK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------ K8: random alm on the device
+// curvedsky.rand_alm (pixell/curvedsky.py:61-77) = rand_alm_white (:620-628: unit normals filled in memory order of the
+// l-major array, fill_gauss :602-606, then transposed to m-major) + colouring with ps^(1/2)/sqrt(2) (:70-72, lmul) + the
+// m = 0 fix (:73-74), fused: one thread per (l, m) draws the white pairs of every component, mixes them and writes the
+// m-major element.  The stream is counter based (Philox4x32-10, key = seed): the pair of element j of the l-major array of
+// component c, j = l (l + 1)/2 + m (mmax = lmax; rectangular part after the triangle otherwise), comes from counter
+// c nlm + j -- the reference's fill order, so realisations at two lmax share their large scales in component 0, as the
+// reference's do.  Box-Muller on two 53-bit uniforms.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t (&out)[4])
+{
+	#pragma unroll
+	for (int r = 0; r < 10; r++) {
+		const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u*c0;
+		const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u*c2;
+		const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+		c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+		k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+	}
+	out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double2 philox_normal_pair(uint64_t counter, uint64_t seed)
+{
+	uint32_t x[4];
+	philox4x32_10((uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+	const uint64_t a = ((uint64_t)x[1] << 32) | x[0], b = ((uint64_t)x[3] << 32) | x[2];
+	const double u1 = ((double)(a >> 11) + 0.5)*0x1p-53, u2 = ((double)(b >> 11) + 0.5)*0x1p-53;      // (0, 1)
+	const double r = sqrt(-2.0*log(u1));
+	double sn, cs; sincospi(2.0*u2, &sn, &cs);
+	return make_double2(r*cs, r*sn);
+}
+
+#define RA_MAXC 4
+template<typename T> __global__ void k_rand_alm(int lmax, int mmax, const int64_t *mstart, int ncomp, uint64_t seed, int64_t nlm,
+	const double *ps12 /* [ncomp][ncomp][lmax+1] or null: white */, typename cplx_of<T>::type *alm, int64_t cstride)
+{
+	const int m = blockIdx.y;
+	const int l = m + blockIdx.x*blockDim.x + threadIdx.x;
+	if (l > lmax) return;
+	// position in the l-major array (cmisc_core.c:116-156: the triangle l <= mmax first, then rows of mmax + 1)
+	const int64_t j = l <= mmax ? (int64_t)l*(l + 1)/2 + m : (int64_t)(mmax + 1)*(mmax + 2)/2 + (int64_t)(l - mmax - 1)*(mmax + 1) + m;
+	double2 w[RA_MAXC];
+	for (int c = 0; c < ncomp; c++) w[c] = philox_normal_pair((uint64_t)(c*nlm + j), seed);
+	const int64_t i = mstart[m] + l;
+	for (int r = 0; r < ncomp; r++) {
+		double2 v;
+		if (ps12) {
+			v = make_double2(0, 0);
+			for (int c = 0; c < ncomp; c++) { const double f = ps12[((int64_t)r*ncomp + c)*(lmax + 1) + l]*0.70710678118654752440; v.x += f*w[c].x; v.y += f*w[c].y; }
+			if (m == 0) { v.x *= 1.41421356237309504880; v.y = 0; }
+		} else v = w[r];
+		typename cplx_of<T>::type o; o.x = (T)v.x; o.y = (T)v.y;
+		alm[r*cstride + i] = o;
+	}
+}
+
+extern "C" int b2_rand_alm(int lmax, int mmax, const int64_t *mstart, int ncomp, uint64_t seed, const double *ps12,
+	int dtype, void *alm, int64_t alm_cstride, int mem, void *stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (check_mstart(lmax, mmax, mstart)) return 1;
+	B2_REQUIRE(alm && ncomp >= 1 && ncomp <= RA_MAXC, "rand_alm: 1 to %d components are supported", RA_MAXC);
+	B2_REQUIRE(dtype == B2_F64 || dtype == B2_F32, "rand_alm: bad dtype");
+	const size_t esz = dtype == B2_F64 ? 16 : 8;
+	const int64_t span = span_of(lmax, mmax, mstart, 1);
+	B2_REQUIRE(ncomp == 1 || alm_cstride >= span, "rand_alm: component stride shorter than one alm");
+	int64_t nlm = 0; for (int m = 0; m <= mmax; m++) nlm += lmax - m + 1;
+	const int64_t *msp; if (mstart_dev(mstart, mmax + 1, &msp)) return 1;
+	Staged a, f;
+	const size_t abytes = ((size_t)(ncomp - 1)*alm_cstride + span)*esz;
+	if (a.in(alm, abytes, mem, true, true, st)) return 1;      // entries outside the layout keep the caller's values
+	if (ps12 && f.in(ps12, sizeof(double)*(size_t)ncomp*ncomp*(lmax + 1), mem, true, false, st)) return 1;
+	dim3 grid((lmax + 256)/256, mmax + 1);
+	if (dtype == B2_F64) k_rand_alm<double><<<grid, 256, 0, st>>>(lmax, mmax, msp, ncomp, seed, nlm, (const double*)f.dev, (double2*)a.dev, alm_cstride);
+	else                 k_rand_alm<float><<<grid, 256, 0, st>>>(lmax, mmax, msp, ncomp, seed, nlm, (const double*)f.dev, (float2*)a.dev, alm_cstride);
+	B2_LAUNCH_CHECK();
+	if (a.finish(st)) return 1;
 	if (mem == 0) B2_CHECK(cudaStreamSynchronize(st));
 	return 0;
 }

@@ -10,9 +10,9 @@ gathered.  Nothing here is a data-path collective.
 Random streams:
   rng="reference"  numpy's legacy global stream on the host, seeded per realisation, exactly as the reference
                    (curvedsky.rand_alm / rand_alm_healpy): bit-identical alm for a given seed, host-RNG bound.
-  rng="device"     torch's Philox generator on the GPU, seeded per realisation: same statistics, different
-                   numbers; colouring (symmetric square root of C_l, lmatmul kernel) and the m = 0 fix-up
-                   follow curvedsky.rand_alm :61-77.
+  rng="device"     the engine's own kernel (b2_rand_alm): counter-based Philox4x32-10 normals in the reference's fill
+                   order, coloured with the symmetric square root of C_l and fixed at m = 0 in the same kernel
+                   (curvedsky.rand_alm :61-77, rand_alm_white :620-628): same statistics, different numbers.
 """
 import numpy as np
 from . import _lib as L, curvedsky, geometry
@@ -77,17 +77,21 @@ def _wps(ps, ncomp, lmax):
 	return ps[..., :lmax+1]
 
 def rand_alm_device(ps12, ainfo, seed, device, dtype=None):
-	"""Coloured Gaussian alm on the GPU: white alm from torch's generator, alm <- ps^(1/2)/sqrt(2) alm (lmatmul
-	kernel), m = 0 made real with the sqrt(2) restored (curvedsky.rand_alm :61-77, device stream)."""
-	import torch
-	ncomp = ps12.shape[0]
-	g = torch.Generator(device=device); g.manual_seed(int(seed))
-	alm = torch.randn((ncomp, ainfo.nelem), dtype=torch.complex128 if dtype is None else dtype, device=device, generator=g)
-	# torch's complex normal has unit total variance; the reference fills re and im with unit variance each
-	alm *= 2**0.5
-	out = ainfo.lmul(alm, ps12/2**0.5)
-	m0 = out[:, :ainfo.lmax+1]
-	out[:, :ainfo.lmax+1] = (m0.real*2**0.5).to(out.dtype)
+	"""Coloured Gaussian alm on the GPU in one kernel launch (b2_rand_alm): Philox normals in the reference's fill order,
+	alm <- ps^(1/2)/sqrt(2) alm, m = 0 made real with the sqrt(2) restored (curvedsky.rand_alm :61-77).
+	ps12: [ncomp, ncomp, lmax+1] float64 torch CUDA tensor (or None for white alm)."""
+	import torch, ctypes
+	ncomp = 1 if ps12 is None else ps12.shape[0]
+	dt = torch.complex128 if dtype is None else dtype
+	out = torch.zeros((ncomp, ainfo.nelem), dtype=dt, device=device)
+	ms = L.as_i64(ainfo.mstart)
+	if ainfo.stride != 1: raise NotImplementedError("rand_alm_device needs a unit-stride alm layout")
+	if ps12 is not None:
+		ps12 = ps12.contiguous()
+		if ps12.shape[-1] != ainfo.lmax+1 or ps12.dtype != torch.float64: raise ValueError("ps12 must be float64 [ncomp, ncomp, lmax+1]")
+	L.check(L.lib().b2_rand_alm(ainfo.lmax, ainfo.mmax, L.p_i64(ms), ncomp, ctypes.c_uint64(int(seed) & (2**64-1)),
+		None if ps12 is None else ps12.data_ptr(), L.F64 if dt == torch.complex128 else L.F32, out.data_ptr(), out.stride(0),
+		L.MEM_DEVICE, L.current_stream(out)))
 	return out
 
 def rand_maps(shape, wcs, ps, seeds, lmax=None, spin=[0, 2], rng="reference", device=None, out=None, return_alm=False):

@@ -45,3 +45,42 @@ def test_device_stream_covariance():
 	a = mc.rand_alm_device(ps12, ainfo, 5, torch.device("cuda")); b = mc.rand_alm_device(ps12, ainfo, 5, torch.device("cuda"))
 	c = mc.rand_alm_device(ps12, ainfo, 6, torch.device("cuda"))
 	assert torch.equal(a, b) and not torch.equal(a, c)
+
+@pytest.mark.parametrize("lmax,mmax,ncomp", [(50, 50, 3), (40, 25, 2), (7, 7, 1)])
+def test_rand_alm_kernel_matches_the_numpy_restatement(lmax, mmax, ncomp):
+	"""b2_rand_alm against oracle/alm_oracle.rand_alm_philox: Philox4x32-10 counters in the reference's fill order
+	(pixell/curvedsky.py:602-628), Box-Muller, colouring and m = 0 fix (:61-77); white and coloured, host and device memory"""
+	import torch, ctypes
+	from pixell_b200 import _lib as L
+	from oracle import alm_oracle as ao
+	L.init()
+	ai = ao.AlmInfo(lmax, mmax)
+	rng = np.random.default_rng(3)
+	A = rng.standard_normal((ncomp, ncomp, lmax+1)); ps12 = np.einsum("acl,bcl->abl", A, A)      # any symmetric matrix per l
+	ms = L.as_i64(ai.mstart)
+	for p12 in (None, ps12):
+		want = ao.rand_alm_philox(ai, ncomp, 12345678901234, p12)
+		got = np.full((ncomp, ai.nelem), 7+7j)
+		L.check(L.lib().b2_rand_alm(lmax, mmax, L.p_i64(ms), ncomp, ctypes.c_uint64(12345678901234), None if p12 is None else p12.ctypes.data,
+			L.F64, got.ctypes.data, ai.nelem, L.MEM_HOST, None))
+		assert np.abs(got-want).max() <= 1e-13*np.abs(want).max()
+		t = torch.zeros((ncomp, ai.nelem), dtype=torch.complex128, device="cuda")
+		tp = None if p12 is None else torch.as_tensor(p12, device="cuda")
+		L.check(L.lib().b2_rand_alm(lmax, mmax, L.p_i64(ms), ncomp, ctypes.c_uint64(12345678901234), None if tp is None else tp.data_ptr(),
+			L.F64, t.data_ptr(), ai.nelem, L.MEM_DEVICE, None))
+		assert np.array_equal(t.cpu().numpy(), got)
+
+def test_rand_alm_kernel_shares_large_scales_between_lmax():
+	"""the property the reference's l-major fill order exists for (pixell/curvedsky.py:62-66): realisations at two lmax agree
+	on the common multipoles (first component; later components start after a longer block, as in the reference)"""
+	import torch
+	from pixell_b200 import mc, curvedsky
+	lo, hi = curvedsky.alm_info(30), curvedsky.alm_info(60)
+	a = mc.rand_alm_device(None, lo, 9, torch.device("cuda")).cpu().numpy()[0]
+	b = mc.rand_alm_device(None, hi, 9, torch.device("cuda")).cpu().numpy()[0]
+	for m in range(31):
+		l = np.arange(m, 31)
+		assert np.array_equal(a[lo.mstart[m]+l], b[hi.mstart[m]+l])
+	# unit normals: mean 0, variance 1 per real and imaginary part
+	big = mc.rand_alm_device(None, curvedsky.alm_info(400), 10, torch.device("cuda")).cpu().numpy()[0]
+	assert abs(big.real.mean()) < 0.02 and abs(big.real.var()-1) < 0.03 and abs(big.imag.var()-1) < 0.03

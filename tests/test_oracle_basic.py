@@ -147,3 +147,31 @@ def test_transpose_alm_vs_reference_c():
 	lib.transpose_alm_dp(ctypes.c_int(lmax), ctypes.c_int(lmax), ai.mstart.ctypes.data_as(ip),
 		a[0].view(np.float64).ctypes.data_as(dp), out.view(np.float64).ctypes.data_as(dp))
 	assert np.array_equal(out, ao.transpose_alm(ai, a[0]))
+
+def test_philox_known_answer():
+	"""Philox4x32-10 of the numpy restatement against the published known-answer vector (Random123 kat_vectors:
+	counter 0, key 0); the device kernel b2_rand_alm is checked against this restatement on the GPU"""
+	x = ao.philox4x32_10(np.array([0], np.uint64), 0)
+	assert [int(v[0]) for v in x] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+	z = ao.philox_normal_pairs(np.arange(200000, dtype=np.uint64), 42)
+	assert abs(z.real.mean()) < 0.01 and abs(z.real.var()-1) < 0.02 and abs(z.imag.var()-1) < 0.02 and abs(np.mean(z.real*z.imag)) < 0.01
+
+@pytest.mark.parametrize("geom,ny,lmax,spin", [("F1", 64, 60, 0), ("CC", 65, 63, 2), ("MW", 181, 150, 1), ("F1", 1024, 1000, 2), ("CC", 1026, 1024, 0)])
+def test_tuned_cpu_legendre_matches_the_checker(geom, ny, lmax, spin):
+	"""oracle/sht_fast.c (the CPU arm of bench.py: SIMD over ring blocks, ring skipping, scaled prologue) against
+	oracle/sht_oracle.c (the checker the CUDA kernels are pinned to), on a subset of m"""
+	theta = so.grid_theta(geom, ny)
+	mstart = so.default_mstart(lmax, lmax); nalm = (lmax+1)*(lmax+2)//2
+	rng = np.random.default_rng(1)
+	nc = 1 if spin == 0 else 2
+	ms = np.unique(np.concatenate([np.arange(0, lmax+1, max(1, lmax//7)), [lmax]])).astype(np.int32)
+	alm = rng.standard_normal((nc, nalm)) + 1j*rng.standard_normal((nc, nalm))
+	want = so.alm2leg(alm, theta, spin, lmax, lmax, mstart)[:, :, ms].transpose(0, 2, 1)
+	got = so.fast_alm2leg(alm, theta, spin, lmax, lmax, mstart, ms)
+	assert np.abs(got-want).max() < 1e-12*np.abs(want).max()
+	leg = rng.standard_normal((nc, len(ms), ny)) + 1j*rng.standard_normal((nc, len(ms), ny))
+	full = np.zeros((nc, ny, lmax+1), complex); full[:, :, ms] = leg.transpose(0, 2, 1)
+	want = so.leg2alm(full, theta, spin, lmax, lmax, mstart, nalm)
+	got = so.fast_leg2alm(leg, theta, spin, lmax, lmax, mstart, nalm, ms)
+	idx = np.concatenate([mstart[m] + np.arange(max(m, spin), lmax+1) for m in ms])
+	assert np.abs(got[:, idx]-want[:, idx]).max() < 1e-12*np.abs(want).max()
