@@ -65,6 +65,15 @@ def alm2cl(ainfo, alm, alm2=None, cl_dtype=None):
 		cache[key] = I
 	return cl
 
+def _check_out(out, alm, shape, what):
+	"""a caller-supplied output must have alm's dtype (the kernel and the staging sizes follow alm), the right shape and a
+	contiguous last axis (cmisc.pyx:168-175 raises ValueError for these)"""
+	if L.is_torch(out) != L.is_torch(alm): raise ValueError("%s: out and alm must both be numpy arrays or both be tensors" % what)
+	if out.dtype != alm.dtype: raise ValueError("%s's out argument must have the same dtype as alm (%s), got %s" % (what, alm.dtype, out.dtype))
+	if tuple(out.shape) != tuple(shape): raise ValueError("%s's out argument must have shape %s, got %s" % (what, tuple(shape), tuple(out.shape)))
+	last = out.stride(-1) == 1 if L.is_torch(out) else out.strides[-1] == out.itemsize
+	if out.shape[-1] > 1 and not last: raise ValueError("%s's out argument must be contiguous along last axis" % what)
+
 def lmul(ainfo, alm, lfun, out=None):
 	"""cmisc.pyx:159-191: alm[..., lm] * lfun[..., l], or the matrix product lfun[r,c,l] alm[c,lm]
 	when lfun is 3-d and alm 2-d.  Returns out (allocated if None)."""
@@ -89,6 +98,7 @@ def lmul(ainfo, alm, lfun, out=None):
 		N, M = lfun.shape[:2]
 		if M != alm.shape[0]: raise ValueError("lmul: matrix and alm component counts differ")
 		if out is None: out = xp.zeros((N,)+tuple(alm.shape[1:]), dtype=alm.dtype, device=alm.device) if tor else np.zeros((N,)+alm.shape[1:], alm.dtype)
+		else: _check_out(out, alm, (N,)+tuple(alm.shape[1:]), "lmul")
 		lf = lfun.contiguous() if tor else np.ascontiguousarray(lfun)
 		pa, mem, _ = L.buffer_info(alm); po = L.buffer_info(out)[0]; pf = L.buffer_info(lf)[0]
 		acs = L.strides_elems(alm)[0] if M > 1 else alm.shape[-1]
@@ -98,6 +108,7 @@ def lmul(ainfo, alm, lfun, out=None):
 	try: pre = np.broadcast_shapes(tuple(alm.shape[:-1]), tuple(lfun.shape[:-1]))
 	except ValueError:
 		raise ValueError("lmul's alm and lfun's dimensions must either broadcast (when ignoring the last dimension), or have shape compatible with a matrix product (again ignoring the last dimension)")
+	if out is not None: _check_out(out, alm, tuple(pre)+(alm.shape[-1],), "lmul")
 	if tor:
 		ab = alm.expand(pre+(alm.shape[-1],)); lb = lfun.expand(pre+(lfun.shape[-1],))
 		if out is None: out = ab.clone()
@@ -142,11 +153,15 @@ def transfer_alm(iainfo, ialm, oainfo, oalm=None, op=None):
 	ims, oms = _mstart(iainfo), _mstart(oainfo)
 	for I in _rows(ialm):
 		src = _contig_last(ialm[I]); dst = oalm[I]
-		if op is None: work = dst
+		dcontig = (dst.stride(-1) == 1) if L.is_torch(dst) else (dst.strides[-1] == dst.itemsize)
+		if dst.dtype != src.dtype: raise ValueError("transfer_alm: ialm and oalm must have the same dtype")
+		if op is None and dcontig: work = dst
+		elif op is None: work = dst.clone() if L.is_torch(dst) else dst.copy()      # strided destination: staged through a contiguous copy
 		else: work = xp.zeros_like(dst)
 		pi, mem, _ = L.buffer_info(src); po = L.buffer_info(work)[0]
 		L.check(L.lib().b2_transfer_alm(iainfo.lmax, iainfo.mmax, L.p_i64(ims), iainfo.stride, pi,
 			oainfo.lmax, oainfo.mmax, L.p_i64(oms), oainfo.stride, po, dt, mem, L.current_stream(src)))
+		if op is None and not dcontig: oalm[I] = work
 		if op is not None:
 			# apply op on the transferred entries only
 			lmax, mmax = min(iainfo.lmax, oainfo.lmax), min(iainfo.mmax, oainfo.mmax)

@@ -250,8 +250,21 @@ def _grouped(pk, op, groups, alm2, map3):
 	sht.run_groups(_plan_of(pk), op, groups, alm2, map3)
 	return True
 
+def _linear_car(wcs):
+	"""True when pixel centres follow the linear plate-carree formulas of geometry.py (dec_of / ra_of / pixsize_rows):
+	CAR (or no projection given) with the equator as reference latitude.  Other projections (CEA, TAN, ...; CAR with
+	crval[1] != 0 is oblique) need a real WCS library for enmap.pix2sky / pixsizemap (pixell/curvedsky.py:1355-1382)."""
+	return _is_cyl(wcs)
+
+def _require_linear_car(wcs, what):
+	if not _linear_car(wcs):
+		ctype = getattr(wcs.wcs, "ctype", ["?"])
+		raise NotImplementedError("%s: pixel positions of projection %s with crval[1]=%g are not the linear plate-carree ones "
+			"pixell_b200.geometry computes; pass locinfo= (pixel centres from a WCS library) to the *_general functions instead"
+			% (what, str(ctype[0]), wcs.wcs.crval[1]))
+
 def _check_method(method, minfo, shape):
-	if method == "general": return          # any map whose pixel centres geometry.py can locate (handled by *_general)
+	if method == "general": return          # handled by *_general, which locate the pixel centres (linear CAR only, or locinfo=)
 	if method not in ("2d", "cyl"): raise ValueError("Unrecognized alm2map method '%s'" % str(method))
 	if minfo.case == "general": raise NotImplementedError("non-cylindrical geometry: only the reference's 'general' method applies")
 	if method == "2d" and minfo.case != "2d":
@@ -543,7 +556,9 @@ def alm2map_general(alm, map, ainfo=None, spin=[0,2], deriv=False, copy=False, v
 		if adjoint and alm is not None: alm = alm.copy()
 		else: map = map.copy()
 	if adjoint: alm, ainfo = prepare_alm(alm=alm, ainfo=ainfo, pre=map.shape[:-2] if not deriv else map.shape[:-3], dtype=_rdtype(map), convert=False, like=map)
-	if locinfo is None: locinfo = calc_locinfo(map.shape, wcs)
+	if locinfo is None:
+		_require_linear_car(wcs, "alm2map_general")
+		locinfo = calc_locinfo(map.shape, wcs)
 	mview = np.asarray(map)
 	for I in np.ndindex(*mview.shape[:-3]):
 		tmap = np.ascontiguousarray(mview[I].reshape(mview[I].shape[:-2]+(-1,)))
@@ -588,6 +603,7 @@ def map2alm_general(map, alm=None, ainfo=None, minfo=None, lmax=None, spin=[0,2]
 		if copy and map is not None: map = map.copy()
 	elif copy and alm is not None: alm = alm.copy()
 	alm, ainfo = prepare_alm(alm=alm, ainfo=ainfo, lmax=lmax, pre=map.shape[:-2], dtype=_rdtype(map), convert=adjoint, like=map)
+	if locinfo is None or weights is None: _require_linear_car(wcs, "map2alm_general")
 	if locinfo is None: locinfo = calc_locinfo(map.shape, wcs)
 	if weights is None: weights = np.repeat(geometry.pixsize_rows(map.shape, wcs), map.shape[-1]).astype(_rdtype(map), copy=False)
 	mview = np.asarray(map)
@@ -841,6 +857,9 @@ def rand_alm_healpy(ps, lmax=None, seed=None, dtype=np.complex128):
 		alm = ainfo.lmul(alm, np.sqrt(cl/2).astype(alm.real.dtype), alm)
 		alm[:lmax+1] = re[:lmax+1]*np.sqrt(cl)
 		return alm
+	import warnings
+	warnings.warn("pixell_b200.rand_alm_healpy: for several components the alm follow pixell's own rand_alm stream (l-major fill, symmetric "
+		"square root), not healpy.synalm's (m-major, Cholesky-like mixing): same covariance, different realisation for a given seed", stacklevel=2)
 	return rand_alm(ps, lmax=lmax, seed=seed, dtype=dtype)
 
 def rand_map(shape, wcs, ps, lmax=None, dtype=np.float64, seed=None, spin=[0,2], method="auto", verbose=False):

@@ -97,6 +97,7 @@ def smooth_gauss(emap, sigma, wcs=None):
 	ny, nx = emap.shape[-2:]
 	ly, lx = laxes(emap.shape, wcs)
 	filt = np.exp(-0.5*sigma**2*(ly[:, None]**2 + lx[None, :nx//2+1]**2))
+	if sigma < 0: filt = 1-filt          # negative sigma: the complementary high-pass filter (pixell/enmap.py:1437-1438)
 	f = enfft.rfft(emap, axes=[-2, -1])
 	if L.is_torch(f):
 		import torch
@@ -134,7 +135,7 @@ def apply_window(emap, pow=1.0, order=0, scale=1, nofft=False, wcs=None):
 	nx = emap.shape[-1]
 	if L.buffer_info(emap)[2].kind == "c":
 		out = ifft(mul(fft(emap, wcs=wcs), wy, wx), wcs=wcs)
-		return out
+		return out.real                  # the reference returns ifft(...).real (pixell/enmap.py:1495)
 	f = mul(enfft.rfft(emap, axes=[-2, -1]), wy, wx[:nx//2+1])
 	out = enfft.irfft(f, n=nx, axes=[-2, -1], normalize=True)
 	w = getattr(emap, "wcs", wcs)

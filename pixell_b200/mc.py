@@ -8,8 +8,10 @@ in the CPU tests), maps and alm never leave their GPU.  Optionally the per-reali
 gathered.  Nothing here is a data-path collective.
 
 Random streams:
-  rng="reference"  numpy's legacy global stream on the host, seeded per realisation, exactly as the reference
-                   (curvedsky.rand_alm / rand_alm_healpy): bit-identical alm for a given seed, host-RNG bound.
+  rng="reference"  numpy's legacy global stream on the host, seeded per realisation (curvedsky.rand_alm_healpy): for a
+                   scalar spectrum the alm are healpy.synalm's, i.e. the reference rand_map's realisation for that seed
+                   (pinned by the reference's golden MM_041121.pkl); for T,Q,U the stream is pixell's rand_alm one (l-major
+                   fill, symmetric square root), NOT healpy's polarised synalm -- same covariance, other numbers.
   rng="device"     the engine's own kernel (b2_rand_alm): counter-based Philox4x32-10 normals in the reference's fill
                    order, coloured with the symmetric square root of C_l and fixed at m = 0 in the same kernel
                    (curvedsky.rand_alm :61-77, rand_alm_white :620-628): same statistics, different numbers.

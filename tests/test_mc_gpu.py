@@ -80,7 +80,7 @@ def test_rand_alm_kernel_shares_large_scales_between_lmax():
 	b = mc.rand_alm_device(None, hi, 9, torch.device("cuda")).cpu().numpy()[0]
 	for m in range(31):
 		l = np.arange(m, 31)
-		assert np.array_equal(a[lo.mstart[m]+l], b[hi.mstart[m]+l])
+		assert np.array_equal(a[int(lo.mstart[m])+l], b[int(hi.mstart[m])+l])
 	# unit normals: mean 0, variance 1 per real and imaginary part
 	big = mc.rand_alm_device(None, curvedsky.alm_info(400), 10, torch.device("cuda")).cpu().numpy()[0]
 	assert abs(big.real.mean()) < 0.02 and abs(big.real.var()-1) < 0.03 and abs(big.imag.var()-1) < 0.03
