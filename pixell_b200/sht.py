@@ -277,16 +277,18 @@ def synthesis_general(*, alm, loc, spin, lmax, mmax=None, mstart=None, lstride=1
 	ncm = 1 if spin == 0 else 2
 	nca = 1 if (spin == 0 or md == L.MODE_DERIV1) else 2
 	if alm.ndim != 2 or alm.shape[0] != nca: raise ValueError("alm must have shape [%d, nalm] for spin %d" % (nca, spin))
-	if L.buffer_info(alm)[2] != np.complex128: raise ValueError("synthesis_general: alm must be complex128")
+	adt = L.buffer_info(alm)[2]
+	if adt not in (np.complex128, np.complex64): raise ValueError("synthesis_general: alm must be complex128 or complex64")
 	dev = torch.device("cuda", L.init())
 	host = not L.is_torch(alm)
-	talm = torch.from_numpy(np.ascontiguousarray(alm)).to(dev) if host else alm.contiguous()
+	# single precision rides on the double-precision pipeline (ducc accepts complex64 alm with float32 maps here)
+	talm = torch.from_numpy(np.ascontiguousarray(alm, dtype=np.complex128)).to(dev) if host else alm.to(torch.complex128).contiguous()
 	tloc = (torch.from_numpy(np.ascontiguousarray(loc, dtype=np.float64)) if not L.is_torch(loc) else loc).to(dev).contiguous()
 	if tloc.ndim != 2 or tloc.shape[1] != 2 or tloc.dtype != torch.float64: raise ValueError("loc must be float64 [npos, 2] = (theta, phi)")
 	npos = tloc.shape[0]
 	# Legendre stage on a Clenshaw-Curtis ring set whose doubled circle has a fast FFT length
 	N = _fast_len(2*lmax+2); nt = N//2+1
-	M = _fast_len(2*(2*lmax+2))
+	M = _fast_len(max(2*(2*lmax+2), 4*GENERAL_W))      # oversampled grid; never smaller than the interpolation kernel needs
 	plan = plan_2d("CC", nt, N, 0.0, lmax, mmax, mstart, lstride)
 	nring_pad = (nt+31)//32*32
 	nm = mmax+1
@@ -306,11 +308,15 @@ def synthesis_general(*, alm, loc, spin, lmax, mmax=None, mstart=None, lstride=1
 	fine = torch.empty((ncm, M, M), dtype=torch.float64, device=dev)
 	enfft.transform(grid, fine, (-2, -1), False, 1.0)            # unnormalised inverse: the Fourier series on the M x M grid
 	del grid
-	tout = torch.empty((ncm, npos), dtype=torch.float64, device=dev) if (host or map is None or not L.is_torch(map)) else map
+	direct = not (host or map is None or not L.is_torch(map)) and map.dtype == torch.float64
+	tout = map if direct else torch.empty((ncm, npos), dtype=torch.float64, device=dev)
 	if tout.shape != (ncm, npos) or tout.stride(-1) != 1: raise ValueError("map must have shape [%d, npos] with a contiguous last axis" % ncm)
 	L.check(lib.b2_general_interp(fine.data_ptr(), ncm, M, tloc.data_ptr(), npos, GENERAL_W, GENERAL_BETA, tout.data_ptr(), int(tout.stride(0)), st))
-	if map is None: return tout.cpu().numpy() if host else tout
+	if map is None:
+		if adt == np.complex64: tout = tout.to(torch.float32)
+		return tout.cpu().numpy() if host else tout
 	if not L.is_torch(map): map[...] = tout.cpu().numpy().astype(map.dtype, copy=False)
+	elif not direct: map.copy_(tout)
 	return map
 
 def adjoint_synthesis_general(*, map, loc, spin, lmax, mmax=None, mstart=None, lstride=1, epsilon=1e-10, alm=None, mode="STANDARD",
@@ -332,7 +338,7 @@ def adjoint_synthesis_general(*, map, loc, spin, lmax, mmax=None, mstart=None, l
 	if tloc.ndim != 2 or tloc.shape[1] != 2 or tloc.shape[0] != tmap.shape[1]: raise ValueError("loc must be float64 [npos, 2] = (theta, phi)")
 	npos = tloc.shape[0]
 	N = _fast_len(2*lmax+2); nt = N//2+1
-	M = _fast_len(2*(2*lmax+2))
+	M = _fast_len(max(2*(2*lmax+2), 4*GENERAL_W))      # oversampled grid; never smaller than the interpolation kernel needs
 	plan = plan_2d("CC", nt, N, 0.0, lmax, mmax, mstart, lstride)
 	nring_pad = (nt+31)//32*32
 	nm = mmax+1
@@ -355,7 +361,9 @@ def adjoint_synthesis_general(*, map, loc, spin, lmax, mmax=None, mstart=None, l
 	nalm = _alm_len(mstart, lmax, lstride)
 	talm = torch.zeros((nca, nalm), dtype=torch.complex128, device=dev)
 	L.check(lib.b2_leg2alm(plan.handle, int(spin), md, talm.data_ptr(), nalm if nca > 1 else 0, leg.data_ptr(), st))
-	if alm is None: return talm.cpu().numpy() if host else talm
+	if alm is None:
+		if L.buffer_info(map)[2] == np.float32: talm = talm.to(torch.complex64)
+		return talm.cpu().numpy() if host else talm
 	if L.is_torch(alm): alm.copy_(talm)
 	else: alm[...] = talm.cpu().numpy().astype(alm.dtype, copy=False)
 	return alm
