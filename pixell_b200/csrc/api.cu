@@ -121,6 +121,7 @@ b2_sht_plan::~b2_sht_plan()
 	for (auto &e : gev) if (e) cudaEventDestroy(e);
 	for (auto &g : gstreams) if (g) cudaStreamDestroy(g);
 	for (auto &e : gjoin) if (e) cudaEventDestroy(e);
+	for (auto &e : sev) if (e) cudaEventDestroy(e);
 	if (gfork) cudaEventDestroy(gfork);
 	if (s_in) cudaStreamDestroy(s_in);
 	if (s_out) cudaStreamDestroy(s_out);
@@ -163,6 +164,49 @@ LegStart *b2_sht_plan::get_start(int spin)
 	return p;
 }
 
+// chunks of the streamed host-memory path (see b2_sht_plan::schunks / mcuts)
+static void plan_stream_setup(b2_sht_plan *p)
+{
+	static const int nchunk = std::min(4, getenv("B2_STREAM_CHUNKS") ? atoi(getenv("B2_STREAM_CHUNKS")) : 4);
+	p->schunks.clear(); p->mcuts.clear();
+	if (nchunk < 2) return;
+	const int np = p->geom.npair_pad;
+	const bool dense_rows = p->nphi > 0 && p->nring > 1 && (p->row_pitch == p->npix || p->row_pitch == -p->npix);
+	if (dense_rows && np >= 2048) {
+		const int step = (int)b2_round_up((np + nchunk - 1)/nchunk, 512);
+		std::vector<b2_sht_plan::StreamChunk> ch;
+		bool ok = true;
+		for (int lo = 0; lo < np && ok; lo += step) {
+			b2_sht_plan::StreamChunk c; c.pair_lo = lo; c.pair_hi = std::min(np, lo + step); c.nrun = 0;
+			std::vector<int> rings;
+			for (int i = c.pair_lo; i < c.pair_hi; i++) { if (p->geom.rn_h[i] >= 0) rings.push_back(p->geom.rn_h[i]); if (p->geom.rs_h[i] >= 0) rings.push_back(p->geom.rs_h[i]); }
+			std::sort(rings.begin(), rings.end());
+			for (size_t i = 0; i < rings.size() && ok; ) {
+				size_t j = i + 1;
+				while (j < rings.size() && rings[j] == rings[j - 1] + 1) j++;
+				if (c.nrun == 2) { ok = false; break; }
+				c.r0[c.nrun] = rings[i]; c.nr[c.nrun] = (int)(j - i); c.nrun++;
+				i = j;
+			}
+			if (c.nrun > 0) ch.push_back(c);
+		}
+		if (ok && ch.size() >= 2) p->schunks = ch;
+	}
+	if (p->alm_dense && p->lstride == 1 && p->mmax >= 256) {
+		bool inc = true;
+		for (int m = 1; m <= p->mmax && inc; m++) inc = p->mstart_h[m] + m == p->mstart_h[m - 1] + p->lmax + 1;
+		if (inc) {
+			int64_t total = 0, acc = 0; for (int m = 0; m <= p->mmax; m++) total += p->lmax - m + 1;
+			p->mcuts.push_back(0);
+			for (int m = 0, k = 1; m <= p->mmax; m++) {
+				acc += p->lmax - m + 1;
+				if (k < nchunk && acc*nchunk >= total*k) { p->mcuts.push_back(m + 1); k++; }
+			}
+			if (p->mcuts.back() != p->mmax + 1) p->mcuts.push_back(p->mmax + 1);
+		}
+	}
+}
+
 static int plan_common(b2_sht_plan *p, int nring, const double *theta, int64_t nphi, double phi0, int xdir,
 	int64_t npix, const int64_t *ringstart, const double *weight, int lmax, int mmax, const int64_t *mstart, int64_t lstride)
 {
@@ -202,6 +246,7 @@ static int plan_common(b2_sht_plan *p, int nring, const double *theta, int64_t n
 	if (p->leg.alloc((size_t)2*(mmax + 1)*p->geom.nring_pad)) return 1;
 	B2_CHECK(cudaMemset(p->leg.p, 0, p->leg.bytes()));
 	for (auto &e : p->ev) B2_CHECK(cudaEventCreate(&e));
+	plan_stream_setup(p);
 	return 0;
 }
 
@@ -341,7 +386,7 @@ struct GroupCtx {
 	void *alm; int64_t alm_cs; void *map; int64_t map_cs;      // caller's operands
 	double2 *dalm; int64_t dalm_cs; float2 *tmp32;             // complex128 alm on the device (+ complex64 scratch)
 	void *dmap; int64_t dmap_cs; char *dmap_base;              // map on the device (element offsets as in the caller's array)
-	bool alm_direct;
+	bool alm_direct, streamed;      // streamed: the results already left for the host chunk by chunk
 	cudaEvent_t ev_in, ev_done;
 };
 
@@ -376,7 +421,7 @@ static int group_stage_in(Exec &E, GroupCtx &G, char *salm, char *smap)
 	b2_sht_plan *p = E.p;
 	const bool to_map = to_map_op(E.op);
 	G.alm_direct = (E.mem == B2_MEM_DEVICE && E.dtype == B2_F64);
-	G.tmp32 = nullptr;
+	G.tmp32 = nullptr; G.streamed = false;
 	if (G.alm_direct) { G.dalm = (double2*)G.alm; G.dalm_cs = G.alm_cs; }
 	else {
 		G.dalm = (double2*)salm; G.dalm_cs = p->alm_span;
@@ -421,7 +466,32 @@ static int group_compute(Exec &E, GroupCtx &G)
 		}
 	}
 	B2_CHECK(cudaEventRecord(p->ev[1], E.st));
-	if (to_map) {
+	const bool host64 = E.mem == B2_MEM_HOST && E.dtype == B2_F64 && E.s_out != E.st;
+	if (to_map && E.op == OP_SYNTH && host64 && !p->schunks.empty() && p->groups.empty()) {
+		// chunks of ring pairs, pole -> equator: Legendre synthesis and ring FFTs of a chunk, then its rows go to the host
+		// on the copy stream while the next chunk is computed; only the last chunk's copy is exposed
+		const size_t span = (size_t)(p->map_hi - p->map_lo);
+		for (size_t c = 0; c < p->schunks.size(); c++) {
+			const b2_sht_plan::StreamChunk &C = p->schunks[c];
+			if (leg_alm2leg(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st, p->get_start(E.spin), C.pair_lo, C.pair_hi)) return 1;
+			if (c + 1 == p->schunks.size()) B2_CHECK(cudaEventRecord(p->ev[2], E.st));
+			for (int r = 0; r < C.nrun; r++)
+				if (ring_leg2map(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.st, C.r0[r], C.nr[r])) return 1;
+			if (!p->sev[c]) B2_CHECK(cudaEventCreateWithFlags(&p->sev[c], cudaEventDisableTiming));
+			B2_CHECK(cudaEventRecord(p->sev[c], E.st));
+			B2_CHECK(cudaStreamWaitEvent(E.s_out, p->sev[c], 0));
+			for (int r = 0; r < C.nrun; r++) {
+				const int64_t a = p->ringstart_h[C.r0[r]], b = p->ringstart_h[C.r0[r] + C.nr[r] - 1];
+				const int64_t lo = std::min(a, b), nel = std::max(a, b) + p->npix - lo;
+				for (int k = 0; k < E.ncm; k++)
+					B2_CHECK(cudaMemcpyAsync((char*)G.map + ((size_t)k*G.map_cs + lo)*E.msz, G.dmap_base + ((size_t)k*span + (lo - p->map_lo))*E.msz,
+						(size_t)nel*E.msz, cudaMemcpyDeviceToHost, E.s_out));
+			}
+		}
+		B2_CHECK(cudaEventRecord(p->ev[3], E.st));
+		B2_CHECK(cudaEventRecord(p->ev[4], E.st));
+		G.streamed = true;
+	} else if (to_map) {
 		if (leg_alm2leg(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st, p->get_start(E.spin))) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[2], E.st));
 		if (E.op == OP_ADJ_ANALYSIS) {
@@ -449,7 +519,23 @@ static int group_compute(Exec &E, GroupCtx &G)
 			}
 		}
 		B2_CHECK(cudaEventRecord(p->ev[3], E.st));
-		if (leg_leg2alm(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st, p->get_start(E.spin))) return 1;
+		// (off by default: one CTA per m takes ~1/5 of the kernel's run time, so every extra launch adds a tail that costs
+		// more than the copy it hides -- measured on B200, C3: map2alm 212 -> 245 ms; B2_STREAM_ALM=1 enables it)
+		static const bool stream_alm = getenv("B2_STREAM_ALM") && atoi(getenv("B2_STREAM_ALM"));
+		if (stream_alm && host64 && !G.alm_direct && p->mcuts.size() >= 3) {
+			// ranges of m with about equal alm bytes: each range's coefficients go to the host while the next is computed
+			for (size_t c = 0; c + 1 < p->mcuts.size(); c++) {
+				const int m_lo = p->mcuts[c], m_hi = p->mcuts[c + 1];
+				if (leg_leg2alm(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st, p->get_start(E.spin), m_lo, m_hi)) return 1;
+				if (!p->sev[4 + c]) B2_CHECK(cudaEventCreateWithFlags(&p->sev[4 + c], cudaEventDisableTiming));
+				B2_CHECK(cudaEventRecord(p->sev[4 + c], E.st));
+				B2_CHECK(cudaStreamWaitEvent(E.s_out, p->sev[4 + c], 0));
+				const int64_t lo = p->mstart_h[m_lo] + m_lo, hi = p->mstart_h[m_hi - 1] + p->lmax + 1;
+				for (int k = 0; k < E.nca; k++)
+					B2_CHECK(cudaMemcpyAsync((char*)G.alm + ((size_t)k*G.alm_cs + lo)*16, G.dalm + (size_t)k*G.dalm_cs + lo, (size_t)(hi - lo)*16, cudaMemcpyDeviceToHost, E.s_out));
+			}
+			G.streamed = true;
+		} else if (leg_leg2alm(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st, p->get_start(E.spin))) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[4], E.st));
 		if (!G.alm_direct && E.dtype == B2_F32) {
 			for (int c = 0; c < E.nca; c++) {
@@ -469,6 +555,7 @@ static int group_stage_out(Exec &E, GroupCtx &G)
 {
 	b2_sht_plan *p = E.p;
 	const bool to_map = to_map_op(E.op);
+	if (G.streamed) return 0;
 	if (E.s_out != E.st) B2_CHECK(cudaStreamWaitEvent(E.s_out, G.ev_done, 0));
 	if (to_map) {
 		if (E.mem == B2_MEM_HOST) {

@@ -128,6 +128,8 @@ int LegGeom::build(int nring_, const double *theta)
 	npair_pad = (int)b2_round_up(npair, 256);
 	PairInfo dead; dead.x = 0; dead.sh = 0; dead.ch = 1; dead.rn = -1; dead.rs = -1;
 	pr.resize(npair_pad, dead);
+	rn_h.resize(npair_pad); rs_h.resize(npair_pad);
+	for (int i = 0; i < npair_pad; i++) { rn_h[i] = pr[i].rn; rs_h[i] = pr[i].rs; }
 	return pairs.upload(pr);
 }
 
@@ -143,6 +145,9 @@ struct LegArgs {
 	int64_t leg_mstride;
 	// start table (st_w == nullptr: none; kernels then start every ring at l = max(m, s))
 	const int *st_w; const double *st_p, *st_pp, *st_q, *st_qp; const signed char *st_sp, *st_sq; int ngroup;
+	// partial launches (host-memory calls stream their results out while the rest is still being computed):
+	// CTA b works on m = m0 + b; the synthesis kernels only touch the ring pairs [pair_lo, pair_hi) (multiples of 256)
+	int m0, pair_lo, pair_hi;
 };
 
 // base^n = mant*2^ex with mant in [0.5,1) (or mant = 1, ex = 0 for n = 0; mant = 0 for base = 0)
@@ -330,7 +335,7 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 	__shared__ __align__(16) double2 raw_alm[TL];       // cp.async staging: alm, (alpha, a)
 	__shared__ __align__(16) double raw_al[TL], raw_a[TL];
 	__shared__ int wslot;
-	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int m = A.m0 + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, l0 = m;
 	const bool tab = A.st_w != nullptr && R*32 == LEG_GROUP;
 	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
@@ -340,14 +345,15 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 	const int nchunk = A.npair_pad/(32*R);
 	double2 *leg = A.leg0 + (int64_t)m*A.leg_mstride;
 	// rounds made of dead rings only write zeros
-	const int round0 = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R*NW);
-	for (int i = tid; i < round0*32*R*NW; i += NW*32) {
+	const int rlive = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R*NW);
+	const int round0 = max(rlive, A.pair_lo/(32*R*NW)), round1 = min(nchunk, A.pair_hi/(32*R));
+	for (int i = A.pair_lo + tid; i < min(rlive*32*R*NW, A.pair_hi); i += NW*32) {
 		PairInfo pi = A.pairs[i];
 		if (pi.rn >= 0) leg[pi.rn] = make_double2(0, 0);
 		if (pi.rs >= 0) leg[pi.rs] = make_double2(0, 0);
 	}
 
-	for (int round = round0; round*NW < nchunk; round++) {
+	for (int round = round0; round*NW < round1; round++) {
 		const int chunk = round*NW + warp;
 		double x[R], g[R], gp[R], acc[R][2][2]; int sc[R], rn[R], rs[R];
 		bool anyuse = false, use[R];
@@ -459,7 +465,7 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 	__shared__ double tiles[2][TL];
 	__shared__ __align__(16) double red[2][NW][NOUT];
 	__shared__ __align__(16) double olds[NOUT], alvs[NOUT];      // running sums and alpha_l of the tile's outputs (cp.async)
-	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int m = A.m0 + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, l0 = m;
 	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
 	const double *ta = A.ta + A.toff[m], *tal = A.talpha + A.toff[m];
@@ -654,13 +660,13 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 	__shared__ __align__(16) double2 raw_e[TL], raw_b[TL];       // cp.async staging: E, B, (a, b, alpha)
 	__shared__ __align__(16) double raw_ta[TL], raw_tb[TL], raw_al[TL];
 	__shared__ int wslot;
-	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int m = A.m0 + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, s = A.spin, l0 = m > s ? m : s;
 	const bool tab = A.st_w != nullptr && R*32 == LEG_GROUP;
 	double2 *legq = A.leg0 + (int64_t)m*A.leg_mstride, *legu = A.leg1 + (int64_t)m*A.leg_mstride;
 	const int nchunk = A.npair_pad/(32*R);
 	if (l0 > lmax) {      // nothing to sum: zero this m column
-		for (int i = tid; i < A.npair_pad; i += NW*32) {
+		for (int i = A.pair_lo + tid; i < min(A.npair_pad, A.pair_hi); i += NW*32) {
 			PairInfo pi = A.pairs[i];
 			if (pi.rn >= 0) legq[pi.rn] = legu[pi.rn] = make_double2(0, 0);
 			if (pi.rs >= 0) legq[pi.rs] = legu[pi.rs] = make_double2(0, 0);
@@ -672,14 +678,15 @@ template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*3
 	const SeqConst sc0 = seq_const(m, s, lmax, A.pref);
 	const double sigma0 = ((l0 + m + s) & 1) ? -1.0 : 1.0;
 	const int64_t ms = A.mstart[m];
-	const int round0 = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R*NW);
-	for (int i = tid; i < round0*32*R*NW; i += NW*32) {
+	const int rlive = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R*NW);
+	const int round0 = max(rlive, A.pair_lo/(32*R*NW)), round1 = min(nchunk, A.pair_hi/(32*R));
+	for (int i = A.pair_lo + tid; i < min(rlive*32*R*NW, A.pair_hi); i += NW*32) {
 		PairInfo pi = A.pairs[i];
 		if (pi.rn >= 0) legq[pi.rn] = legu[pi.rn] = make_double2(0, 0);
 		if (pi.rs >= 0) legq[pi.rs] = legu[pi.rs] = make_double2(0, 0);
 	}
 
-	for (int round = round0; round*NW < nchunk; round++) {
+	for (int round = round0; round*NW < round1; round++) {
 		const int chunk = round*NW + warp;
 		double x[R], p[R], pp[R], q[R], qp[R], acc[R][8]; int sp[R], sq[R], rn[R], rs[R];
 		bool anyuse = false, use[R];
@@ -827,7 +834,7 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 	__shared__ __align__(16) TileAB tiles[2][TL];
 	__shared__ __align__(16) double red[2][NW][NOUT];
 	__shared__ __align__(16) double olds[NOUT], alvs[NOUT];      // running sums and alpha_l of the tile's outputs (cp.async)
-	const int m = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int m = A.m0 + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int lmax = A.lmax, s = A.spin, l0 = m > s ? m : s;
 	double *alme = (double*)A.alm0, *almb = (double*)A.alm1;
 	const int64_t ms = A.mstart[m];
@@ -1119,6 +1126,7 @@ static LegArgs make_args(const LegTables &T, const LegGeom &G, const AlmLayout &
 		A.st_w = S->w.p; A.st_p = S->p.p; A.st_pp = S->pp.p; A.st_q = S->q.p; A.st_qp = S->qp.p; A.st_sp = S->sp.p; A.st_sq = S->sq.p;
 	}
 	A.lmax = L.lmax; A.mmax = L.mmax; A.spin = T.spin; A.deriv1 = deriv1;
+	A.m0 = 0; A.pair_lo = 0; A.pair_hi = G.npair_pad;
 	A.toff = T.toff.p; A.ta = T.a.p; A.tb = T.b.p; A.talpha = T.alpha.p; A.pref = T.pref.p;
 	A.pairs = G.pairs.p; A.npair_pad = G.npair_pad; A.npair = G.npair;
 	A.mstart = L.mstart_d; A.lstride = L.lstride;
@@ -1135,7 +1143,7 @@ static int check_args(const LegTables &T, const AlmLayout &L, int deriv1)
 	return 0;
 }
 
-#define LAUNCH(K, ...) K<__VA_ARGS__><<<L.mmax + 1, launch_threads<__VA_ARGS__>(), 0, st>>>(A)
+#define LAUNCH(K, ...) K<__VA_ARGS__><<<nm_launch, launch_threads<__VA_ARGS__>(), 0, st>>>(A)
 template<int R, int NW, int... REST> constexpr int launch_threads() { return NW*32; }
 
 int leg_build_start(LegStart &S, const LegTables &T, const LegGeom &G)
@@ -1156,10 +1164,15 @@ int leg_build_start(LegStart &S, const LegTables &T, const LegGeom &G)
 }
 
 int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
-	const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st, const LegStart *S)
+	const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st, const LegStart *S, int pair_lo, int pair_hi)
 {
 	if (check_args(T, L, deriv1)) return 1;
 	LegArgs A = make_args(T, G, L, deriv1, (double2*)alm, alm_cstride, leg, S);
+	const int nm_launch = L.mmax + 1;
+	if (pair_hi > pair_lo) {
+		B2_REQUIRE(pair_lo % 256 == 0 && (pair_hi % 256 == 0 || pair_hi >= G.npair_pad), "alm2leg: ring-pair ranges must be multiples of 256");
+		A.pair_lo = pair_lo; A.pair_hi = std::min(pair_hi, G.npair_pad);
+	}
 	// template arguments: R, NW, MINB, TL (variant 0 = fastest measured on B200 at lmax 8000, profiles/r1*_tune_*)
 	if (T.spin == 0) switch (variant_of(0)) {
 		case 0: LAUNCH(k_synth0, 4, 2, 8, 64); break;
@@ -1178,10 +1191,12 @@ int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 }
 
 int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
-	double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st, const LegStart *S)
+	double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st, const LegStart *S, int m_lo, int m_hi)
 {
 	if (check_args(T, L, deriv1)) return 1;
 	LegArgs A = make_args(T, G, L, deriv1, alm, alm_cstride, (double2*)leg, S);
+	int nm_launch = L.mmax + 1;
+	if (m_hi > m_lo) { A.m0 = m_lo; nm_launch = std::min(m_hi, L.mmax + 1) - m_lo; if (nm_launch <= 0) return 0; }
 	// template arguments: R, NW, MINB, TL, W
 	if (T.spin == 0) switch (variant_of(1)) {
 		case 0: LAUNCH(k_adj0, 8, 1, 8, 32, 8); break;

@@ -28,6 +28,7 @@ struct LegGeom {
 	int64_t nring_pad = 0;    // leg row length (rings padded to a multiple of 32)
 	DevBuf<PairInfo> pairs;   // sorted pole -> equator, padded to a multiple of 256 pairs with rn = -1
 	int npair_pad = 0;
+	std::vector<int> rn_h, rs_h;   // host copy of the pairs' ring indices (which rings a range of pairs covers)
 	int build(int nring, const double *theta);
 	size_t bytes() const { return pairs.bytes(); }
 };
@@ -54,10 +55,14 @@ struct AlmLayout {
 
 // leg[ncomp_map][mmax+1][nring_pad] complex128; alm component c at alm + c*alm_cstride (complex elements)
 // S (nullable): start table built by leg_build_start for this (T, G)
+// pair_lo < pair_hi: only the ring pairs [pair_lo, pair_hi) of the sorted pair list (multiples of 256) are computed;
+// m_lo < m_hi: only the orders m_lo <= m < m_hi (partial launches: results stream out while the rest is computed)
 int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
-                const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st, const LegStart *S = nullptr);
+                const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st, const LegStart *S = nullptr,
+                int pair_lo = 0, int pair_hi = 0);
 int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
-                double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st, const LegStart *S = nullptr);
+                double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st, const LegStart *S = nullptr,
+                int m_lo = 0, int m_hi = 0);
 int leg_build_start(LegStart &S, const LegTables &T, const LegGeom &G);
 int dfma_peak_gflops(double *out);
 int leg_set_variant(int which, int v);

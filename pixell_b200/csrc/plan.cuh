@@ -48,6 +48,12 @@ struct b2_sht_plan {
 	cudaStream_t s_in = nullptr, s_out = nullptr, s_comp = nullptr;
 	cudaEvent_t gev[2*B2_MAX_GROUPS] = {};      // per group: operands on the device, results ready
 	double timing[4] = {0, 0, 0, 0};
+	// streamed host-memory transforms: the synthesis runs in chunks of ring pairs (pole -> equator) whose rows leave for the
+	// host while the next chunk is computed; the adjoint Legendre stage runs in ranges of m whose alm leave likewise
+	struct StreamChunk { int pair_lo, pair_hi, nrun, r0[2], nr[2]; };
+	std::vector<StreamChunk> schunks;      // empty: rows of a chunk are not at most two dense row bands (no streaming)
+	std::vector<int> mcuts;                // m range boundaries with about equal alm bytes (empty: alm layout not dense)
+	cudaEvent_t sev[8] = {};
 	LegTables *get_tables(int spin);
 	LegStart *get_start(int spin);      // nullptr when disabled (B2_NO_START_TABLE=1) or on allocation failure
 	size_t bytes() const;

@@ -222,7 +222,8 @@ struct RingArgs {
 	int half, nfft, mmax, xdir, nring, twoff;
 	int64_t nphi, npix, nring_pad;
 	const double2 *phase; const int64_t *ringstart; const double *weight;
-	const int *ring_ids; const double *phi0s;      // ring groups (null: block b = ring b, phases from the table)
+	const int *ring_ids; const double *phi0s;      // ring groups (null: block b = ring ring0 + b, phases from the table)
+	int ring0;
 	double2 *leg; void *map; int64_t map_cstride;
 };
 
@@ -244,7 +245,7 @@ __device__ __forceinline__ double2 leg_phase(const RingArgs &A, const double2 *l
 template<typename MapT> __global__ void __launch_bounds__(512) k_leg2map(RingArgs A)
 {
 	extern __shared__ __align__(16) double2 s[];
-	const int ring = A.ring_ids ? A.ring_ids[blockIdx.x] : blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+	const int ring = A.ring_ids ? A.ring_ids[blockIdx.x] : A.ring0 + blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
 	const double2 *legc = A.leg + ((int64_t)comp*(A.mmax + 1))*A.nring_pad + ring;
 	MapT *row = (MapT*)A.map + (int64_t)comp*A.map_cstride + A.ringstart[ring];
 	const int n = (int)A.nphi, nf = A.nfft, mmax = A.mmax;
@@ -315,7 +316,7 @@ template<typename MapT> __global__ void __launch_bounds__(512) k_leg2map(RingArg
 template<typename MapT> __global__ void __launch_bounds__(512) k_map2leg(RingArgs A)
 {
 	extern __shared__ __align__(16) double2 s[];
-	const int ring = A.ring_ids ? A.ring_ids[blockIdx.x] : blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+	const int ring = A.ring_ids ? A.ring_ids[blockIdx.x] : A.ring0 + blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
 	double2 *legc = A.leg + ((int64_t)comp*(A.mmax + 1))*A.nring_pad + ring;
 	const MapT *row = (const MapT*)A.map + (int64_t)comp*A.map_cstride + A.ringstart[ring];
 	const int n = (int)A.nphi, nf = A.nfft, mmax = A.mmax;
@@ -379,7 +380,7 @@ static RingArgs ring_args(const RingFft &F, const double2 *leg, int64_t nring_pa
 	A.nphi = F.nphi; A.npix = F.npix; A.nring_pad = nring_pad;
 	A.phase = F.phase.p; A.ringstart = F.ringstart.p; A.weight = (use_weight && F.weight.n) ? F.weight.p : nullptr;
 	A.ring_ids = F.ring_ids.n ? F.ring_ids.p : nullptr; A.phi0s = F.phi0s.n ? F.phi0s.p : nullptr;
-	A.leg = (double2*)leg; A.map = (void*)map; A.map_cstride = map_cstride;
+	A.leg = (double2*)leg; A.map = (void*)map; A.map_cstride = map_cstride; A.ring0 = 0;
 	return A;
 }
 
@@ -399,10 +400,11 @@ template<typename K> static int set_smem(K kern, size_t smem)
 }
 
 int ring_leg2map(const RingFft &F, int ncomp, const double2 *leg, int64_t nring_pad,
-	void *map, int64_t map_cstride, int dtype, cudaStream_t st)
+	void *map, int64_t map_cstride, int dtype, cudaStream_t st, int ring0, int nrings)
 {
 	RingArgs A = ring_args(F, leg, nring_pad, map, map_cstride, 0);
 	dim3 grid(F.nring, ncomp);
+	if (nrings > 0) { B2_REQUIRE(!F.ring_ids.n && ring0 >= 0 && ring0 + nrings <= F.nring, "leg2map: bad ring range"); A.ring0 = ring0; grid.x = nrings; }
 	if (dtype == 0) { if (set_smem(k_leg2map<double>, F.smem)) return 1; k_leg2map<double><<<grid, F.threads, F.smem, st>>>(A); }
 	else            { if (set_smem(k_leg2map<float>,  F.smem)) return 1; k_leg2map<float><<<grid, F.threads, F.smem, st>>>(A); }
 	B2_LAUNCH_CHECK();

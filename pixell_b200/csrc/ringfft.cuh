@@ -31,7 +31,8 @@ struct RingFft {
 };
 
 // leg: [ncomp][mmax+1][nring_pad] complex128 (device); map component c at map + c*map_cstride (elements of MapT)
+// nrings > 0: only the rings [ring0, ring0 + nrings) (cylindrical plans)
 int ring_leg2map(const RingFft &F, int ncomp, const double2 *leg, int64_t nring_pad,
-                 void *map, int64_t map_cstride, int dtype, cudaStream_t st);
+                 void *map, int64_t map_cstride, int dtype, cudaStream_t st, int ring0 = 0, int nrings = 0);
 int ring_map2leg(const RingFft &F, int ncomp, double2 *leg, int64_t nring_pad,
                  const void *map, int64_t map_cstride, int dtype, int use_weight, cudaStream_t st);
