@@ -880,3 +880,194 @@ def rand_map(shape, wcs, ps, lmax=None, dtype=np.float64, seed=None, spin=[0,2],
 	alm2map(alm, map, spin=spin, method=method, verbose=verbose)
 	if len(shape) == 2: map = map[0]
 	return map
+
+# ------------------------------------------------------------------ named entry points of the reference's transform layers
+# pixell/curvedsky.py:756-873 (per-method helpers) and :900-1086 (raw helpers).  In the reference the "raw" functions work on
+# flipped / padded buffers (map2buffer / buffer2map, :1384-1411); here flips and cuts are index arithmetic inside the engine,
+# so every layer forwards to alm2map / map2alm with the method fixed and no copy is ever made.
+
+def alm2map_2d(alm, map, ainfo=None, minfo=None, spin=[0,2], deriv=False, copy=False, verbose=False, adjoint=False, nthread=None, pix_tol=1e-6, wcs=None):
+	"""pixell/curvedsky.py:756-774"""
+	return alm2map(alm, map, spin=spin, deriv=deriv, adjoint=adjoint, copy=copy, method="2d", ainfo=ainfo, verbose=verbose, pix_tol=pix_tol, wcs=wcs)
+
+def alm2map_cyl(alm, map, ainfo=None, minfo=None, spin=[0,2], deriv=False, copy=False, verbose=False, adjoint=False, nthread=None, pix_tol=1e-6, wcs=None):
+	"""pixell/curvedsky.py:776-794"""
+	return alm2map(alm, map, spin=spin, deriv=deriv, adjoint=adjoint, copy=copy, method="cyl", ainfo=ainfo, verbose=verbose, pix_tol=pix_tol, wcs=wcs)
+
+def map2alm_2d(map, alm=None, ainfo=None, minfo=None, lmax=None, spin=[0,2], deriv=False, copy=False, verbose=False, adjoint=False, nthread=None, pix_tol=1e-6, wcs=None):
+	"""pixell/curvedsky.py:822-841"""
+	return map2alm(map, alm=alm, lmax=lmax, spin=spin, deriv=deriv, adjoint=adjoint, copy=copy, method="2d", ainfo=ainfo, verbose=verbose, pix_tol=pix_tol, wcs=wcs)
+
+def map2alm_cyl(map, alm=None, ainfo=None, minfo=None, lmax=None, spin=[0,2], weights=None, deriv=False, copy=False, verbose=False, adjoint=False,
+		nthread=None, pix_tol=1e-6, niter=0, wcs=None):
+	"""pixell/curvedsky.py:843-873"""
+	return map2alm(map, alm=alm, lmax=lmax, spin=spin, deriv=deriv, adjoint=adjoint, copy=copy, method="cyl", ainfo=ainfo, verbose=verbose,
+		niter=niter, pix_tol=pix_tol, weights=weights, wcs=wcs)
+
+def alm2map_raw_2d(alm, map, ainfo=None, spin=[0,2], deriv=False, copy=False, verbose=False, adjoint=False, nthread=None, wcs=None):
+	"""pixell/curvedsky.py:900-924: the map must be a full ducc grid (any orientation: no buffer is needed here)"""
+	return alm2map_2d(alm, map, ainfo=ainfo, spin=spin, deriv=deriv, copy=copy, verbose=verbose, adjoint=adjoint, wcs=wcs)
+
+def alm2map_raw_cyl(alm, map, ainfo=None, minfo=None, spin=[0,2], deriv=False, copy=False, verbose=False, adjoint=False, nthread=None, wcs=None):
+	"""pixell/curvedsky.py:926-962"""
+	return alm2map_cyl(alm, map, ainfo=ainfo, spin=spin, deriv=deriv, copy=copy, verbose=verbose, adjoint=adjoint, wcs=wcs)
+
+def map2alm_raw_2d(map, alm=None, ainfo=None, lmax=None, spin=[0,2], deriv=False, copy=False, verbose=False, adjoint=False, nthread=None, wcs=None):
+	"""pixell/curvedsky.py:1018-1046"""
+	return map2alm_2d(map, alm=alm, ainfo=ainfo, lmax=lmax, spin=spin, deriv=deriv, copy=copy, verbose=verbose, adjoint=adjoint, wcs=wcs)
+
+def map2alm_raw_cyl(map, alm=None, ainfo=None, lmax=None, spin=[0,2], weights=None, deriv=False, copy=False, verbose=False, adjoint=False, niter=0,
+		nthread=None, wcs=None):
+	"""pixell/curvedsky.py:1050-1086"""
+	return map2alm_cyl(map, alm=alm, ainfo=ainfo, lmax=lmax, spin=spin, weights=weights, deriv=deriv, copy=copy, verbose=verbose, adjoint=adjoint,
+		niter=niter, wcs=wcs)
+
+def get_ducc_maxlmax(name, ny):
+	"""pixell/curvedsky.py:1349-1353"""
+	return sht.maxlmax(name, ny)
+
+def dangerous_dtype(dtype):
+	"""pixell/curvedsky.py:1448-1449"""
+	return np.dtype(dtype).byteorder not in ("=", "|", "<" if np.little_endian else ">")
+
+# buffers (pixell/curvedsky.py:1236-1250, 1384-1411): kept for callers that use them directly; the transforms above do not
+def flip2slice(flips):
+	res = (Ellipsis,)
+	for flip in flips: res = res + (slice(None, None, 1-2*int(flip)),)
+	return res
+def flip_array(arr, flips): return arr[flip2slice(flips)]
+def flip_geometry(shape, wcs, flips):
+	return tuple(shape), _flipped(shape, wcs, [bool(f) for f in flips])
+def pad_geometry(shape, wcs, pad):
+	pad = np.asarray(pad)
+	w, h = int(pad[0, 0]+shape[-2]+pad[1, 0]), int(pad[0, 1]+shape[-1]+pad[1, 1])
+	ww = wcs.wcs
+	owcs = geometry.CarWCS(ww.crval, ww.cdelt, np.array(ww.crpix, float)+pad[0, ::-1], getattr(ww, "ctype", ("RA---CAR", "DEC--CAR")))
+	return tuple(shape[:-2])+(w, h), owcs
+def map2buffer(map, flip, pad, obuf=False, wcs=None):
+	"""north-first, ra-increasing, zero-padded copy of a host map (pixell/curvedsky.py:1384-1404)"""
+	pad = np.asarray(pad)
+	wcs = geometry.wcs_of(map, wcs)
+	shape, w = pad_geometry(*flip_geometry(map.shape, wcs, flip), pad)
+	buf = geometry.zeros(shape, w, np.asarray(map).dtype.newbyteorder("="))
+	if not obuf: buf[..., pad[0, 0]:buf.shape[-2]-pad[1, 0], pad[0, 1]:buf.shape[-1]-pad[1, 1]] = flip_array(np.asarray(map), flip)
+	return buf
+def buffer2map(map, flip, pad):
+	"""pixell/curvedsky.py:1406-1411"""
+	pad = np.array(pad)
+	map = map[..., pad[0, 0]:map.shape[-2]-pad[1, 0], pad[0, 1]:map.shape[-1]-pad[1, 1]]
+	return flip_array(map, flip)
+
+def prepare_raw(alm, map, ainfo=None, lmax=None, deriv=False, verbose=False, nthread=None, pixdims=2, convert_alm=False):
+	"""pixell/curvedsky.py:1429-1446: validated, dimension-padded views of alm and map"""
+	alm, ainfo = prepare_alm(alm, ainfo, lmax=lmax, pre=map.shape[:-pixdims], dtype=_rdtype(map), convert=convert_alm)
+	alm_full = _atleast(alm, 2 if deriv else 3)
+	map_full = _atleast(map if L.is_torch(map) else np.asarray(map), pixdims+2)
+	if deriv:
+		assert map_full.ndim >= pixdims+1 and map_full.shape[-pixdims-1] == 2, "map must have shape [...,2,%s] when deriv is True" % ("nloc" if pixdims == 1 else "ny,nx")
+		assert tuple(map_full.shape[:-1-pixdims]) == tuple(alm_full.shape[:-1]), "map and alm must agree on pre-dimensions"
+	else:
+		assert tuple(map_full.shape[:-pixdims]) == tuple(alm_full.shape[:-1]), "map and alm must agree on pre-dimensions"
+	return alm_full, map_full, ainfo, 0
+
+# ------------------------------------------------------------------ iterative inverses (pixell/curvedsky.py:1122-1168)
+
+def jacobi_inverse(forward, approx_backward, y, niter=0):
+	"""x from y = forward(x) by Jacobi iteration with the approximate inverse approx_backward (pixell/curvedsky.py:1122-1136)"""
+	x = approx_backward(y)
+	for i in range(niter):
+		x -= approx_backward(forward(x)-y)
+	return x
+
+class _Minres:
+	"""MINRES for a symmetric operator A given as a function on flat real vectors (Paige & Saunders 1975; what
+	pixell/utils.py's Minres class provides to minres_inverse)"""
+	def __init__(self, A, b):
+		self.A = A; self.x = np.zeros_like(b)
+		self.r = b.copy(); self.beta = float(np.sqrt(self.r @ self.r)); self.b2 = max(self.beta**2, 1e-300)
+		self.v_old = np.zeros_like(b); self.v = self.r/self.beta if self.beta > 0 else self.r
+		self.w_old = np.zeros_like(b); self.w = np.zeros_like(b)
+		self.c_old = self.c = 1.0; self.s_old = self.s = 0.0; self.eta = self.beta; self.i = 0
+		self.abserr = self.beta**2/self.b2
+	def step(self):
+		Av = self.A(self.v)
+		alpha = float(self.v @ Av)
+		v_new = Av - alpha*self.v - self.beta*self.v_old
+		beta_new = float(np.sqrt(v_new @ v_new))
+		if beta_new > 0: v_new = v_new/beta_new
+		# previous rotations
+		delta = self.c*alpha - self.c_old*self.s*self.beta
+		rho2 = self.s*alpha + self.c_old*self.c*self.beta
+		rho3 = self.s_old*self.beta
+		rho1 = np.sqrt(delta*delta + beta_new*beta_new)
+		c_new, s_new = (delta/rho1, beta_new/rho1) if rho1 > 0 else (1.0, 0.0)
+		w_new = (self.v - rho3*self.w_old - rho2*self.w)/rho1 if rho1 > 0 else np.zeros_like(self.v)
+		self.x = self.x + c_new*self.eta*w_new
+		self.eta = -s_new*self.eta
+		self.v_old, self.v, self.beta = self.v, v_new, beta_new
+		self.w_old, self.w = self.w, w_new
+		self.c_old, self.c, self.s_old, self.s = self.c, c_new, self.s, s_new
+		self.i += 1
+		self.abserr = self.eta**2/self.b2
+
+def minres_inverse(forward, approx_backward, y, epsilon=1e-6, maxiter=100, zip=None, unzip=None, verbose=False):
+	"""the maximum-likelihood x of y = forward(x) by MINRES on approx_backward(forward(x)) = approx_backward(y)
+	(pixell/curvedsky.py:1138-1168)"""
+	rhs = approx_backward(y)
+	rhs = np.asarray(rhs.cpu().numpy() if L.is_torch(rhs) else rhs)
+	rtype = np.zeros(1, rhs.dtype).real.dtype
+	if zip is None:
+		def zip(a): return np.ascontiguousarray(a).view(rtype).reshape(-1)
+	if unzip is None:
+		def unzip(x): return x.view(rhs.dtype).reshape(rhs.shape)
+	def A(x): return zip(approx_backward(forward(unzip(x)))).astype(rtype, copy=True)
+	solver = _Minres(A, zip(rhs).astype(rtype, copy=True))
+	while solver.abserr**0.5 > epsilon and solver.i < maxiter:
+		solver.step()
+		if verbose: print("Minres %4d %15.7e" % (solver.i, solver.abserr**0.5))
+	return unzip(solver.x)
+
+# ------------------------------------------------------------------ real packing of alm (pixell/curvedsky.py:1451-1473)
+
+def alm_complex2real(alm, ainfo=None):
+	alm = np.asarray(alm)
+	dtype = np.zeros(1, alm.dtype).real.dtype
+	if ainfo is None: ainfo = alm_info(nalm=alm.shape[-1])
+	i = int(ainfo.mstart[1]+1)
+	return np.concatenate([alm[..., :i].real, 2**0.5*np.ascontiguousarray(alm[..., i:]).view(dtype)], -1)
+
+def alm_real2complex(ralm, ainfo=None):
+	ralm = np.asarray(ralm)
+	ctype = np.result_type(ralm.dtype, 0j)
+	if ainfo is None:
+		lmax = int(np.rint((ralm.shape[-1]-1)**0.5))-1
+		ainfo = alm_info(lmax=lmax)
+	i = int(ainfo.mstart[1]+1)
+	oalm = np.zeros(ralm.shape[:-1]+(ainfo.nelem,), ctype)
+	oalm[..., :i] = ralm[..., :i]
+	oalm[..., i:] = np.ascontiguousarray(ralm[..., i:]).view(ctype)/2**0.5
+	return oalm
+
+# ------------------------------------------------------------------ profiles on the sky (pixell/curvedsky.py:558-585)
+
+def prof2alm(profile, dir=[0, np.pi/2], spin=0, geometry="CC", nthread=None, norot=False):
+	"""alm of a 1-d equispaced profile[..., n] (colatitude 0..pi on the named ring grid) oriented along dir = [ra, dec]:
+	exact analysis of the m = 0 map, expansion to mmax = lmax, rotation of the pole to the target direction"""
+	profile = np.asarray(profile)
+	n = profile.shape[-1]
+	lmax = get_ducc_maxlmax(geometry, n)
+	iainfo = alm_info(lmax=lmax, mmax=0)
+	oainfo = alm_info(lmax=lmax, mmax=lmax if not norot else 0)
+	ctype = np.result_type(profile.dtype, 0j)
+	oalm = np.zeros(profile.shape[:-1]+(oainfo.nelem,), ctype)
+	spins = np.array(spin).reshape(-1)
+	for I in np.ndindex(*profile.shape[:-1]):
+		s = int(spins[(I[-1] if len(I) else 0) % len(spins)]) if len(spins) > 1 else int(spins[0])
+		if s != 0: raise NotImplementedError("prof2alm: only scalar profiles (spin 0) are provided")
+		prof = np.ascontiguousarray(profile[I], dtype=np.float64)[None, :, None]
+		alm = np.asarray(sht.analysis_2d(map=prof, spin=0, lmax=lmax, mmax=0, geometry=geometry))
+		if not norot:
+			alm = transfer_alm(iainfo, alm, oainfo)
+			alm = rotate_alm(alm, 0, np.pi/2-dir[1], dir[0])
+		oalm[I] = alm[0] if alm.ndim == 2 else alm
+	return oalm

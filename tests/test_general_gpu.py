@@ -154,6 +154,36 @@ def test_rotate_alm():
 	top = np.sum(bl*np.sqrt((2*l+1)/(4*np.pi)))
 	assert abs(peak[0]-top) < 1e-6*top and peak[1] < peak[0] and peak[2] < peak[0] and peak[3] < 0.01*top
 
+@pytest.mark.parametrize("ang", [(0.3, 1.1, -2.0), (-1.3, 0.4, 0.7), (2.5, 2.9, 0.1), (0.0, 0.5, 0.0)])
+def test_rotate_alm_against_the_wigner_oracle(ang):
+	"""every Euler angle non-zero, non-axisymmetric alm: the engine's rotate_alm (synthesis at the back-rotated nodes +
+	exact analysis) against oracle/rotate_oracle.py (Wigner-D by the explicit sum, itself checked against a convention-free
+	quadrature and against the reference's published gal -> equ angles in tests/test_oracle_basic.py); also prof2alm"""
+	from pixell_b200 import curvedsky as cs
+	from oracle import rotate_oracle as ro
+	lmax = 24
+	alm = rand_alm(1, lmax, 60)[0]
+	want = ro.rotate_alm_wigner(alm, lmax, *ang)
+	got = cs.rotate_alm(alm, *ang)
+	assert rel(got, want) < 1e-10
+	got32 = cs.rotate_alm(alm.astype(np.complex64), *ang)
+	assert got32.dtype == np.complex64 and rel(got32, want) < 1e-5
+
+def test_prof2alm_places_a_profile_on_the_sky():
+	"""reference pixell/curvedsky.py:558-585: a polar profile analysed at m = 0 and rotated to [ra, dec]"""
+	from pixell_b200 import curvedsky as cs
+	n = 65                                         # CC grid: lmax = 63
+	theta = np.arange(n)*np.pi/(n-1)
+	prof = np.exp(-0.5*(theta/0.15)**2)
+	ra, dec = 0.7, -0.4
+	alm = cs.prof2alm(prof, dir=[ra, dec])
+	assert alm.shape == (cs.alm_info(63).nelem,)
+	pos = np.array([[dec, dec, dec+0.15, np.pi/2-1e-3], [ra, ra+0.15/np.cos(dec), ra, 0.0]])
+	val = cs.alm2map_pos(alm[None], pos)[0]
+	assert abs(val[0]-1) < 2e-3 and abs(val[2]-np.exp(-0.5)) < 5e-3 and abs(val[1]-np.exp(-0.5)) < 2e-2 and abs(val[3]) < 1e-3
+	flat = cs.prof2alm(prof, norot=True)
+	assert flat.shape == (64,) and abs(np.sum(flat.real*np.sqrt((2*np.arange(64)+1)/(4*np.pi)))-1) < 2e-3
+
 def test_golden_lensed_map():
 	"""The reference's lensing golden MM_lensed_071123.fits (reference tests/test_pixell.py:351-356 through
 	lensing.rand_map -> lens_map_curved, lensing.py:468-492): rand_alm(seed=1) -> phi gradient with alm2map(deriv=True)

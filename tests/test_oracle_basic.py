@@ -175,3 +175,28 @@ def test_tuned_cpu_legendre_matches_the_checker(geom, ny, lmax, spin):
 	got = so.fast_leg2alm(leg, theta, spin, lmax, lmax, mstart, nalm, ms)
 	idx = np.concatenate([mstart[m] + np.arange(max(m, spin), lmax+1) for m in ms])
 	assert np.abs(got[:, idx]-want[:, idx]).max() < 1e-12*np.abs(want).max()
+
+def test_rotate_alm_oracles_agree_and_follow_the_published_euler_angles():
+	"""oracle/rotate_oracle.py: the Wigner-D rotation against the convention-free brute force (quadrature of the rotated field),
+	all three Euler angles non-zero, non-axisymmetric alm; and the convention against pixell/curvedsky.py:714-716: with the
+	gal -> equ angles the galactic pole must land on (ra, dec) of the NGP and the celestial pole's galactic direction on z"""
+	from oracle import rotate_oracle as ro
+	lmax = 9
+	rng = np.random.default_rng(8)
+	nalm = (lmax+1)*(lmax+2)//2
+	alm = rng.standard_normal(nalm) + 1j*rng.standard_normal(nalm); alm[:lmax+1] = alm[:lmax+1].real
+	for ang in [(0.3, 1.1, -2.0), (-1.3, 0.4, 0.7), (0.0, 0.5, 0.0), (1.0, 0.0, 0.0)]:
+		a = ro.rotate_alm_wigner(alm, lmax, *ang); b = ro.rotate_alm_bruteforce(alm, lmax, *ang)
+		assert np.abs(a-b).max() < 1e-12*np.abs(alm).max(), ang
+	deg = np.pi/180
+	psi, theta, phi = 57.06793215*deg, 62.87115487*deg, -167.14056929*deg
+	R = ro.rotmat(psi, theta, phi)
+	ngp = R @ np.array([0, 0, 1.0])                      # galactic pole in equatorial coordinates: ra 192.859, dec 27.128
+	assert abs(np.arctan2(ngp[1], ngp[0])/deg % 360 - 192.85948) < 1e-3 and abs(np.arcsin(ngp[2])/deg - 27.12825) < 1e-3
+	l, b = 122.93192*deg, 27.12825*deg                   # celestial pole in galactic coordinates
+	ncp = R @ np.array([np.cos(b)*np.cos(l), np.cos(b)*np.sin(l), np.sin(b)])
+	assert np.abs(ncp - np.array([0, 0, 1.0])).max() < 1e-4
+	# a pure dipole along z, rotated: a'_1m follows the moved axis
+	d = np.zeros(3, complex); d[1] = 1.0                 # lmax = 1: (00, 10, 11)
+	out = ro.rotate_alm_wigner(d, 1, 0.0, np.pi/2, 0.0)  # z -> x: f' = Y_10(R^-1 x) ~ x/r = -(Y_11 - Y_1-1)/sqrt 2 -> a_11 = -1/sqrt 2
+	assert abs(out[1]) < 1e-14 and abs(out[2] + 2**-0.5) < 1e-14

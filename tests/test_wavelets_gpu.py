@@ -62,3 +62,63 @@ def test_wavelet_on_band_and_device_tensors():
 	w_t = wt.map2wave(torch.from_numpy(m).cuda())
 	for a, b_ in zip(w_np.maps, w_t.maps):
 		assert b_.is_cuda and rel(b_.cpu().numpy(), np.asarray(a)) < 1e-12
+
+# ---- against the reference's own WaveletTransform (pixell/wavelets.py, unmodified) running on the engine through the scaffolding
+
+@pytest.fixture(scope="module")
+def refmods():
+	import importlib, refshim
+	if refshim.reference_root() is None: pytest.skip("reference files not staged (scripts/stage_reference.py)")
+	from pixell_b200 import sht, cmisc, fft as b2fft
+	mods = refshim.install(sht, cmisc)
+	b2fft.register(mods["fft"])
+	for name in ("multimap", "uharm", "wavelets"): mods[name] = importlib.import_module("pixell."+name)
+	return mods
+
+@pytest.mark.parametrize("basis", ["ButterTrim", "Butterworth", "CosineNeedlet"])
+def test_curved_transform_matches_the_reference(refmods, basis):
+	"""map2wave / wave2map of the mirror (alm resident on the device path) against the reference's composition of its own
+	curvedsky calls (reference wavelets.py:307-368), full-sky map, band-limited input"""
+	from pixell_b200 import wavelets as W, uharm as U, geometry, curvedsky as cs
+	R, RU, enmap, rcs = refmods["wavelets"], refmods["uharm"], refmods["enmap"], refmods["curvedsky"]
+	lmax = 90
+	shape, wcs = enmap.fullsky_geometry(res=np.deg2rad(1.0))
+	myshape, mywcs = geometry.fullsky_geometry(res=np.deg2rad(1.0))
+	rng = np.random.default_rng(2)
+	ai = cs.alm_info(lmax)
+	alm = rng.standard_normal(ai.nelem) + 1j*rng.standard_normal(ai.nelem); alm[:lmax+1] = alm[:lmax+1].real
+	m = np.asarray(cs.alm2map(alm, geometry.zeros(myshape, mywcs), spin=[0]))
+	mk = (lambda M: M.CosineNeedlet(np.array([4, 12, 30, 60, 90]))) if basis == "CosineNeedlet" else (lambda M: getattr(M, basis)(lmin=5, lmax=lmax))
+	wt_r = R.WaveletTransform(RU.UHT(shape, wcs, mode="curved", lmax=lmax), basis=mk(R))
+	wt_m = W.WaveletTransform(U.UHT(myshape, mywcs, mode="curved", lmax=lmax), basis=mk(W))
+	assert wt_r.nlevel == wt_m.nlevel and np.allclose(wt_r.norms, wt_m.norms, rtol=1e-12) and np.allclose(wt_r.lmids, wt_m.lmids, rtol=1e-12)
+	wr = wt_r.map2wave(enmap.enmap(m, wcs)); wm = wt_m.map2wave(geometry.ndmap(m, mywcs))
+	for a, b in zip(wm.maps, wr.maps):
+		assert a.shape == b.shape and np.abs(np.asarray(a)-np.asarray(b)).max() < 1e-10*np.abs(np.asarray(b)).max()
+	br = wt_r.wave2map(wr); bm = wt_m.wave2map(wm)
+	assert np.abs(np.asarray(bm)-np.asarray(br)).max() < 1e-10*np.abs(np.asarray(br)).max()
+
+def test_flat_transform_matches_the_reference(refmods):
+	"""flat-sky mode (reference wavelets.py:328-340, 346-356): FFT, corner resampling per scale, filters, and back; numpy and
+	torch device maps"""
+	import torch
+	from pixell_b200 import wavelets as W, uharm as U, geometry
+	R, RU, enmap = refmods["wavelets"], refmods["uharm"], refmods["enmap"]
+	shape, wcs = enmap.geometry(pos=(0, 0), shape=(96, 128), res=np.deg2rad(0.1))
+	mywcs = geometry.CarWCS(wcs.wcs.crval, wcs.wcs.cdelt, wcs.wcs.crpix)
+	rng = np.random.default_rng(3)
+	m = rng.standard_normal((2,)+tuple(shape))
+	basis = dict(lmin=60, lmax=1700)
+	wt_r = R.WaveletTransform(RU.UHT(shape, wcs, mode="flat"), basis=R.ButterTrim(**basis))
+	wt_m = W.WaveletTransform(U.UHT(tuple(shape), mywcs, mode="flat"), basis=W.ButterTrim(**basis))
+	assert [tuple(int(v) for v in g[0][-2:]) for g in wt_r.geometries] == [tuple(g[0][-2:]) for g in wt_m.geometries]
+	assert np.allclose(wt_r.norms, wt_m.norms, rtol=1e-10) and np.allclose(wt_r.lmids, wt_m.lmids, rtol=1e-10)
+	wr = wt_r.map2wave(enmap.enmap(m, wcs)); wm = wt_m.map2wave(geometry.ndmap(m, mywcs))
+	for a, b in zip(wm.maps, wr.maps):
+		assert a.shape == b.shape and np.abs(np.asarray(a)-np.asarray(b)).max() < 1e-10*np.abs(np.asarray(b)).max()
+	br = wt_r.wave2map(wr); bm = wt_m.wave2map(wm)
+	assert np.abs(np.asarray(bm)-np.asarray(br)).max() < 1e-10*np.abs(np.asarray(br)).max()
+	wd = wt_m.map2wave(torch.from_numpy(m).cuda())
+	for a, b in zip(wd.maps, wr.maps): assert a.is_cuda and np.abs(a.cpu().numpy()-np.asarray(b)).max() < 1e-10*np.abs(np.asarray(b)).max()
+	vt = wt_m.get_variance_transform(); vr = wt_r.get_variance_transform()
+	assert np.allclose(vt.norms, vr.norms, rtol=1e-10)
