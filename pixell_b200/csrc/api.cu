@@ -5,6 +5,8 @@
 #include <string.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <thread>
+#include <atomic>
 
 // ------------------------------------------------------------------------------------ errors
 
@@ -279,12 +281,27 @@ extern "C" int b2_sht_plan_rings_general(b2_sht_plan **out, int nring, const dou
 	}
 	p->dense_rings = (total == p->map_hi - p->map_lo);
 	p->row_pitch = 0; p->nphi = 0; p->npix = 0;
-	for (auto &g : by_nphi) {
-		std::vector<double> ph(g.second.size());
-		for (size_t i = 0; i < ph.size(); i++) ph[i] = phi0[g.second[i]];
-		std::unique_ptr<RingFft> f(new RingFft());
-		if (f->build_group(g.first, (int)g.second.size(), g.second.data(), ph.data(), nring, ringstart, weight, mmax)) return 1;
-		p->groups.push_back(std::move(f));
+	// the FFT tables of the distinct ring lengths (HEALPix nside 2048: 2048 lengths, about half of them Bluestein) are
+	// host work in long double: computed by all host cores, uploaded afterwards
+	{
+		std::vector<std::unique_ptr<RingFft>> pre;
+		for (auto &g : by_nphi) { pre.emplace_back(new RingFft()); (void)g; }
+		std::vector<int64_t> lens; for (auto &g : by_nphi) lens.push_back(g.first);
+		unsigned nth = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+		std::atomic<size_t> next(0); std::atomic<int> failed(0);
+		std::vector<std::thread> pool;
+		for (unsigned t = 0; t < nth && t < lens.size(); t++) pool.emplace_back([&]() {
+			for (size_t i = next++; i < lens.size(); i = next++) if (pre[i]->prepare_tables(lens[i])) failed = 1;
+		});
+		for (auto &th : pool) th.join();
+		B2_REQUIRE(!failed, "plan: FFT table construction failed");
+		size_t i = 0;
+		for (auto &g : by_nphi) {
+			std::vector<double> ph(g.second.size());
+			for (size_t k = 0; k < ph.size(); k++) ph[k] = phi0[g.second[k]];
+			if (pre[i]->build_group(g.first, (int)g.second.size(), g.second.data(), ph.data(), nring, ringstart, weight, mmax)) return 1;
+			p->groups.push_back(std::move(pre[i])); i++;
+		}
 	}
 	const int ns = (int)std::min<size_t>(16, p->groups.size());
 	p->gstreams.assign(ns, nullptr); p->gjoin.assign(ns, nullptr);

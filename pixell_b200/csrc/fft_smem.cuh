@@ -45,6 +45,11 @@ struct FftTables {
 	DevBuf<int> rev;
 	// n: complex transform length, ntab: twiddle table length (multiple of n; 2n for packed real transforms)
 	int build(int n, int ntab);
+	// build() in two steps: prepare() computes the tables on the host (pure CPU work, safe to run for many plans in
+	// parallel threads), commit() uploads them; build() skips the first step when prepare() already ran for (n, ntab)
+	struct HostTables { std::vector<double2> tw, btw, chirp, bhat; std::vector<int> rev; int n = 0, ntab = 0; bool ready = false; } host;
+	int prepare(int n, int ntab);
+	int commit();
 	static bool smooth(int64_t n);
 	static int bluestein_len(int n);
 	// shared-memory elements a transform of length n needs (padding included; twiddle tables not included)

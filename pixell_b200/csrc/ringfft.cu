@@ -34,22 +34,19 @@ int FftTables::bluestein_len(int n)
 typedef std::complex<long double> cld;
 static const long double TAU = 6.283185307179586476925286766559005768L;
 
-// plain recursive mixed-radix FFT in long double (host, plan time only)
-static void host_fft(std::vector<cld> &x)
+// plain recursive mixed-radix FFT in long double (host, plan time only); roots[k] = exp(-2 pi i k/N) for the top length N
+static void host_fft(std::vector<cld> &x, const std::vector<cld> &roots)
 {
 	size_t n = x.size();
 	if (n <= 1) return;
 	size_t r = n;
 	for (size_t p = 2; p*p <= n; p++) if (n % p == 0) { r = p; break; }
-	size_t m = n/r;
+	size_t m = n/r, step = roots.size()/n;
 	std::vector<std::vector<cld>> sub(r, std::vector<cld>(m));
-	for (size_t q = 0; q < r; q++) { for (size_t j = 0; j < m; j++) sub[q][j] = x[j*r + q]; host_fft(sub[q]); }
+	for (size_t q = 0; q < r; q++) { for (size_t j = 0; j < m; j++) sub[q][j] = x[j*r + q]; host_fft(sub[q], roots); }
 	for (size_t k = 0; k < n; k++) {
 		cld acc = 0;
-		for (size_t q = 0; q < r; q++) {
-			long double a = -TAU*(long double)((q*k) % n)/(long double)n;
-			acc += sub[q][k % m]*cld(cosl(a), sinl(a));
-		}
+		for (size_t q = 0; q < r; q++) acc += sub[q][k % m]*roots[((q*k) % n)*step];
 		x[k] = acc;
 	}
 }
@@ -126,51 +123,68 @@ static std::vector<double2> twiddles(int n)
 	return t;
 }
 
-int FftTables::build(int n, int ntab)
+int FftTables::prepare(int n, int ntab)
 {
 	B2_REQUIRE(n >= 1 && ntab % n == 0, "bad FFT table request n=%d ntab=%d", n, ntab);
+	host = HostTables(); host.n = n; host.ntab = ntab;
 	d.n = n; d.ntab = ntab; d.twmul = ntab/n;
-	if (tw.upload(twiddles(ntab))) return 1;
-	d.tw = tw.p;
-	d.fast = 0; d.pad_shift = 31; d.ntw_hi = 0;
+	host.tw = twiddles(ntab);
+	d.fast = 0; d.pad_shift = 31; d.ntw_hi = 0; d.bluestein = 0;
+	d.tw = nullptr; d.rev = nullptr; d.btw = nullptr; d.chirp = nullptr; d.bhat = nullptr;
 	if (fast_ok(n)) {
-		d.bluestein = 0; d.nt = n; d.fast = 1;
+		d.nt = n; d.fast = 1;
 		factorize_fast(n, d.fac, d.nfac);
 		d.pad_shift = pad_shift_of(n); d.nsmem = (int)smem_len(n); d.ntw_hi = (ntab + FFT_TWLO - 1)/FFT_TWLO;
-		if (rev.upload(digit_reversal(n, d.fac, d.nfac))) return 1;
-		d.rev = rev.p; d.btw = nullptr; d.chirp = nullptr; d.bhat = nullptr;
-		return 0;
-	}
-	if (smooth(n)) {
-		d.bluestein = 0; d.nt = n; d.nsmem = n;
+		host.rev = digit_reversal(n, d.fac, d.nfac);
+	} else if (smooth(n)) {
+		d.nt = n; d.nsmem = n;
 		factorize(n, d.fac, d.nfac);
 		B2_REQUIRE(d.nfac <= FFT_MAX_FAC, "too many FFT factors");
-		if (rev.upload(digit_reversal(n, d.fac, d.nfac))) return 1;
-		d.rev = rev.p; d.btw = nullptr; d.chirp = nullptr; d.bhat = nullptr;
-		return 0;
+		host.rev = digit_reversal(n, d.fac, d.nfac);
+	} else {
+		// Bluestein: chirp c_k = exp(-i pi k^2/n); X = c .* IFFT_M(FFT_M(x .* c) .* FFT_M(conj c wrapped))
+		const int M = bluestein_len(n);
+		d.bluestein = 1; d.nt = M; d.nsmem = M;
+		factorize(M, d.fac, d.nfac);
+		std::vector<int> rv = digit_reversal(M, d.fac, d.nfac);
+		host.chirp.resize(n);
+		std::vector<cld> b(M, cld(0, 0)), roots(M);
+		for (int k = 0; k < M; k++) { long double a = TAU*(long double)k/(long double)M; roots[k] = cld(cosl(a), -sinl(a)); }
+		for (int k = 0; k < n; k++) {
+			long long k2 = ((long long)k*k) % (2LL*n);
+			long double a = TAU*(long double)k2/(2.0L*n);
+			host.chirp[k].x = (double)cosl(a); host.chirp[k].y = (double)-sinl(a);
+			cld bc(cosl(a), sinl(a));
+			b[k] = bc; if (k) b[M - k] = bc;
+		}
+		host_fft(b, roots);
+		host.bhat.resize(M);
+		for (int k = 0; k < M; k++) { host.bhat[rv[k]].x = (double)(b[k].real()/M); host.bhat[rv[k]].y = (double)(b[k].imag()/M); }
+		host.rev.resize(n);
+		for (int k = 0; k < n; k++) host.rev[k] = k;
+		host.btw = twiddles(M);
 	}
-	// Bluestein: chirp c_k = exp(-i pi k^2/n); X = c .* IFFT_M(FFT_M(x .* c) .* FFT_M(conj c wrapped))
-	const int M = bluestein_len(n);
-	d.bluestein = 1; d.nt = M; d.nsmem = M;
-	factorize(M, d.fac, d.nfac);
-	std::vector<int> rv = digit_reversal(M, d.fac, d.nfac);
-	std::vector<double2> ch(n);
-	std::vector<cld> b(M, cld(0, 0));
-	for (int k = 0; k < n; k++) {
-		long long k2 = ((long long)k*k) % (2LL*n);
-		long double a = TAU*(long double)k2/(2.0L*n);
-		ch[k].x = (double)cosl(a); ch[k].y = (double)-sinl(a);
-		cld bc(cosl(a), sinl(a));
-		b[k] = bc; if (k) b[M - k] = bc;
-	}
-	host_fft(b);
-	std::vector<double2> bh(M);
-	for (int k = 0; k < M; k++) { bh[rv[k]].x = (double)(b[k].real()/M); bh[rv[k]].y = (double)(b[k].imag()/M); }
-	std::vector<int> ident(n);
-	for (int k = 0; k < n; k++) ident[k] = k;
-	if (btw.upload(twiddles(M)) || chirp.upload(ch) || bhat.upload(bh) || rev.upload(ident)) return 1;
-	d.btw = btw.p; d.chirp = chirp.p; d.bhat = bhat.p; d.rev = rev.p;
+	host.ready = true;
 	return 0;
+}
+
+int FftTables::commit()
+{
+	B2_REQUIRE(host.ready, "FFT tables were not prepared");
+	if (tw.upload(host.tw) || rev.upload(host.rev)) return 1;
+	d.tw = tw.p; d.rev = rev.p;
+	if (d.bluestein) {
+		if (btw.upload(host.btw) || chirp.upload(host.chirp) || bhat.upload(host.bhat)) return 1;
+		d.btw = btw.p; d.chirp = chirp.p; d.bhat = bhat.p;
+	}
+	host = HostTables();
+	return 0;
+}
+
+int FftTables::build(int n, int ntab)
+{
+	if (!(host.ready && host.n == n && host.ntab == ntab) && prepare(n, ntab)) return 1;
+	return commit();
 }
 
 __global__ void k_phase(double2 *ph, int mmax, double phi0)
@@ -179,6 +193,12 @@ __global__ void k_phase(double2 *ph, int mmax, double phi0)
 	if (m > mmax) return;
 	double s, c; sincos((double)m*phi0, &s, &c);
 	ph[m] = make_double2(c, s);
+}
+
+int RingFft::prepare_tables(int64_t nphi_)
+{
+	const int hf = (nphi_ % 2 == 0) ? 1 : 0;
+	return tab.prepare((int)(hf ? nphi_/2 : nphi_), (int)nphi_);
 }
 
 int RingFft::build(int64_t nphi_, double phi0, int xdir_, int64_t npix_, int nring_, const int64_t *rs,

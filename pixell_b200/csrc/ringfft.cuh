@@ -24,6 +24,8 @@ struct RingFft {
 	int twoff = 0;          // offset (elements) of the twiddle tables inside the dynamic shared memory
 	int build(int64_t nphi, double phi0, int xdir, int64_t npix, int nring, const int64_t *ringstart,
 	          const double *weight, int mmax);
+	// host-only part of build / build_group (the FFT tables of this ring length): thread-safe, for parallel plan construction
+	int prepare_tables(int64_t nphi);
 	// group form: `ids` lists the plan rings with this nphi, phi0_of_id their phi0 (all rings' ringstart / weight arrays are passed whole)
 	int build_group(int64_t nphi, int nids, const int *ids, const double *phi0_of_id, int nring_total, const int64_t *ringstart,
 	                const double *weight, int mmax);

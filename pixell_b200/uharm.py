@@ -7,8 +7,8 @@ so that filtering code is written once:
 	omap = uht.harm2map(uht.hmul(beam, uht.map2harm(map)))
 
 Provided: map2harm, harm2map and their adjoints, quad_weights, lprof2hprof, rprof2hprof / hprof2rprof (curved mode),
-hprof2harm, hmul, harm2powspec, sum_hprof, mean_hprof.  Flat-sky radial profiles (profile2harm_flat_2d, which needs
-enmap's rbin / modrmap), hrand and hprof_rpow are not provided.
+hprof2harm, hmul, hrand and hprof_rpow (curved mode), harm2powspec, sum_hprof, mean_hprof, beam2res, beam2rmax.  The
+flat-sky radial profile helpers (profile2harm_flat(_2d), harm2profile_flat_2d: enmap's rbin / lbin / modrmap) are not provided.
 """
 import numpy as np
 from . import enmap, curvedsky, geometry, _lib as L
@@ -117,3 +117,23 @@ class UHT:
 		if self.mode == "flat": return np.sum(hprof*self.nper, (-2, -1))
 		return np.sum(hprof*self.nper, -1)
 	def mean_hprof(self, hprof): return self.sum_hprof(hprof)/self.ntot
+	def hrand(self, hprof, seed=None):
+		"""random realisation with harmonic profile hprof (pixell/uharm.py:166-172; curved mode: curvedsky.rand_alm)"""
+		if self.mode == "flat": raise NotImplementedError("flat-sky hrand (enmap.rand_gauss_harm) is not provided by pixell_b200")
+		return curvedsky.rand_alm(hprof, lmax=self.lmax, seed=seed)
+	def hprof_rpow(self, hprof, power):
+		"""hprof raised to `power` in real space: map2harm(harm2map(hprof)**power) on profiles (pixell/uharm.py:191-208)"""
+		if self.mode == "flat": raise NotImplementedError("flat-sky hprof_rpow is not provided by pixell_b200")
+		hprof = np.asarray(hprof)
+		sigma = 1/max(1, np.where(hprof > np.max(hprof)*np.exp(-0.5))[0][-1])
+		r = np.arange(0, 20*sigma, sigma/10)
+		return self.rprof2hprof(self.hprof2rprof(hprof, r)**power, r)
+
+def beam2res(br, r):
+	"""a third of the beam's full width at half maximum (pixell/uharm.py:255-258)"""
+	return 2*r[np.where(br >= br[0]*0.5)[0][-1]]/3
+
+def beam2rmax(br, r, tol=1e-5, return_index=False):
+	"""radius beyond which the beam stays below tol of its peak (pixell/uharm.py:260-263)"""
+	imax = np.where(br >= br[0]*tol)[0][-1]
+	return (r[imax], imax) if return_index else r[imax]
