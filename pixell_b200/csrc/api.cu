@@ -128,11 +128,19 @@ b2_sht_plan::~b2_sht_plan()
 	if (s_in) cudaStreamDestroy(s_in);
 	if (s_out) cudaStreamDestroy(s_out);
 	if (s_comp) cudaStreamDestroy(s_comp);
+	if (s_fft) cudaStreamDestroy(s_fft);
+	if (sig_flag_h) cudaFreeHost(sig_flag_h);
+	if (gate_src_h) cudaFreeHost(gate_src_h);
+	if (ev_fork) cudaEventDestroy(ev_fork);
+	if (ev_join) cudaEventDestroy(ev_join);
+	for (auto &e : ev_ready) if (e) cudaEventDestroy(e);
+	for (auto &e : ev_free) if (e) cudaEventDestroy(e);
+	for (auto &e : ev_chunk) if (e) cudaEventDestroy(e);
 }
 
 size_t b2_sht_plan::bytes() const
 {
-	size_t b = mstart.bytes() + geom.bytes() + fft.bytes() + leg.bytes() + w2d.bytes() + stage_alm.bytes() + stage_map.bytes();
+	size_t b = mstart.bytes() + geom.bytes() + fft.bytes() + leg.bytes() + leg2.bytes() + w2d.bytes() + stage_alm.bytes() + stage_map.bytes();
 	for (auto &g : groups) b += g->bytes();
 	for (auto &t : tables) b += t.second->bytes();
 	for (auto &t : starts) if (t.second) b += t.second->bytes();
@@ -166,20 +174,32 @@ LegStart *b2_sht_plan::get_start(int spin)
 	return p;
 }
 
-// chunks of the streamed host-memory path (see b2_sht_plan::schunks / mcuts)
+// chunks of the streamed host-memory path (see b2_sht_plan::schunks / mcuts).  Both lists shrink towards their end: what
+// stays exposed is the copy of the last chunk, and the later chunks are the expensive ones to compute (rings near the
+// equator, resp. nothing left to hide behind), so their copies still finish under the next chunk's kernels.
 static void plan_stream_setup(b2_sht_plan *p)
 {
-	static const int nchunk = std::min(4, getenv("B2_STREAM_CHUNKS") ? atoi(getenv("B2_STREAM_CHUNKS")) : 4);
+	static const int enable = getenv("B2_STREAM_CHUNKS") ? atoi(getenv("B2_STREAM_CHUNKS")) : 1;
 	p->schunks.clear(); p->mcuts.clear();
-	if (nchunk < 2) return;
+	if (enable < 1) return;
 	const int np = p->geom.npair_pad;
 	const bool dense_rows = p->nphi > 0 && p->nring > 1 && (p->row_pitch == p->npix || p->row_pitch == -p->npix);
 	if (dense_rows && np >= 2048) {
-		const int step = (int)b2_round_up((np + nchunk - 1)/nchunk, 512);
+		// units of 256 ring pairs, shares 6 : 4 : 3 : 2 : 1
+		const int unit = 256, U = np/unit;
+		static const int share[5] = {6, 4, 3, 2, 1};
+		std::vector<int> bounds(1, 0);
+		for (int k = 0, acc = 0; k < 5; k++) {
+			acc += share[k];
+			int b = std::max(bounds.back() + 1, (U*acc + 8)/16);
+			if (k == 4) b = U;
+			if (b > U) b = U;
+			if (b > bounds.back()) bounds.push_back(b);
+		}
 		std::vector<b2_sht_plan::StreamChunk> ch;
 		bool ok = true;
-		for (int lo = 0; lo < np && ok; lo += step) {
-			b2_sht_plan::StreamChunk c; c.pair_lo = lo; c.pair_hi = std::min(np, lo + step); c.nrun = 0;
+		for (size_t k = 0; k + 1 < bounds.size() && ok; k++) {
+			b2_sht_plan::StreamChunk c; c.pair_lo = bounds[k]*unit; c.pair_hi = (k + 2 == bounds.size()) ? np : bounds[k + 1]*unit; c.nrun = 0;
 			std::vector<int> rings;
 			for (int i = c.pair_lo; i < c.pair_hi; i++) { if (p->geom.rn_h[i] >= 0) rings.push_back(p->geom.rn_h[i]); if (p->geom.rs_h[i] >= 0) rings.push_back(p->geom.rs_h[i]); }
 			std::sort(rings.begin(), rings.end());
@@ -192,17 +212,20 @@ static void plan_stream_setup(b2_sht_plan *p)
 			}
 			if (c.nrun > 0) ch.push_back(c);
 		}
-		if (ok && ch.size() >= 2) p->schunks = ch;
+		if (ok && ch.size() >= 2 && ch.size() <= 8) p->schunks = ch;
 	}
 	if (p->alm_dense && p->lstride == 1 && p->mmax >= 256) {
 		bool inc = true;
 		for (int m = 1; m <= p->mmax && inc; m++) inc = p->mstart_h[m] + m == p->mstart_h[m - 1] + p->lmax + 1;
 		if (inc) {
+			// ranges of m holding 5 : 5 : 5 : 4 : 3 : 2 of the coefficients
+			static const int share[6] = {5, 5, 5, 4, 3, 2};
 			int64_t total = 0, acc = 0; for (int m = 0; m <= p->mmax; m++) total += p->lmax - m + 1;
 			p->mcuts.push_back(0);
-			for (int m = 0, k = 1; m <= p->mmax; m++) {
+			int64_t want = share[0];
+			for (int m = 0, k = 0; m <= p->mmax && k < 5; m++) {
 				acc += p->lmax - m + 1;
-				if (k < nchunk && acc*nchunk >= total*k) { p->mcuts.push_back(m + 1); k++; }
+				if (acc*24 >= total*want) { if (m + 1 <= p->mmax) p->mcuts.push_back(m + 1); k++; want += share[k]; }
 			}
 			if (p->mcuts.back() != p->mmax + 1) p->mcuts.push_back(p->mmax + 1);
 		}
@@ -391,8 +414,34 @@ __global__ void k_scale_rows(double2 *leg, const double *w, int nring, int64_t n
 
 enum { OP_SYNTH, OP_ADJ_SYNTH, OP_ANALYSIS, OP_ADJ_ANALYSIS };
 
+// B2_TRACE=1: stage timeline of every host-memory call on stderr (debugging aid; events are created per mark)
+struct Trace {
+	bool on = false; std::vector<std::pair<std::string, cudaEvent_t>> ev;
+	Trace() { on = getenv("B2_TRACE") && atoi(getenv("B2_TRACE")); }
+	void mark(const char *name, int g, cudaStream_t s) {
+		if (!on) return;
+		cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return;
+		cudaEventRecord(e, s);
+		char b[96]; snprintf(b, sizeof b, "g%d %s", g, name); ev.emplace_back(b, e);
+	}
+	void dump(const char *title) {
+		if (!on || ev.empty()) return;
+		cudaDeviceSynchronize();
+		std::vector<std::pair<float, std::string>> rows;
+		for (auto &x : ev) { float t = 0; cudaEventElapsedTime(&t, ev[0].second, x.second); rows.emplace_back(t, x.first); }
+		for (auto &x : ev) cudaEventDestroy(x.second);
+		std::sort(rows.begin(), rows.end());
+		fprintf(stderr, "[b2 trace] %s\n", title);
+		for (auto &r : rows) fprintf(stderr, "  %9.3f ms  %s\n", r.first, r.second.c_str());
+		ev.clear();
+	}
+};
+static Trace g_trace;
+#define TR(name, s) g_trace.mark(name, G.gi, s)
+
 struct Exec {
-	b2_sht_plan *p; int op, spin, mode, dtype, mem; cudaStream_t st;      // st: compute stream
+	b2_sht_plan *p; int op, spin, mode, dtype, mem; cudaStream_t st;      // st: compute stream (Legendre kernels)
+	cudaStream_t sf;                                                      // stream of the ring FFT / theta stages (== st: no overlap)
 	cudaStream_t s_in, s_out;                                             // copy streams (host-memory calls)
 	int nca, ncm;              // alm / map components
 	size_t asz, msz;           // bytes per complex alm element / real map element
@@ -404,6 +453,7 @@ struct GroupCtx {
 	double2 *dalm; int64_t dalm_cs; float2 *tmp32;             // complex128 alm on the device (+ complex64 scratch)
 	void *dmap; int64_t dmap_cs; char *dmap_base;              // map on the device (element offsets as in the caller's array)
 	bool alm_direct, streamed;      // streamed: the results already left for the host chunk by chunk
+	int gi; int lane; double2 *leg; bool lane_reused; bool last, poll, gated; LegSignal gate;      // poll: alm ranges leave as the kernel's flags come in      // which of the plan's two leg buffers this group works in
 	cudaEvent_t ev_in, ev_done;
 };
 
@@ -445,7 +495,29 @@ static int group_stage_in(Exec &E, GroupCtx &G, char *salm, char *smap)
 		G.tmp32 = (float2*)(salm + (size_t)E.nca*p->alm_span*16);
 		// the input direction needs the values; the output direction needs them too so that entries the
 		// transform does not own survive the round trip
-		for (int c = 0; c < E.nca; c++) {
+		// first group of a host-memory synthesis: nothing hides this copy, so it goes range by range of m, each followed by
+		// its arrival flag, and the Legendre kernel's CTAs start as soon as their own range is there (B2_GATE_ALM=0: off)
+		static const bool gate_alm = !(getenv("B2_GATE_ALM") && !atoi(getenv("B2_GATE_ALM")));
+		if (gate_alm && to_map && G.gi == 0 && E.mem == B2_MEM_HOST && E.dtype == B2_F64 && E.s_in != E.st
+			&& p->mcuts.size() >= 3 && (int)p->mcuts.size() <= LEG_MAXCUT) {
+			if (!p->gate_src_h) {
+				B2_CHECK(cudaHostAlloc((void**)&p->gate_src_h, LEG_MAXCUT*sizeof(int), cudaHostAllocDefault));
+				if (p->gate_flag.alloc(16*LEG_MAXCUT)) return 1;
+				B2_CHECK(cudaMemset(p->gate_flag.p, 0, p->gate_flag.bytes()));
+			}
+			LegSignal &sg = G.gate; sg.ncut = (int)p->mcuts.size(); sg.epoch = ++p->gate_epoch; sg.count = nullptr; sg.flag = p->gate_flag.p;
+			for (int i = 0; i < sg.ncut; i++) sg.cut[i] = p->mcuts[i];
+			for (int r = 0; r + 1 < sg.ncut; r++) {
+				const int m_lo = p->mcuts[r], m_hi = p->mcuts[r + 1];
+				const int64_t lo = p->mstart_h[m_lo] + m_lo, hi = p->mstart_h[m_hi - 1] + p->lmax + 1;
+				for (int c = 0; c < E.nca; c++)
+					B2_CHECK(cudaMemcpyAsync(G.dalm + (size_t)c*G.dalm_cs + lo, (char*)G.alm + ((size_t)c*G.alm_cs + lo)*16, (size_t)(hi - lo)*16, cudaMemcpyHostToDevice, E.s_in));
+				p->gate_src_h[r] = sg.epoch;
+				B2_CHECK(cudaMemcpyAsync((void*)sg.flag_of(r), &p->gate_src_h[r], sizeof(int), cudaMemcpyHostToDevice, E.s_in));
+			}
+			G.gated = true;
+		}
+		for (int c = 0; c < E.nca && !G.gated; c++) {
 			if (!to_map && p->alm_dense) break;      // every entry of the span is overwritten
 			char *src = (char*)G.alm + (size_t)c*G.alm_cs*E.asz;
 			if (E.dtype == B2_F64) B2_CHECK(cudaMemcpyAsync(G.dalm + c*G.dalm_cs, src, p->alm_span*16, cudaMemcpyDefault, E.s_in));
@@ -461,20 +533,39 @@ static int group_stage_in(Exec &E, GroupCtx &G, char *salm, char *smap)
 			if (copy_map(E, (char*)G.map + (size_t)c*G.map_cs*E.msz, smap + (size_t)c*span*E.msz, true, E.s_in)) return 1;
 	}
 	if (E.s_in != E.st) B2_CHECK(cudaEventRecord(G.ev_in, E.s_in));
+	TR("h2d done", E.s_in);
 	return 0;
 }
 
-// phase 2: the transform (compute stream)
+// phase 2: the transform.  Legendre kernels (and the alm precision conversions) on E.st, the HBM-bound stages (ring
+// FFTs, theta weighting) on E.sf; E.sf == E.st runs everything in order on one stream.
+static int hop(cudaStream_t from, cudaStream_t to, cudaEvent_t ev)
+{
+	if (from == to) return 0;
+	B2_CHECK(cudaEventRecord(ev, from));
+	B2_CHECK(cudaStreamWaitEvent(to, ev, 0));
+	return 0;
+}
+
 static int group_compute(Exec &E, GroupCtx &G)
 {
 	b2_sht_plan *p = E.p;
 	const bool to_map = to_map_op(E.op);
+	const bool two = E.sf != E.st;
 	LegTables *T = p->get_tables(E.spin);
 	if (!T) return 1;
 	AlmLayout L; L.lmax = p->lmax; L.mmax = p->mmax; L.mstart_d = p->mstart.p; L.lstride = p->lstride;
 	const int deriv1 = E.mode == B2_MODE_DERIV1;
+	double2 *leg = G.leg;
 	B2_CHECK(cudaEventRecord(p->ev[0], E.st));
-	if (E.s_in != E.st) B2_CHECK(cudaStreamWaitEvent(E.st, G.ev_in, 0));
+	TR("compute enqueued (stream position)", E.st);
+	if (E.s_in != E.st) {
+		if (!G.gated) B2_CHECK(cudaStreamWaitEvent(E.st, G.ev_in, 0));      // gated: the kernel's CTAs wait for their own range of alm
+		if (two) B2_CHECK(cudaStreamWaitEvent(E.sf, G.ev_in, 0));
+	}
+	const LegSignal *gate = G.gated ? &G.gate : nullptr;
+	// the group that used this leg buffer before must be through with it: its last reader ran on the other stream
+	if (two && G.lane_reused) B2_CHECK(cudaStreamWaitEvent(to_map ? E.st : E.sf, p->ev_free[G.lane], 0));
 	if (!G.alm_direct && E.dtype == B2_F32 && !(!to_map && p->alm_dense)) {
 		for (int c = 0; c < E.nca; c++) {
 			const float2 *s32 = E.mem == B2_MEM_HOST ? G.tmp32 + c*p->alm_span : (const float2*)((char*)G.alm + (size_t)c*G.alm_cs*E.asz);
@@ -482,20 +573,27 @@ static int group_compute(Exec &E, GroupCtx &G)
 			B2_LAUNCH_CHECK();
 		}
 	}
-	B2_CHECK(cudaEventRecord(p->ev[1], E.st));
+	B2_CHECK(cudaEventRecord(p->ev[1], to_map ? E.st : E.sf));
 	const bool host64 = E.mem == B2_MEM_HOST && E.dtype == B2_F64 && E.s_out != E.st;
 	if (to_map && E.op == OP_SYNTH && host64 && !p->schunks.empty() && p->groups.empty()) {
 		// chunks of ring pairs, pole -> equator: Legendre synthesis and ring FFTs of a chunk, then its rows go to the host
 		// on the copy stream while the next chunk is computed; only the last chunk's copy is exposed
 		const size_t span = (size_t)(p->map_hi - p->map_lo);
+		B2_CHECK(cudaEventRecord(p->ev[5], E.st));
 		for (size_t c = 0; c < p->schunks.size(); c++) {
 			const b2_sht_plan::StreamChunk &C = p->schunks[c];
-			if (leg_alm2leg(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st, p->get_start(E.spin), C.pair_lo, C.pair_hi)) return 1;
+			if (leg_alm2leg(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, leg, E.st, p->get_start(E.spin), C.pair_lo, C.pair_hi, gate)) return 1;
 			if (c + 1 == p->schunks.size()) B2_CHECK(cudaEventRecord(p->ev[2], E.st));
+			TR("K1 chunk done", E.st);
+			if (two) {
+				if (!p->ev_chunk[c]) B2_CHECK(cudaEventCreateWithFlags(&p->ev_chunk[c], cudaEventDisableTiming));
+				if (hop(E.st, E.sf, p->ev_chunk[c])) return 1;
+			}
 			for (int r = 0; r < C.nrun; r++)
-				if (ring_leg2map(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.st, C.r0[r], C.nr[r])) return 1;
+				if (ring_leg2map(p->fft, E.ncm, leg, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.sf, C.r0[r], C.nr[r])) return 1;
 			if (!p->sev[c]) B2_CHECK(cudaEventCreateWithFlags(&p->sev[c], cudaEventDisableTiming));
-			B2_CHECK(cudaEventRecord(p->sev[c], E.st));
+			B2_CHECK(cudaEventRecord(p->sev[c], E.sf));
+			TR("K3 chunk done", E.sf);
 			B2_CHECK(cudaStreamWaitEvent(E.s_out, p->sev[c], 0));
 			for (int r = 0; r < C.nrun; r++) {
 				const int64_t a = p->ringstart_h[C.r0[r]], b = p->ringstart_h[C.r0[r] + C.nr[r] - 1];
@@ -504,56 +602,71 @@ static int group_compute(Exec &E, GroupCtx &G)
 					B2_CHECK(cudaMemcpyAsync((char*)G.map + ((size_t)k*G.map_cs + lo)*E.msz, G.dmap_base + ((size_t)k*span + (lo - p->map_lo))*E.msz,
 						(size_t)nel*E.msz, cudaMemcpyDeviceToHost, E.s_out));
 			}
+			TR("d2h chunk done", E.s_out);
 		}
-		B2_CHECK(cudaEventRecord(p->ev[3], E.st));
-		B2_CHECK(cudaEventRecord(p->ev[4], E.st));
+		B2_CHECK(cudaEventRecord(p->ev[3], E.sf));
+		B2_CHECK(cudaEventRecord(p->ev[4], E.sf));
+		if (two) B2_CHECK(cudaEventRecord(p->ev_free[G.lane], E.sf));
 		G.streamed = true;
 	} else if (to_map) {
-		if (leg_alm2leg(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st, p->get_start(E.spin))) return 1;
+		B2_CHECK(cudaEventRecord(p->ev[5], E.st));
+		if (leg_alm2leg(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, leg, E.st, p->get_start(E.spin), 0, 0, gate)) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[2], E.st));
+		TR("K1 done", E.st);
+		if (hop(E.st, E.sf, p->ev_ready[G.lane])) return 1;
 		if (E.op == OP_ADJ_ANALYSIS) {
-			if (p->resamp) { if (p->resamp->apply(p->leg.p, E.ncm, E.spin, E.st, true)) return 1; }
+			if (p->resamp) { if (p->resamp->apply(leg, E.ncm, E.spin, E.sf, true)) return 1; }
 			else {
 				int64_t nrow = (int64_t)E.ncm*(p->mmax + 1);
-				k_scale_rows<<<(unsigned)((nrow*p->geom.nring_pad + 255)/256), 256, 0, E.st>>>(p->leg.p, p->w2d.p, p->nring, p->geom.nring_pad, nrow);
+				k_scale_rows<<<(unsigned)((nrow*p->geom.nring_pad + 255)/256), 256, 0, E.sf>>>(leg, p->w2d.p, p->nring, p->geom.nring_pad, nrow);
 				B2_LAUNCH_CHECK();
 			}
 		}
-		B2_CHECK(cudaEventRecord(p->ev[3], E.st));
-		if (p->groups.empty()) { if (ring_leg2map(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.st)) return 1; }
-		else if (run_groups(p, E.st, [&](const RingFft &g, cudaStream_t s) { return ring_leg2map(g, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, s); })) return 1;
-		B2_CHECK(cudaEventRecord(p->ev[4], E.st));
+		B2_CHECK(cudaEventRecord(p->ev[3], E.sf));
+		if (p->groups.empty()) { if (ring_leg2map(p->fft, E.ncm, leg, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.sf)) return 1; }
+		else if (run_groups(p, E.sf, [&](const RingFft &g, cudaStream_t s) { return ring_leg2map(g, E.ncm, leg, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, s); })) return 1;
+		B2_CHECK(cudaEventRecord(p->ev[4], E.sf));
+		TR("K3 done", E.sf);
+		if (two) B2_CHECK(cudaEventRecord(p->ev_free[G.lane], E.sf));
 	} else {
-		if (p->groups.empty()) { if (ring_map2leg(p->fft, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, E.st)) return 1; }
-		else if (run_groups(p, E.st, [&](const RingFft &g, cudaStream_t s) { return ring_map2leg(g, E.ncm, p->leg.p, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, s); })) return 1;
-		B2_CHECK(cudaEventRecord(p->ev[2], E.st));
+		if (p->groups.empty()) { if (ring_map2leg(p->fft, E.ncm, leg, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, E.sf)) return 1; }
+		else if (run_groups(p, E.sf, [&](const RingFft &g, cudaStream_t s) { return ring_map2leg(g, E.ncm, leg, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, s); })) return 1;
+		B2_CHECK(cudaEventRecord(p->ev[2], E.sf));
+		TR("K4 done", E.sf);
 		if (E.op == OP_ANALYSIS) {
-			if (p->resamp) { if (p->resamp->apply(p->leg.p, E.ncm, E.spin, E.st)) return 1; }
+			if (p->resamp) { if (p->resamp->apply(leg, E.ncm, E.spin, E.sf)) return 1; }
 			else {
 				int64_t nrow = (int64_t)E.ncm*(p->mmax + 1);
-				k_scale_rows<<<(unsigned)((nrow*p->geom.nring_pad + 255)/256), 256, 0, E.st>>>(p->leg.p, p->w2d.p, p->nring, p->geom.nring_pad, nrow);
+				k_scale_rows<<<(unsigned)((nrow*p->geom.nring_pad + 255)/256), 256, 0, E.sf>>>(leg, p->w2d.p, p->nring, p->geom.nring_pad, nrow);
 				B2_LAUNCH_CHECK();
 			}
 		}
-		B2_CHECK(cudaEventRecord(p->ev[3], E.st));
-		// (off by default: one CTA per m takes ~1/5 of the kernel's run time, so every extra launch adds a tail that costs
-		// more than the copy it hides -- measured on B200, C3: map2alm 212 -> 245 ms; B2_STREAM_ALM=1 enables it)
-		static const bool stream_alm = getenv("B2_STREAM_ALM") && atoi(getenv("B2_STREAM_ALM"));
-		if (stream_alm && host64 && !G.alm_direct && p->mcuts.size() >= 3) {
-			// ranges of m with about equal alm bytes: each range's coefficients go to the host while the next is computed
-			for (size_t c = 0; c + 1 < p->mcuts.size(); c++) {
-				const int m_lo = p->mcuts[c], m_hi = p->mcuts[c + 1];
-				if (leg_leg2alm(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st, p->get_start(E.spin), m_lo, m_hi)) return 1;
-				if (!p->sev[4 + c]) B2_CHECK(cudaEventCreateWithFlags(&p->sev[4 + c], cudaEventDisableTiming));
-				B2_CHECK(cudaEventRecord(p->sev[4 + c], E.st));
-				B2_CHECK(cudaStreamWaitEvent(E.s_out, p->sev[4 + c], 0));
-				const int64_t lo = p->mstart_h[m_lo] + m_lo, hi = p->mstart_h[m_hi - 1] + p->lmax + 1;
-				for (int k = 0; k < E.nca; k++)
-					B2_CHECK(cudaMemcpyAsync((char*)G.alm + ((size_t)k*G.alm_cs + lo)*16, G.dalm + (size_t)k*G.dalm_cs + lo, (size_t)(hi - lo)*16, cudaMemcpyDeviceToHost, E.s_out));
+		B2_CHECK(cudaEventRecord(p->ev[3], E.sf));
+		TR("K5 done", E.sf);
+		if (hop(E.sf, E.st, p->ev_ready[G.lane])) return 1;
+		B2_CHECK(cudaEventRecord(p->ev[5], E.st));
+		// Last group of a host-memory call: nothing is left to hide its alm copy behind, so the kernel reports every range
+		// of m it completes (LegSignal) and execute_groups sends that range to the host while the kernel works on the rest.
+		// (Separate launches per range were measured too: every launch ends in a tail of single-warp CTAs that costs more
+		// than the copy it hides, C3 map2alm 212 -> 245 ms.)  B2_STREAM_ALM=0 disables it.
+		static const bool stream_alm = !(getenv("B2_STREAM_ALM") && !atoi(getenv("B2_STREAM_ALM")));
+		if (stream_alm && host64 && !G.alm_direct && G.last && p->mcuts.size() >= 3 && (int)p->mcuts.size() <= LEG_MAXCUT) {
+			if (!p->sig_flag_h) {
+				B2_CHECK(cudaHostAlloc((void**)&p->sig_flag_h, 16*LEG_MAXCUT*sizeof(int), cudaHostAllocMapped));
+				memset(p->sig_flag_h, 0, 16*LEG_MAXCUT*sizeof(int));
+				B2_CHECK(cudaHostGetDevicePointer((void**)&p->sig_flag_d, p->sig_flag_h, 0));
+				if (p->sig_count.alloc(LEG_MAXCUT)) return 1;
 			}
-			G.streamed = true;
-		} else if (leg_leg2alm(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, p->leg.p, E.st, p->get_start(E.spin))) return 1;
+			LegSignal sg; sg.ncut = (int)p->mcuts.size(); sg.epoch = ++p->sig_epoch;
+			for (int i = 0; i < sg.ncut; i++) sg.cut[i] = p->mcuts[i];
+			sg.count = p->sig_count.p; sg.flag = p->sig_flag_d;
+			B2_CHECK(cudaMemsetAsync(p->sig_count.p, 0, LEG_MAXCUT*sizeof(unsigned), E.st));
+			if (leg_leg2alm(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, leg, E.st, p->get_start(E.spin), 0, 0, &sg)) return 1;
+			G.streamed = true; G.poll = true;
+		} else if (leg_leg2alm(*T, p->geom, L, deriv1, G.dalm, G.dalm_cs, leg, E.st, p->get_start(E.spin))) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[4], E.st));
+		TR("K2 done", E.st);
+		if (two) B2_CHECK(cudaEventRecord(p->ev_free[G.lane], E.st));
 		if (!G.alm_direct && E.dtype == B2_F32) {
 			for (int c = 0; c < E.nca; c++) {
 				float2 *d32 = E.mem == B2_MEM_HOST ? G.tmp32 + c*p->alm_span : (float2*)((char*)G.alm + (size_t)c*G.alm_cs*E.asz);
@@ -563,7 +676,7 @@ static int group_compute(Exec &E, GroupCtx &G)
 		}
 	}
 	p->timing[0] = to_map ? 1 : -1;
-	if (E.s_out != E.st) B2_CHECK(cudaEventRecord(G.ev_done, E.st));
+	if (E.s_out != E.st) B2_CHECK(cudaEventRecord(G.ev_done, to_map ? E.sf : E.st));
 	return 0;
 }
 
@@ -574,6 +687,7 @@ static int group_stage_out(Exec &E, GroupCtx &G)
 	const bool to_map = to_map_op(E.op);
 	if (G.streamed) return 0;
 	if (E.s_out != E.st) B2_CHECK(cudaStreamWaitEvent(E.s_out, G.ev_done, 0));
+	struct Done { GroupCtx &G; cudaStream_t s; ~Done() { TR("d2h done", s); } } done_mark{G, E.s_out};
 	if (to_map) {
 		if (E.mem == B2_MEM_HOST) {
 			size_t span = (size_t)(p->map_hi - p->map_lo);
@@ -603,6 +717,30 @@ static int check_exec_args(b2_sht_plan *plan, int op, int spin, int mode, int dt
 	return 0;
 }
 
+// Host side of LegSignal: as soon as the kernel has published a range of m, its coefficients go to the host.
+static int poll_and_copy(Exec &E, GroupCtx &G)
+{
+	b2_sht_plan *p = E.p;
+	const int nr = (int)p->mcuts.size() - 1;
+	bool drained = false;
+	static const int dbg = getenv("B2_SIG_DEBUG") ? atoi(getenv("B2_SIG_DEBUG")) : 0;      // 1: no polling, 2: poll, copy at the end
+	if (dbg == 1) { B2_CHECK(cudaStreamSynchronize(E.st)); drained = true; }
+	if (dbg == 2) { for (int r = 0; r < nr; r++) { volatile int *f = p->sig_flag_h + 16*r; while (*f != p->sig_epoch) {} } drained = true; }
+	for (int r = 0; r < nr; r++) {
+		volatile int *f = p->sig_flag_h + 16*r;
+		for (unsigned spin = 0; !drained && *f != p->sig_epoch; spin++) {
+			// the stream running dry (kernel finished, or failed) also ends the wait: stream order then covers the copy
+			if ((spin & 255) == 255 && cudaStreamQuery(E.st) != cudaErrorNotReady) { drained = true; B2_CHECK(cudaStreamSynchronize(E.st)); }
+		}
+		const int m_lo = p->mcuts[r], m_hi = p->mcuts[r + 1];
+		const int64_t lo = p->mstart_h[m_lo] + m_lo, hi = p->mstart_h[m_hi - 1] + p->lmax + 1;
+		for (int k = 0; k < E.nca; k++)
+			B2_CHECK(cudaMemcpyAsync((char*)G.alm + ((size_t)k*G.alm_cs + lo)*16, G.dalm + (size_t)k*G.dalm_cs + lo, (size_t)(hi - lo)*16, cudaMemcpyDeviceToHost, E.s_out));
+		g_trace.mark("alm range copy queued (s_out position)", G.gi, E.s_out);
+	}
+	return 0;
+}
+
 // Runs a list of spin groups.  Device memory: everything on the caller's stream, in order.  Host memory: three
 // streams -- the H2D copies of group g+1 and the D2H copies of group g-1 overlap the kernels of group g.
 static int execute_groups(b2_sht_plan *plan, int op, int ngroups, const int *spins, int mode, int dtype,
@@ -618,6 +756,32 @@ static int execute_groups(b2_sht_plan *plan, int op, int ngroups, const int *spi
 		if (!plan->s_comp) B2_CHECK(cudaStreamCreateWithFlags(&plan->s_comp, cudaStreamNonBlocking));
 		E.s_in = plan->s_in; E.s_out = plan->s_out;
 		if (!E.st) E.st = plan->s_comp;      // never the legacy stream: it would serialise with the copy streams' neighbours
+	}
+	// several groups: two-stage pipeline (see b2_sht_plan::s_fft)
+	// Off by default (B2_OVERLAP=1 enables it): measured on B200 at C3 it gains nothing -- the Legendre grids keep every SM's
+	// register file full, a 512-thread FFT CTA only fits once six of their CTAs have left one SM, and what does get in
+	// displaces FP64 work one for one (map2alm 174.6 ms in order, 177.4 ms pipelined).
+	static const bool overlap = getenv("B2_OVERLAP") && atoi(getenv("B2_OVERLAP"));
+	E.sf = E.st;
+	if (ngroups > 1 && overlap) {
+		if (!plan->s_fft) {
+			int lo = 0, hi = 0;
+			B2_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+			B2_CHECK(cudaStreamCreateWithPriority(&plan->s_fft, cudaStreamNonBlocking, hi));
+			B2_CHECK(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
+			B2_CHECK(cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming));
+			for (int i = 0; i < 2; i++) {
+				B2_CHECK(cudaEventCreateWithFlags(&plan->ev_ready[i], cudaEventDisableTiming));
+				B2_CHECK(cudaEventCreateWithFlags(&plan->ev_free[i], cudaEventDisableTiming));
+			}
+		}
+		if (!plan->leg2.n) {
+			if (plan->leg2.alloc(plan->leg.n)) return 1;
+			B2_CHECK(cudaMemsetAsync(plan->leg2.p, 0, plan->leg2.bytes(), E.st));
+		}
+		E.sf = plan->s_fft;
+		B2_CHECK(cudaEventRecord(plan->ev_fork, E.st));
+		B2_CHECK(cudaStreamWaitEvent(E.sf, plan->ev_fork, 0));
 	}
 	GroupCtx G[B2_MAX_GROUPS];
 	size_t off_a[B2_MAX_GROUPS + 1] = {0}, off_m[B2_MAX_GROUPS + 1] = {0};
@@ -638,7 +802,10 @@ static int execute_groups(b2_sht_plan *plan, int op, int ngroups, const int *spi
 		E.spin = spins[g]; E.ncm = E.spin == 0 ? 1 : 2; E.nca = (E.spin == 0 || mode == B2_MODE_DERIV1) ? 1 : 2;
 		G[g].alm = alms[g]; G[g].alm_cs = alm_cs[g]; G[g].map = maps[g]; G[g].map_cs = map_cs[g];
 		G[g].ev_in = plan->gev[2*g]; G[g].ev_done = plan->gev[2*g + 1];
+		G[g].gi = g; G[g].last = (g == ngroups - 1); G[g].lane = (E.sf != E.st) ? (g & 1) : 0; G[g].leg = G[g].lane ? plan->leg2.p : plan->leg.p; G[g].lane_reused = g >= 2;
 	};
+	for (int g = 0; g < ngroups; g++) { G[g].poll = false; G[g].gated = false; }
+	g_trace.mark("start", -1, E.s_in);
 	// all copies in are queued first (they run back to back on the copy stream), then each group's kernels and copies out
 	for (int g = 0; g < ngroups; g++) { setup(g); if (group_stage_in(E, G[g], plan->stage_alm.p + off_a[g], plan->stage_map.p + off_m[g])) return 1; }
 	for (int g = 0; g < ngroups; g++) {
@@ -646,7 +813,16 @@ static int execute_groups(b2_sht_plan *plan, int op, int ngroups, const int *spi
 		if (group_compute(E, G[g])) return 1;
 		if (group_stage_out(E, G[g])) return 1;
 	}
+	for (int g = 0; g < ngroups; g++) if (G[g].poll) {
+		E.spin = spins[g]; E.ncm = E.spin == 0 ? 1 : 2; E.nca = (E.spin == 0 || mode == B2_MODE_DERIV1) ? 1 : 2;
+		if (poll_and_copy(E, G[g])) return 1;
+	}
+	if (E.sf != E.st) {
+		B2_CHECK(cudaEventRecord(plan->ev_join, E.sf));
+		B2_CHECK(cudaStreamWaitEvent(E.st, plan->ev_join, 0));
+	}
 	if (mem == B2_MEM_HOST) { B2_CHECK(cudaStreamSynchronize(E.s_out)); B2_CHECK(cudaStreamSynchronize(E.st)); }
+	if (mem == B2_MEM_HOST) g_trace.dump(to_map_op(op) ? "alm -> map" : "map -> alm");
 	return 0;
 }
 
@@ -699,13 +875,16 @@ extern "C" int b2_sht_last_timing(b2_sht_plan *p, double out[4])
 {
 	B2_REQUIRE(p && out, "timing: null argument");
 	B2_CHECK(cudaEventSynchronize(p->ev[4]));
-	float t01, t12, t23, t34;
+	B2_CHECK(cudaEventSynchronize(p->ev[2])); B2_CHECK(cudaEventSynchronize(p->ev[3]));
+	float t01, tleg, tfft, t23;
+	const bool to_map = p->timing[0] >= 0;
 	B2_CHECK(cudaEventElapsedTime(&t01, p->ev[0], p->ev[1]));
-	B2_CHECK(cudaEventElapsedTime(&t12, p->ev[1], p->ev[2]));
+	// ev5 sits right before the Legendre kernel on its stream: ev5..ev2 (alm -> map) or ev5..ev4 (map -> alm); the ring
+	// FFTs are ev3..ev4 resp. ev1..ev2, the theta stage ev2..ev3 (with several groups in flight that one includes waiting)
+	B2_CHECK(cudaEventElapsedTime(&tleg, p->ev[5], to_map ? p->ev[2] : p->ev[4]));
+	B2_CHECK(cudaEventElapsedTime(&tfft, to_map ? p->ev[3] : p->ev[1], to_map ? p->ev[4] : p->ev[2]));
 	B2_CHECK(cudaEventElapsedTime(&t23, p->ev[2], p->ev[3]));
-	B2_CHECK(cudaEventElapsedTime(&t34, p->ev[3], p->ev[4]));
-	// ev1..ev2 and ev3..ev4 are (Legendre, ring FFT) for alm->map and (ring FFT, Legendre) for map->alm
-	out[0] = p->timing[0] < 0 ? t34 : t12; out[1] = p->timing[0] < 0 ? t12 : t34; out[2] = t23; out[3] = t01;
+	out[0] = tleg; out[1] = tfft; out[2] = t23; out[3] = t01;
 	return 0;
 }
 

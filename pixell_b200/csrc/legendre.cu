@@ -148,6 +148,7 @@ struct LegArgs {
 	// partial launches (host-memory calls stream their results out while the rest is still being computed):
 	// CTA b works on m = m0 + b; the synthesis kernels only touch the ring pairs [pair_lo, pair_hi) (multiples of 256)
 	int m0, pair_lo, pair_hi;
+	LegSignal sig;      // adjoint kernels: completion flags per range of m (sig.count == nullptr: none)
 };
 
 // base^n = mant*2^ex with mant in [0.5,1) (or mant = 1, ex = 0 for n = 0; mant = 0 for base = 0)
@@ -301,6 +302,53 @@ template<int NW> __device__ __forceinline__ int cta_min(int v, int *slot)
 	return r;
 }
 
+// The CTA of order m has written its alm row: count it in its range of m; whoever completes a range publishes the
+// call's epoch in the range's flag (mapped host memory), which the host thread of a host-memory call polls to start that
+// range's device -> host copy while the kernel is still working on the other ranges.
+template<int NW> __device__ __forceinline__ void signal_done_body(const LegArgs &A)
+{
+	cta_sync<NW>();
+	if (threadIdx.x == 0 && A.sig.count) {
+		const int m = A.m0 + blockIdx.x;
+		int r = 0;
+		#pragma unroll 1
+		while (r + 2 < A.sig.ncut && m >= A.sig.cut[r + 1]) r++;
+		// release at GPU scope per CTA (a system-scope fence here costs the whole kernel 6 %: 107 -> 114 ms at C3); the one
+		// CTA that completes a range acquires the others' rows through the counter and fences at system scope
+		unsigned old;
+		asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(&A.sig.count[r]), "r"(1u) : "memory");
+		const unsigned done = old + 1u;
+		if (done == (unsigned)(A.sig.cut[r + 1] - A.sig.cut[r])) {
+			__threadfence_system();
+			*A.sig.flag_of(r) = A.sig.epoch;
+		}
+	}
+}
+
+// SIG = 1: inlined, SIG = 2: behind a call (the kernels' register allocation, and with it the bank conflicts of their DFMA
+// operands, differs between the two and from SIG = 0: measured on B200 at C3, 107 ms without, 114 ms with SIG = 1)
+template<int NW> __device__ __noinline__ void signal_done_call(const LegArgs &A) { signal_done_body<NW>(A); }
+template<int NW, int SIG> __device__ __forceinline__ void signal_done(const LegArgs &A)
+{
+	if (SIG == 1) signal_done_body<NW>(A); else signal_done_call<NW>(A);
+}
+
+// The mirror image for the synthesis kernels of a host-memory call: the alm of the first group arrive range by range
+// (LegSignal::flag lives in device memory here, written by the copy stream after each range); a CTA waits for its range.
+template<int NW> __device__ __forceinline__ void gate_wait(const LegArgs &A)
+{
+	if (threadIdx.x == 0) {
+		const int m = A.m0 + blockIdx.x;
+		int r = 0;
+		#pragma unroll 1
+		while (r + 2 < A.sig.ncut && m >= A.sig.cut[r + 1]) r++;
+		const volatile int *f = A.sig.flag_of(r);
+		while (*f != A.sig.epoch) __nanosleep(500);
+		__threadfence();
+	}
+	cta_sync<NW>();
+}
+
 // ------------------------------------------------------------------------------------ spin 0
 
 struct Tile0 { double ar, ai, a, pad; };            // alm*alpha (re, im), recurrence a_l
@@ -329,8 +377,9 @@ template<int MODE, int R> __device__ __forceinline__ void synth0_window(const Ti
 	}
 }
 
-template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*32, MINB) k_synth0(LegArgs A)
+template<int R, int NW, int MINB, int TL, int GATE> __global__ void __launch_bounds__(NW*32, MINB) k_synth0(LegArgs A)
 {
+	if (GATE) gate_wait<NW>(A);
 	__shared__ __align__(16) Tile0 tiles[2][TL];
 	__shared__ __align__(16) double2 raw_alm[TL];       // cp.async staging: alm, (alpha, a)
 	__shared__ __align__(16) double raw_al[TL], raw_a[TL];
@@ -458,7 +507,7 @@ template<int MODE, int R, int W> __device__ __forceinline__ void adj0_window(con
 	}
 }
 
-template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds__(NW*32, MINB) k_adj0(LegArgs A)
+template<int R, int NW, int MINB, int TL, int W, int SIG> __global__ void __launch_bounds__(NW*32, MINB) k_adj0(LegArgs A)
 {
 	constexpr int NV = 2*W, NOUT = 2*TL;
 	constexpr int NT = NW*32, NH = (NOUT + NT - 1)/NT;
@@ -616,6 +665,7 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 		first = false;
 	}
 	if (first) for (int i = tid; i < nl; i += NW*32) { double *o = almr + 2*(int64_t)(l0 + i)*A.lstride; o[0] = 0; o[1] = 0; }
+	if (SIG) signal_done<NW, SIG>(A);
 }
 
 // ------------------------------------------------------------------------------------ spin > 0
@@ -654,8 +704,9 @@ template<int MODE, int R> __device__ __forceinline__ void synth2_window(const Ti
 	}
 }
 
-template<int R, int NW, int MINB, int TL> __global__ void __launch_bounds__(NW*32, MINB) k_synth2(LegArgs A)
+template<int R, int NW, int MINB, int TL, int GATE> __global__ void __launch_bounds__(NW*32, MINB) k_synth2(LegArgs A)
 {
+	if (GATE) gate_wait<NW>(A);
 	__shared__ __align__(16) Tile2 tiles[2][TL];
 	__shared__ __align__(16) double2 raw_e[TL], raw_b[TL];       // cp.async staging: E, B, (a, b, alpha)
 	__shared__ __align__(16) double raw_ta[TL], raw_tb[TL], raw_al[TL];
@@ -827,7 +878,7 @@ template<int MODE, int R, int W> __device__ __forceinline__ void adj2_window(con
 	}
 }
 
-template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds__(NW*32, MINB) k_adj2(LegArgs A)
+template<int R, int NW, int MINB, int TL, int W, int SIG> __global__ void __launch_bounds__(NW*32, MINB) k_adj2(const __grid_constant__ LegArgs A)
 {
 	constexpr int NV = 4*W, NOUT = 4*TL;
 	constexpr int NT = NW*32, NH = (NOUT + NT - 1)/NT;
@@ -844,7 +895,7 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 		alme[idx] = alme[idx + 1] = 0;
 		if (!A.deriv1) almb[idx] = almb[idx + 1] = 0;
 	}
-	if (l0 > lmax) return;
+	if (l0 > lmax) { if (SIG) signal_done<NW, SIG>(A); return; }
 	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
 	const double *ta = A.ta + A.toff[m], *tb = A.tb + A.toff[m], *tal = A.talpha + A.toff[m];
 	const SeqConst sc0 = seq_const(m, s, lmax, A.pref);
@@ -1035,6 +1086,7 @@ template<int R, int NW, int MINB, int TL, int W> __global__ void __launch_bounds
 		alme[idx] = alme[idx + 1] = 0;
 		if (!A.deriv1) almb[idx] = almb[idx + 1] = 0;
 	}
+	if (SIG) signal_done<NW, SIG>(A);
 }
 
 // ------------------------------------------------------------------------------------ start table
@@ -1115,6 +1167,7 @@ int leg_set_variant(int which, int v)
 	g_variant[which] = v;
 	return 0;
 }
+static int sig_style() { static const int v = getenv("B2_SIG_STYLE") ? atoi(getenv("B2_SIG_STYLE")) : 1; return v; }
 static int variant_of(int which) { variant_init(); return g_variant[which]; }
 
 static LegArgs make_args(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
@@ -1127,6 +1180,7 @@ static LegArgs make_args(const LegTables &T, const LegGeom &G, const AlmLayout &
 	}
 	A.lmax = L.lmax; A.mmax = L.mmax; A.spin = T.spin; A.deriv1 = deriv1;
 	A.m0 = 0; A.pair_lo = 0; A.pair_hi = G.npair_pad;
+	A.sig.count = nullptr; A.sig.flag = nullptr; A.sig.ncut = 0; A.sig.epoch = 0;
 	A.toff = T.toff.p; A.ta = T.a.p; A.tb = T.b.p; A.talpha = T.alpha.p; A.pref = T.pref.p;
 	A.pairs = G.pairs.p; A.npair_pad = G.npair_pad; A.npair = G.npair;
 	A.mstart = L.mstart_d; A.lstride = L.lstride;
@@ -1164,10 +1218,15 @@ int leg_build_start(LegStart &S, const LegTables &T, const LegGeom &G)
 }
 
 int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
-	const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st, const LegStart *S, int pair_lo, int pair_hi)
+	const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st, const LegStart *S, int pair_lo, int pair_hi, const LegSignal *gate)
 {
 	if (check_args(T, L, deriv1)) return 1;
 	LegArgs A = make_args(T, G, L, deriv1, (double2*)alm, alm_cstride, leg, S);
+	if (gate) {
+		B2_REQUIRE(gate->ncut >= 2 && gate->ncut <= LEG_MAXCUT && gate->cut[0] == 0 && gate->cut[gate->ncut - 1] == L.mmax + 1 && gate->flag,
+			"alm2leg: arrival ranges must cover all orders");
+		A.sig = *gate;
+	}
 	const int nm_launch = L.mmax + 1;
 	if (pair_hi > pair_lo) {
 		B2_REQUIRE(pair_lo % 256 == 0 && (pair_hi % 256 == 0 || pair_hi >= G.npair_pad), "alm2leg: ring-pair ranges must be multiples of 256");
@@ -1175,15 +1234,15 @@ int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 	}
 	// template arguments: R, NW, MINB, TL (variant 0 = fastest measured on B200 at lmax 8000, profiles/r1*_tune_*)
 	if (T.spin == 0) switch (variant_of(0)) {
-		case 0: LAUNCH(k_synth0, 4, 2, 8, 64); break;
-		case 1: LAUNCH(k_synth0, 4, 1, 16, 32); break;
-		case 2: LAUNCH(k_synth0, 2, 4, 6, 64); break;
+		case 0: if (gate) LAUNCH(k_synth0, 4, 2, 8, 64, 1); else LAUNCH(k_synth0, 4, 2, 8, 64, 0); break;
+		case 1: if (gate) LAUNCH(k_synth0, 4, 1, 16, 32, 1); else LAUNCH(k_synth0, 4, 1, 16, 32, 0); break;
+		case 2: if (gate) LAUNCH(k_synth0, 2, 4, 6, 64, 1); else LAUNCH(k_synth0, 2, 4, 6, 64, 0); break;
 		default: B2_REQUIRE(0, "unknown k_synth0 variant");
 	} else switch (variant_of(2)) {
-		case 0: LAUNCH(k_synth2, 4, 2, 6, 64); break;
-		case 1: LAUNCH(k_synth2, 4, 4, 3, 64); break;
-		case 2: LAUNCH(k_synth2, 4, 1, 12, 32); break;
-		case 3: LAUNCH(k_synth2, 2, 4, 3, 64); break;
+		case 0: if (gate) LAUNCH(k_synth2, 4, 2, 6, 64, 1); else LAUNCH(k_synth2, 4, 2, 6, 64, 0); break;
+		case 1: if (gate) LAUNCH(k_synth2, 4, 4, 3, 64, 1); else LAUNCH(k_synth2, 4, 4, 3, 64, 0); break;
+		case 2: if (gate) LAUNCH(k_synth2, 4, 1, 12, 32, 1); else LAUNCH(k_synth2, 4, 1, 12, 32, 0); break;
+		case 3: if (gate) LAUNCH(k_synth2, 2, 4, 3, 64, 1); else LAUNCH(k_synth2, 2, 4, 3, 64, 0); break;
 		default: B2_REQUIRE(0, "unknown k_synth2 variant");
 	}
 	B2_LAUNCH_CHECK();
@@ -1191,23 +1250,28 @@ int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 }
 
 int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
-	double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st, const LegStart *S, int m_lo, int m_hi)
+	double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st, const LegStart *S, int m_lo, int m_hi, const LegSignal *sig)
 {
 	if (check_args(T, L, deriv1)) return 1;
 	LegArgs A = make_args(T, G, L, deriv1, alm, alm_cstride, (double2*)leg, S);
+	if (sig) {
+		B2_REQUIRE(sig->ncut >= 2 && sig->ncut <= LEG_MAXCUT && sig->cut[0] == 0 && sig->cut[sig->ncut - 1] == L.mmax + 1 && m_hi <= m_lo,
+			"leg2alm: completion ranges must cover all orders of a whole launch");
+		A.sig = *sig;
+	}
 	int nm_launch = L.mmax + 1;
 	if (m_hi > m_lo) { A.m0 = m_lo; nm_launch = std::min(m_hi, L.mmax + 1) - m_lo; if (nm_launch <= 0) return 0; }
 	// template arguments: R, NW, MINB, TL, W
 	if (T.spin == 0) switch (variant_of(1)) {
-		case 0: LAUNCH(k_adj0, 8, 1, 8, 32, 8); break;
-		case 1: LAUNCH(k_adj0, 8, 1, 10, 32, 4); break;
-		case 2: LAUNCH(k_adj0, 4, 4, 3, 64, 8); break;
+		case 0: if (sig) { if (sig_style() == 2) LAUNCH(k_adj0, 8, 1, 8, 32, 8, 2); else LAUNCH(k_adj0, 8, 1, 8, 32, 8, 1); } else LAUNCH(k_adj0, 8, 1, 8, 32, 8, 0); break;
+		case 1: if (sig) { if (sig_style() == 2) LAUNCH(k_adj0, 8, 1, 10, 32, 4, 2); else LAUNCH(k_adj0, 8, 1, 10, 32, 4, 1); } else LAUNCH(k_adj0, 8, 1, 10, 32, 4, 0); break;
+		case 2: if (sig) { if (sig_style() == 2) LAUNCH(k_adj0, 4, 4, 3, 64, 8, 2); else LAUNCH(k_adj0, 4, 4, 3, 64, 8, 1); } else LAUNCH(k_adj0, 4, 4, 3, 64, 8, 0); break;
 		default: B2_REQUIRE(0, "unknown k_adj0 variant");
 	} else switch (variant_of(3)) {
-		case 0: LAUNCH(k_adj2, 4, 1, 10, 32, 4); break;
-		case 1: LAUNCH(k_adj2, 4, 1, 8, 32, 4); break;
-		case 2: LAUNCH(k_adj2, 2, 4, 3, 32, 8); break;
-		case 3: LAUNCH(k_adj2, 2, 1, 12, 32, 8); break;
+		case 0: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 10, 32, 4, 2); else LAUNCH(k_adj2, 4, 1, 10, 32, 4, 1); } else LAUNCH(k_adj2, 4, 1, 10, 32, 4, 0); break;
+		case 1: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 8, 32, 4, 2); else LAUNCH(k_adj2, 4, 1, 8, 32, 4, 1); } else LAUNCH(k_adj2, 4, 1, 8, 32, 4, 0); break;
+		case 2: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 2, 4, 3, 32, 8, 2); else LAUNCH(k_adj2, 2, 4, 3, 32, 8, 1); } else LAUNCH(k_adj2, 2, 4, 3, 32, 8, 0); break;
+		case 3: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 2, 1, 12, 32, 8, 2); else LAUNCH(k_adj2, 2, 1, 12, 32, 8, 1); } else LAUNCH(k_adj2, 2, 1, 12, 32, 8, 0); break;
 		default: B2_REQUIRE(0, "unknown k_adj2 variant");
 	}
 	B2_LAUNCH_CHECK();

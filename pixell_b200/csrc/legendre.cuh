@@ -47,6 +47,15 @@ struct LegStart {
 	size_t bytes() const { return w.bytes() + p.bytes() + pp.bytes() + q.bytes() + qp.bytes() + sp.bytes() + sq.bytes(); }
 };
 
+// Completion signalling of the adjoint Legendre kernels: the orders are cut into ranges [cut[r], cut[r+1]), r < ncut - 1;
+// count: device counters (zeroed by the caller before the launch), flag: mapped host memory, one int per range on its
+// own 64-byte line, set to `epoch` by the CTA that completes the range.
+#define LEG_MAXCUT 10
+struct LegSignal {
+	int ncut, epoch; int cut[LEG_MAXCUT]; unsigned *count; volatile int *flag;
+	__host__ __device__ volatile int *flag_of(int r) const { return flag + 16*r; }
+};
+
 struct AlmLayout {
 	int lmax, mmax;
 	const int64_t *mstart_d;  // device [mmax+1]
@@ -56,13 +65,14 @@ struct AlmLayout {
 // leg[ncomp_map][mmax+1][nring_pad] complex128; alm component c at alm + c*alm_cstride (complex elements)
 // S (nullable): start table built by leg_build_start for this (T, G)
 // pair_lo < pair_hi: only the ring pairs [pair_lo, pair_hi) of the sorted pair list (multiples of 256) are computed;
+// gate (nullable): the kernel's CTAs wait for the arrival flag of their range of m (LegSignal, flags in device memory)
 // m_lo < m_hi: only the orders m_lo <= m < m_hi (partial launches: results stream out while the rest is computed)
 int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
                 const double2 *alm, int64_t alm_cstride, double2 *leg, cudaStream_t st, const LegStart *S = nullptr,
-                int pair_lo = 0, int pair_hi = 0);
+                int pair_lo = 0, int pair_hi = 0, const LegSignal *gate = nullptr);
 int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
                 double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st, const LegStart *S = nullptr,
-                int m_lo = 0, int m_hi = 0);
+                int m_lo = 0, int m_hi = 0, const LegSignal *sig = nullptr);
 int leg_build_start(LegStart &S, const LegTables &T, const LegGeom &G);
 int dfma_peak_gflops(double *out);
 int leg_set_variant(int which, int v);

@@ -35,6 +35,12 @@ struct b2_sht_plan {
 	std::map<int, std::unique_ptr<LegTables>> tables;   // by spin
 	std::map<int, std::unique_ptr<LegStart>> starts;    // by spin: where every ring group's recurrence becomes live (see LegStart)
 	DevBuf<double2> leg;               // [2][mmax+1][nring_pad]
+	// Two-stage pipeline over the spin groups of one call: the FP64-bound Legendre kernels run on the caller's stream, the
+	// HBM-bound stages (ring FFTs, theta weighting) on s_fft, so that group g+1's memory-bound work hides under group g's
+	// Legendre kernel (and vice versa for alm -> map).  Groups alternate between two leg buffers ("lanes").
+	DevBuf<double2> leg2;              // second lane, allocated by the first multi-group call
+	cudaStream_t s_fft = nullptr;      // high priority: its short kernels take the SM slots the long Legendre CTAs free
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_chunk[8] = {};
 	// 2d plans
 	bool is2d = false;
 	std::string geometry;
@@ -43,7 +49,7 @@ struct b2_sht_plan {
 	DevBuf<double> w2d;                // direct quadrature weights / nphi (ring order of the plan)
 	// staging for host-memory calls
 	DevBuf<char> stage_alm, stage_map;
-	cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	// host-memory calls are pipelined over three streams (copies in, kernels, copies out)
 	cudaStream_t s_in = nullptr, s_out = nullptr, s_comp = nullptr;
 	cudaEvent_t gev[2*B2_MAX_GROUPS] = {};      // per group: operands on the device, results ready
@@ -54,6 +60,15 @@ struct b2_sht_plan {
 	std::vector<StreamChunk> schunks;      // empty: rows of a chunk are not at most two dense row bands (no streaming)
 	std::vector<int> mcuts;                // m range boundaries with about equal alm bytes (empty: alm layout not dense)
 	cudaEvent_t sev[8] = {};
+	// completion flags of the adjoint Legendre kernel (LegSignal): the alm of the last group of a host-memory call leave
+	// range by range while the kernel is still running
+	DevBuf<unsigned> sig_count;
+	int *sig_flag_h = nullptr, *sig_flag_d = nullptr;      // mapped pinned host memory and its device address
+	int sig_epoch = 0;
+	// arrival flags for the synthesis kernels (the first group's alm of a host-memory call arrive range by range)
+	DevBuf<int> gate_flag;
+	int *gate_src_h = nullptr;         // pinned: the epoch value the copy stream writes into a range's flag
+	int gate_epoch = 0;
 	LegTables *get_tables(int spin);
 	LegStart *get_start(int spin);      // nullptr when disabled (B2_NO_START_TABLE=1) or on allocation failure
 	size_t bytes() const;

@@ -311,7 +311,11 @@ def alm2map(alm, map, spin=[0,2], deriv=False, adjoint=False, copy=False, method
 				m[0] *= -1
 				if mcopied: map_full[I] = m
 		else:
-			for s, j1, j2 in spin_helper(spin, alm_full.shape[-2]):
+			groups = list(spin_helper(spin, alm_full.shape[-2]))
+			# all spin groups in one engine call: the copies of one group then overlap the kernels of the next
+			if pk["kind"] != "rings" or pk.get("weight") is None:
+				if _grouped(pk, "adjoint_synthesis" if adjoint else "synthesis", groups, alm_full[I], map_full[I]): continue
+			for s, j1, j2 in groups:
 				a, acopied = _comp_block(alm_full[I], j1, j2, 1)
 				m, mcopied = _comp_block(map_full[I], j1, j2, 2)
 				_synth(pk, a, m, s, adjoint=adjoint)
