@@ -22,7 +22,7 @@
 #define B2_DEF_SYNTH0 0
 #define B2_DEF_ADJ0 0
 #define B2_DEF_SYNTH2 0
-#define B2_DEF_ADJ2 0
+#define B2_DEF_ADJ2 5
 
 #define SMALLV 0x1p-512
 // A sequence counts as "live" (enters the sums) once its magnitude has reached 2^-LIVE_EXP: what it misses before is
@@ -367,7 +367,7 @@ template<int MODE, int R> __device__ __forceinline__ void synth0_window(const Ti
 				acc[r][j & 1][0] = fma(gv, t.ar, acc[r][j & 1][0]);
 				acc[r][j & 1][1] = fma(gv, t.ai, acc[r][j & 1][1]);
 			}
-			double ng = fma(t.a*x[r], g[r], -gp[r]);
+			double ng = fma(t.a, x[r]*g[r], -gp[r]);
 			gp[r] = g[r]; g[r] = ng;
 		}
 	}
@@ -497,7 +497,7 @@ template<int MODE, int R, int W> __device__ __forceinline__ void adj0_window(con
 				v[j]     = fma(gv, in[r][j & 1][0], v[j]);
 				v[W + j] = fma(gv, in[r][j & 1][1], v[W + j]);
 			}
-			double ng = fma(a*x[r], g[r], -gp[r]);
+			double ng = fma(a, x[r]*g[r], -gp[r]);
 			gp[r] = g[r]; g[r] = ng;
 		}
 	}
@@ -1243,6 +1243,7 @@ int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 		case 1: if (gate) LAUNCH(k_synth2, 4, 4, 3, 64, 1); else LAUNCH(k_synth2, 4, 4, 3, 64, 0); break;
 		case 2: if (gate) LAUNCH(k_synth2, 4, 1, 12, 32, 1); else LAUNCH(k_synth2, 4, 1, 12, 32, 0); break;
 		case 3: if (gate) LAUNCH(k_synth2, 2, 4, 3, 64, 1); else LAUNCH(k_synth2, 2, 4, 3, 64, 0); break;
+		case 4: if (gate) LAUNCH(k_synth2, 4, 2, 5, 64, 1); else LAUNCH(k_synth2, 4, 2, 5, 64, 0); break;
 		default: B2_REQUIRE(0, "unknown k_synth2 variant");
 	}
 	B2_LAUNCH_CHECK();
@@ -1272,6 +1273,9 @@ int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 		case 1: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 8, 32, 4, 2); else LAUNCH(k_adj2, 4, 1, 8, 32, 4, 1); } else LAUNCH(k_adj2, 4, 1, 8, 32, 4, 0); break;
 		case 2: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 2, 4, 3, 32, 8, 2); else LAUNCH(k_adj2, 2, 4, 3, 32, 8, 1); } else LAUNCH(k_adj2, 2, 4, 3, 32, 8, 0); break;
 		case 3: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 2, 1, 12, 32, 8, 2); else LAUNCH(k_adj2, 2, 1, 12, 32, 8, 1); } else LAUNCH(k_adj2, 2, 1, 12, 32, 8, 0); break;
+		case 4: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 9, 32, 8, 2); else LAUNCH(k_adj2, 4, 1, 9, 32, 8, 1); } else LAUNCH(k_adj2, 4, 1, 9, 32, 8, 0); break;
+		case 5: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 8, 32, 8, 2); else LAUNCH(k_adj2, 4, 1, 8, 32, 8, 1); } else LAUNCH(k_adj2, 4, 1, 8, 32, 8, 0); break;
+		case 6: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 11, 32, 4, 2); else LAUNCH(k_adj2, 4, 1, 11, 32, 4, 1); } else LAUNCH(k_adj2, 4, 1, 11, 32, 4, 0); break;
 		default: B2_REQUIRE(0, "unknown k_adj2 variant");
 	}
 	B2_LAUNCH_CHECK();
