@@ -48,6 +48,14 @@ def recorded_traffic(kernel):
 		return t.get(kernel)
 	except Exception: return None
 
+def operand_model(kernel):
+	"""ceiling of the FP64 pipe for this kernel's main window from its SASS (register-file operand bandwidth, see
+	scripts/sass_operand_model.py); None if profiles/operand_model.json has no entry"""
+	try:
+		with open(os.path.join(ROOT, "profiles", "operand_model.json")) as f: t = json.load(f)
+		return t.get(kernel, {}).get("main_window_ceiling")
+	except Exception: return None
+
 def algorithmic_bytes(w):
 	nalm = (w["lmax"]+1)*(w["lmax"]+2)//2
 	one = 16*w["ncomp"]*nalm + 8*w["ncomp"]*w["ny"]*w["nx"]
@@ -225,7 +233,9 @@ def run_ours(args, w):
 				"note": "FP64-FMA bound kernel (intensity ~ lmax/12 flop/byte): see roofline_fp64"},
 			"roofline_fp64": {"bound": "fp64", "achieved": kflops/(kms*1e-3)/1e12, "peak": dpk.value/1e3, "unit": "TFLOP/s",
 				"frac": kflops/(kms*1e-3)/1e9/dpk.value, "peak_source": "DFMA microbenchmark in this run",
-				"flops_model": "canonical, SURVEY.md 8d (no credit for polar skipping)"},
+				"flops_model": "canonical, SURVEY.md 8d (no credit for polar skipping)",
+				"operand_bandwidth_ceiling": operand_model("k_adj2" if w["ncomp"] == 3 else "k_adj0"),
+				"operand_bandwidth_note": "a DFMA that has to fetch three register operands issues every 3 cycles, not 2 (measured: 24.6 vs 36.9 TFLOP/s); the ceiling is the fraction of the DFMA peak the kernel's own instruction stream can reach (scripts/sass_operand_model.py)"},
 			"stage_ms_last_map2alm_group": tim,
 			"clocks": clocks,
 			"configs": configs,

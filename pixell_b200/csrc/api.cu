@@ -131,6 +131,7 @@ b2_sht_plan::~b2_sht_plan()
 	if (s_fft) cudaStreamDestroy(s_fft);
 	if (sig_flag_h) cudaFreeHost(sig_flag_h);
 	if (gate_src_h) cudaFreeHost(gate_src_h);
+	if (ev_last) cudaEventDestroy(ev_last);
 	if (ev_fork) cudaEventDestroy(ev_fork);
 	if (ev_join) cudaEventDestroy(ev_join);
 	for (auto &e : ev_ready) if (e) cudaEventDestroy(e);
@@ -757,6 +758,9 @@ static int execute_groups(b2_sht_plan *plan, int op, int ngroups, const int *spi
 		E.s_in = plan->s_in; E.s_out = plan->s_out;
 		if (!E.st) E.st = plan->s_comp;      // never the legacy stream: it would serialise with the copy streams' neighbours
 	}
+	// one call at a time on this plan's scratch (see b2_sht_plan::ev_last)
+	if (!plan->ev_last) B2_CHECK(cudaEventCreateWithFlags(&plan->ev_last, cudaEventDisableTiming));
+	else B2_CHECK(cudaStreamWaitEvent(E.st, plan->ev_last, 0));
 	// several groups: two-stage pipeline (see b2_sht_plan::s_fft)
 	// Off by default (B2_OVERLAP=1 enables it): measured on B200 at C3 it gains nothing -- the Legendre grids keep every SM's
 	// register file full, a 512-thread FFT CTA only fits once six of their CTAs have left one SM, and what does get in
@@ -821,6 +825,7 @@ static int execute_groups(b2_sht_plan *plan, int op, int ngroups, const int *spi
 		B2_CHECK(cudaEventRecord(plan->ev_join, E.sf));
 		B2_CHECK(cudaStreamWaitEvent(E.st, plan->ev_join, 0));
 	}
+	B2_CHECK(cudaEventRecord(plan->ev_last, E.st));
 	if (mem == B2_MEM_HOST) { B2_CHECK(cudaStreamSynchronize(E.s_out)); B2_CHECK(cudaStreamSynchronize(E.st)); }
 	if (mem == B2_MEM_HOST) g_trace.dump(to_map_op(op) ? "alm -> map" : "map -> alm");
 	return 0;

@@ -54,6 +54,10 @@ struct b2_sht_plan {
 	cudaStream_t s_in = nullptr, s_out = nullptr, s_comp = nullptr;
 	cudaEvent_t gev[2*B2_MAX_GROUPS] = {};      // per group: operands on the device, results ready
 	double timing[4] = {0, 0, 0, 0};
+	// the plan's scratch (leg, theta-stage buffers, staging) serves one call at a time: every call waits for the previous
+	// one's last kernel, whatever streams the two run on (a device-memory call on the caller's stream followed by a
+	// host-memory call on the plan's own streams would otherwise overlap in the scratch)
+	cudaEvent_t ev_last = nullptr;
 	// streamed host-memory transforms: the synthesis runs in chunks of ring pairs (pole -> equator) whose rows leave for the
 	// host while the next chunk is computed; the adjoint Legendre stage runs in ranges of m whose alm leave likewise
 	struct StreamChunk { int pair_lo, pair_hi, nrun, r0[2], nr[2]; };

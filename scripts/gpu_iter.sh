@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
 T=${1:-it}
-timeout 1500 python -m pytest tests -q -x -m gpu > gpurun_out/${T}_pytest_gpu.txt 2>&1; tail -5 gpurun_out/${T}_pytest_gpu.txt
-python scripts/tune_legendre.py c3 1 0123 > gpurun_out/${T}_tune.txt 2>&1; cat gpurun_out/${T}_tune.txt
-python scripts/e2e_probe.py > gpurun_out/${T}_probe.json 2> gpurun_out/${T}_probe.err; cat gpurun_out/${T}_probe.json
+python -m pytest tests/test_curvedsky_gpu.py -x -q -m gpu -k "one_plan or grouped_host or streamed_host" 2>&1 | tail -3
+for i in 1 2 3; do timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_curvedsky_gpu.py -x -q -m gpu -k "grouped_host or one_plan" 2>&1 | grep "passed\|failed\|ERROR SUMMARY" | head -4; done
+timeout 1500 python -m pytest tests -q -x -m gpu 2>&1 | tail -2

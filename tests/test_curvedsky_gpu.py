@@ -278,3 +278,34 @@ def test_grouped_host_pair_matches_the_device_path(cs):
 	cs.map2alm(hmap, hback, spin=[0, 2], ainfo=ai)
 	assert np.array_equal(hback, dback.cpu().numpy())
 	assert np.abs(hback-alm).max() < 1e-11*np.abs(alm).max()
+
+def test_calls_on_one_plan_do_not_overlap_in_its_scratch(cs):
+	"""a device-memory call (asynchronous, on the caller's stream) followed at once by a host-memory call (on the plan's own
+	streams) share the plan's leg / theta-stage scratch: the second must wait for the first (b2_sht_plan::ev_last).  With
+	pinned host arrays the copies are short enough that the two would otherwise run at the same time."""
+	import torch
+	from pixell_b200 import geometry
+	lmax, ny, nx = 900, 4608, 2048
+	shape, wcs = geometry.fullsky_geometry(shape=(ny, nx))
+	ai = cs.alm_info(lmax)
+	rng = np.random.default_rng(12)
+	alm = rng.standard_normal((3, ai.nelem)) + 1j*rng.standard_normal((3, ai.nelem))
+	alm[:, :lmax+1] = alm[:, :lmax+1].real
+	alm[1:, [0, 1, lmax+1]] = 0
+	dmap = torch.empty((3,)+shape, dtype=torch.float64, device="cuda")
+	cs.alm2map(torch.from_numpy(alm).cuda(), dmap, spin=[0, 2], wcs=wcs, ainfo=ai)
+	want = torch.zeros((3, ai.nelem), dtype=torch.complex128, device="cuda")
+	cs.map2alm(dmap, want, spin=[0, 2], wcs=wcs, ainfo=ai)
+	torch.cuda.synchronize()
+	want = want.cpu().numpy()
+	pmap = torch.empty((3,)+shape, dtype=torch.float64, pin_memory=True); pmap.copy_(dmap)
+	palm = torch.empty((3, ai.nelem), dtype=torch.complex128, pin_memory=True)
+	hmap = geometry.ndmap(pmap.numpy(), wcs)
+	for rep in range(3):
+		dback = torch.zeros((3, ai.nelem), dtype=torch.complex128, device="cuda")
+		palm.zero_()
+		cs.map2alm(dmap, dback, spin=[0, 2], wcs=wcs, ainfo=ai)          # still running when the next call starts
+		cs.map2alm(hmap, palm.numpy(), spin=[0, 2], ainfo=ai)
+		torch.cuda.synchronize()
+		assert np.array_equal(dback.cpu().numpy(), want)
+		assert np.array_equal(palm.numpy(), want)
