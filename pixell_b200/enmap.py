@@ -63,9 +63,29 @@ def _norm(shape, wcs, normalize, flip_phys):
 		norm = norm/pixsize(shape, wcs)**0.5 if flip_phys else norm*pixsize(shape, wcs)**0.5
 	return norm
 
+def _dct2(emap, omap, normalize, flip_phys, wcs, inverse):
+	"""dct=True branch of fft / ifft (pixell/enmap.py:1314-1320, 1327-1333): DCT-I over the last two axes; the reference
+	normalises by prod(2 n - 1)^(1/2) per call, mirrored as written"""
+	res = enfft.idct(emap, omap, axes=[-2, -1], normalize=False) if inverse else enfft.dct(emap, omap, axes=[-2, -1])
+	norm = 1.0
+	if normalize: norm /= float(np.prod(2*np.array(emap.shape[-2:])-1))**0.5
+	if normalize in ["phy", "phys", "physical"]:
+		w = _wcs(emap, wcs)
+		norm = norm/pixsize(emap.shape, w)**0.5 if flip_phys else norm*pixsize(emap.shape, w)**0.5
+	if norm != 1: res *= norm
+	if not L.is_torch(res) and getattr(emap, "wcs", wcs) is not None: res = geometry.ndmap(res, getattr(emap, "wcs", wcs))
+	return res
+
+def dct(emap, omap=None, nthread=0, normalize=True, wcs=None):
+	"""pixell/enmap.py:1339-1340"""
+	return fft(emap, omap=omap, nthread=nthread, normalize=normalize, dct=True, wcs=wcs)
+def idct(emap, omap=None, nthread=0, normalize=True, wcs=None):
+	"""pixell/enmap.py:1341-1342"""
+	return ifft(emap, omap=omap, nthread=nthread, normalize=normalize, dct=True, wcs=wcs)
+
 def fft(emap, omap=None, nthread=0, normalize=True, adjoint_ifft=False, dct=False, wcs=None):
 	"""2-D FFT of the map pixels -> complex map (pixell/enmap.py:1307-1322)."""
-	if dct: raise NotImplementedError("dct=True is not provided by pixell_b200")
+	if dct: return _dct2(emap, omap, normalize, adjoint_ifft, wcs, False)
 	ctype = _complex_like(emap)
 	if omap is None: omap = enfft._empty_like(emap, emap.shape, ctype)
 	src = emap
@@ -80,7 +100,7 @@ def fft(emap, omap=None, nthread=0, normalize=True, adjoint_ifft=False, dct=Fals
 
 def ifft(emap, omap=None, nthread=0, normalize=True, adjoint_fft=False, dct=False, wcs=None):
 	"""2-D inverse FFT (pixell/enmap.py:1323-1337)."""
-	if dct: raise NotImplementedError("dct=True is not provided by pixell_b200")
+	if dct: return _dct2(emap, omap, normalize, not adjoint_fft, wcs, True)
 	if omap is None: omap = enfft._empty_like(emap, emap.shape, L.buffer_info(emap)[2])
 	w = None
 	if normalize in ["phy", "phys", "physical"]: w = _wcs(emap, wcs)

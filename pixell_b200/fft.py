@@ -92,10 +92,14 @@ class FFTW:
 	def __init__(self, a, b, axes=(-1,), direction="FFTW_FORWARD", threads=1, flags=None, *args, **kwargs):
 		self.a, self.b = a, b
 		self.axes = tuple(axes) if np.ndim(axes) else (axes,)
-		if not isinstance(direction, str): raise NotImplementedError("pixell_b200.fft: r2r (DCT/DST) transforms are not provided")
-		if direction not in ("FFTW_FORWARD", "FFTW_BACKWARD"): raise ValueError("unknown direction %s" % direction)
+		if not isinstance(direction, str):
+			# r2r: one FFTW kind per axis (pixell/fft.py:66-71, 211-259)
+			direction = list(direction)
+			if len(direction) != len(self.axes) or any(d not in _R2R for d in direction): raise ValueError("unknown r2r direction %s" % (direction,))
+		elif direction not in ("FFTW_FORWARD", "FFTW_BACKWARD"): raise ValueError("unknown direction %s" % direction)
 		self.direction = direction
 	def __call__(self, normalise_idft=False):
+		if not isinstance(self.direction, str): return r2r(self.a, self.b, self.axes, self.direction)
 		fwd = self.direction == "FFTW_FORWARD"
 		scale = 1.0
 		if not fwd and normalise_idft:
@@ -142,6 +146,9 @@ def fft(tod, ft=None, nthread=0, axes=[-1], flags=None, _direction="FFTW_FORWARD
 	tod = _asfc(tod)
 	axes = _astuple(-1 if axes is None else axes)
 	if _size(tod) == 0: return
+	if not isinstance(_direction, str):
+		if ft is None: ft = _empty_like(tod, tod.shape, _dtype(tod))
+		return r2r(tod, ft, axes, list(_direction))
 	if ft is None:
 		otype = np.result_type(_dtype(tod), 0j)
 		ft = _empty_like(tod, tod.shape, otype)
@@ -178,6 +185,110 @@ def irfft(ft, tod=None, n=None, nthread=0, normalize=False, axes=[-1], flags=Non
 	axes = _astuple(-1 if axes is None else axes)
 	if tod is None: tod = _empty_like(ft, irfft_shape(ft.shape, axes=axes, n=n), np.zeros([], _dtype(ft)).real.dtype)
 	return ifft(ft, tod, nthread, normalize, axes, flags=flags)
+
+# ------------------------------------------------------------------ r2r: DCT / DST (pixell/fft.py:211-317)
+# FFTW's eight real-to-real kinds, unnormalised as FFTW defines them.  Every kind is a cosine (sine) sum
+#   Y_k = sum_j c_j X_j cos|sin(2 pi P_j Q_k / Lc)   with integer P_j, Q_k,
+# i.e. entries Q_k of the DFT of a real sequence of length Lc that holds X_j at P_j and its even (odd) image at Lc - P_j.
+# So one r2c transform of the engine per axis does the work (length 2(n-1) ... 8n: these transforms are not on the hot
+# path, pixell uses them for enmap.fft(dct=True) and the Chebyshev helpers only).
+#             name:          (sine, Lc(n),              P(j),          Q(k))
+_R2R = {
+	"FFTW_REDFT00": (False, lambda n: 2*(n-1), lambda j: j,     lambda k: k),
+	"FFTW_REDFT10": (False, lambda n: 4*n,     lambda j: 2*j+1, lambda k: k),
+	"FFTW_REDFT01": (False, lambda n: 4*n,     lambda j: j,     lambda k: 2*k+1),
+	"FFTW_REDFT11": (False, lambda n: 8*n,     lambda j: 2*j+1, lambda k: 2*k+1),
+	"FFTW_RODFT00": (True,  lambda n: 2*(n+1), lambda j: j+1,   lambda k: k+1),
+	"FFTW_RODFT10": (True,  lambda n: 4*n,     lambda j: 2*j+1, lambda k: k+1),
+	"FFTW_RODFT01": (True,  lambda n: 4*n,     lambda j: j+1,   lambda k: 2*k+1),
+	"FFTW_RODFT11": (True,  lambda n: 8*n,     lambda j: 2*j+1, lambda k: 2*k+1),
+}
+_dct_names = {"DCT-I": "FFTW_REDFT00", "DCT-II": "FFTW_REDFT10", "DCT-III": "FFTW_REDFT01", "DCT-IV": "FFTW_REDFT11",
+	"DST-I": "FFTW_RODFT00", "DST-II": "FFTW_RODFT10", "DST-III": "FFTW_RODFT01", "DST-IV": "FFTW_RODFT11"}
+_dct_names.update({v: v for v in list(_dct_names.values())})
+_dct_inverses = {"FFTW_REDFT00": "FFTW_REDFT00", "FFTW_REDFT10": "FFTW_REDFT01", "FFTW_REDFT01": "FFTW_REDFT10", "FFTW_REDFT11": "FFTW_REDFT11",
+	"FFTW_RODFT00": "FFTW_RODFT00", "FFTW_RODFT10": "FFTW_RODFT01", "FFTW_RODFT01": "FFTW_RODFT10", "FFTW_RODFT11": "FFTW_RODFT11"}
+_dct_sizes = {"FFTW_REDFT00": -1, "FFTW_RODFT00": +1}
+
+def _r2r_last(x, kind):
+	"""one r2r kind along the last axis of a contiguous real torch CUDA tensor [batch, n]"""
+	import torch
+	sine, Lc, P, Q = _R2R[kind]
+	nb, n = x.shape
+	if kind == "FFTW_REDFT00" and n < 2: raise ValueError("DCT-I needs at least two points")
+	L_ = Lc(n)
+	j = torch.arange(n, device=x.device)
+	p = P(j); mir = (L_ - p) % L_
+	z = torch.zeros((nb, L_), dtype=x.dtype, device=x.device)
+	if kind == "FFTW_RODFT01":
+		x = x.clone(); x[:, -1] *= 0.5          # FFTW counts the last input once: (-1)^k X_{n-1}
+	z[:, p] = x
+	img = mir != p                               # points that are their own image (DCT-I / DCT-III end points) enter once
+	z[:, mir[img]] = -x[:, img] if sine else x[:, img]
+	Z = torch.empty((nb, L_//2+1), dtype=torch.complex128 if x.dtype == torch.float64 else torch.complex64, device=x.device)
+	transform(z, Z, [-1], True)
+	q = Q(j)
+	return -Z[:, q].imag if sine else Z[:, q].real
+
+def r2r(a, b, axes, kinds):
+	"""b = the r2r transform of kind kinds[i] along axes[i] of a (FFTW_REDFTxx / FFTW_RODFTxx), unnormalised"""
+	import torch
+	if tuple(a.shape) != tuple(b.shape): raise ValueError("r2r: input and output shapes differ")
+	dt = _dtype(a)
+	if dt.kind != "f" or _dtype(b) != dt: raise ValueError("r2r transforms map real arrays to real arrays of the same precision")
+	dev = L.init()
+	x = a if L.is_torch(a) else torch.from_numpy(np.ascontiguousarray(a)).to("cuda:%d" % dev)
+	nd = x.ndim
+	for ax, kind in zip(axes, kinds):
+		ax = ax+nd if ax < 0 else ax
+		xm = x.movedim(ax, -1)
+		sh = xm.shape
+		y = _r2r_last(xm.reshape(-1, sh[-1]).contiguous(), kind)
+		x = y.reshape(sh).movedim(-1, ax)
+	if L.is_torch(b): b.copy_(x)
+	else: b[...] = x.cpu().numpy()
+	return b
+
+def dct(tod, dt=None, nthread=0, normalize=False, axes=[-1], flags=None, type="DCT-I", engine="auto"):
+	"""pixell/fft.py:211-231"""
+	tod = _asfc(tod)
+	kind = _dct_names[type]
+	axes = _astuple(-1 if axes is None else axes)
+	if dt is None: dt = _empty_like(tod, tod.shape, _dtype(tod))
+	return fft(tod, dt, nthread=nthread, axes=axes, flags=flags, _direction=[kind]*len(axes))
+
+def idct(dt, tod=None, nthread=0, normalize=False, axes=[-1], flags=None, type="DCT-I", engine="auto"):
+	"""pixell/fft.py:233-265: the matching inverse kind; normalize=True divides by prod 2 (N + d)"""
+	dt = _asfc(dt)
+	kind = _dct_inverses[_dct_names[type]]
+	off = _dct_sizes.get(kind, 0)
+	axes = _astuple(-1 if axes is None else axes)
+	if tod is None: tod = _empty_like(dt, dt.shape, _dtype(dt))
+	fft(dt, tod, nthread=nthread, axes=axes, flags=flags, _direction=[kind]*len(axes))
+	if normalize: tod /= float(np.prod([2*(tod.shape[i]+off) for i in axes]))
+	return tod
+
+def redft00(a, b=None, nthread=0, normalize=False, flags=None, engine="auto"):
+	"""pixell/fft.py:290-305 (DCT-I along the last axis)"""
+	a = _asfc(a)
+	if b is None: b = _empty_like(a, a.shape, _dtype(a))
+	r2r(a, b, [-1], ["FFTW_REDFT00"])
+	if normalize: b /= 2*(a.shape[-1]-1)
+	return b
+
+def chebt(a, b=None, nthread=0, flags=None, engine="auto"):
+	"""pixell/fft.py:307-311: the Chebyshev transform of a along its last dimension (the reference scales b[1:-1] along the
+	FIRST axis of b: for one-dimensional input that is the same thing; mirrored as written)"""
+	b = redft00(a, b, nthread, normalize=True, flags=flags)
+	b[1:-1] *= 2
+	return b
+
+def ichebt(a, b=None, nthread=0, engine="auto"):
+	"""pixell/fft.py:313-317"""
+	a = _asfc(a)
+	a = a.clone() if L.is_torch(a) else a.copy()
+	a[1:-1] *= 0.5
+	return redft00(a, b, nthread)
 
 def fftfreq(n, d=1.0, dtype=np.float64): return np.fft.fftfreq(n, d=d).astype(dtype, copy=False)
 def rfftfreq(n, d=1.0, dtype=np.float64): return np.arange(n//2+1, dtype=dtype)/(n*d)

@@ -335,3 +335,49 @@ def test_apply_window(order):
 	assert rel(np.asarray(enmap.unapply_window(got, order=order)), np.asarray(m)) < 1e-10
 	f = enmap.fft(m)
 	assert rel(np.asarray(enmap.apply_window(f, order=order, nofft=True)), np.asarray(f)*wy[:, None]*wx[None, :]) < 1e-13
+
+# ------------------------------------------------------------------ r2r (DCT / DST), reference pixell/fft.py:211-317
+
+_SCIPY = {"DCT-I": ("dct", 1), "DCT-II": ("dct", 2), "DCT-III": ("dct", 3), "DCT-IV": ("dct", 4),
+	"DST-I": ("dst", 1), "DST-II": ("dst", 2), "DST-III": ("dst", 3), "DST-IV": ("dst", 4)}
+
+@pytest.mark.parametrize("type", sorted(_SCIPY))
+@pytest.mark.parametrize("shape,axes", [((3, 17), [-1]), ((2, 64), [-1]), ((6, 9, 20), [-2, -1]), ((33, 4), [0])])
+def test_dct_dst_all_kinds(F, type, shape, axes):
+	"""every FFTW r2r kind against scipy.fft (pocketfft), unnormalised as FFTW / the reference define them, and the
+	matching inverse with the reference's normalisation 2 (N + d) per axis"""
+	import scipy.fft as sf
+	a = np.random.default_rng(7).standard_normal(shape)
+	fn, t = _SCIPY[type]
+	want = a
+	for ax in axes: want = getattr(sf, fn)(want, type=t, axis=ax)
+	got = F.dct(a, axes=axes, type=type)
+	assert rel(got, want) < 1e-12
+	back = F.idct(got, axes=axes, type=type, normalize=True)
+	assert rel(back, a) < 1e-12
+
+def test_dct_torch_and_chebyshev(F):
+	import torch, scipy.fft as sf
+	a = np.random.default_rng(8).standard_normal((4, 33))
+	got = F.dct(torch.from_numpy(a).cuda(), type="DCT-II")
+	assert got.is_cuda and rel(got.cpu().numpy(), sf.dct(a, type=2, axis=-1)) < 1e-12
+	assert rel(F.redft00(a), sf.dct(a, type=1, axis=-1)) < 1e-12
+	# chebt / ichebt are inverses of each other (one-dimensional input, reference fft.py:307-317)
+	c = np.random.default_rng(9).standard_normal(40)
+	assert rel(F.ichebt(F.chebt(c)), c) < 1e-12
+	# the engine plug-in takes the r2r kinds as a list of directions, one per axis (reference fft.py:66-71)
+	b = np.empty_like(a)
+	F.engine.FFTW(a, b, axes=(-1,), direction=["FFTW_REDFT10"])()
+	assert rel(b, sf.dct(a, type=2, axis=-1)) < 1e-12
+
+def test_enmap_dct_roundtrip():
+	"""enmap.fft(dct=True) / ifft(dct=True) (reference enmap.py:1314-1333): DCT-I over both axes with the reference's
+	prod(2 n - 1)^(1/2) normalisation on each side"""
+	import scipy.fft as sf
+	from pixell_b200 import enmap
+	m = np.random.default_rng(10).standard_normal((2, 24, 36))
+	got = enmap.dct(m)
+	want = sf.dct(sf.dct(m, type=1, axis=-1), type=1, axis=-2)/np.sqrt((2*24-1)*(2*36-1))
+	assert rel(np.asarray(got), want) < 1e-12
+	back = enmap.idct(got)
+	assert rel(np.asarray(back), m*(4*23*35)/((2*24-1)*(2*36-1))) < 1e-12
