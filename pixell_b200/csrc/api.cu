@@ -141,7 +141,7 @@ b2_sht_plan::~b2_sht_plan()
 
 size_t b2_sht_plan::bytes() const
 {
-	size_t b = mstart.bytes() + geom.bytes() + fft.bytes() + leg.bytes() + leg2.bytes() + w2d.bytes() + stage_alm.bytes() + stage_map.bytes();
+	size_t b = mstart.bytes() + geom.bytes() + fft.bytes() + leg.bytes() + leg2.bytes() + legb.bytes() + w2d.bytes() + stage_alm.bytes() + stage_map.bytes();
 	for (auto &g : groups) b += g->bytes();
 	for (auto &t : tables) b += t.second->bytes();
 	for (auto &t : starts) if (t.second) b += t.second->bytes();
@@ -831,6 +831,34 @@ static int execute_groups(b2_sht_plan *plan, int op, int ngroups, const int *spi
 	return 0;
 }
 
+// Device-resident float64 synthesis of a batch of alm sets of one spin (Monte-Carlo realisations): blocks of
+// leg_batch_size(spin) members go through the batched Legendre kernels, which pay the recurrence once per block; bit-identical
+// to member-by-member calls.  done = the number of members finished (the caller runs the rest one by one).
+static int execute_synth_batch(b2_sht_plan *p, int spin, int nbatch, const double2 *alm, int64_t acs, int64_t abs_,
+	double *map, int64_t mcs, int64_t mbs, cudaStream_t st, int &done)
+{
+	static const bool off = getenv("B2_BATCH") && !atoi(getenv("B2_BATCH"));
+	done = 0;
+	if (off || nbatch < 2 || !p->groups.empty() || p->nphi <= 0) return 0;
+	LegTables *T = p->get_tables(spin);
+	if (!T) return 1;
+	const int ncm = spin == 0 ? 1 : 2;
+	const int64_t plane = (int64_t)(p->mmax + 1)*p->geom.nring_pad;
+	if (!p->legb.n && p->legb.alloc((size_t)4*plane)) return 1;
+	if (!p->ev_last) B2_CHECK(cudaEventCreateWithFlags(&p->ev_last, cudaEventDisableTiming));
+	else B2_CHECK(cudaStreamWaitEvent(st, p->ev_last, 0));
+	AlmLayout L; L.lmax = p->lmax; L.mmax = p->mmax; L.mstart_d = p->mstart.p; L.lstride = p->lstride;
+	while (nbatch - done >= 2) {
+		const int nb = (spin == 0 && nbatch - done >= 4) ? 4 : 2;
+		if (leg_alm2leg_batch(*T, p->geom, L, nb, alm + (int64_t)done*abs_, acs, abs_, p->legb.p, ncm*plane, st, p->get_start(spin))) return 1;
+		for (int b = 0; b < nb; b++)
+			if (ring_leg2map(p->fft, ncm, p->legb.p + (int64_t)b*ncm*plane, p->geom.nring_pad, map + (int64_t)(done + b)*mbs, mcs, B2_F64, st)) return 1;
+		done += nb;
+	}
+	B2_CHECK(cudaEventRecord(p->ev_last, st));
+	return 0;
+}
+
 static int execute(b2_sht_plan *plan, int op, int spin, int mode, int dtype, int nbatch,
 	void *alm, int64_t alm_cstride, int64_t alm_bstride, void *map, int64_t map_cstride, int64_t map_bstride,
 	int mem, void *stream)
@@ -839,6 +867,12 @@ static int execute(b2_sht_plan *plan, int op, int spin, int mode, int dtype, int
 	B2_REQUIRE(nbatch >= 1, "transform: nbatch must be >= 1");
 	if (check_exec_args(plan, op, spin, mode, dtype, mem)) return 1;
 	const size_t asz = dtype == B2_F64 ? 16 : 8, msz = dtype == B2_F64 ? 8 : 4;
+	if (op == OP_SYNTH && mem == B2_MEM_DEVICE && dtype == B2_F64 && mode == B2_MODE_STANDARD && nbatch >= 2) {
+		int done = 0;
+		if (execute_synth_batch(plan, spin, nbatch, (const double2*)alm, alm_cstride, alm_bstride, (double*)map, map_cstride, map_bstride, (cudaStream_t)stream, done)) return 1;
+		alm = (char*)alm + (size_t)done*alm_bstride*asz; map = (char*)map + (size_t)done*map_bstride*msz; nbatch -= done;
+		if (nbatch == 0) return 0;
+	}
 	// batches run as groups of the same spin, B2_MAX_GROUPS at a time
 	for (int b0 = 0; b0 < nbatch; b0 += B2_MAX_GROUPS) {
 		int ng = std::min(B2_MAX_GROUPS, nbatch - b0);

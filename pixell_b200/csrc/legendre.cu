@@ -149,6 +149,7 @@ struct LegArgs {
 	// CTA b works on m = m0 + b; the synthesis kernels only touch the ring pairs [pair_lo, pair_hi) (multiples of 256)
 	int m0, pair_lo, pair_hi;
 	LegSignal sig;      // adjoint kernels: completion flags per range of m (sig.count == nullptr: none)
+	int64_t alm_bstride, leg_bstride;      // batched synthesis (k_synth0b / k_synth2b): element strides between the batch members
 };
 
 // base^n = mant*2^ex with mant in [0.5,1) (or mant = 1, ex = 0 for n = 0; mant = 0 for base = 0)
@@ -1089,6 +1090,336 @@ template<int R, int NW, int MINB, int TL, int W, int SIG> __global__ void __laun
 	if (SIG) signal_done<NW, SIG>(A);
 }
 
+// ------------------------------------------------------------------------------------ batched synthesis
+// NB alm sets of one spin (Monte-Carlo realisations of one geometry, pixell/curvedsky.py:17-36 called in a loop) share
+// the recurrence: per l and ring pair the 2 (spin 0) or 4 (spin s) recurrence DFMAs are paid once and only the 2 / 8
+// accumulations per member, i.e. (2 + 2 NB)/NB instead of 4 and (4 + 8 NB)/NB instead of 12 FP64 instructions per member.
+// The accumulations of one member are the very sequence of FMAs the single-map kernels execute, so the results are
+// bit-identical to theirs.  Same structure as k_synth0 / k_synth2 (rounds of 32 R NW ring pairs, l tiles through cp.async,
+// start table, live / masked / plain windows); whole launches only.
+
+template<int NB> struct Tile0B { double a, pad; double ar[NB], ai[NB]; };
+
+template<int MODE, int R, int NB> __device__ __forceinline__ void synth0b_window(const Tile0B<NB> *T,
+	const double (&x)[R], double (&g)[R], double (&gp)[R], int (&sc)[R], double (&acc)[NB][R][2][2])
+{
+	#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const Tile0B<NB> t = T[j];
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (MODE != 0) {
+				double gv = (MODE == 1) ? (sc[r] == 0 ? g[r] : 0.0) : g[r];
+				#pragma unroll
+				for (int b = 0; b < NB; b++) {
+					acc[b][r][j & 1][0] = fma(gv, t.ar[b], acc[b][r][j & 1][0]);
+					acc[b][r][j & 1][1] = fma(gv, t.ai[b], acc[b][r][j & 1][1]);
+				}
+			}
+			double ng = fma(t.a, x[r]*g[r], -gp[r]);
+			gp[r] = g[r]; g[r] = ng;
+		}
+	}
+	if (MODE != 2) {
+		#pragma unroll
+		for (int r = 0; r < R; r++) rescale(g[r], gp[r], sc[r]);
+	}
+}
+
+template<int R, int NW, int MINB, int TL, int NB> __global__ void __launch_bounds__(NW*32, MINB) k_synth0b(LegArgs A)
+{
+	__shared__ __align__(16) Tile0B<NB> tiles[2][TL];
+	__shared__ __align__(16) double2 raw_alm[NB][TL];
+	__shared__ __align__(16) double raw_al[TL], raw_a[TL];
+	__shared__ int wslot;
+	const int m = A.m0 + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int lmax = A.lmax, l0 = m;
+	const bool tab = A.st_w != nullptr && R*32 == LEG_GROUP;
+	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
+	const double *ta = A.ta + A.toff[m], *tal = A.talpha + A.toff[m];
+	const double2 *alm = A.alm0 + A.mstart[m];
+	const SeqConst sc0 = seq_const(m, 0, lmax, A.pref);
+	const int nchunk = A.npair_pad/(32*R);
+	double2 *leg = A.leg0 + (int64_t)m*A.leg_mstride;
+	const int rlive = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R*NW);
+	for (int i = tid; i < rlive*32*R*NW; i += NW*32) {
+		PairInfo pi = A.pairs[i];
+		#pragma unroll
+		for (int b = 0; b < NB; b++) {
+			if (pi.rn >= 0) leg[b*A.leg_bstride + pi.rn] = make_double2(0, 0);
+			if (pi.rs >= 0) leg[b*A.leg_bstride + pi.rs] = make_double2(0, 0);
+		}
+	}
+	for (int round = rlive; round*NW < nchunk; round++) {
+		const int chunk = round*NW + warp;
+		double x[R], g[R], gp[R], acc[NB][R][2][2]; int sc[R], rn[R], rs[R];
+		bool anyuse = false, use[R];
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			PairInfo pi; pi.rn = -1; pi.rs = -1; pi.x = 0; pi.sh = 0; pi.ch = 1;
+			if (chunk < nchunk) pi = A.pairs[(chunk*R + r)*32 + lane];
+			double dummy; int dsc;
+			if (!tab) { use[r] = init_pair(pi, sc0, m, 0, lmax, x[r], dummy, dsc, g[r], sc[r]); gp[r] = 0; }
+			else {
+				x[r] = pi.x;
+				use[r] = pi.rn >= 0 && 2.0*pi.sh*pi.ch >= sc0.dead_sth;
+				g[r] = gp[r] = 0; sc[r] = 0;
+				if (chunk < nchunk) { int64_t k = (int64_t)m*A.npair_pad + (chunk*R + r)*32 + lane; g[r] = A.st_p[k]; gp[r] = A.st_pp[k]; sc[r] = A.st_sp[k]; }
+			}
+			rn[r] = pi.rn; rs[r] = pi.rs;
+			#pragma unroll
+			for (int b = 0; b < NB; b++) acc[b][r][0][0] = acc[b][r][0][1] = acc[b][r][1][0] = acc[b][r][1][1] = 0;
+			anyuse |= use[r];
+		}
+		int wc = 0;
+		if (tab) { wc = chunk < nchunk ? A.st_w[m*A.ngroup + chunk] : LEG_NEVER; if (wc == LEG_NEVER) anyuse = false; }
+		const int wc_cta = tab ? cta_min<NW>(wc, &wslot) : 0;
+		const bool wuse = __any_sync(0xffffffffu, anyuse);
+		int phase = 0;
+		if (cta_or<NW>(anyuse)) {
+			auto issue = [&](int tile) {
+				int i = tile*TL + tid;
+				if (tid < TL && i < nl) {
+					#pragma unroll
+					for (int b = 0; b < NB; b++) cp_async16(&raw_alm[b][tid], &alm[b*A.alm_bstride + (int64_t)(l0 + i)*A.lstride]);
+					cp_async8(&raw_al[tid], &tal[i]); cp_async8(&raw_a[tid], &ta[i]);
+				}
+				cp_async_commit();
+			};
+			auto finish = [&](int tile, int buf) {
+				cp_async_wait_all();
+				int i = tile*TL + tid;
+				if (tid < TL) {
+					Tile0B<NB> t; t.a = t.pad = 0;
+					#pragma unroll
+					for (int b = 0; b < NB; b++) t.ar[b] = t.ai[b] = 0;
+					if (i < nl) {
+						double al = raw_al[tid]; t.a = raw_a[tid];
+						#pragma unroll
+						for (int b = 0; b < NB; b++) { double2 v = raw_alm[b][tid]; t.ar[b] = v.x*al; t.ai[b] = v.y*al; }
+					}
+					tiles[buf][tid] = t;
+				}
+			};
+			const int tile0 = min(wc_cta*8/TL, ntile - 1);
+			issue(tile0); finish(tile0, tile0 & 1);
+			cta_sync<NW>();
+			for (int tile = tile0; tile < ntile; tile++) {
+				const int buf = tile & 1;
+				if (tile + 1 < ntile) issue(tile + 1);
+				const int nwin = (min(TL, nl - tile*TL) + 7) >> 3;
+				for (int w = 0; wuse && w < nwin; w++) {
+					if (tile*(TL/8) + w < wc) continue;
+					if (phase < 2) {
+						bool mylive = true, anylive = false;
+						#pragma unroll
+						for (int r = 0; r < R; r++) { mylive &= (sc[r] == 0); anylive |= (sc[r] == 0 && use[r]); }
+						phase = __all_sync(0xffffffffu, mylive) ? 2 : __any_sync(0xffffffffu, anylive) ? 1 : 0;
+					}
+					const Tile0B<NB> *T = &tiles[buf][w*8];
+					if (phase == 2) synth0b_window<2, R, NB>(T, x, g, gp, sc, acc);
+					else if (phase == 1) synth0b_window<1, R, NB>(T, x, g, gp, sc, acc);
+					else synth0b_window<0, R, NB>(T, x, g, gp, sc, acc);
+				}
+				if (tile + 1 < ntile) finish(tile + 1, buf ^ 1);
+				cta_sync<NW>();
+			}
+		}
+		#pragma unroll
+		for (int b = 0; b < NB; b++) {
+			#pragma unroll
+			for (int r = 0; r < R; r++) {
+				if (rn[r] >= 0) leg[b*A.leg_bstride + rn[r]] = make_double2(acc[b][r][0][0] + acc[b][r][1][0], acc[b][r][0][1] + acc[b][r][1][1]);
+				if (rs[r] >= 0) leg[b*A.leg_bstride + rs[r]] = make_double2(acc[b][r][0][0] - acc[b][r][1][0], acc[b][r][0][1] - acc[b][r][1][1]);
+			}
+		}
+	}
+}
+
+template<int NB> struct Tile2B { double a, b; double apr[NB], api[NB], amr[NB], ami[NB]; };
+
+template<int MODE, int R, int NB> __device__ __forceinline__ void synth2b_window(const Tile2B<NB> *T,
+	const double (&x)[R], double (&p)[R], double (&pp)[R], double (&q)[R], double (&qp)[R],
+	int (&sp)[R], int (&sq)[R], double (&acc)[NB][R][8])
+{
+	#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const Tile2B<NB> t = T[j];
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (MODE != 0) {
+				double pv = (MODE == 1) ? (sp[r] == 0 ? p[r] : 0.0) : p[r];
+				double qv = (MODE == 1) ? (sq[r] == 0 ? q[r] : 0.0) : q[r];
+				double ps = (j & 1) ? -pv : pv, qs = (j & 1) ? -qv : qv;
+				#pragma unroll
+				for (int b = 0; b < NB; b++) {
+					double (&c)[8] = acc[b][r];
+					c[0] = fma(pv, t.apr[b], c[0]); c[1] = fma(pv, t.api[b], c[1]);
+					c[2] = fma(ps, t.amr[b], c[2]); c[3] = fma(ps, t.ami[b], c[3]);
+					c[4] = fma(qs, t.apr[b], c[4]); c[5] = fma(qs, t.api[b], c[5]);
+					c[6] = fma(qv, t.amr[b], c[6]); c[7] = fma(qv, t.ami[b], c[7]);
+				}
+			}
+			double np = fma(fma(t.a, x[r],  t.b), p[r], -pp[r]);
+			double nq = fma(fma(t.a, x[r], -t.b), q[r], -qp[r]);
+			pp[r] = p[r]; p[r] = np; qp[r] = q[r]; q[r] = nq;
+		}
+	}
+	if (MODE != 2) {
+		#pragma unroll
+		for (int r = 0; r < R; r++) { rescale(p[r], pp[r], sp[r]); rescale(q[r], qp[r], sq[r]); }
+	}
+}
+
+// batch member b: alm (E, B) at alm0 / alm1 + b alm_bstride, leg (Q, U) at leg0 / leg1 + b leg_bstride
+template<int R, int NW, int MINB, int TL, int NB> __global__ void __launch_bounds__(NW*32, MINB) k_synth2b(LegArgs A)
+{
+	__shared__ __align__(16) Tile2B<NB> tiles[2][TL];
+	__shared__ __align__(16) double2 raw_e[NB][TL], raw_b[NB][TL];
+	__shared__ __align__(16) double raw_ta[TL], raw_tb[TL], raw_al[TL];
+	__shared__ int wslot;
+	const int m = A.m0 + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int lmax = A.lmax, s = A.spin, l0 = m > s ? m : s;
+	const bool tab = A.st_w != nullptr && R*32 == LEG_GROUP;
+	double2 *legq = A.leg0 + (int64_t)m*A.leg_mstride, *legu = A.leg1 + (int64_t)m*A.leg_mstride;
+	const int nchunk = A.npair_pad/(32*R);
+	if (l0 > lmax) {
+		for (int i = tid; i < A.npair_pad; i += NW*32) {
+			PairInfo pi = A.pairs[i];
+			#pragma unroll
+			for (int b = 0; b < NB; b++) {
+				if (pi.rn >= 0) legq[b*A.leg_bstride + pi.rn] = legu[b*A.leg_bstride + pi.rn] = make_double2(0, 0);
+				if (pi.rs >= 0) legq[b*A.leg_bstride + pi.rs] = legu[b*A.leg_bstride + pi.rs] = make_double2(0, 0);
+			}
+		}
+		return;
+	}
+	const int nl = lmax - l0 + 1, ntile = (nl + TL - 1)/TL;
+	const double *ta = A.ta + A.toff[m], *tb = A.tb + A.toff[m], *tal = A.talpha + A.toff[m];
+	const SeqConst sc0 = seq_const(m, s, lmax, A.pref);
+	const double sigma0 = ((l0 + m + s) & 1) ? -1.0 : 1.0;
+	const int64_t ms = A.mstart[m];
+	const int rlive = first_live_pair(A.pairs, A.npair, sc0.dead_sth)/(32*R*NW);
+	for (int i = tid; i < rlive*32*R*NW; i += NW*32) {
+		PairInfo pi = A.pairs[i];
+		#pragma unroll
+		for (int b = 0; b < NB; b++) {
+			if (pi.rn >= 0) legq[b*A.leg_bstride + pi.rn] = legu[b*A.leg_bstride + pi.rn] = make_double2(0, 0);
+			if (pi.rs >= 0) legq[b*A.leg_bstride + pi.rs] = legu[b*A.leg_bstride + pi.rs] = make_double2(0, 0);
+		}
+	}
+	for (int round = rlive; round*NW < nchunk; round++) {
+		const int chunk = round*NW + warp;
+		double x[R], p[R], pp[R], q[R], qp[R], acc[NB][R][8]; int sp[R], sq[R], rn[R], rs[R];
+		bool anyuse = false, use[R];
+		#pragma unroll
+		for (int r = 0; r < R; r++) {
+			PairInfo pi; pi.rn = -1; pi.rs = -1; pi.x = 0; pi.sh = 0; pi.ch = 1;
+			if (chunk < nchunk) pi = A.pairs[(chunk*R + r)*32 + lane];
+			if (!tab) { use[r] = init_pair(pi, sc0, m, s, lmax, x[r], p[r], sp[r], q[r], sq[r]); pp[r] = qp[r] = 0; }
+			else {
+				x[r] = pi.x;
+				use[r] = pi.rn >= 0 && 2.0*pi.sh*pi.ch >= sc0.dead_sth;
+				p[r] = pp[r] = q[r] = qp[r] = 0; sp[r] = sq[r] = 0;
+				if (chunk < nchunk) {
+					int64_t k = (int64_t)m*A.npair_pad + (chunk*R + r)*32 + lane;
+					p[r] = A.st_p[k]; pp[r] = A.st_pp[k]; q[r] = A.st_q[k]; qp[r] = A.st_qp[k]; sp[r] = A.st_sp[k]; sq[r] = A.st_sq[k];
+				}
+			}
+			rn[r] = pi.rn; rs[r] = pi.rs;
+			#pragma unroll
+			for (int b = 0; b < NB; b++) {
+				#pragma unroll
+				for (int k = 0; k < 8; k++) acc[b][r][k] = 0;
+			}
+			anyuse |= use[r];
+		}
+		int wc = 0;
+		if (tab) { wc = chunk < nchunk ? A.st_w[m*A.ngroup + chunk] : LEG_NEVER; if (wc == LEG_NEVER) anyuse = false; }
+		const int wc_cta = tab ? cta_min<NW>(wc, &wslot) : 0;
+		const bool wuse = __any_sync(0xffffffffu, anyuse);
+		int phase = 0;
+		if (cta_or<NW>(anyuse)) {
+			auto issue = [&](int tile) {
+				int i = tile*TL + tid;
+				if (tid < TL && i < nl) {
+					int64_t idx = ms + (int64_t)(l0 + i)*A.lstride;
+					#pragma unroll
+					for (int b = 0; b < NB; b++) {
+						cp_async16(&raw_e[b][tid], &A.alm0[b*A.alm_bstride + idx]);
+						cp_async16(&raw_b[b][tid], &A.alm1[b*A.alm_bstride + idx]);
+					}
+					cp_async8(&raw_ta[tid], &ta[i]); cp_async8(&raw_tb[tid], &tb[i]); cp_async8(&raw_al[tid], &tal[i]);
+				}
+				cp_async_commit();
+			};
+			auto finish = [&](int tile, int buf) {
+				cp_async_wait_all();
+				int i = tile*TL + tid;
+				if (tid < TL) {
+					Tile2B<NB> t; t.a = t.b = 0;
+					#pragma unroll
+					for (int b = 0; b < NB; b++) t.apr[b] = t.api[b] = t.amr[b] = t.ami[b] = 0;
+					if (i < nl) {
+						double h = -0.5*raw_al[tid];
+						t.a = raw_ta[tid]; t.b = raw_tb[tid];
+						#pragma unroll
+						for (int b = 0; b < NB; b++) {
+							double2 E = raw_e[b][tid], B = raw_b[b][tid];
+							t.apr[b] = h*(E.x - B.y); t.api[b] = h*(E.y + B.x);
+							t.amr[b] = h*(E.x + B.y); t.ami[b] = h*(E.y - B.x);
+						}
+					}
+					tiles[buf][tid] = t;
+				}
+			};
+			const int tile0 = min(wc_cta*8/TL, ntile - 1);
+			issue(tile0); finish(tile0, tile0 & 1);
+			cta_sync<NW>();
+			for (int tile = tile0; tile < ntile; tile++) {
+				const int buf = tile & 1;
+				if (tile + 1 < ntile) issue(tile + 1);
+				const int nwin = (min(TL, nl - tile*TL) + 7) >> 3;
+				for (int w = 0; wuse && w < nwin; w++) {
+					if (tile*(TL/8) + w < wc) continue;
+					if (phase < 2) {
+						bool mylive = true, anylive = false;
+						#pragma unroll
+						for (int r = 0; r < R; r++) {
+							mylive &= (sp[r] == 0) & (sq[r] == 0);
+							anylive |= use[r] & ((sp[r] == 0) | (sq[r] == 0));
+						}
+						phase = __all_sync(0xffffffffu, mylive) ? 2 : __any_sync(0xffffffffu, anylive) ? 1 : 0;
+					}
+					const Tile2B<NB> *T = &tiles[buf][w*8];
+					if (phase == 2) synth2b_window<2, R, NB>(T, x, p, pp, q, qp, sp, sq, acc);
+					else if (phase == 1) synth2b_window<1, R, NB>(T, x, p, pp, q, qp, sp, sq, acc);
+					else synth2b_window<0, R, NB>(T, x, p, pp, q, qp, sp, sq, acc);
+				}
+				if (tile + 1 < ntile) finish(tile + 1, buf ^ 1);
+				cta_sync<NW>();
+			}
+		}
+		#pragma unroll
+		for (int b = 0; b < NB; b++) {
+			#pragma unroll
+			for (int r = 0; r < R; r++) {
+				const double (&c)[8] = acc[b][r];
+				if (rn[r] >= 0) {
+					double spr = c[0], spi = c[1], sqr = c[6], sqi = c[7];
+					legq[b*A.leg_bstride + rn[r]] = make_double2(spr + sqr, spi + sqi);
+					legu[b*A.leg_bstride + rn[r]] = make_double2(spi - sqi, sqr - spr);
+				}
+				if (rs[r] >= 0) {
+					double spr = sigma0*c[4], spi = sigma0*c[5], sqr = sigma0*c[2], sqi = sigma0*c[3];
+					legq[b*A.leg_bstride + rs[r]] = make_double2(spr + sqr, spi + sqi);
+					legu[b*A.leg_bstride + rs[r]] = make_double2(spi - sqi, sqr - spr);
+				}
+			}
+		}
+	}
+}
+
 // ------------------------------------------------------------------------------------ start table
 
 // One warp per (group of LEG_GROUP ring pairs, m): runs the recurrence exactly as the kernels' pre-phase does (same
@@ -1181,6 +1512,7 @@ static LegArgs make_args(const LegTables &T, const LegGeom &G, const AlmLayout &
 	A.lmax = L.lmax; A.mmax = L.mmax; A.spin = T.spin; A.deriv1 = deriv1;
 	A.m0 = 0; A.pair_lo = 0; A.pair_hi = G.npair_pad;
 	A.sig.count = nullptr; A.sig.flag = nullptr; A.sig.ncut = 0; A.sig.epoch = 0;
+	A.alm_bstride = 0; A.leg_bstride = 0;
 	A.toff = T.toff.p; A.ta = T.a.p; A.tb = T.b.p; A.talpha = T.alpha.p; A.pref = T.pref.p;
 	A.pairs = G.pairs.p; A.npair_pad = G.npair_pad; A.npair = G.npair;
 	A.mstart = L.mstart_d; A.lstride = L.lstride;
@@ -1278,6 +1610,23 @@ int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 		case 6: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 11, 32, 4, 2); else LAUNCH(k_adj2, 4, 1, 11, 32, 4, 1); } else LAUNCH(k_adj2, 4, 1, 11, 32, 4, 0); break;
 		default: B2_REQUIRE(0, "unknown k_adj2 variant");
 	}
+	B2_LAUNCH_CHECK();
+	return 0;
+}
+
+int leg_batch_size(int spin) { return spin == 0 ? 4 : 2; }
+
+int leg_alm2leg_batch(const LegTables &T, const LegGeom &G, const AlmLayout &L, int nb,
+	const double2 *alm, int64_t alm_cstride, int64_t alm_bstride, double2 *leg, int64_t leg_bstride, cudaStream_t st, const LegStart *S)
+{
+	if (check_args(T, L, 0)) return 1;
+	B2_REQUIRE(nb == leg_batch_size(T.spin) || (T.spin == 0 && nb == 2), "alm2leg_batch: unsupported batch size %d for spin %d", nb, T.spin);
+	LegArgs A = make_args(T, G, L, 0, (double2*)alm, alm_cstride, leg, S);
+	A.alm_bstride = alm_bstride; A.leg_bstride = leg_bstride;
+	const int nm_launch = L.mmax + 1;
+	// template arguments: R, NW, MINB, TL, NB (8 warps per SM: the accumulators of the batch take the registers)
+	if (T.spin == 0) { if (nb == 4) LAUNCH(k_synth0b, 4, 2, 4, 64, 4); else LAUNCH(k_synth0b, 4, 2, 6, 64, 2); }
+	else LAUNCH(k_synth2b, 4, 2, 4, 64, 2);
 	B2_LAUNCH_CHECK();
 	return 0;
 }

@@ -73,6 +73,13 @@ int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int deriv1,
                 double2 *alm, int64_t alm_cstride, const double2 *leg, cudaStream_t st, const LegStart *S = nullptr,
                 int m_lo = 0, int m_hi = 0, const LegSignal *sig = nullptr);
+// batched synthesis: nb alm sets of one spin share the recurrence (nb = leg_batch_size(spin), or 2 for spin 0); member b reads
+// alm + b*alm_bstride (+ c*alm_cstride for the second component) and writes leg + b*leg_bstride (second component of a
+// spin > 0 member at + (mmax+1)*nring_pad, as in leg_alm2leg).  Bit-identical to nb calls of leg_alm2leg.
+int leg_batch_size(int spin);
+int leg_alm2leg_batch(const LegTables &T, const LegGeom &G, const AlmLayout &L, int nb,
+                      const double2 *alm, int64_t alm_cstride, int64_t alm_bstride, double2 *leg, int64_t leg_bstride,
+                      cudaStream_t st, const LegStart *S = nullptr);
 int leg_build_start(LegStart &S, const LegTables &T, const LegGeom &G);
 int dfma_peak_gflops(double *out);
 int leg_set_variant(int which, int v);

@@ -39,6 +39,7 @@ struct b2_sht_plan {
 	// HBM-bound stages (ring FFTs, theta weighting) on s_fft, so that group g+1's memory-bound work hides under group g's
 	// Legendre kernel (and vice versa for alm -> map).  Groups alternate between two leg buffers ("lanes").
 	DevBuf<double2> leg2;              // second lane, allocated by the first multi-group call
+	DevBuf<double2> legb;              // four leg planes for batched synthesis (leg_alm2leg_batch), allocated on first use
 	cudaStream_t s_fft = nullptr;      // high priority: its short kernels take the SM slots the long Legendre CTAs free
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_chunk[8] = {};
 	// 2d plans

@@ -151,6 +151,24 @@ def run_groups(plan, op, groups, alm, map, mode=L.MODE_STANDARD):
 	a_cs = (ctypes.c_int64*n)(*[int(acs)]*n); m_cs = (ctypes.c_int64*n)(*[int(mcs)]*n)
 	L.check(L.lib().b2_sht_execute_groups(plan.handle, OPS[op], n, spins, mode, dtype, alms, a_cs, maps, m_cs, mema, L.current_stream(map)))
 
+def run_batch(plan, spin, alm, map):
+	"""Synthesis of a batch of alm sets of one spin in one engine call (b2_synthesis with nbatch > 1): alm [nb, nca, nalm],
+	map [nb, ncm, ny, nx] (or [nb, ncm, npix]), device tensors or host arrays, trailing axes contiguous, uniform batch and
+	component strides.  Device-resident float64 batches go through the batched Legendre kernels (the members share the
+	recurrence); the results are bit-identical to member-by-member calls."""
+	pa, mema, dta = L.buffer_info(alm); pm, memm, dtm = L.buffer_info(map)
+	if mema != memm: raise ValueError("alm and map must both be host arrays or both be CUDA tensors")
+	if dta == np.complex128 and dtm == np.float64: dtype = L.F64
+	elif dta == np.complex64 and dtm == np.float32: dtype = L.F32
+	else: raise ValueError("alm/map dtypes must be (complex128, float64) or (complex64, float32), got (%s, %s)" % (dta, dtm))
+	ncm = 1 if spin == 0 else 2
+	if alm.ndim != 3 or alm.shape[1] != ncm or map.ndim < 3 or map.shape[1] != ncm or map.shape[0] != alm.shape[0]:
+		raise ValueError("run_batch: alm must be [nb, %d, nalm] and map [nb, %d, ...] for spin %d" % (ncm, ncm, spin))
+	_check_last_contig(alm, "alm", 1); _check_last_contig(map, "map", map.ndim-2)
+	sa, sm = L.strides_elems(alm), L.strides_elems(map)
+	L.check(L.lib().b2_synthesis(plan.handle, int(spin), L.MODE_STANDARD, dtype, int(alm.shape[0]), pa, sa[1] if ncm > 1 else 0, sa[0],
+		pm, sm[1] if ncm > 1 else 0, sm[0], mema, L.current_stream(map)))
+
 def _alm_len(mstart, lmax, lstride): return int(np.max(mstart) + lmax*lstride + 1)
 
 # ------------------------------------------------------------------ ducc0.sht.experimental look-alikes

@@ -84,3 +84,21 @@ def test_rand_alm_kernel_shares_large_scales_between_lmax():
 	# unit normals: mean 0, variance 1 per real and imaginary part
 	big = mc.rand_alm_device(None, curvedsky.alm_info(400), 10, torch.device("cuda")).cpu().numpy()[0]
 	assert abs(big.real.mean()) < 0.02 and abs(big.real.var()-1) < 0.03 and abs(big.imag.var()-1) < 0.03
+
+@pytest.mark.parametrize("geom,ny,nx,lmax,ncomp", [("F1", 400, 800, 300, 3), ("CC", 301, 600, 280, 3), ("F1", 256, 512, 200, 1), ("F1", 2304, 1024, 500, 3)])
+def test_batched_synthesis_is_bit_identical(geom, ny, nx, lmax, ncomp):
+	"""mc.rand_maps runs blocks of realisations through the batched Legendre kernels (k_synth0b / k_synth2b: the members of
+	a block share the recurrence); every member's accumulations are the single-map kernels' sequence of FMAs, so the maps
+	must be bit-identical to the one-by-one path.  7 realisations: blocks of 4, 2 and a single one."""
+	import torch
+	from pixell_b200 import mc, geometry
+	if geom == "F1": shape, wcs = geometry.fullsky_geometry(shape=(ny, nx))
+	else: shape, wcs = geometry.fullsky_geometry(shape=(ny, nx), variant="CC")
+	ps = _ps(lmax) if ncomp == 3 else _ps(lmax)[0, 0]
+	seeds = list(range(40, 47))
+	full = (ncomp,)+tuple(shape) if ncomp > 1 else tuple(shape)
+	one = mc.rand_maps(full, wcs, ps, seeds, lmax=lmax, rng="device", batch=1)
+	blk, alms = mc.rand_maps(full, wcs, ps, seeds, lmax=lmax, rng="device", batch=4, return_alm=True)
+	assert torch.equal(one, blk) and len(alms) == len(seeds)
+	three = mc.rand_maps(full, wcs, ps, seeds[:3], lmax=lmax, rng="device", batch=3)      # one pair + one single inside the engine call
+	assert torch.equal(three, one[:3])
