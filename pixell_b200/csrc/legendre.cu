@@ -1152,7 +1152,7 @@ template<int R, int NW, int MINB, int TL, int NB> __global__ void __launch_bound
 	}
 	for (int round = rlive; round*NW < nchunk; round++) {
 		const int chunk = round*NW + warp;
-		double x[R], g[R], gp[R], acc[NB][R][2][2]; int sc[R], rn[R], rs[R];
+		double x[R], g[R], gp[R], acc[NB][R][2][2]; int sc[R];
 		bool anyuse = false, use[R];
 		#pragma unroll
 		for (int r = 0; r < R; r++) {
@@ -1166,7 +1166,6 @@ template<int R, int NW, int MINB, int TL, int NB> __global__ void __launch_bound
 				g[r] = gp[r] = 0; sc[r] = 0;
 				if (chunk < nchunk) { int64_t k = (int64_t)m*A.npair_pad + (chunk*R + r)*32 + lane; g[r] = A.st_p[k]; gp[r] = A.st_pp[k]; sc[r] = A.st_sp[k]; }
 			}
-			rn[r] = pi.rn; rs[r] = pi.rs;
 			#pragma unroll
 			for (int b = 0; b < NB; b++) acc[b][r][0][0] = acc[b][r][0][1] = acc[b][r][1][0] = acc[b][r][1][1] = 0;
 			anyuse |= use[r];
@@ -1226,11 +1225,13 @@ template<int R, int NW, int MINB, int TL, int NB> __global__ void __launch_bound
 			}
 		}
 		#pragma unroll
-		for (int b = 0; b < NB; b++) {
+		for (int r = 0; r < R; r++) {
+			int rn = -1, rs = -1;
+			if (chunk < nchunk) { const PairInfo &pi = A.pairs[(chunk*R + r)*32 + lane]; rn = pi.rn; rs = pi.rs; }
 			#pragma unroll
-			for (int r = 0; r < R; r++) {
-				if (rn[r] >= 0) leg[b*A.leg_bstride + rn[r]] = make_double2(acc[b][r][0][0] + acc[b][r][1][0], acc[b][r][0][1] + acc[b][r][1][1]);
-				if (rs[r] >= 0) leg[b*A.leg_bstride + rs[r]] = make_double2(acc[b][r][0][0] - acc[b][r][1][0], acc[b][r][0][1] - acc[b][r][1][1]);
+			for (int b = 0; b < NB; b++) {
+				if (rn >= 0) leg[b*A.leg_bstride + rn] = make_double2(acc[b][r][0][0] + acc[b][r][1][0], acc[b][r][0][1] + acc[b][r][1][1]);
+				if (rs >= 0) leg[b*A.leg_bstride + rs] = make_double2(acc[b][r][0][0] - acc[b][r][1][0], acc[b][r][0][1] - acc[b][r][1][1]);
 			}
 		}
 	}
@@ -1310,7 +1311,7 @@ template<int R, int NW, int MINB, int TL, int NB> __global__ void __launch_bound
 	}
 	for (int round = rlive; round*NW < nchunk; round++) {
 		const int chunk = round*NW + warp;
-		double x[R], p[R], pp[R], q[R], qp[R], acc[NB][R][8]; int sp[R], sq[R], rn[R], rs[R];
+		double x[R], p[R], pp[R], q[R], qp[R], acc[NB][R][8]; int sp[R], sq[R];
 		bool anyuse = false, use[R];
 		#pragma unroll
 		for (int r = 0; r < R; r++) {
@@ -1326,7 +1327,6 @@ template<int R, int NW, int MINB, int TL, int NB> __global__ void __launch_bound
 					p[r] = A.st_p[k]; pp[r] = A.st_pp[k]; q[r] = A.st_q[k]; qp[r] = A.st_qp[k]; sp[r] = A.st_sp[k]; sq[r] = A.st_sq[k];
 				}
 			}
-			rn[r] = pi.rn; rs[r] = pi.rs;
 			#pragma unroll
 			for (int b = 0; b < NB; b++) {
 				#pragma unroll
@@ -1400,20 +1400,23 @@ template<int R, int NW, int MINB, int TL, int NB> __global__ void __launch_bound
 				cta_sync<NW>();
 			}
 		}
+		// (the ring indices are read again here instead of being carried through the l loop: the accumulators need the registers)
 		#pragma unroll
-		for (int b = 0; b < NB; b++) {
+		for (int r = 0; r < R; r++) {
+			int rn = -1, rs = -1;
+			if (chunk < nchunk) { const PairInfo &pi = A.pairs[(chunk*R + r)*32 + lane]; rn = pi.rn; rs = pi.rs; }
 			#pragma unroll
-			for (int r = 0; r < R; r++) {
+			for (int b = 0; b < NB; b++) {
 				const double (&c)[8] = acc[b][r];
-				if (rn[r] >= 0) {
+				if (rn >= 0) {
 					double spr = c[0], spi = c[1], sqr = c[6], sqi = c[7];
-					legq[b*A.leg_bstride + rn[r]] = make_double2(spr + sqr, spi + sqi);
-					legu[b*A.leg_bstride + rn[r]] = make_double2(spi - sqi, sqr - spr);
+					legq[b*A.leg_bstride + rn] = make_double2(spr + sqr, spi + sqi);
+					legu[b*A.leg_bstride + rn] = make_double2(spi - sqi, sqr - spr);
 				}
-				if (rs[r] >= 0) {
+				if (rs >= 0) {
 					double spr = sigma0*c[4], spi = sigma0*c[5], sqr = sigma0*c[2], sqi = sigma0*c[3];
-					legq[b*A.leg_bstride + rs[r]] = make_double2(spr + sqr, spi + sqi);
-					legu[b*A.leg_bstride + rs[r]] = make_double2(spi - sqi, sqr - spr);
+					legq[b*A.leg_bstride + rs] = make_double2(spr + sqr, spi + sqi);
+					legu[b*A.leg_bstride + rs] = make_double2(spi - sqi, sqr - spr);
 				}
 			}
 		}
