@@ -1636,18 +1636,26 @@ int leg_alm2leg_batch(const LegTables &T, const LegGeom &G, const AlmLayout &L, 
 
 // ------------------------------------------------------------------------------------ DFMA peak
 
-__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters)
+// Sixteen independent chains d = fma(x, m, d) with m shared and x per chain: two operands to fetch per instruction, the
+// most the register file delivers at full DFMA rate (d = fma(d, m, c) as used in round 1 measures 33-36 TFLOP/s instead of
+// 36.9 because ptxas leaves some of its instructions with three fetched operands: scripts/ubench/ubench_dfma_operands.cu).
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double m_)
 {
-	double a0 = threadIdx.x*1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-	const double m = 1.0000001, c = 1e-9;
-	for (int i = 0; i < iters; i++) {
+	double d[16], x[16];
+	const double m = m_;
+	#pragma unroll
+	for (int i = 0; i < 16; i++) { d[i] = threadIdx.x*1e-9 + i; x[i] = 1e-9*(i + 1 + threadIdx.x); }
+	for (int it = 0; it < iters; it++) {
 		#pragma unroll
-		for (int k = 0; k < 8; k++) {
-			a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-			a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+		for (int k = 0; k < 4; k++) {
+			#pragma unroll
+			for (int i = 0; i < 16; i++) d[i] = fma(x[i], m, d[i]);
 		}
 	}
-	out[blockIdx.x*blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+	double sum = 0;
+	#pragma unroll
+	for (int i = 0; i < 16; i++) sum += d[i];
+	out[blockIdx.x*blockDim.x + threadIdx.x] = sum;
 }
 
 int dfma_peak_gflops(double *out)
@@ -1660,7 +1668,7 @@ int dfma_peak_gflops(double *out)
 	double best = 0;
 	for (int rep = 0; rep < 4; rep++) {
 		B2_CHECK(cudaEventRecord(e0));
-		k_dfma_peak<<<nb, nt>>>(buf.p, iters);
+		k_dfma_peak<<<nb, nt>>>(buf.p, iters, 1.0000001);
 		B2_CHECK(cudaEventRecord(e1));
 		B2_CHECK(cudaEventSynchronize(e1));
 		float ms; B2_CHECK(cudaEventElapsedTime(&ms, e0, e1));

@@ -1,19 +1,6 @@
 set -x
 mkdir -p gpurun_out
 T=${1:-it}
-python -m pytest tests/test_mc_gpu.py -x -q -m gpu 2>&1 | tail -15
-python - <<'PY' 2>&1 | tail -8
-import sys, json; sys.path.insert(0, '.')
-import torch, bench
-from pixell_b200 import _lib as L
-L.init(0)
-class D: pass
-for b in (1, 4):
-    import pixell_b200.mc as mc
-    orig = mc.rand_maps
-    def patched(*a, **k): k.setdefault("batch", b); return orig(*a, **k)
-    mc.rand_maps = patched
-    r = bench.bench_c4(torch, None, torch.device("cuda", 0), 0, 1)
-    mc.rand_maps = orig
-    print("batch", b, r["value"], "realisations/s", r["ms_total"], "var", r["var_T_rank0"])
-PY
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.txt 2>&1; tail -2 gpurun_out/${T}_smoke.txt
+timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/${T}_pytest_gpu.txt 2>&1; tail -3 gpurun_out/${T}_pytest_gpu.txt
+python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_bench_c3_1gpu.json 2> gpurun_out/${T}_bench.err; tail -2 gpurun_out/${T}_bench.err; cut -c1-300 gpurun_out/${T}_bench_c3_1gpu.json

@@ -137,7 +137,7 @@ def test_engine_object(F):
 	rr = F.engine.empty_aligned((3, 90), np.float64)
 	F.engine.FFTW(fr, rr, axes=(-1,), direction="FFTW_BACKWARD")()
 	assert rel(rr, r*90) < 1e-12
-	with pytest.raises(NotImplementedError): F.engine.FFTW(r, rr, direction=["FFTW_REDFT00"])
+	with pytest.raises(ValueError): F.engine.FFTW(r, rr, direction=["FFTW_NOSUCHKIND"])      # r2r kinds: see test_dct_dst_all_kinds
 
 def test_errors(F):
 	a = cdata((4, 8));
