@@ -20,9 +20,9 @@
 #include <cstdlib>
 
 #define B2_DEF_SYNTH0 0
-#define B2_DEF_ADJ0 0
-#define B2_DEF_SYNTH2 0
-#define B2_DEF_ADJ2 5
+#define B2_DEF_ADJ0 9
+#define B2_DEF_SYNTH2 5
+#define B2_DEF_ADJ2 7
 
 #define SMALLV 0x1p-512
 // A sequence counts as "live" (enters the sums) once its magnitude has reached 2^-LIVE_EXP: what it misses before is
@@ -433,20 +433,24 @@ template<int R, int NW, int MINB, int TL, int GATE> __global__ void __launch_bou
 		if (cta_or<NW>(anyuse)) {
 			// each of the first TL threads fetches one l of the next tile (issue), later scales it into the tile (finish)
 			auto issue = [&](int tile) {
-				int i = tile*TL + tid;
-				if (tid < TL && i < nl) {
-					cp_async16(&raw_alm[tid], &alm[(int64_t)(l0 + i)*A.lstride]);
-					cp_async8(&raw_al[tid], &tal[i]); cp_async8(&raw_a[tid], &ta[i]);
+				#pragma unroll
+				for (int t = tid; t < TL; t += NW*32) {      // one pass when TL <= NW*32
+					int i = tile*TL + t;
+					if (i < nl) {
+						cp_async16(&raw_alm[t], &alm[(int64_t)(l0 + i)*A.lstride]);
+						cp_async8(&raw_al[t], &tal[i]); cp_async8(&raw_a[t], &ta[i]);
+					}
 				}
 				cp_async_commit();
 			};
 			auto finish = [&](int tile, int buf) {
 				cp_async_wait_all();
-				int i = tile*TL + tid;
-				if (tid < TL) {
-					Tile0 t; t.ar = t.ai = t.a = t.pad = 0;
-					if (i < nl) { double al = raw_al[tid]; double2 v = raw_alm[tid]; t.ar = v.x*al; t.ai = v.y*al; t.a = raw_a[tid]; }
-					tiles[buf][tid] = t;
+				#pragma unroll
+				for (int t = tid; t < TL; t += NW*32) {
+					int i = tile*TL + t;
+					Tile0 e; e.ar = e.ai = e.a = e.pad = 0;
+					if (i < nl) { double al = raw_al[t]; double2 v = raw_alm[t]; e.ar = v.x*al; e.ai = v.y*al; e.a = raw_a[t]; }
+					tiles[buf][t] = e;
 				}
 			};
 			const int tile0 = min(wc_cta*8/TL, ntile - 1);
@@ -768,31 +772,35 @@ template<int R, int NW, int MINB, int TL, int GATE> __global__ void __launch_bou
 		int phase = 0;
 		if (cta_or<NW>(anyuse)) {
 			auto issue = [&](int tile) {
-				int i = tile*TL + tid;
-				if (tid < TL && i < nl) {
-					int64_t idx = ms + (int64_t)(l0 + i)*A.lstride;
-					cp_async16(&raw_e[tid], &A.alm0[idx]);
-					if (!A.deriv1) cp_async16(&raw_b[tid], &A.alm1[idx]);
-					cp_async8(&raw_ta[tid], &ta[i]); cp_async8(&raw_tb[tid], &tb[i]); cp_async8(&raw_al[tid], &tal[i]);
+				#pragma unroll
+				for (int t = tid; t < TL; t += NW*32) {      // one pass when TL <= NW*32
+					int i = tile*TL + t;
+					if (i < nl) {
+						int64_t idx = ms + (int64_t)(l0 + i)*A.lstride;
+						cp_async16(&raw_e[t], &A.alm0[idx]);
+						if (!A.deriv1) cp_async16(&raw_b[t], &A.alm1[idx]);
+						cp_async8(&raw_ta[t], &ta[i]); cp_async8(&raw_tb[t], &tb[i]); cp_async8(&raw_al[t], &tal[i]);
+					}
 				}
 				cp_async_commit();
 			};
 			auto finish = [&](int tile, int buf) {
 				cp_async_wait_all();
-				int i = tile*TL + tid;
-				if (tid < TL) {
-					Tile2 t; t.a = t.b = t.apr = t.api = t.amr = t.ami = 0;
+				#pragma unroll
+				for (int t = tid; t < TL; t += NW*32) {
+					int i = tile*TL + t;
+					Tile2 e; e.a = e.b = e.apr = e.api = e.amr = e.ami = 0;
 					if (i < nl) {
 						int l = l0 + i;
-						double2 E = raw_e[tid], B = make_double2(0, 0);
+						double2 E = raw_e[t], B = make_double2(0, 0);
 						if (A.deriv1) { double f = sqrt((double)l*(l + 1.0)); E.x *= f; E.y *= f; }
-						else B = raw_b[tid];
-						double h = -0.5*raw_al[tid];
-						t.a = raw_ta[tid]; t.b = raw_tb[tid];
-						t.apr = h*(E.x - B.y); t.api = h*(E.y + B.x);
-						t.amr = h*(E.x + B.y); t.ami = h*(E.y - B.x);
+						else B = raw_b[t];
+						double h = -0.5*raw_al[t];
+						e.a = raw_ta[t]; e.b = raw_tb[t];
+						e.apr = h*(E.x - B.y); e.api = h*(E.y + B.x);
+						e.amr = h*(E.x + B.y); e.ami = h*(E.y - B.x);
 					}
-					tiles[buf][tid] = t;
+					tiles[buf][t] = e;
 				}
 			};
 			const int tile0 = min(wc_cta*8/TL, ntile - 1);
@@ -1572,6 +1580,8 @@ int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 		case 0: if (gate) LAUNCH(k_synth0, 4, 2, 8, 64, 1); else LAUNCH(k_synth0, 4, 2, 8, 64, 0); break;
 		case 1: if (gate) LAUNCH(k_synth0, 4, 1, 16, 32, 1); else LAUNCH(k_synth0, 4, 1, 16, 32, 0); break;
 		case 2: if (gate) LAUNCH(k_synth0, 2, 4, 6, 64, 1); else LAUNCH(k_synth0, 2, 4, 6, 64, 0); break;
+		case 3: if (gate) LAUNCH(k_synth0, 4, 2, 8, 128, 1); else LAUNCH(k_synth0, 4, 2, 8, 128, 0); break;
+		case 4: if (gate) LAUNCH(k_synth0, 4, 2, 8, 256, 1); else LAUNCH(k_synth0, 4, 2, 8, 256, 0); break;
 		default: B2_REQUIRE(0, "unknown k_synth0 variant");
 	} else switch (variant_of(2)) {
 		case 0: if (gate) LAUNCH(k_synth2, 4, 2, 6, 64, 1); else LAUNCH(k_synth2, 4, 2, 6, 64, 0); break;
@@ -1579,6 +1589,8 @@ int leg_alm2leg(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 		case 2: if (gate) LAUNCH(k_synth2, 4, 1, 12, 32, 1); else LAUNCH(k_synth2, 4, 1, 12, 32, 0); break;
 		case 3: if (gate) LAUNCH(k_synth2, 2, 4, 3, 64, 1); else LAUNCH(k_synth2, 2, 4, 3, 64, 0); break;
 		case 4: if (gate) LAUNCH(k_synth2, 4, 2, 5, 64, 1); else LAUNCH(k_synth2, 4, 2, 5, 64, 0); break;
+		case 5: if (gate) LAUNCH(k_synth2, 4, 2, 6, 128, 1); else LAUNCH(k_synth2, 4, 2, 6, 128, 0); break;
+		case 6: if (gate) LAUNCH(k_synth2, 4, 2, 6, 256, 1); else LAUNCH(k_synth2, 4, 2, 6, 256, 0); break;
 		default: B2_REQUIRE(0, "unknown k_synth2 variant");
 	}
 	B2_LAUNCH_CHECK();
@@ -1602,6 +1614,13 @@ int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 		case 0: if (sig) { if (sig_style() == 2) LAUNCH(k_adj0, 8, 1, 8, 32, 8, 2); else LAUNCH(k_adj0, 8, 1, 8, 32, 8, 1); } else LAUNCH(k_adj0, 8, 1, 8, 32, 8, 0); break;
 		case 1: if (sig) { if (sig_style() == 2) LAUNCH(k_adj0, 8, 1, 10, 32, 4, 2); else LAUNCH(k_adj0, 8, 1, 10, 32, 4, 1); } else LAUNCH(k_adj0, 8, 1, 10, 32, 4, 0); break;
 		case 2: if (sig) { if (sig_style() == 2) LAUNCH(k_adj0, 4, 4, 3, 64, 8, 2); else LAUNCH(k_adj0, 4, 4, 3, 64, 8, 1); } else LAUNCH(k_adj0, 4, 4, 3, 64, 8, 0); break;
+		case 3: if (sig) { if (sig_style() == 2) LAUNCH(k_adj0, 4, 1, 12, 32, 8, 2); else LAUNCH(k_adj0, 4, 1, 12, 32, 8, 1); } else LAUNCH(k_adj0, 4, 1, 12, 32, 8, 0); break;
+		case 4: if (sig) { if (sig_style() == 2) LAUNCH(k_adj0, 4, 1, 16, 32, 8, 2); else LAUNCH(k_adj0, 4, 1, 16, 32, 8, 1); } else LAUNCH(k_adj0, 4, 1, 16, 32, 8, 0); break;
+		case 5: if (sig) { if (sig_style() == 2) LAUNCH(k_adj0, 8, 1, 8, 32, 4, 2); else LAUNCH(k_adj0, 8, 1, 8, 32, 4, 1); } else LAUNCH(k_adj0, 8, 1, 8, 32, 4, 0); break;
+		case 6: if (sig) { if (sig_style() == 2) LAUNCH(k_adj0, 4, 1, 16, 32, 4, 2); else LAUNCH(k_adj0, 4, 1, 16, 32, 4, 1); } else LAUNCH(k_adj0, 4, 1, 16, 32, 4, 0); break;
+		case 7: if (sig) { if (sig_style() == 2) LAUNCH(k_adj0, 8, 1, 8, 128, 8, 2); else LAUNCH(k_adj0, 8, 1, 8, 128, 8, 1); } else LAUNCH(k_adj0, 8, 1, 8, 128, 8, 0); break;
+		case 8: if (sig) { if (sig_style() == 2) LAUNCH(k_adj0, 8, 1, 8, 256, 8, 2); else LAUNCH(k_adj0, 8, 1, 8, 256, 8, 1); } else LAUNCH(k_adj0, 8, 1, 8, 256, 8, 0); break;
+		case 9: if (sig) { if (sig_style() == 2) LAUNCH(k_adj0, 8, 1, 8, 64, 8, 2); else LAUNCH(k_adj0, 8, 1, 8, 64, 8, 1); } else LAUNCH(k_adj0, 8, 1, 8, 64, 8, 0); break;
 		default: B2_REQUIRE(0, "unknown k_adj0 variant");
 	} else switch (variant_of(3)) {
 		case 0: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 10, 32, 4, 2); else LAUNCH(k_adj2, 4, 1, 10, 32, 4, 1); } else LAUNCH(k_adj2, 4, 1, 10, 32, 4, 0); break;
@@ -1611,6 +1630,9 @@ int leg_leg2alm(const LegTables &T, const LegGeom &G, const AlmLayout &L, int de
 		case 4: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 9, 32, 8, 2); else LAUNCH(k_adj2, 4, 1, 9, 32, 8, 1); } else LAUNCH(k_adj2, 4, 1, 9, 32, 8, 0); break;
 		case 5: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 8, 32, 8, 2); else LAUNCH(k_adj2, 4, 1, 8, 32, 8, 1); } else LAUNCH(k_adj2, 4, 1, 8, 32, 8, 0); break;
 		case 6: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 11, 32, 4, 2); else LAUNCH(k_adj2, 4, 1, 11, 32, 4, 1); } else LAUNCH(k_adj2, 4, 1, 11, 32, 4, 0); break;
+		case 7: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 8, 64, 8, 2); else LAUNCH(k_adj2, 4, 1, 8, 64, 8, 1); } else LAUNCH(k_adj2, 4, 1, 8, 64, 8, 0); break;
+		case 8: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 8, 128, 8, 2); else LAUNCH(k_adj2, 4, 1, 8, 128, 8, 1); } else LAUNCH(k_adj2, 4, 1, 8, 128, 8, 0); break;
+		case 9: if (sig) { if (sig_style() == 2) LAUNCH(k_adj2, 4, 1, 10, 64, 4, 2); else LAUNCH(k_adj2, 4, 1, 10, 64, 4, 1); } else LAUNCH(k_adj2, 4, 1, 10, 64, 4, 0); break;
 		default: B2_REQUIRE(0, "unknown k_adj2 variant");
 	}
 	B2_LAUNCH_CHECK();

@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
 T=${1:-it}
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.txt 2>&1; tail -2 gpurun_out/${T}_smoke.txt
-timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/${T}_pytest_gpu.txt 2>&1; tail -3 gpurun_out/${T}_pytest_gpu.txt
-python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_bench_c3_1gpu.json 2> gpurun_out/${T}_bench.err; tail -2 gpurun_out/${T}_bench.err; cut -c1-300 gpurun_out/${T}_bench_c3_1gpu.json
+B2_TRACE=1 python scripts/e2e_probe.py > gpurun_out/${T}_probe.json 2> gpurun_out/${T}_trace.txt; cat gpurun_out/${T}_probe.json; grep -n "map -> alm" -A20 gpurun_out/${T}_trace.txt | tail -21 | grep "K5 done\|K2 done"
+B2_LEG_VARIANT=0,9,5,8 python scripts/e2e_probe.py 2>/dev/null
+python -m pytest tests/test_sht_gpu.py tests/test_curvedsky_gpu.py tests/test_baseline_parity_gpu.py -x -q -m gpu 2>&1 | tail -2

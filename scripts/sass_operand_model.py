@@ -57,7 +57,7 @@ def regions(ins, min_dfma=90):
 if __name__ == "__main__":
 	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 	lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(root, "pixell_b200", "libb200sht.so")
-	pats = sys.argv[2:] or ["k_synth0ILi4ELi2ELi8ELi64ELi0", "k_adj0ILi8ELi1ELi8ELi32ELi8ELi0", "k_synth2ILi4ELi2ELi6ELi64ELi0", "k_adj2ILi4ELi1ELi8ELi32ELi8ELi0", "k_adj2ILi4ELi1ELi10ELi32ELi4ELi0"]
+	pats = sys.argv[2:] or ["k_synth0ILi4ELi2ELi8ELi64ELi0", "k_adj0ILi8ELi1ELi8ELi64ELi8ELi0", "k_synth2ILi4ELi2ELi6ELi128ELi0", "k_adj2ILi4ELi1ELi8ELi64ELi8ELi0", "k_adj2ILi4ELi1ELi10ELi32ELi4ELi0"]
 	for name, lines in functions(lib).items():
 		if not any(p in name for p in pats): continue
 		print(name)
