@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #define B2_DEF_SYNTH0 0
 #define B2_DEF_ADJ0 9
@@ -608,11 +609,14 @@ template<int R, int NW, int MINB, int TL, int W, int SIG> __global__ void __laun
 				}
 			}
 			cp_async_commit();
+			// (two instances of the window loop: only a tile in which a ring group starts pays for the start-table check; left
+			// in the common loop it compiles to 24 predicated loads per window, 8 % of the kernel's issue slots)
+			auto windows = [&](auto CHECK) {
 			#pragma unroll 1
 			for (int w = 0; w < TL/W; w++) {
 				double tot = 0;
 				if (wuse && w < nwin && tile*TL + w*W >= wc*8) {
-					if (tab) {
+					if (decltype(CHECK)::value) {
 						#pragma unroll
 						for (int k = 0; k < NG; k++) if (tile*TL + w*W == wg[k]*8) {      // inject group k (warp-uniform)
 							#pragma unroll
@@ -641,6 +645,13 @@ template<int R, int NW, int MINB, int TL, int W, int SIG> __global__ void __laun
 				// element 2 (l - l_window) + re/im; lanes holding the same element write the same value
 				red[buf][warp][w*NV + bfly_element<2, W>(lane)] = tot;
 			}
+			};
+			bool inj_tile = false;
+			if (tab) {
+				#pragma unroll
+				for (int k = 0; k < NG; k++) inj_tile |= (wg[k] != LEG_NEVER && wg[k]*8 >= tile*TL && wg[k]*8 < (tile + 1)*TL);
+			}
+			if (inj_tile) windows(std::true_type()); else windows(std::false_type());
 			cp_async_wait_all();
 			cta_sync<NW>();
 			if constexpr (NW == 1) {
