@@ -1,6 +1,4 @@
 set -x
 mkdir -p gpurun_out
 T=${1:-it}
-python scripts/tune_legendre.py c3 0 0123 2>&1 | tail -4
-python scripts/e2e_probe.py 2>/dev/null
-python -m pytest tests/test_sht_gpu.py tests/test_curvedsky_gpu.py tests/test_baseline_parity_gpu.py tests/test_mc_gpu.py -x -q -m gpu 2>&1 | tail -2
+python scripts/tune_legendre.py c3 10 02 > gpurun_out/${T}_tune.txt 2>&1; cat gpurun_out/${T}_tune.txt
