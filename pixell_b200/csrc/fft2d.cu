@@ -115,7 +115,7 @@ template<bool INV> __global__ void k_fft_axis(AxisArgs A)
 	for (int idx = tid; idx < tot; idx += T) {
 		int line, kk;
 		if (A.jfast) { line = idx/nl; kk = idx - line*nl; } else { kk = idx/nb; line = idx - kk*nb; }
-		if (line < nbv) fft_st(A, bout + line*A.os_in, p + P*kk, s[line*ls + fft_pad(A.d, __ldg(&A.d.rev[kk]))]);
+		if (line < nbv) fft_st(A, bout + line*A.os_in, p + P*kk, s[line*ls + fft_pad(A.d, fft_rev(A.d, kk))]);
 	}
 }
 
@@ -188,7 +188,7 @@ template<bool INV, int MODE, int P> __global__ void __launch_bounds__(512) k_fft
 		const int line = ot.line, kk = ot.j;
 		if (line >= nbv) continue;
 		const int k = p + P*kk;
-		const double2 x = s[line*ls + fft_pad(A.d, __ldg(&A.d.rev[kk]))];
+		const double2 x = s[line*ls + fft_pad(A.d, fft_rev(A.d, kk))];
 		const int64_t bo = bout + line*A.os_in;
 		if (MODE == FM_C2C) ((double2*)A.out)[bo + k*A.os_t] = make_double2(x.x*A.scale, x.y*A.scale);
 		else if (MODE == FM_C2R_PACKED) {
@@ -197,7 +197,7 @@ template<bool INV, int MODE, int P> __global__ void __launch_bounds__(512) k_fft
 		} else {
 			// partner nc - k has the same residue mod P (P <= 2)
 			const int kp = k ? nc - k : 0;
-			const double2 y = s[line*ls + fft_pad(A.d, __ldg(&A.d.rev[(kp - p)/P]))];
+			const double2 y = s[line*ls + fft_pad(A.d, fft_rev(A.d, (kp - p)/P))];
 			double2 sm = make_double2(x.x + y.x, x.y - y.y), df = make_double2(x.x - y.x, x.y + y.y);
 			double2 u = cmul(df, __ldg(&A.d.tw[k]));                    // w_n^k (Z_k - conj Z_{nc-k})
 			double2 X = make_double2(0.5*(sm.x + u.y), 0.5*(sm.y - u.x));
@@ -340,7 +340,7 @@ template<bool INV, int MODE, int P> __global__ void __launch_bounds__(512) k_fft
 		for (int idx = tid; idx < tot; idx += T, ot.next()) {
 			const int line = ot.line, kk = ot.j;
 			if (line >= nbv) continue;
-			const double2 x = s[line*ls + fft_pad(A.d, __ldg(&A.d.rev[kk]))];
+			const double2 x = s[line*ls + fft_pad(A.d, fft_rev(A.d, kk))];
 			((double2*)A.out)[bout + line*A.os_in + (int64_t)(r + P*kk)*A.os_t] = make_double2(x.x*A.scale, x.y*A.scale);
 		}
 		return;         // the last remote access (radix-P step) lies before the previous cluster barrier
@@ -357,8 +357,8 @@ template<bool INV, int MODE, int P> __global__ void __launch_bounds__(512) k_fft
 		for (int idx = tid; idx < nb*nh; idx += T, pt.next()) {
 			const int line = pt.line, k = pt.j, kp = nc - k;
 			if (line >= nbv) continue;
-			const double2 x = s[line*ls + fft_pad(A.d, __ldg(&A.d.rev[k]))];
-			const double2 y = k ? s[line*ls + fft_pad(A.d, __ldg(&A.d.rev[kp]))] : x;
+			const double2 x = s[line*ls + fft_pad(A.d, fft_rev(A.d, k))];
+			const double2 y = k ? s[line*ls + fft_pad(A.d, fft_rev(A.d, kp))] : x;
 			const double2 sm = make_double2(x.x + y.x, x.y - y.y), df = make_double2(x.x - y.x, x.y + y.y);
 			const double2 u = cmul(df, fft_tw<false>(twsm, nhi, k));       // w_n^k (Z_k - conj Z_{nc-k})
 			const double h = 0.5*A.scale;
@@ -380,7 +380,7 @@ template<bool INV, int MODE, int P> __global__ void __launch_bounds__(512) k_fft
 		const int line = gt.line, kl = gt.j;
 		if (line >= nbv) continue;
 		const int k = r*nl + kl;
-		const double2 x = owner(k)[line*ls + fft_pad(A.d, __ldg(&A.d.rev[k/P]))];
+		const double2 x = owner(k)[line*ls + fft_pad(A.d, fft_rev(A.d, k/P))];
 		const int64_t bo = bout + line*A.os_in;
 		if (MODE == FM_C2C) ((double2*)A.out)[bo + k*A.os_t] = make_double2(x.x*A.scale, x.y*A.scale);
 		else if (MODE == FM_C2R_PACKED) {
@@ -388,7 +388,7 @@ template<bool INV, int MODE, int P> __global__ void __launch_bounds__(512) k_fft
 			else ((float2*)((float*)A.out + bo))[k] = make_float2((float)(x.x*A.scale), (float)(x.y*A.scale));
 		} else {
 			const int kp = k ? nc - k : 0;
-			const double2 y = owner(kp)[line*ls + fft_pad(A.d, __ldg(&A.d.rev[kp/P]))];
+			const double2 y = owner(kp)[line*ls + fft_pad(A.d, fft_rev(A.d, kp/P))];
 			double2 sm = make_double2(x.x + y.x, x.y - y.y), df = make_double2(x.x - y.x, x.y + y.y);
 			double2 u = cmul(df, fft_tw<false>(twsm, nhi, k));             // w_n^k (Z_k - conj Z_{nc-k})
 			double2 X = make_double2(0.5*(sm.x + u.y), 0.5*(sm.y - u.x));

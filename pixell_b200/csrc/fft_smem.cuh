@@ -27,6 +27,10 @@ struct FftDesc {
 	int ntab;
 	const double2 *tw;     // tw[k] = exp(-2 pi i k / ntab), ntab a multiple of n (caller-visible table)
 	const int *rev;        // position of X[k] after fft_smem (identity for Bluestein); apply fft_pad() to it
+	// when every factor is a power of two the digit reversal is a handful of shifts: bits per factor, one nibble each
+	// (first factor lowest), 0 = use the table; rev_total = log2(nt).  Consumers call fft_rev(): no dependent global load
+	// in front of their shared-memory reads.
+	unsigned rev_bits; int rev_total;
 	// fast path (all factors in {2,3,4,5,8,16}): register butterflies, padded shared memory, two-level
 	// twiddle tables in shared memory (no global loads inside the passes)
 	int fast;
@@ -159,6 +163,19 @@ template<bool INV, bool DIT> __device__ void fft_passes(double2 *s, int nt, int 
 // ------------------------------------------------------------------------------------ fast path
 
 __device__ __forceinline__ int fft_pad(const FftDesc &d, int i) { return i + (i >> d.pad_shift); }
+__device__ __forceinline__ int fft_rev(const FftDesc &d, int k)
+{
+	if (d.rev_bits == 0) return __ldg(&d.rev[k]);
+	int pos = 0, sh = d.rev_total;
+	unsigned bits = d.rev_bits;
+	#pragma unroll
+	for (int f = 0; f < 8; f++) {
+		const int b = bits & 15;
+		if (b) { sh -= b; pos |= (k & ((1 << b) - 1)) << sh; k >>= b; }
+		bits >>= 4;
+	}
+	return pos;
+}
 
 // copy the two-level twiddle tables into shared memory (twsm: d.ntw_hi + FFT_TWLO elements); the caller
 // synchronises before the first fft_smem call

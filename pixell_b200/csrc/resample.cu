@@ -90,7 +90,7 @@ template<int STAGE, int P> __global__ void __launch_bounds__(512) k_resamp(Resam
 	#pragma unroll 8
 	for (int kk = tid; kk < Nl; kk += T) {
 		const int k = p + P*kk;
-		double2 x = s[fft_pad(R.d, __ldg(&R.d.rev[kk]))];
+		double2 x = s[fft_pad(R.d, fft_rev(R.d, kk))];
 		const int f = (2*k <= N) ? k : k - N;
 		const bool nyq = (2*k == N);
 		if (STAGE == 1) {
@@ -175,7 +175,7 @@ template<int STAGE, int P> __global__ void __launch_bounds__(512) k_resamp_adj(R
 	#pragma unroll 8
 	for (int kk = tid; kk < Nl; kk += T) {
 		const int k = p + P*kk;
-		double2 x = s[fft_pad(R.d, __ldg(&R.d.rev[kk]))];
+		double2 x = s[fft_pad(R.d, fft_rev(R.d, kk))];
 		const int f = (2*k <= N) ? k : k - N;
 		const bool nyq = (2*k == N);
 		if (STAGE == 1) {

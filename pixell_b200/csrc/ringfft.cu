@@ -130,7 +130,7 @@ int FftTables::prepare(int n, int ntab)
 	d.n = n; d.ntab = ntab; d.twmul = ntab/n;
 	host.tw = twiddles(ntab);
 	d.fast = 0; d.pad_shift = 31; d.ntw_hi = 0; d.bluestein = 0;
-	d.tw = nullptr; d.rev = nullptr; d.btw = nullptr; d.chirp = nullptr; d.bhat = nullptr;
+	d.tw = nullptr; d.rev = nullptr; d.btw = nullptr; d.chirp = nullptr; d.bhat = nullptr; d.rev_bits = 0; d.rev_total = 0;
 	if (fast_ok(n)) {
 		d.nt = n; d.fast = 1;
 		factorize_fast(n, d.fac, d.nfac);
@@ -163,6 +163,24 @@ int FftTables::prepare(int n, int ntab)
 		host.rev.resize(n);
 		for (int k = 0; k < n; k++) host.rev[k] = k;
 		host.btw = twiddles(M);
+	}
+	// arithmetic digit reversal for power-of-two factorisations (checked against the table)
+	if (!d.bluestein && d.nfac <= 8) {
+		unsigned bits = 0; int total = 0; bool ok = true;
+		for (int f = 0; f < d.nfac && ok; f++) {
+			int r = d.fac[f], b = 0;
+			while ((1 << b) < r) b++;
+			ok = ((1 << b) == r) && b >= 1 && b <= 15;
+			bits |= (unsigned)b << (4*f); total += b;
+		}
+		if (ok && (1 << total) == d.nt) {
+			for (int k = 0; k < d.nt && ok; k++) {
+				int pos = 0, sh = total, kk = k;
+				for (int f = 0; f < d.nfac; f++) { int b = (bits >> (4*f)) & 15; sh -= b; pos |= (kk & ((1 << b) - 1)) << sh; kk >>= b; }
+				ok = (pos == host.rev[k]);
+			}
+			if (ok) { d.rev_bits = bits; d.rev_total = total; }
+		}
 	}
 	host.ready = true;
 	return 0;
@@ -317,7 +335,7 @@ template<typename MapT> __global__ void __launch_bounds__(512) k_leg2map(RingArg
 		fft_smem<true>(s, A.d, tid, T, 1, twsm);
 		#pragma unroll 8
 		for (int64_t i = tid; i < A.npix; i += T) {
-			double2 z = s[SI(__ldg(&A.d.rev[i >> 1]))];
+			double2 z = s[SI(fft_rev(A.d, (int)(i >> 1)))];
 			row[i] = (MapT)((i & 1) ? z.y : z.x);
 		}
 	} else {
@@ -358,7 +376,7 @@ template<typename MapT> __global__ void __launch_bounds__(512) k_map2leg(RingArg
 			#pragma unroll 4
 			for (int m = tid; m <= mmax; m += T) {
 				const int k2 = m == 0 ? 0 : nf - m;
-				double2 zk = s[SI(__ldg(&A.d.rev[m]))], zc = cconj(s[SI(__ldg(&A.d.rev[k2]))]);
+				double2 zk = s[SI(fft_rev(A.d, m))], zc = cconj(s[SI(fft_rev(A.d, k2))]);
 				double2 e = make_double2(0.5*(zk.x + zc.x), 0.5*(zk.y + zc.y));
 				double2 dd = make_double2(0.5*(zk.x - zc.x), 0.5*(zk.y - zc.y));
 				double2 o = make_double2(dd.y, -dd.x);

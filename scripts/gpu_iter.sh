@@ -1,4 +1,5 @@
 set -x
 mkdir -p gpurun_out
 T=${1:-it}
-python scripts/tune_legendre.py c3 10 02 > gpurun_out/${T}_tune.txt 2>&1; cat gpurun_out/${T}_tune.txt
+python scripts/e2e_probe.py 2>/dev/null
+python -m pytest tests/test_fft_gpu.py tests/test_sht_gpu.py tests/test_curvedsky_gpu.py tests/test_baseline_parity_gpu.py -x -q -m gpu 2>&1 | tail -2
