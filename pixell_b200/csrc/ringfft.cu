@@ -10,6 +10,7 @@
 #include <map>
 #include <algorithm>
 #include <complex>
+#include <type_traits>
 
 // ------------------------------------------------------------------------------------ tables
 
@@ -273,6 +274,15 @@ __device__ __forceinline__ double2 ring_phase(const RingArgs &A, int m)
 	return make_double2(c, sn);
 }
 
+// TAB = true: the plan's table (cylindrical maps).  The choice is made OUTSIDE the hot loops: a branch inside them keeps the
+// loads of an unrolled loop from being issued together (one outstanding load per thread, profiles/r3m_fftk_stalls.txt).
+template<bool TAB> __device__ __forceinline__ double2 ring_phase_t(const RingArgs &A, int m)
+{
+	if (TAB) return __ldg(&A.phase[m]);
+	double sn, c; sincos((double)m*A.phi0s[blockIdx.x], &sn, &c);
+	return make_double2(c, sn);
+}
+
 __device__ __forceinline__ double2 leg_phase(const RingArgs &A, const double2 *legc, int m)
 {
 	double2 g = cmul(legc[(int64_t)m*A.nring_pad], ring_phase(A, m));
@@ -294,15 +304,18 @@ template<typename MapT> __global__ void __launch_bounds__(512) k_leg2map(RingArg
 		if (mmax < nf) {
 			// no aliasing: X[k] = leg_k e^{i k phi0} for k <= mmax, 0 above; branch-free so that the loads of a thread overlap
 			const bool flip = A.xdir < 0;
-			#pragma unroll 4
-			for (int k = tid; k <= nf; k += T) {
-				const int kc = min(k, mmax);
-				double2 g = cmul(__ldg(&legc[(int64_t)kc*A.nring_pad]), ring_phase(A, kc));
-				if (flip) g.y = -g.y;
-				if (k == 0) g = make_double2(g.x, 0.0);
-				if (k > mmax) g = make_double2(0, 0);
-				s[SI(k)] = g;
-			}
+			auto fill = [&](auto TAB) {
+				#pragma unroll 8
+				for (int k = tid; k <= nf; k += T) {
+					const int kc = min(k, mmax);
+					double2 g = cmul(__ldg(&legc[(int64_t)kc*A.nring_pad]), ring_phase_t<decltype(TAB)::value>(A, kc));
+					if (flip) g.y = -g.y;
+					if (k == 0) g = make_double2(g.x, 0.0);
+					if (k > mmax) g = make_double2(0, 0);
+					s[SI(k)] = g;
+				}
+			};
+			if (A.phi0s) fill(std::false_type()); else fill(std::true_type());
 		} else {
 			// half spectrum X[0..nf] of the real ring, |m| aliased mod nphi
 			for (int k = tid; k <= nf; k += T) {

@@ -1,5 +1,5 @@
 set -x
 mkdir -p gpurun_out
 T=${1:-it}
+timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/${T}_pytest_gpu.txt 2>&1; tail -3 gpurun_out/${T}_pytest_gpu.txt
 python scripts/e2e_probe.py 2>/dev/null
-python -m pytest tests/test_fft_gpu.py tests/test_sht_gpu.py tests/test_curvedsky_gpu.py tests/test_baseline_parity_gpu.py -x -q -m gpu 2>&1 | tail -2
