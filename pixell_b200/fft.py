@@ -290,5 +290,95 @@ def ichebt(a, b=None, nthread=0, engine="auto"):
 	a[1:-1] *= 0.5
 	return redft00(a, b, nthread)
 
+# ------------------------------------------------------------------ host helpers of pixell.fft (:319-433)
+
+def fft_len(n, direction="below", factors=None):
+	"""pixell/fft.py:319-321: the largest product of powers of `factors` not above n ("below"), or the smallest one
+	not below n ("above")"""
+	factors = [2, 3, 5, 7, 11, 13] if factors is None else [int(f) for f in factors]
+	below = direction == "below"
+	target = int(np.floor(n)) if below else int(np.ceil(n))
+	if 1 in factors: return target
+	# The reference walks the smooth numbers i = 1, 2, ... in ascending order and, for "below", keeps the LAST product i*f <= n
+	# it meets (factors in the order given) -- not the largest: fft_len(7) is 6, because 2*3 is met after 1*7.  Mirrored as
+	# it behaves (callers size their arrays with it); "above" keeps the smallest product >= n.
+	top = target if below else max(target, 1)*min(factors)
+	smooth = np.zeros(top+2, bool); smooth[1] = True
+	best = None
+	for i in range(1, target+1):
+		if not smooth[i]: continue
+		for f in factors:
+			m = i*f
+			if below:
+				if m <= n: best = m
+			elif m >= n and (best is None or m < best): best = m
+			if m <= top: smooth[m] = True
+	return best
+
+def asfcarray(a):
+	"""pixell/fft.py:323-325"""
+	return _asfc(a)
+
+def empty(shape, dtype):
+	"""pixell/fft.py:327-328"""
+	return empty_aligned(shape, dtype)
+
+def ind2freq(n, i, d=1.0): return np.where(np.asarray(i) < n/2, i, -n+np.asarray(i))/(d*n)
+def int2rfreq(n, i, d=1.0): return np.asarray(i)/(n*d)
+def freq2ind(n, f, d=1.0):
+	j = np.asarray(f)*(d*n)
+	return np.where(j >= 0, j, n+j)
+def rfreq2ind(n, f, d=1.0): return np.asarray(f)*(n*d)
+
+def shift(a, shift, axes=None, nofft=False, deriv=None, engine="auto"):
+	"""pixell/fft.py:350-369: shift a by a (fractional) number of samples along the given axes (Fourier shift theorem);
+	deriv = i also differentiates along axis i; nofft: a is already the transform and the transform is returned"""
+	a = np.asanyarray(a)
+	work = a.astype(np.result_type(a.dtype, np.complex64), copy=True)
+	shift = np.atleast_1d(shift)
+	axes = tuple(range(-len(shift), 0)) if axes is None else _astuple(axes)
+	fa = work if nofft else fft(work, axes=list(axes))
+	for i, ax in enumerate(axes):
+		ax %= work.ndim
+		fr = fftfreq(work.shape[ax])
+		ph = np.exp(-2j*np.pi*fr*shift[i])
+		if deriv == i: ph = ph*(-2j*np.pi*fr)
+		fa *= ph.reshape((1,)*ax + (-1,) + (1,)*(work.ndim-ax-1))
+	res = fa if nofft else ifft(fa, work, axes=list(axes), normalize=True)
+	return res if np.iscomplexobj(a) else res.real
+
+def resample_fft(fa, n, out=None, axes=-1, norm=1, op=lambda a, b: b):
+	"""pixell/fft.py:389-433: pad or truncate the transform fa along `axes` to n samples (low frequencies of both signs are
+	kept: the first c//2 and the last c - c//2 entries, c = min(old, new) length), times norm; out = op(out, ...)"""
+	fa = np.asanyarray(fa)
+	axes = _astuple(axes)
+	n = [int(v) for v in (np.zeros(len(axes), int) + n)]
+	oshape = list(fa.shape)
+	for ax, m in zip(axes, n): oshape[ax] = m
+	oshape = tuple(oshape)
+	if out is None: out = np.zeros(oshape, fa.dtype)
+	elif tuple(out.shape) != oshape: raise ValueError("out argument has wrong shape in resample. Expected %s but got %s" % (str(oshape), str(out.shape)))
+	for corner in np.ndindex(*([2]*len(axes))):
+		sel = [slice(None)]*len(oshape)
+		for which, ax in zip(corner, axes):
+			c = min(fa.shape[ax], oshape[ax])
+			sel[ax] = slice(0, c//2) if which == 0 else slice(-(c-c//2), None)
+		sel = tuple(sel)
+		src = fa[sel] if norm == 1 else fa[sel]*norm
+		out[sel] = op(out[sel], src)
+	return out
+
+def resample(a, n, axes=None, nthread=0, engine="auto"):
+	"""pixell/fft.py:371-387: Fourier resampling of the given axes (default: the last ones) to length n"""
+	a = np.asarray(a)
+	n = _astuple(n)
+	if axes is None: axes = [-len(n)+i for i in range(len(n))]
+	axes = list(_astuple(axes))
+	if len(n) != len(axes): raise ValueError("Resize size n = %s does not match axes = %s" % (str(n), str(axes)))
+	fa = fft(a.astype(np.result_type(a.dtype, np.complex64)), axes=axes)
+	fa = resample_fft(fa, n, axes=axes, norm=1/np.prod([a.shape[ax] for ax in axes]))
+	out = ifft(fa, axes=axes, normalize=False)
+	return out if np.iscomplexobj(a) else out.real
+
 def fftfreq(n, d=1.0, dtype=np.float64): return np.fft.fftfreq(n, d=d).astype(dtype, copy=False)
 def rfftfreq(n, d=1.0, dtype=np.float64): return np.arange(n//2+1, dtype=dtype)/(n*d)

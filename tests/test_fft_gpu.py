@@ -381,3 +381,20 @@ def test_enmap_dct_roundtrip():
 	assert rel(np.asarray(got), want) < 1e-12
 	back = enmap.idct(got)
 	assert rel(np.asarray(back), m*(4*23*35)/((2*24-1)*(2*36-1))) < 1e-12
+
+def test_shift_and_resample(F):
+	"""fft.shift / fft.resample (reference fft.py:350-387) on the engine: integer shifts are rolls, a band-limited signal
+	resampled to a finer grid is the signal evaluated there, and back"""
+	x = np.random.default_rng(11).standard_normal((3, 40))
+	assert rel(F.shift(x, 3), np.roll(x, 3, -1)) < 1e-12
+	assert rel(F.shift(x+0j, [1, -2], axes=(0, 1)), np.roll(np.roll(x, 1, 0), -2, 1)+0j) < 1e-12
+	t = np.arange(40)/40.0
+	sig = np.cos(2*np.pi*3*t) + 0.5*np.sin(2*np.pi*7*t)
+	dsig = -2*np.pi*3/40*np.sin(2*np.pi*3*t) + 0.5*2*np.pi*7/40*np.cos(2*np.pi*7*t)
+	assert rel(F.shift(sig, 0.0, deriv=0), -dsig) < 1e-11      # the derivative with respect to the SHIFT, d/ds a(x - s) = -a'(x), as the reference defines it
+	t2 = np.arange(100)/100.0
+	fine = F.resample(sig, 100)
+	assert rel(fine, np.cos(2*np.pi*3*t2) + 0.5*np.sin(2*np.pi*7*t2)) < 1e-12
+	assert rel(F.resample(fine, 40), sig) < 1e-12
+	img = np.random.default_rng(12).standard_normal((2, 12, 18))
+	assert F.resample(img, (24, 36)).shape == (2, 24, 36) and rel(F.resample(F.resample(img, (24, 36)), (12, 18)), img) < 1e-12

@@ -230,3 +230,35 @@ def test_wavelet_bases_and_scale_geometries():
 	assert cs_[-1] == 180 and dec.min() <= -30+1e-9 and dec.max() >= 10 and cs_[-2] <= 22      # 2 degree grid (minres), 21 rows
 	cut, cutw = geometry.slice_geometry(shape, wcs, 0, shape[0], 0, shape[1]//2)
 	with pytest.raises(NotImplementedError): wavelets.make_wavelet_geometry_curved(cut, cutw, np.pi/60)
+
+def test_fft_host_helpers():
+	"""pixell.fft's pure host helpers (reference fft.py:319-345, 389-433) as the reference behaves: values below were
+	produced by the reference's functions (fft_len keeps the last product it meets, not the largest: fft_len(7) == 6)"""
+	from pixell_b200 import fft as F
+	want = {(7, "below"): 6, (7, "above"): 7, (100, "below"): 100, (100, "above"): 100, (1000, "below"): 1000, (1000, "above"): 1000,
+		(4099, "below"): 4096, (4099, "above"): 4116, (10000.5, "below"): 10000, (10000.5, "above"): 10010}
+	for (n, d), v in want.items(): assert F.fft_len(n, d) == v, (n, d)
+	assert F.fft_len(1, "below") is None and F.fft_len(1, "above") == 2
+	i = np.arange(10)
+	assert np.allclose(F.ind2freq(10, i, 0.5), np.fft.fftfreq(10, 0.5)) and np.allclose(F.freq2ind(10, np.fft.fftfreq(10, 0.5), 0.5), i)
+	assert np.allclose(F.int2rfreq(10, i[:6], 0.5), np.fft.rfftfreq(10, 0.5)) and np.allclose(F.rfreq2ind(10, np.fft.rfftfreq(10, 0.5), 0.5), i[:6])
+	# resample_fft: low frequencies of both signs survive, the rest is zero padding / dropped
+	fa = np.arange(8.0)+0j
+	up = F.resample_fft(fa, 12)
+	assert np.array_equal(up, np.array([0, 1, 2, 3, 0, 0, 0, 0, 4, 5, 6, 7])+0j)
+	down = F.resample_fft(fa, 5, norm=2)
+	assert np.array_equal(down, 2*np.array([0, 1, 5, 6, 7])+0j)
+	acc = np.ones(12, complex)
+	F.resample_fft(fa, 12, out=acc, op=lambda a, b: a+b)
+	assert np.array_equal(acc, up+1)
+	try:
+		sys_path_added = False
+		import sys
+		if "/root/reference" not in sys.path: sys.path.insert(0, "/root/reference"); sys_path_added = True
+		from pixell import fft as RF
+	except Exception: RF = None
+	if RF is not None:
+		rng = np.random.default_rng(0); big = rng.standard_normal((3, 8, 9))+0j
+		for n, axes in ((12, -1), ((5, 20), (-2, -1)), (4, 0)):
+			assert np.array_equal(F.resample_fft(big, n, axes=axes, norm=0.5), RF.resample_fft(big, n, axes=axes, norm=0.5))
+		for n in (2, 17.2, 360, 8191): assert F.fft_len(n) == RF.fft_len(n) and F.fft_len(n, "above", [3, 7]) == RF.fft_len(n, "above", [3, 7])
