@@ -1,2 +1,4 @@
 set -x
-python -m pytest tests/test_fft_gpu.py -x -q -m gpu -k "shift_and_resample or engine_object or dct" 2>&1 | tail -3
+python scripts/tune_legendre.py c3 0 0123 2>&1 | tail -4
+python scripts/e2e_probe.py 2>/dev/null
+python -m pytest tests/test_sht_gpu.py tests/test_curvedsky_gpu.py tests/test_baseline_parity_gpu.py tests/test_mc_gpu.py -x -q -m gpu 2>&1 | tail -2
