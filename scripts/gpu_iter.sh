@@ -1,4 +1,5 @@
+# scratch script of the current experiment: rewritten before every `gpurun -- 'bash scripts/gpu_iter.sh <tag>'`
 set -x
-python scripts/tune_legendre.py c3 0 0123 2>&1 | tail -4
-python scripts/e2e_probe.py 2>/dev/null
-python -m pytest tests/test_sht_gpu.py tests/test_curvedsky_gpu.py tests/test_baseline_parity_gpu.py tests/test_mc_gpu.py -x -q -m gpu 2>&1 | tail -2
+mkdir -p gpurun_out
+T=${1:-it}
+python scripts/e2e_probe.py > gpurun_out/${T}_probe.json 2>/dev/null; cat gpurun_out/${T}_probe.json
