@@ -143,6 +143,7 @@ size_t b2_sht_plan::bytes() const
 {
 	size_t b = mstart.bytes() + geom.bytes() + fft.bytes() + leg.bytes() + leg2.bytes() + legb.bytes() + w2d.bytes() + stage_alm.bytes() + stage_map.bytes();
 	for (auto &g : groups) b += g->bytes();
+	b += pack.bytes();
 	for (auto &t : tables) b += t.second->bytes();
 	for (auto &t : starts) if (t.second) b += t.second->bytes();
 	if (resamp) b += resamp->bytes();
@@ -327,6 +328,7 @@ extern "C" int b2_sht_plan_rings_general(b2_sht_plan **out, int nring, const dou
 			p->groups.push_back(std::move(pre[i])); i++;
 		}
 	}
+	if (p->pack.build(p->groups)) return 1;
 	const int ns = (int)std::min<size_t>(16, p->groups.size());
 	p->gstreams.assign(ns, nullptr); p->gjoin.assign(ns, nullptr);
 	for (int i = 0; i < ns; i++) {
@@ -336,6 +338,13 @@ extern "C" int b2_sht_plan_rings_general(b2_sht_plan **out, int nring, const dou
 	B2_CHECK(cudaEventCreateWithFlags(&p->gfork, cudaEventDisableTiming));
 	*out = p.release();
 	return 0;
+}
+
+// packed launches (RingPack) unless B2_NO_PACK=1 asks for one launch per group on the side streams
+static bool use_pack(const b2_sht_plan *p)
+{
+	static const bool off = getenv("B2_NO_PACK") && atoi(getenv("B2_NO_PACK"));
+	return !off && !p->pack.buckets.empty();
 }
 
 // ring FFTs of a general plan: fork the groups over the side streams, join back into st
@@ -625,12 +634,14 @@ static int group_compute(Exec &E, GroupCtx &G)
 		}
 		B2_CHECK(cudaEventRecord(p->ev[3], E.sf));
 		if (p->groups.empty()) { if (ring_leg2map(p->fft, E.ncm, leg, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.sf)) return 1; }
+		else if (use_pack(p)) { if (ring_leg2map_pack(p->pack, *p->groups[0], E.ncm, leg, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.sf)) return 1; }
 		else if (run_groups(p, E.sf, [&](const RingFft &g, cudaStream_t s) { return ring_leg2map(g, E.ncm, leg, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, s); })) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[4], E.sf));
 		TR("K3 done", E.sf);
 		if (two) B2_CHECK(cudaEventRecord(p->ev_free[G.lane], E.sf));
 	} else {
 		if (p->groups.empty()) { if (ring_map2leg(p->fft, E.ncm, leg, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, E.sf)) return 1; }
+		else if (use_pack(p)) { if (ring_map2leg_pack(p->pack, *p->groups[0], E.ncm, leg, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, E.sf)) return 1; }
 		else if (run_groups(p, E.sf, [&](const RingFft &g, cudaStream_t s) { return ring_map2leg(g, E.ncm, leg, p->geom.nring_pad, G.dmap, G.dmap_cs, E.dtype, E.op == OP_ADJ_SYNTH, s); })) return 1;
 		B2_CHECK(cudaEventRecord(p->ev[2], E.sf));
 		TR("K4 done", E.sf);

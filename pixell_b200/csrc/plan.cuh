@@ -26,6 +26,7 @@ struct b2_sht_plan {
 	RingFft fft;
 	// ring sets with per-ring nphi / phi0 (b2_sht_plan_rings_general): one RingFft per distinct nphi instead of `fft`
 	std::vector<std::unique_ptr<RingFft>> groups;
+	RingPack pack;                      // the groups' ring FFTs in a few launches (one per block size) instead of one per group
 	std::vector<int64_t> npix_h;        // pixels of every ring (general plans)
 	// the groups' launches are small (a cap ring pair each): they are spread over side streams so that they overlap
 	std::vector<cudaStream_t> gstreams;

@@ -267,33 +267,34 @@ struct RingArgs {
 };
 
 // e^{i m phi0} of this block's ring
-__device__ __forceinline__ double2 ring_phase(const RingArgs &A, int m)
+__device__ __forceinline__ double2 ring_phase(const RingArgs &A, int m, int bx)
 {
 	if (!A.phi0s) return __ldg(&A.phase[m]);
-	double sn, c; sincos((double)m*A.phi0s[blockIdx.x], &sn, &c);
+	double sn, c; sincos((double)m*A.phi0s[bx], &sn, &c);
 	return make_double2(c, sn);
 }
 
 // TAB = true: the plan's table (cylindrical maps).  The choice is made OUTSIDE the hot loops: a branch inside them keeps the
 // loads of an unrolled loop from being issued together (one outstanding load per thread, profiles/r3m_fftk_stalls.txt).
-template<bool TAB> __device__ __forceinline__ double2 ring_phase_t(const RingArgs &A, int m)
+template<bool TAB> __device__ __forceinline__ double2 ring_phase_t(const RingArgs &A, int m, int bx)
 {
 	if (TAB) return __ldg(&A.phase[m]);
-	double sn, c; sincos((double)m*A.phi0s[blockIdx.x], &sn, &c);
+	double sn, c; sincos((double)m*A.phi0s[bx], &sn, &c);
 	return make_double2(c, sn);
 }
 
-__device__ __forceinline__ double2 leg_phase(const RingArgs &A, const double2 *legc, int m)
+__device__ __forceinline__ double2 leg_phase(const RingArgs &A, const double2 *legc, int m, int bx)
 {
-	double2 g = cmul(legc[(int64_t)m*A.nring_pad], ring_phase(A, m));
+	double2 g = cmul(legc[(int64_t)m*A.nring_pad], ring_phase(A, m, bx));
 	if (A.xdir < 0) g.y = -g.y;
 	return g;
 }
 
-template<typename MapT> __global__ void __launch_bounds__(512) k_leg2map(RingArgs A)
+// bx: index of this block's ring in the launch (the block index, or the position inside its group for the packed launches)
+template<typename MapT> __device__ __forceinline__ void leg2map_body(const RingArgs &A, const int bx)
 {
 	extern __shared__ __align__(16) double2 s[];
-	const int ring = A.ring_ids ? A.ring_ids[blockIdx.x] : A.ring0 + blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+	const int ring = A.ring_ids ? A.ring_ids[bx] : A.ring0 + bx, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
 	const double2 *legc = A.leg + ((int64_t)comp*(A.mmax + 1))*A.nring_pad + ring;
 	MapT *row = (MapT*)A.map + (int64_t)comp*A.map_cstride + A.ringstart[ring];
 	const int n = (int)A.nphi, nf = A.nfft, mmax = A.mmax;
@@ -308,7 +309,7 @@ template<typename MapT> __global__ void __launch_bounds__(512) k_leg2map(RingArg
 				#pragma unroll 8
 				for (int k = tid; k <= nf; k += T) {
 					const int kc = min(k, mmax);
-					double2 g = cmul(__ldg(&legc[(int64_t)kc*A.nring_pad]), ring_phase_t<decltype(TAB)::value>(A, kc));
+					double2 g = cmul(__ldg(&legc[(int64_t)kc*A.nring_pad]), ring_phase_t<decltype(TAB)::value>(A, kc, bx));
 					if (flip) g.y = -g.y;
 					if (k == 0) g = make_double2(g.x, 0.0);
 					if (k > mmax) g = make_double2(0, 0);
@@ -321,10 +322,10 @@ template<typename MapT> __global__ void __launch_bounds__(512) k_leg2map(RingArg
 			for (int k = tid; k <= nf; k += T) {
 				double2 acc = make_double2(0, 0);
 				if (k == 0 || k == nf) {
-					for (int m = k; m <= mmax; m += n) { double2 g = leg_phase(A, legc, m); acc.x += (m == 0 ? 1.0 : 2.0)*g.x; }
+					for (int m = k; m <= mmax; m += n) { double2 g = leg_phase(A, legc, m, bx); acc.x += (m == 0 ? 1.0 : 2.0)*g.x; }
 				} else {
-					for (int m = k; m <= mmax; m += n) acc = cadd(acc, leg_phase(A, legc, m));
-					for (int m = n - k; m <= mmax; m += n) acc = cadd(acc, cconj(leg_phase(A, legc, m)));
+					for (int m = k; m <= mmax; m += n) acc = cadd(acc, leg_phase(A, legc, m, bx));
+					for (int m = n - k; m <= mmax; m += n) acc = cadd(acc, cconj(leg_phase(A, legc, m, bx)));
 				}
 				s[SI(k)] = acc;
 			}
@@ -354,8 +355,8 @@ template<typename MapT> __global__ void __launch_bounds__(512) k_leg2map(RingArg
 	} else {
 		for (int k = tid; k < n; k += T) {
 			double2 acc = make_double2(0, 0);
-			for (int m = k; m <= mmax; m += n) { double2 g = leg_phase(A, legc, m); if (m == 0) g.y = 0; acc = cadd(acc, g); }
-			for (int m = (k == 0 ? n : n - k); m <= mmax; m += n) acc = cadd(acc, cconj(leg_phase(A, legc, m)));
+			for (int m = k; m <= mmax; m += n) { double2 g = leg_phase(A, legc, m, bx); if (m == 0) g.y = 0; acc = cadd(acc, g); }
+			for (int m = (k == 0 ? n : n - k); m <= mmax; m += n) acc = cadd(acc, cconj(leg_phase(A, legc, m, bx)));
 			s[SI(k)] = acc;
 		}
 		__syncthreads();
@@ -364,10 +365,10 @@ template<typename MapT> __global__ void __launch_bounds__(512) k_leg2map(RingArg
 	}
 }
 
-template<typename MapT> __global__ void __launch_bounds__(512) k_map2leg(RingArgs A)
+template<typename MapT> __device__ __forceinline__ void map2leg_body(const RingArgs &A, const int bx)
 {
 	extern __shared__ __align__(16) double2 s[];
-	const int ring = A.ring_ids ? A.ring_ids[blockIdx.x] : A.ring0 + blockIdx.x, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+	const int ring = A.ring_ids ? A.ring_ids[bx] : A.ring0 + bx, comp = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
 	double2 *legc = A.leg + ((int64_t)comp*(A.mmax + 1))*A.nring_pad + ring;
 	const MapT *row = (const MapT*)A.map + (int64_t)comp*A.map_cstride + A.ringstart[ring];
 	const int n = (int)A.nphi, nf = A.nfft, mmax = A.mmax;
@@ -395,7 +396,7 @@ template<typename MapT> __global__ void __launch_bounds__(512) k_map2leg(RingArg
 				double2 o = make_double2(dd.y, -dd.x);
 				double2 x = cadd(e, cmul(__ldg(&A.d.tw[m]), o));
 				if (flip) x.y = -x.y;
-				legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, ring_phase(A, m)), wgt);
+				legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, ring_phase(A, m, bx)), wgt);
 			}
 		} else
 		for (int m = tid; m <= mmax; m += T) {
@@ -408,7 +409,7 @@ template<typename MapT> __global__ void __launch_bounds__(512) k_map2leg(RingArg
 			double2 x = cadd(e, cmul(A.d.tw[k], o));
 			if (fold) x.y = -x.y;
 			if (A.xdir < 0) x.y = -x.y;
-			legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, ring_phase(A, m)), wgt);
+			legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, ring_phase(A, m, bx)), wgt);
 		}
 	} else {
 		for (int j = tid; j < n; j += T) s[SI(j)] = make_double2(j < A.npix ? (double)row[j] : 0.0, 0.0);
@@ -417,9 +418,39 @@ template<typename MapT> __global__ void __launch_bounds__(512) k_map2leg(RingArg
 		for (int m = tid; m <= mmax; m += T) {
 			double2 x = s[SI(A.d.rev[m % n])];
 			if (A.xdir < 0) x.y = -x.y;
-			legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, ring_phase(A, m)), wgt);
+			legc[(int64_t)m*A.nring_pad] = cscale(cmulc(x, ring_phase(A, m, bx)), wgt);
 		}
 	}
+}
+
+template<typename MapT> __global__ void __launch_bounds__(512) k_leg2map(RingArgs A) { leg2map_body<MapT>(A, blockIdx.x); }
+template<typename MapT> __global__ void __launch_bounds__(512) k_map2leg(RingArgs A) { map2leg_body<MapT>(A, blockIdx.x); }
+
+// Packed launches for ring sets with many distinct ring lengths (HEALPix: one group per nphi, two rings each in the caps):
+// all groups whose transforms want the same block size share ONE launch; block b looks up its group and its position in
+// it, takes the group's FFT description from device memory and runs the same body.  (One launch per group made a HEALPix
+// transform at nside 2048 a string of 4096 small launches.)
+struct GroupDesc { FftDesc d; int half, nfft, twoff, nring; int64_t nphi, npix; const int *ring_ids; const double *phi0s; };
+
+__device__ __forceinline__ RingArgs pack_args(const RingArgs &base, const GroupDesc *D, const int2 *blk, int &bx)
+{
+	const int2 b = blk[blockIdx.x];
+	const GroupDesc &G = D[b.x];
+	RingArgs A = base;
+	A.d = G.d; A.half = G.half; A.nfft = G.nfft; A.twoff = G.twoff; A.nring = G.nring; A.nphi = G.nphi; A.npix = G.npix;
+	A.ring_ids = G.ring_ids; A.phi0s = G.phi0s;
+	bx = b.y;
+	return A;
+}
+template<typename MapT> __global__ void __launch_bounds__(512) k_leg2map_pack(RingArgs base, const GroupDesc *D, const int2 *blk)
+{
+	int bx; const RingArgs A = pack_args(base, D, blk, bx);
+	leg2map_body<MapT>(A, bx);
+}
+template<typename MapT> __global__ void __launch_bounds__(512) k_map2leg_pack(RingArgs base, const GroupDesc *D, const int2 *blk)
+{
+	int bx; const RingArgs A = pack_args(base, D, blk, bx);
+	map2leg_body<MapT>(A, bx);
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -470,5 +501,65 @@ int ring_map2leg(const RingFft &F, int ncomp, double2 *leg, int64_t nring_pad,
 	if (dtype == 0) { if (set_smem(k_map2leg<double>, F.smem)) return 1; k_map2leg<double><<<grid, F.threads, F.smem, st>>>(A); }
 	else            { if (set_smem(k_map2leg<float>,  F.smem)) return 1; k_map2leg<float><<<grid, F.threads, F.smem, st>>>(A); }
 	B2_LAUNCH_CHECK();
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------ packed groups
+
+int RingPack::build(const std::vector<std::unique_ptr<RingFft>> &groups)
+{
+	buckets.clear();
+	if (groups.empty()) return 0;
+	std::vector<GroupDesc> gd(groups.size());
+	for (size_t g = 0; g < groups.size(); g++) {
+		const RingFft &F = *groups[g];
+		GroupDesc &G = gd[g];
+		G.d = F.tab.d; G.half = F.half; G.nfft = F.nfft; G.twoff = F.twoff; G.nring = F.nring; G.nphi = F.nphi; G.npix = F.npix;
+		G.ring_ids = F.ring_ids.p; G.phi0s = F.phi0s.p;
+	}
+	if (desc.alloc(sizeof(GroupDesc)*gd.size())) return 1;
+	B2_CHECK(cudaMemcpy(desc.p, gd.data(), sizeof(GroupDesc)*gd.size(), cudaMemcpyHostToDevice));
+	// one bucket per block size; inside a bucket the long rings go first
+	std::map<int, std::vector<int>> by_threads;
+	for (size_t g = 0; g < groups.size(); g++) by_threads[groups[g]->threads].push_back((int)g);
+	std::vector<int2> all;
+	for (auto &bt : by_threads) {
+		std::vector<int> &gs = bt.second;
+		std::sort(gs.begin(), gs.end(), [&](int a, int b) { return groups[a]->nfft > groups[b]->nfft; });
+		Bucket B; B.threads = bt.first; B.first = (int)all.size(); B.smem = 0;
+		for (int g : gs) {
+			B.smem = std::max(B.smem, groups[g]->smem);
+			for (int i = 0; i < groups[g]->nring; i++) all.push_back(make_int2(g, i));
+		}
+		B.nblocks = (int)all.size() - B.first;
+		buckets.push_back(B);
+	}
+	if (blocks.upload(all)) return 1;
+	return 0;
+}
+
+int ring_leg2map_pack(const RingPack &P, const RingFft &F0, int ncomp, const double2 *leg, int64_t nring_pad, void *map, int64_t map_cstride, int dtype, cudaStream_t st)
+{
+	RingArgs A = ring_args(F0, leg, nring_pad, map, map_cstride, 0);
+	for (const RingPack::Bucket &B : P.buckets) {
+		dim3 grid(B.nblocks, ncomp);
+		const int2 *blk = P.blocks.p + B.first;
+		if (dtype == 0) { if (set_smem(k_leg2map_pack<double>, B.smem)) return 1; k_leg2map_pack<double><<<grid, B.threads, B.smem, st>>>(A, (const GroupDesc*)P.desc.p, blk); }
+		else            { if (set_smem(k_leg2map_pack<float>,  B.smem)) return 1; k_leg2map_pack<float><<<grid, B.threads, B.smem, st>>>(A, (const GroupDesc*)P.desc.p, blk); }
+		B2_LAUNCH_CHECK();
+	}
+	return 0;
+}
+
+int ring_map2leg_pack(const RingPack &P, const RingFft &F0, int ncomp, double2 *leg, int64_t nring_pad, const void *map, int64_t map_cstride, int dtype, int use_weight, cudaStream_t st)
+{
+	RingArgs A = ring_args(F0, leg, nring_pad, map, map_cstride, use_weight);
+	for (const RingPack::Bucket &B : P.buckets) {
+		dim3 grid(B.nblocks, ncomp);
+		const int2 *blk = P.blocks.p + B.first;
+		if (dtype == 0) { if (set_smem(k_map2leg_pack<double>, B.smem)) return 1; k_map2leg_pack<double><<<grid, B.threads, B.smem, st>>>(A, (const GroupDesc*)P.desc.p, blk); }
+		else            { if (set_smem(k_map2leg_pack<float>,  B.smem)) return 1; k_map2leg_pack<float><<<grid, B.threads, B.smem, st>>>(A, (const GroupDesc*)P.desc.p, blk); }
+		B2_LAUNCH_CHECK();
+	}
 	return 0;
 }

@@ -1,6 +1,8 @@
 // ringfft.cuh -- K3 (leg -> map, c2r ring FFT) and K4 (map -> leg, r2c ring FFT) of the SHT engine.
 #pragma once
 #include "fft_smem.cuh"
+#include <vector>
+#include <memory>
 
 struct RingFft {
 	int64_t nphi = 0;       // pixels per full circle
@@ -38,3 +40,18 @@ int ring_leg2map(const RingFft &F, int ncomp, const double2 *leg, int64_t nring_
                  void *map, int64_t map_cstride, int dtype, cudaStream_t st, int ring0 = 0, int nrings = 0);
 int ring_map2leg(const RingFft &F, int ncomp, double2 *leg, int64_t nring_pad,
                  const void *map, int64_t map_cstride, int dtype, int use_weight, cudaStream_t st);
+
+// All ring groups of a general plan (HEALPix) in a few launches: see k_leg2map_pack in ringfft.cu.  F0 is any group of the
+// plan (mmax, phase table, ringstart and weight arrays are the plan's and common to all groups).
+struct RingPack {
+	struct Bucket { int threads, first, nblocks; size_t smem; };
+	std::vector<Bucket> buckets;
+	DevBuf<char> desc;          // GroupDesc per group
+	DevBuf<int2> blocks;        // (group, position in the group) per block, bucket after bucket
+	int build(const std::vector<std::unique_ptr<RingFft>> &groups);
+	size_t bytes() const { return desc.bytes() + blocks.bytes(); }
+};
+int ring_leg2map_pack(const RingPack &P, const RingFft &F0, int ncomp, const double2 *leg, int64_t nring_pad,
+                      void *map, int64_t map_cstride, int dtype, cudaStream_t st);
+int ring_map2leg_pack(const RingPack &P, const RingFft &F0, int ncomp, double2 *leg, int64_t nring_pad,
+                      const void *map, int64_t map_cstride, int dtype, int use_weight, cudaStream_t st);
