@@ -2,8 +2,5 @@
 set -x
 mkdir -p gpurun_out
 T=${1:-it}
-python -m pytest tests/test_healpix_gpu.py tests/test_sht_gpu.py tests/test_general_gpu.py -x -q -m gpu 2>&1 | tail -2
-python scripts/bench_healpix.py 2048 4096 2 2>/dev/null | tee gpurun_out/${T}_healpix_pack.json
-B2_NO_PACK=1 python scripts/bench_healpix.py 2048 4096 2 2>/dev/null | tee gpurun_out/${T}_healpix_nopack.json
-python scripts/bench_healpix.py 512 1024 2 2>/dev/null
-python scripts/e2e_probe.py 2>/dev/null | cut -c1-120
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/${T}_pytest_gpu.txt 2>&1; tail -3 gpurun_out/${T}_pytest_gpu.txt
