@@ -178,6 +178,13 @@ void b2_fft_plan_destroy(b2_fft_plan *plan);
 int b2_queb_rotate(void *data, int64_t comp_stride, int64_t nbatch, int64_t batch_stride, int ny, int nx,
                    const double *ly, const double *lx, int spin, int sign, int dtype, int mem, void *stream);
 
+/* Fourier-space filter of complex [nbatch][ny][nx] maps, in place, DEVICE pointers: data[b][y][x] *= fy[y]*fx[x] (both given)
+ * or *= f2[y][x] (f2 given): what enmap.smooth_gauss / apply_window do between enmap.fft and enmap.ifft with numpy
+ * broadcasting (pixell/enmap.py:1429-1460), as one pass over the array.  Strides in complex elements; the filters have the
+ * real dtype of the data. */
+int b2_fourier_filter(void *data, int64_t nbatch, int64_t batch_stride, int64_t row_stride, int ny, int nx,
+                      const void *fy, const void *fx, const void *f2, int dtype, void *stream);
+
 /* ---- synthesis at arbitrary positions: the steps of ducc0.sht.experimental.synthesis_general (call site
  * pixell/curvedsky.py:993-1016) around the Legendre stage (b2_alm2leg on a Clenshaw-Curtis plan) and the FFT
  * engine (b2_fft_*).  All pointers are DEVICE pointers, complex128 / float64.

@@ -55,6 +55,7 @@ _PROTOS = {
 	"b2_general_spread": ([c_vp, c_int, c_int, c_vp, c_i64, c_int, c_dbl, c_vp, c_i64, c_vp], c_int),
 	"b2_general_gather": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
 	"b2_general_fold": ([c_vp, c_vp, c_int, c_int, c_int, c_i64, c_int, c_vp], c_int),
+	"b2_fourier_filter": ([c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp], c_int),
 	"b2_queb_rotate": ([c_vp, c_i64, c_i64, c_i64, c_int, c_int, _dblp, _dblp, c_int, c_int, c_int, c_int, c_vp], c_int),
 }
 

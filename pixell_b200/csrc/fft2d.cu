@@ -809,3 +809,33 @@ extern "C" int b2_queb_rotate(void *data, int64_t comp_stride, int64_t nbatch, i
 	B2_CHECK(cudaStreamSynchronize(st));      // the l table (and the staging buffer) are released on return
 	return 0;
 }
+
+// ------------------------------------------------------------------------------------ Fourier-space filter
+// data[b][y][x] *= fy[y]*fx[x] (separable, e.g. a Gaussian beam exp(-l^2 sigma^2/2) = gy(ly) gx(lx)) or *= f2[y][x]: the
+// harmonic filter between enmap.fft and enmap.ifft (pixell/enmap.py:1429-1439 smooth_gauss, apply_window :1441-1460) in one
+// pass over the array: two 16-byte elements per thread, rows by blockIdx.y, batch members by blockIdx.z.
+template<typename C, typename Rr> __global__ void __launch_bounds__(256) k_fourier_filter(C *data, int64_t batch_stride, int64_t row_stride,
+	int ny, int nx, const Rr *fy, const Rr *fx, const Rr *f2)
+{
+	const int y = blockIdx.y;
+	C *row = data + (int64_t)blockIdx.z*batch_stride + (int64_t)y*row_stride;
+	const Rr gy = fy ? fy[y] : (Rr)1;
+	for (int x = blockIdx.x*blockDim.x + threadIdx.x; x < nx; x += gridDim.x*blockDim.x) {
+		const Rr g = f2 ? f2[(int64_t)y*nx + x] : gy*fx[x];
+		C v = row[x]; v.x *= g; v.y *= g; row[x] = v;
+	}
+}
+
+extern "C" int b2_fourier_filter(void *data, int64_t nbatch, int64_t batch_stride, int64_t row_stride, int ny, int nx,
+	const void *fy, const void *fx, const void *f2, int dtype, void *stream)
+{
+	B2_REQUIRE(data && ((fy && fx) || f2), "fourier_filter: need fy and fx, or f2");
+	B2_REQUIRE(ny >= 1 && nx >= 1 && nbatch >= 1 && nbatch < 65536 && ny <= 65535, "fourier_filter: bad extents");
+	B2_REQUIRE(dtype == B2_F64 || dtype == B2_F32, "fourier_filter: bad dtype");
+	cudaStream_t st = (cudaStream_t)stream;
+	dim3 grid((unsigned)std::min<int64_t>((nx + 511)/512, 64), ny, (unsigned)nbatch);
+	if (dtype == B2_F64) k_fourier_filter<double2, double><<<grid, 256, 0, st>>>((double2*)data, batch_stride, row_stride, ny, nx, (const double*)fy, (const double*)fx, (const double*)f2);
+	else k_fourier_filter<float2, float><<<grid, 256, 0, st>>>((float2*)data, batch_stride, row_stride, ny, nx, (const float*)fy, (const float*)fx, (const float*)f2);
+	B2_LAUNCH_CHECK();
+	return 0;
+}

@@ -119,9 +119,7 @@ def smooth_gauss(emap, sigma, wcs=None):
 	filt = np.exp(-0.5*sigma**2*(ly[:, None]**2 + lx[None, :nx//2+1]**2))
 	if sigma < 0: filt = 1-filt          # negative sigma: the complementary high-pass filter (pixell/enmap.py:1437-1438)
 	f = enfft.rfft(emap, axes=[-2, -1])
-	if L.is_torch(f):
-		import torch
-		f *= torch.as_tensor(filt, device=f.device).to(f.real.dtype)
+	if L.is_torch(f): enfft.fourier_filter(f, f2=filt)
 	else: f *= filt.astype(f.real.dtype)
 	out = enfft.irfft(f, n=nx, axes=[-2, -1], normalize=True)
 	if not L.is_torch(out): out = geometry.ndmap(out, wcs)

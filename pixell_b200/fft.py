@@ -290,6 +290,32 @@ def ichebt(a, b=None, nthread=0, engine="auto"):
 	a[1:-1] *= 0.5
 	return redft00(a, b, nthread)
 
+def fourier_filter(ft, fy=None, fx=None, f2=None):
+	"""ft[..., y, x] *= fy[y]*fx[x] (or *= f2[y, x]) in place on the device, one pass (b2_fourier_filter): the harmonic
+	filter between a forward and a backward 2-D transform.  ft: complex torch CUDA tensor, contiguous in x, uniform row
+	and batch strides; the filters: real arrays / tensors of the matching precision"""
+	import torch
+	if not L.is_torch(ft): raise ValueError("fourier_filter works on device tensors (use numpy broadcasting for host arrays)")
+	ny, nx = ft.shape[-2:]
+	nb = int(np.prod(ft.shape[:-2])) if ft.ndim > 2 else 1
+	st = L.strides_elems(ft)
+	if st[-1] != 1: raise ValueError("fourier_filter: the last axis must be contiguous")
+	bs = st[-3] if ft.ndim > 2 else 0
+	if ft.ndim > 3 and not ft.reshape(nb, ny, nx).data_ptr() == ft.data_ptr(): raise ValueError("fourier_filter: leading axes must be mergeable")
+	if ft.ndim > 3:
+		ft3 = ft.view(nb, ny, nx); bs = L.strides_elems(ft3)[0]
+	rdt = torch.float64 if ft.dtype == torch.complex128 else torch.float32
+	dev = ft.device
+	def prep(a, shape):
+		if a is None: return None
+		t = torch.as_tensor(a, device=dev).to(rdt).contiguous()
+		if tuple(t.shape) != shape: raise ValueError("fourier_filter: filter has shape %s, expected %s" % (tuple(t.shape), shape))
+		return t
+	ty, tx, t2 = prep(fy, (ny,)), prep(fx, (nx,)), prep(f2, (ny, nx))
+	L.check(L.lib().b2_fourier_filter(ft.data_ptr(), nb, bs, st[-2], ny, nx, None if ty is None else ty.data_ptr(), None if tx is None else tx.data_ptr(),
+		None if t2 is None else t2.data_ptr(), L.F64 if rdt == torch.float64 else L.F32, L.current_stream(ft)))
+	return ft
+
 # ------------------------------------------------------------------ host helpers of pixell.fft (:319-433)
 
 def fft_len(n, direction="below", factors=None):

@@ -405,3 +405,18 @@ def test_shift_and_resample(F):
 	up = F.resample(img, (26, 38))
 	assert up.shape == (2, 26, 38) and rel(up, want) < 1e-12
 	assert rel(F.resample(up, (13, 19)), img) < 1e-12
+
+def test_fourier_filter(F):
+	"""b2_fourier_filter: the separable and the full 2-D filter against numpy broadcasting, float64 and float32, batches"""
+	import torch
+	rng = np.random.default_rng(13)
+	for dt, tol in ((np.complex128, 1e-15), (np.complex64, 1e-6)):
+		a = (rng.standard_normal((3, 17, 40)) + 1j*rng.standard_normal((3, 17, 40))).astype(dt)
+		fy, fx, f2 = rng.standard_normal(17), rng.standard_normal(40), rng.standard_normal((17, 40))
+		t = torch.from_numpy(a.copy()).cuda()
+		assert rel(F.fourier_filter(t, fy=fy, fx=fx).cpu().numpy(), a*fy[:, None]*fx[None, :]) < tol
+		t = torch.from_numpy(a.copy()).cuda()
+		assert rel(F.fourier_filter(t, f2=f2).cpu().numpy(), a*f2) < tol
+		t = torch.from_numpy(a[0].copy()).cuda()
+		assert rel(F.fourier_filter(t, fy=fy, fx=fx).cpu().numpy(), a[0]*fy[:, None]*fx[None, :]) < tol
+	with pytest.raises(ValueError): F.fourier_filter(torch.zeros((4, 5), dtype=torch.complex128, device="cuda"), fy=np.ones(3), fx=np.ones(5))
