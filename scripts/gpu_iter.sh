@@ -2,5 +2,4 @@
 set -x
 mkdir -p gpurun_out
 T=${1:-it}
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.txt 2>&1; tail -1 gpurun_out/${T}_smoke.txt
-timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/${T}_pytest_gpu.txt 2>&1; tail -3 gpurun_out/${T}_pytest_gpu.txt
+python scripts/e2e_probe.py > gpurun_out/${T}_probe.json 2>/dev/null; cat gpurun_out/${T}_probe.json
