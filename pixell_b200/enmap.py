@@ -142,7 +142,8 @@ def apply_window(emap, pow=1.0, order=0, scale=1, nofft=False, wcs=None):
 	wy, wx = calc_window(emap.shape, order=order, scale=scale)
 	wy, wx = wy**pow, wx**pow
 	def mul(f, wy, wx):
-		if L.is_torch(f):
+		if L.is_torch(f) and f.is_contiguous(): enfft.fourier_filter(f, fy=wy, fx=wx)      # one pass (b2_fourier_filter)
+		elif L.is_torch(f):
 			import torch
 			f *= torch.as_tensor(wy, device=f.device).to(f.real.dtype)[:, None]
 			f *= torch.as_tensor(wx, device=f.device).to(f.real.dtype)[None, :]

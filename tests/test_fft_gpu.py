@@ -335,6 +335,11 @@ def test_apply_window(order):
 	assert rel(np.asarray(enmap.unapply_window(got, order=order)), np.asarray(m)) < 1e-10
 	f = enmap.fft(m)
 	assert rel(np.asarray(enmap.apply_window(f, order=order, nofft=True)), np.asarray(f)*wy[:, None]*wx[None, :]) < 1e-13
+	# device tensors take the one-pass filter kernel
+	import torch
+	tm = torch.from_numpy(np.asarray(m)).cuda()
+	assert rel(enmap.apply_window(tm, order=order, wcs=wcs).cpu().numpy(), want) < 1e-12
+	assert rel(enmap.smooth_gauss(tm, 0.01, wcs=wcs).cpu().numpy(), np.asarray(enmap.smooth_gauss(m, 0.01))) < 1e-12
 
 # ------------------------------------------------------------------ r2r (DCT / DST), reference pixell/fft.py:211-317
 
